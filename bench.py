@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
+
+Metric      : CT volumes/s through the 3D multi-scale deformable attention hot path (forward + gradient).
+Workload    : `visceral_refine_fwd_bwd` = configs[1]: the deformable FPN refinement of the Focused-Decoder model at
+              synthetic 160x160x256 volumes, fp32 -- per training step a batch of 2 volumes (yaml batch_size 2) passes
+              `layers: 2` DefAttnLayers, i.e. 2 x (MSDeformAttn3D forward + backward) at N=2, S=Lq=117000,
+              L=4 levels (40,40,64)..(5,5,8), M=6 heads x C=64, P=4 points.  Sampling locations follow the model's own
+              pattern (dist "B": voxel-centre reference points + directional offsets + N(0,1) voxels of jitter).
+Step        : one pass of that hot path over one batch (4 kernel launches + 2 grad_value zero-fills).
+Multi-GPU   : one process per GPU, each rank owns its own batch (volume sharding, weak scaling), no data-path collective.
+
+Keys beyond the base contract: `roofline` (dominant kernel vs the measured HBM peak), `cpu_baseline` (the reference's
+use_cuda=False route restated on host cores), `e2e` (same metric through the host-buffer C-ABI entry point, copies
+inside the timed region), `kernels` (per-launch CUDA-event times), `clocks`.
+`--impl reference` runs the CPU arm: the reference's CPU implementation of this path (restated in oracle/) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ct_volumes_per_sec"
+UNIT = "volumes/s"
+LAYERS = 2            # config/attn_fpn_foc_dec_visceral.yaml:83  `layers: 2`
+BATCH = 2             # config/attn_fpn_foc_dec_visceral.yaml:25  `batch_size: 2`
+GEOM = "visceral_refine"
+DIST = "B"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Algorithmic bytes (SURVEY.md 8d / DESIGN.md): compulsory HBM traffic of one launch
+# ---------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, S, M, C, L, Lq, P, ev=4, eg=4):
+    T = N * Lq * M * L * P
+    val = min(N * S * M * C, 8 * T * C)
+    out = N * Lq * M * C
+    fwd = ev * (val + out) + eg * 4 * T
+    bwd = ev * (val + out) + eg * 2 * val + eg * 4 * T + eg * 4 * T     # value + gOut reads, gV zero-fill + write-back, loc/aw, gLoc/gAw
+    return fwd, bwd
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Clock sampling during the timed region
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU implementation of the path (restated in oracle/), bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(sample_queries, seed=1234, threads=None):
+    """One fwd+bwd of the use_cuda=False route (oracle.gridsample_path == func.py:41-65) for one volume, first
+    `sample_queries` queries, value over the full S.  Returns seconds."""
+    import torch
+    from oracle import msda3d_oracle as O
+    from transoar_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    g = synth.GEOMETRIES[GEOM]
+    gq = synth.Geometry(g.name, g.shapes, g.heads, g.channels, g.points, queries=sample_queries if sample_queries < g.spatial_size else 0)
+    x = synth.make_inputs(gq, 1, DIST, seed=seed)
+    v, loc, aw = (x[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
+    t0 = time.perf_counter()
+    out = O.gridsample_path(v, list(g.shapes), loc, aw)
+    out.backward(x["grad_out"])
+    return time.perf_counter() - t0
+
+
+def cpu_arm_value(seconds, sample_queries):
+    """volumes/s a host running only this sample's rate would reach on the full step (BATCH volumes x LAYERS passes)."""
+    from transoar_b200 import synth
+    frac = min(1.0, sample_queries / synth.GEOMETRIES[GEOM].spatial_size)        # fraction of one volume-layer pass
+    return frac / (LAYERS * seconds)
+
+
+def calibrate_cpu_sample(budget_s):
+    """Pick the number of queries so one fwd+bwd costs about `budget_s` seconds (probe with 4096 queries first)."""
+    from transoar_b200 import synth
+    S = synth.GEOMETRIES[GEOM].spatial_size
+    cpu_reference_pass(1024)
+    t = cpu_reference_pass(4096)
+    per_q = max(t / 4096, 1e-9)
+    return int(max(4096, min(S, budget_s / per_q)))
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total_budget = 150.0
+    per_step = total_budget / max(1, args.steps + args.warmup)
+    q = calibrate_cpu_sample(min(per_step, 20.0))
+    for _ in range(args.warmup):
+        cpu_reference_pass(q)
+    times = [cpu_reference_pass(q) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = cpu_arm_value(t, q)
+    from transoar_b200 import synth
+    S = synth.GEOMETRIES[GEOM].spatial_size
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{q} of {S} queries of one volume, one layer, fwd+bwd via the restated use_cuda=False route "
+                                   f"(F.grid_sample, func.py:41-65); {t:.2f} s per sample; step time extrapolated linearly"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config():
+    from transoar_b200 import synth
+    g = synth.GEOMETRIES[GEOM]
+    return {"workload": "visceral_refine_fwd_bwd", "volume": "160x160x256", "batch_per_gpu": BATCH, "layers": LAYERS,
+            "levels": [list(s) for s in g.shapes], "S": g.spatial_size, "Lq": g.num_query, "heads": g.heads,
+            "channels_per_head": g.channels, "points": g.points, "loc_dist": "B (model-like: voxel-centre refs + directional offsets + N(0,1))",
+            "l2": "per-layer inputs (2.2 GB) exceed the 126 MB L2 and alternate between two buffer sets; no explicit flush",
+            "parallelism": "volume-sharded, no data-path collective"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dist", default=DIST, choices=["A", "B"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from transoar_b200 import MultiScaleDeformableAttention as MSDA
+    from transoar_b200 import _lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: transoar_b200 has no CPU path")
+    lib = _lib.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    g = synth.GEOMETRIES[GEOM]
+    N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
+    # one buffer set per layer; every rank has its own volumes (seed depends on rank)
+    layers = [synth.make_inputs(g, N, args.dist, seed=1234 + 17 * rank + li, device=dev) for li in range(LAYERS)]
+
+    def step(record=None):
+        for x in layers:
+            if record is not None:
+                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
+            out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], 64)
+            if record is not None:
+                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
+            grads = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], x["grad_out"], 64)
+            if record is not None:
+                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
+        return out, grads
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    fence()
+    launches0 = lib.msda3d_launch_count()
+    ev = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        fence()
+        start.record()
+        for _ in range(args.steps):
+            step(ev)
+        stop.record()
+        fence()
+    launches = lib.msda3d_launch_count() - launches0
+    ms_total = start.elapsed_time(stop)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # per-launch times (events sit between launches on the launching stream): [fwd, bwd(+zero-fill)] per layer
+    fwd_ms, bwd_ms = [], []
+    for i in range(0, len(ev), 3):
+        fwd_ms.append(ev[i].elapsed_time(ev[i + 1]))
+        bwd_ms.append(ev[i + 1].elapsed_time(ev[i + 2]))
+    fwd_avg, bwd_avg = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    bf, bb = algorithmic_bytes(N, S, M, C, L, Lq, P)
+    peak, peak_src = load_peaks()
+    dom = "backward" if bwd_avg >= fwd_avg else "forward"
+    dom_bytes, dom_ms = (bb, bwd_avg) if dom == "backward" else (bf, fwd_avg)
+    roofline = {"bound": "hbm", "kernel": f"msda3d {dom} (bwd_vec_kernel<float,16,1> incl. grad_value zero-fill)" if dom == "backward"
+                else "msda3d forward (fwd_vec_kernel<float,16,1>)",
+                "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": dom_bytes,
+                "forward": {"ms": fwd_avg, "bytes": bf, "gbs": bf / (fwd_avg * 1e-3) / 1e9, "frac": bf / (fwd_avg * 1e-3) / 1e9 / peak},
+                "backward": {"ms": bwd_avg, "bytes": bb, "gbs": bb / (bwd_avg * 1e-3) / 1e9, "frac": bb / (bwd_avg * 1e-3) / 1e9 / peak},
+                "note": "gather path: 8 corner reads per sample go through L1/L2, requested bytes = "
+                        f"{8 * N * Lq * M * L * P * C * 4 / 1e9:.1f} GB per launch vs {bf / 1e9:.2f} GB compulsory; see DESIGN.md"}
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host = [{k: v.cpu().pin_memory() for k, v in x.items()} for x in layers]
+        res = [{"out": torch.empty(N, Lq, M * C).pin_memory(), "gv": torch.empty(N, S, M, C).pin_memory(),
+                "gl": torch.empty(N, Lq, M, L, P, 3).pin_memory(), "ga": torch.empty(N, Lq, M, L, P).pin_memory()} for _ in layers]
+        p = lambda t_: ctypes.c_void_p(t_.data_ptr())
+
+        def e2e_step():
+            for h, r in zip(host, res):
+                rc = lib.msda3d_forward_backward_host(local, _lib.F32, p(h["grad_out"]), p(h["value"]), p(h["shapes"]), p(h["starts"]),
+                                                      p(h["loc"]), p(h["aw"]), N, S, M, C, L, Lq, P, p(r["out"]), p(r["gv"]), p(r["gl"]), p(r["ga"]))
+                _lib.check(rc, "msda3d_forward_backward_host")
+
+        e2e_steps = max(3, min(args.steps, 8))
+        e2e_step(); e2e_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        fence()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = LAYERS * sum(host[0][k].numel() * host[0][k].element_size() for k in ("value", "loc", "aw", "grad_out", "shapes", "starts"))
+        d2h = LAYERS * sum(v.numel() * v.element_size() for v in res[0].values())
+        e2e = {"value": world * BATCH * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "ms_per_step": 1e3 * float(tt.item()) / e2e_steps,
+               "api": "msda3d_forward_backward_host (include/msda3d.h), pinned host tensors, synchronous return"}
+        lib.msda3d_host_release()
+        del host, res
+
+    # ---- baselines (rank 0, single-GPU runs only): reference CPU route + the reference's own compiled CUDA op
+    cpu_baseline, ref_cuda = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import msda3d_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        q = calibrate_cpu_sample(15.0)
+        tsec = cpu_reference_pass(q)
+        cpu_baseline = {"value": cpu_arm_value(tsec, q), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{q} of {S} queries of one volume, one layer, fwd+bwd via the restated use_cuda=False route "
+                                  f"(F.grid_sample, func.py:41-65): {tsec:.2f} s; step time extrapolated linearly"}
+        if O.refcuda_available():
+            x = layers[0]
+            for _ in range(2):
+                O.refcuda_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"])
+            zeros = (torch.zeros_like(x["value"]), torch.zeros_like(x["loc"]), torch.zeros_like(x["aw"]))
+            O.refcuda_backward(x["grad_out"], x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], out=zeros)
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            reps = 3
+            e[0].record()
+            for _ in range(reps):
+                O.refcuda_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"])
+            e[1].record()
+            for _ in range(reps):
+                for z in zeros:
+                    z.zero_()
+                O.refcuda_backward(x["grad_out"], x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], out=zeros)
+            e[2].record()
+            torch.cuda.synchronize()
+            rf, rb = e[0].elapsed_time(e[1]) / reps, e[1].elapsed_time(e[2]) / reps
+            ref_cuda = {"what": "the reference's own CUDA kernels (oracle/_ref, compiled from /root/reference for sm_100a) on layer-0 inputs, N=2",
+                        "fwd_ms": rf, "bwd_ms": rb, "value": BATCH / (LAYERS * (rf + rb) * 1e-3), "unit": UNIT,
+                        "speedup_fwd": rf / fwd_avg, "speedup_bwd": rb / bwd_avg}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(workload_config(), loc_dist=args.dist),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "kernels": {"fwd_ms": fwd_avg, "bwd_ms": bwd_avg, "fwd_ms_min": min(fwd_ms), "bwd_ms_min": min(bwd_ms),
+                        "share_fwd": fwd_avg / (fwd_avg + bwd_avg), "share_bwd": bwd_avg / (fwd_avg + bwd_avg)},
+            "ref_cuda_op": ref_cuda, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only host and exports exactly what include/msda3d.h declares.
+Argument validation that returns before touching the device is exercised too (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from transoar_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "msda3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msda3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.lib()
+    declared = _declared()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/msda3d.h but not exported"
+    assert sorted(_lib.exported_symbols()) == declared, "python binding table out of sync with the header"
+
+
+def test_abi_version_and_error_strings():
+    lib = _lib.lib()
+    assert lib.msda3d_abi_version() == 1
+    assert lib.msda3d_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4):
+        assert lib.msda3d_error_string(code).startswith(b"msda3d:")
+    assert b"invalid" in lib.msda3d_error_string(1).lower()           # cudaErrorInvalidValue
+
+
+def test_null_and_bad_dimension_arguments_are_rejected_before_any_launch():
+    lib = _lib.lib()
+    buf = (ctypes.c_double * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    before = lib.msda3d_launch_count()
+    dims = (1, 8, 1, 1, 1, 1, 1)
+    assert lib.msda3d_forward(None, 0, None, p, p, p, p, *dims, p) == -1
+    assert lib.msda3d_forward(None, 0, p, p, p, p, p, 0, 8, 1, 1, 1, 1, 1, p) == -1
+    assert lib.msda3d_forward(None, 9, p, p, p, p, p, *dims, p) == -1
+    assert lib.msda3d_backward(None, 0, p, p, p, p, p, p, *dims, p, p, None) == -1
+    assert lib.msda3d_debug_indices(None, 0, p, p, 1, 1, 1, 0, 1, p, p) == -1
+    odd = ctypes.c_void_p(p.value + 2)
+    assert lib.msda3d_forward(None, 0, odd, p, p, p, p, *dims, p) == -3
+    assert lib.msda3d_forward_host(99, 0, p, p, p, p, p, *dims, p) == -4
+    assert lib.msda3d_launch_count() == before
+
+
+def test_header_cites_the_reference_interfaces_it_replaces():
+    text = open(os.path.join(ROOT, "include", "msda3d.h")).read()
+    for needle in ("ms_deform_im2col_cuda.cuh:1094-1125", "cuh:1127-1507", "ms_deform_attn_cuda.cu", "vision.cpp:13-16"):
+        assert needle in text

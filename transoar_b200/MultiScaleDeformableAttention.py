@@ -1,0 +1,98 @@
+"""Stand-in for the reference's compiled extension module ``MultiScaleDeformableAttention``
+(transoar/models/ops/setup.py:53, exported by transoar/models/ops/src/vision.cpp:13-16).
+
+Same two entry points, same argument order, same error behaviour as the reference's host wrappers
+(transoar/models/ops/src/ms_deform_attn.h:20-61, cuda/ms_deform_attn_cuda.cu:20-80,83-154):
+contiguity / device checks raise RuntimeError, CPU tensors raise "Not implemented on the CPU",
+``batch % min(batch, im2col_step) == 0`` is enforced although one launch now covers the whole batch.
+
+Extension over the reference: ``value`` may be bf16/fp16 with fp32 ``sampling_loc`` / ``attn_weight``
+-- the case the reference's own trainer produces under autocast and its op rejects.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _p(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _check(named, im2col_step):
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")           # ms_deform_attn_cuda.cu:28-32
+    value = named[0][1]
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")                          # ms_deform_attn.h:38,60
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")                   # ms_deform_attn_cuda.cu:34-38
+        if t.device != value.device:
+            raise RuntimeError(f"{name} must live on {value.device}")
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn: unsupported dtype {value.dtype}")    # AT_DISPATCH_FLOATING_TYPES, .cu:64
+    batch = value.size(0)
+    step = min(batch, int(im2col_step))
+    if step <= 0 or batch % step != 0:
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")     # ms_deform_attn_cuda.cu:52
+    return _DTYPES[value.dtype]
+
+
+def _aux_dtype(value):
+    return torch.float64 if value.dtype == torch.float64 else torch.float32
+
+
+def _dims(value, spatial_shapes, sampling_loc):
+    N, S, M, C = value.shape
+    L = spatial_shapes.size(0)
+    Lq, P = sampling_loc.size(1), sampling_loc.size(4)
+    if sampling_loc.shape != (N, Lq, M, L, P, 3):
+        raise RuntimeError(f"sampling_loc has shape {tuple(sampling_loc.shape)}, expected {(N, Lq, M, L, P, 3)}")
+    return N, S, M, C, L, Lq, P
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """-> output [N, Lq, M*C]   (vision.cpp:14, ms_deform_attn_cuda_forward)."""
+    dt = _check([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                 ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)], im2col_step)
+    aux = _aux_dtype(value)
+    if sampling_loc.dtype != aux or attn_weight.dtype != aux:
+        sampling_loc, attn_weight = sampling_loc.to(aux), attn_weight.to(aux)
+    N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_loc)
+    out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().msda3d_forward(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(value), _p(spatial_shapes),
+            _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P, _p(out))
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]   (vision.cpp:15, ms_deform_attn_cuda_backward)."""
+    dt = _check([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                 ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)], im2col_step)
+    aux = _aux_dtype(value)
+    loc_dtype, aw_dtype = sampling_loc.dtype, attn_weight.dtype
+    if loc_dtype != aux or aw_dtype != aux:
+        sampling_loc, attn_weight = sampling_loc.to(aux), attn_weight.to(aux)
+    if grad_output.dtype != value.dtype:
+        grad_output = grad_output.to(value.dtype)
+    N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_loc)
+    grad_value = torch.empty(value.shape, dtype=aux, device=value.device)       # zero-filled by the library
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_aw = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().msda3d_backward(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(grad_output), _p(value), _p(spatial_shapes),
+            _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P,
+            _p(grad_value), _p(grad_loc), _p(grad_aw))
+    _lib.check(rc, "ms_deform_attn_backward")
+    return [grad_value.to(value.dtype), grad_loc.to(loc_dtype), grad_aw.to(aw_dtype)]

@@ -1,0 +1,64 @@
+"""ctypes binding of libmsda3d.so (C ABI: include/msda3d.h).  Fails loudly: no fallback of any kind."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsda3d.so")
+_lib = None
+
+F32, F64, BF16, F16 = 0, 1, 2, 3
+
+_vp, _ci = ctypes.c_void_p, ctypes.c_int
+_DIMS = [_ci] * 7
+
+_SIGNATURES = {
+    "msda3d_abi_version": (_ci, []),
+    "msda3d_error_string": (ctypes.c_char_p, [_ci]),
+    "msda3d_launch_count": (ctypes.c_ulonglong, []),
+    "msda3d_forward": (_ci, [_vp, _ci] + [_vp] * 5 + _DIMS + [_vp]),
+    "msda3d_backward": (_ci, [_vp, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
+    "msda3d_forward_host": (_ci, [_ci, _ci] + [_vp] * 5 + _DIMS + [_vp]),
+    "msda3d_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
+    "msda3d_forward_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 4),
+    "msda3d_host_release": (None, []),
+    "msda3d_debug_indices": (_ci, [_vp, _ci, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ -> libmsda3d.so for sm_100a with nvcc (no GPU needed)."""
+    res = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libmsda3d.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C transoar_b200/csrc`).  transoar_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.msda3d_abi_version() != 1:
+            raise RuntimeError("libmsda3d.so ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().msda3d_error_string(rc).decode()} (code {rc})")
+
+
+def exported_symbols():
+    return list(_SIGNATURES)

@@ -1,0 +1,379 @@
+// msda3d_capi.cu -- the C ABI declared in include/msda3d.h: argument checks, kernel selection, launches, and the
+// host-buffer staging path.  No torch types anywhere; linked against the static CUDA runtime only.
+//
+// Mirrors (and replaces) the reference's host side:
+//   transoar/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80,83-154   (asserts, shapes, im2col_step loop, zero-init)
+//   transoar/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:1094-1125   (forward launcher)
+//   transoar/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:1127-1507   (backward launcher + channel dispatch table)
+#include "msda3d_kernels.cuh"
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/msda3d.h"
+
+using namespace msda3d;
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+struct Dims {
+  int N, S, M, C, L, Lq, P;
+};
+
+int check_dims(const Dims &d)
+{
+  if (d.N <= 0 || d.S <= 0 || d.M <= 0 || d.C <= 0 || d.L <= 0 || d.Lq <= 0 || d.P <= 0) return MSDA3D_EINVAL;
+  // generic kernels index with 64-bit arithmetic; only the per-sample count must fit the loop counters
+  const long long lp = (long long)d.L * d.P;
+  if (lp > (1 << 20)) return MSDA3D_ERANGE;
+  return MSDA3D_OK;
+}
+
+size_t elem_size(int dtype) { return dtype == MSDA3D_F64 ? 8 : dtype == MSDA3D_F32 ? 4 : 2; }
+size_t aux_size(int dtype) { return dtype == MSDA3D_F64 ? 8 : 4; }   // loc / aw / grad_loc / grad_aw / grad_value(16-bit)
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int grid_for(long long units, int units_per_block)
+{
+  long long g = (units + units_per_block - 1) / units_per_block;
+  const long long cap = 148LL * 8 * 64;   // grid-stride loops cover the rest; keeps index math away from 2^31
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Vector-kernel eligibility: C = G * NV * VEC with G a power of two <= 32 (NV = 2 only on top of G = 32), <= 16 levels,
+// 16-byte aligned slabs and int32 element offsets inside one batch element.
+template <typename VT> bool vec_shape(int C, int &G, int &NV)
+{
+  constexpr int VEC = Vec16<VT>::N;
+  if (C % VEC) return false;
+  const int q = C / VEC;
+  if (q <= 32 && (q & (q - 1)) == 0) { G = q; NV = 1; return true; }
+  if (q == 64) { G = 32; NV = 2; return true; }
+  return false;
+}
+
+template <typename VT>
+bool vec_ok(const Dims &d, const void *a, const void *b, int &G, int &NV)
+{
+  if (!vec_shape<VT>(d.C, G, NV)) return false;
+  if (d.L > kMaxLevels) return false;
+  if ((long long)d.S * d.M * d.C >= (1LL << 31)) return false;
+  if ((long long)d.L * d.P * 3 >= (1LL << 20)) return false;
+  return aligned(a, 16) && aligned(b, 16);
+}
+
+#define VEC_DISPATCH(G_, NV_, ...)                        \
+  switch ((G_) * 4 + (NV_)) {                              \
+    case 1 * 4 + 1: { constexpr int G = 1, NV = 1; __VA_ARGS__; } break;   \
+    case 2 * 4 + 1: { constexpr int G = 2, NV = 1; __VA_ARGS__; } break;   \
+    case 4 * 4 + 1: { constexpr int G = 4, NV = 1; __VA_ARGS__; } break;   \
+    case 8 * 4 + 1: { constexpr int G = 8, NV = 1; __VA_ARGS__; } break;   \
+    case 16 * 4 + 1: { constexpr int G = 16, NV = 1; __VA_ARGS__; } break; \
+    case 32 * 4 + 1: { constexpr int G = 32, NV = 1; __VA_ARGS__; } break; \
+    case 32 * 4 + 2: { constexpr int G = 32, NV = 2; __VA_ARGS__; } break; \
+    default: return MSDA3D_EINVAL;                         \
+  }
+
+template <typename VT>
+int forward_half_or_float(cudaStream_t st, const Dims &d, const void *value, const int64_t *shapes, const int64_t *starts,
+                          const void *loc, const void *aw, void *out)
+{
+  const long long units = (long long)d.N * d.Lq * d.M;
+  int g_ = 0, nv_ = 0;
+  if (vec_ok<VT>(d, value, out, g_, nv_)) {
+    const int upb = (kThreads / 32) * (32 / g_);
+    const int grid = grid_for(units, upb);
+    VEC_DISPATCH(g_, nv_, fwd_vec_kernel<VT, G, NV><<<grid, kThreads, 0, st>>>(
+                              (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq,
+                              d.P, (VT *)out));
+  } else {
+    fwd_generic_kernel<VT, float><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
+        (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.C, d.L, d.Lq, d.P, (VT *)out);
+  }
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+template <typename VT>
+int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, const void *value, const int64_t *shapes,
+                           const int64_t *starts, const void *loc, const void *aw, void *gv, void *gl, void *ga)
+{
+  const long long units = (long long)d.N * d.Lq * d.M;
+  cudaError_t e = cudaMemsetAsync(gv, 0, (size_t)d.N * d.S * d.M * d.C * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  int g_ = 0, nv_ = 0;
+  if (vec_ok<VT>(d, value, gout, g_, nv_) && aligned(gv, 16)) {
+    const int upb = (kThreads / 32) * (32 / g_);
+    const int grid = grid_for(units, upb);
+    VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV><<<grid, kThreads, 0, st>>>(
+                              (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S,
+                              d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga));
+  } else {
+    bwd_generic_kernel<VT, float><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
+        (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.C, d.L, d.Lq,
+        d.P, (float *)gv, (float *)gl, (float *)ga);
+  }
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda3d_abi_version(void) { return MSDA3D_ABI_VERSION; }
+
+unsigned long long msda3d_launch_count(void) { return g_launches.load(); }
+
+const char *msda3d_error_string(int code)
+{
+  switch (code) {
+    case MSDA3D_OK: return "ok";
+    case MSDA3D_EINVAL: return "msda3d: invalid argument (null pointer, non-positive dimension or unknown dtype)";
+    case MSDA3D_ERANGE: return "msda3d: dimension product out of range";
+    case MSDA3D_EALIGN: return "msda3d: pointer not aligned to its element type";
+    case MSDA3D_ENODEV: return "msda3d: no usable CUDA device";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "msda3d: unknown error";
+  }
+}
+
+int msda3d_forward(void *stream, int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                   const void *sampling_loc, const void *attn_weight, int batch, int spatial_size, int num_heads, int channels,
+                   int num_levels, int num_query, int num_point, void *output)
+{
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output) return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int rc = check_dims(d)) return rc;
+  if (dtype < MSDA3D_F32 || dtype > MSDA3D_F16) return MSDA3D_EINVAL;
+  if (!aligned(value, elem_size(dtype)) || !aligned(output, elem_size(dtype)) || !aligned(sampling_loc, aux_size(dtype)) ||
+      !aligned(attn_weight, aux_size(dtype)) || !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case MSDA3D_F32:
+      return forward_half_or_float<float>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    case MSDA3D_BF16:
+      return forward_half_or_float<__nv_bfloat16>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    case MSDA3D_F16:
+      return forward_half_or_float<__half>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    default: {
+      const long long units = (long long)d.N * d.Lq * d.M;
+      fwd_generic_kernel<double, double><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
+          (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc, (const double *)attn_weight, d.N,
+          d.S, d.M, d.C, d.L, d.Lq, d.P, (double *)output);
+      ++g_launches;
+      return (int)cudaGetLastError();
+    }
+  }
+}
+
+int msda3d_backward(void *stream, int dtype, const void *grad_output, const void *value, const int64_t *spatial_shapes,
+                    const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight, int batch,
+                    int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point, void *grad_value,
+                    void *grad_sampling_loc, void *grad_attn_weight)
+{
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_value ||
+      !grad_sampling_loc || !grad_attn_weight)
+    return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int rc = check_dims(d)) return rc;
+  if (dtype < MSDA3D_F32 || dtype > MSDA3D_F16) return MSDA3D_EINVAL;
+  if (!aligned(value, elem_size(dtype)) || !aligned(grad_output, elem_size(dtype)) || !aligned(sampling_loc, aux_size(dtype)) ||
+      !aligned(attn_weight, aux_size(dtype)) || !aligned(grad_value, aux_size(dtype)) || !aligned(grad_sampling_loc, aux_size(dtype)) ||
+      !aligned(grad_attn_weight, aux_size(dtype)) || !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case MSDA3D_F32:
+      return backward_half_or_float<float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                           grad_value, grad_sampling_loc, grad_attn_weight);
+    case MSDA3D_BF16:
+      return backward_half_or_float<__nv_bfloat16>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                                   attn_weight, grad_value, grad_sampling_loc, grad_attn_weight);
+    case MSDA3D_F16:
+      return backward_half_or_float<__half>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                            grad_value, grad_sampling_loc, grad_attn_weight);
+    default: {
+      const long long units = (long long)d.N * d.Lq * d.M;
+      cudaError_t e = cudaMemsetAsync(grad_value, 0, (size_t)d.N * d.S * d.M * d.C * sizeof(double), st);
+      if (e != cudaSuccess) return (int)e;
+      bwd_generic_kernel<double, double><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
+          (const double *)grad_output, (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc,
+          (const double *)attn_weight, d.N, d.S, d.M, d.C, d.L, d.Lq, d.P, (double *)grad_value, (double *)grad_sampling_loc,
+          (double *)grad_attn_weight);
+      ++g_launches;
+      return (int)cudaGetLastError();
+    }
+  }
+}
+
+int msda3d_debug_indices(void *stream, int dtype, const int64_t *spatial_shapes, const void *sampling_loc, int batch, int num_heads,
+                         int num_levels, int num_query, int num_point, int32_t *idx, void *frac)
+{
+  if (!spatial_shapes || !sampling_loc || !idx || !frac) return MSDA3D_EINVAL;
+  if (batch <= 0 || num_heads <= 0 || num_levels <= 0 || num_query <= 0 || num_point <= 0) return MSDA3D_EINVAL;
+  const long long T = (long long)batch * num_query * num_heads * num_levels * num_point;
+  const int grid = (int)((T + 255) / 256 > 148 * 64 ? 148 * 64 : (T + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MSDA3D_F64)
+    indices_kernel<double><<<grid, 256, 0, st>>>(spatial_shapes, (const double *)sampling_loc, T, num_levels, num_point, idx, (double *)frac);
+  else
+    indices_kernel<float><<<grid, 256, 0, st>>>(spatial_shapes, (const float *)sampling_loc, T, num_levels, num_point, idx, (float *)frac);
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer path
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct HostCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  // grow-only device scratch: 0 value, 1 loc, 2 aw, 3 gout, 4 out, 5 gv, 6 gloc, 7 gaw, 8 shapes, 9 starts
+  void *buf[10] = {nullptr};
+  size_t cap[10] = {0};
+};
+
+struct DeviceGuard {
+  int prev = 0;
+  DeviceGuard() { cudaGetDevice(&prev); }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+std::mutex g_host_mu;
+HostCtx g_host[16];
+
+int ensure(HostCtx &c, int i, size_t bytes)
+{
+  if (c.cap[i] >= bytes) return 0;
+  if (c.buf[i]) cudaFree(c.buf[i]);
+  c.buf[i] = nullptr;
+  c.cap[i] = 0;
+  cudaError_t e = cudaMalloc(&c.buf[i], bytes);
+  if (e != cudaSuccess) return (int)e;
+  c.cap[i] = bytes;
+  return 0;
+}
+
+#define CU(x)                                \
+  do {                                       \
+    cudaError_t e_ = (x);                    \
+    if (e_ != cudaSuccess) return (int)e_;   \
+  } while (0)
+
+int host_run(int device, int dtype, bool do_fwd, bool do_bwd, const void *gout, const void *value, const int64_t *shapes,
+             const int64_t *starts, const void *loc, const void *aw, const Dims &d, void *out, void *gv, void *gl, void *ga)
+{
+  if (device < 0 || device >= 16) return MSDA3D_ENODEV;
+  if (dtype < MSDA3D_F32 || dtype > MSDA3D_F16) return MSDA3D_EINVAL;
+  if (int rc = check_dims(d)) return rc;
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  HostCtx &c = g_host[device];
+  DeviceGuard guard;
+  CU(cudaSetDevice(device));
+  if (!c.stream) {
+    CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.device = device;
+  }
+  const size_t es = elem_size(dtype), as = aux_size(dtype);
+  const size_t n_val = (size_t)d.N * d.S * d.M * d.C, n_out = (size_t)d.N * d.Lq * d.M * d.C;
+  const size_t n_aw = (size_t)d.N * d.Lq * d.M * d.L * d.P, n_loc = n_aw * 3;
+  int rc = 0;
+  if ((rc = ensure(c, 0, n_val * es)) || (rc = ensure(c, 1, n_loc * as)) || (rc = ensure(c, 2, n_aw * as)) ||
+      (rc = ensure(c, 8, (size_t)d.L * 3 * 8)) || (rc = ensure(c, 9, (size_t)d.L * 8)))
+    return rc;
+  cudaStream_t st = c.stream;
+  CU(cudaMemcpyAsync(c.buf[8], shapes, (size_t)d.L * 3 * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c.buf[9], starts, (size_t)d.L * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c.buf[0], value, n_val * es, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c.buf[1], loc, n_loc * as, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c.buf[2], aw, n_aw * as, cudaMemcpyHostToDevice, st));
+  if (do_fwd) {
+    if ((rc = ensure(c, 4, n_out * es))) return rc;
+    rc = msda3d_forward(st, dtype, c.buf[0], (const int64_t *)c.buf[8], (const int64_t *)c.buf[9], c.buf[1], c.buf[2], d.N, d.S, d.M,
+                        d.C, d.L, d.Lq, d.P, c.buf[4]);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, c.buf[4], n_out * es, cudaMemcpyDeviceToHost, st));
+  }
+  if (do_bwd) {
+    if ((rc = ensure(c, 3, n_out * es)) || (rc = ensure(c, 5, n_val * as)) || (rc = ensure(c, 6, n_loc * as)) ||
+        (rc = ensure(c, 7, n_aw * as)))
+      return rc;
+    CU(cudaMemcpyAsync(c.buf[3], gout, n_out * es, cudaMemcpyHostToDevice, st));
+    rc = msda3d_backward(st, dtype, c.buf[3], c.buf[0], (const int64_t *)c.buf[8], (const int64_t *)c.buf[9], c.buf[1], c.buf[2], d.N,
+                         d.S, d.M, d.C, d.L, d.Lq, d.P, c.buf[5], c.buf[6], c.buf[7]);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(gv, c.buf[5], n_val * as, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(gl, c.buf[6], n_loc * as, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ga, c.buf[7], n_aw * as, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // namespace
+
+int msda3d_forward_host(int device, int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_loc, const void *attn_weight, int batch, int spatial_size, int num_heads, int channels,
+                        int num_levels, int num_query, int num_point, void *output)
+{
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output) return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  return host_run(device, dtype, true, false, nullptr, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, output,
+                  nullptr, nullptr, nullptr);
+}
+
+int msda3d_backward_host(int device, int dtype, const void *grad_output, const void *value, const int64_t *spatial_shapes,
+                         const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight, int batch,
+                         int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point, void *grad_value,
+                         void *grad_sampling_loc, void *grad_attn_weight)
+{
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_value ||
+      !grad_sampling_loc || !grad_attn_weight)
+    return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  return host_run(device, dtype, false, true, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
+                  nullptr, grad_value, grad_sampling_loc, grad_attn_weight);
+}
+
+int msda3d_forward_backward_host(int device, int dtype, const void *grad_output, const void *value, const int64_t *spatial_shapes,
+                                 const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight, int batch,
+                                 int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                 void *output, void *grad_value, void *grad_sampling_loc, void *grad_attn_weight)
+{
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output || !grad_value ||
+      !grad_sampling_loc || !grad_attn_weight)
+    return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  return host_run(device, dtype, true, true, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
+                  output, grad_value, grad_sampling_loc, grad_attn_weight);
+}
+
+void msda3d_host_release(void)
+{
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  for (HostCtx &c : g_host) {
+    if (c.device < 0) continue;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c.device);
+    for (int i = 0; i < 10; ++i) {
+      if (c.buf[i]) cudaFree(c.buf[i]);
+      c.buf[i] = nullptr;
+      c.cap[i] = 0;
+    }
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.device = -1;
+    cudaSetDevice(prev);
+  }
+}
+
+}  // extern "C"

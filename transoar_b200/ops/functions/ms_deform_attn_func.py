@@ -1,0 +1,29 @@
+"""Autograd surface of the op -- mirror of transoar/models/ops/functions/ms_deform_attn_func.py:21-38.
+
+``MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+im2col_step)`` returns ``[N, Lq, M*C]``; backward yields ``(grad_value, None, None, grad_sampling_loc,
+grad_attn_weight, None)`` and is once-differentiable, exactly like the reference.
+
+The reference's ``ms_deform_attn_core_pytorch`` (the ``use_cuda=False`` debug route, func.py:41-65) is deliberately
+NOT provided: this package has no non-CUDA compute path (its restatement lives in oracle/ as a test checker).
+"""
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import MultiScaleDeformableAttention as MSDA
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+        return MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                           attention_weights, im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        saved = ctx.saved_tensors
+        g_value, g_loc, g_attn = MSDA.ms_deform_attn_backward(*saved, grad_output.contiguous(), ctx.im2col_step)
+        return g_value, None, None, g_loc, g_attn, None

@@ -1,0 +1,89 @@
+"""``MSDeformAttn`` -- mirror of transoar/models/ops/modules/ms_deform_attn.py:30-141.
+
+Same constructor, parameter names (``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj`` -- so
+reference checkpoints load unchanged), initialisation and forward semantics; the sampling itself always runs on the
+sm_100a kernels behind ``MSDeformAttnFunction``.  ``use_cuda=False`` selected the pure-PyTorch debug route in the
+reference (ms_deform_attn.py:137-138); this package has no such route and raises instead of silently falling back.
+"""
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..functions import MSDeformAttnFunction
+
+
+def _power_of_two(n):
+    if not isinstance(n, int) or n < 0:
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return n != 0 and (n & (n - 1)) == 0
+
+
+def _direction_table(n_heads):
+    """Unit steps the offset bias is initialised with (ms_deform_attn.py:63-73): 6 face or 26 neighbour directions."""
+    cube = torch.cartesian_prod(*([torch.tensor([-1, 0, 1])] * 3)).float()
+    l1 = cube.abs().sum(1)
+    if n_heads == 26:
+        return cube[l1 > 0]
+    if n_heads == 6:
+        return cube[l1 == 1]
+    raise ValueError("Only nheads of value 26 or 6 are supported.")           # ms_deform_attn.py:72-73
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, use_cuda=True):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError('d_model must be divisible by n_heads, but got {} and {}'.format(d_model, n_heads))
+        if not _power_of_two(d_model // n_heads):
+            warnings.warn("d_model // n_heads is not a power of two: the op falls back from the vector kernels to the "
+                          "generic (slower) CUDA kernels.")
+        self.im2col_step = 64                                                  # ms_deform_attn.py:48
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        self.use_cuda = use_cuda
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 3)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """ms_deform_attn.py:63-91: zero offset/attention weights, directional offset bias scaled by (p+1), xavier projections."""
+        nn.init.zeros_(self.sampling_offsets.weight)
+        steps = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+        bias = _direction_table(self.n_heads).view(self.n_heads, 1, 1, 3) * steps          # [M,1,P,3]
+        bias = bias.expand(self.n_heads, self.n_levels, self.n_points, 3).reshape(-1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(bias.clone())            # stays trainable, as in the reference (:80-82)
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        for proj in (self.value_proj, self.output_proj):
+            nn.init.xavier_uniform_(proj.weight)
+            nn.init.zeros_(proj.bias)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """query [N,Lq,C]; reference_points [N|1,Lq,L,3] in (x,y,z); input_flatten [N,S,C]; shapes [L,3]=(D,H,W) -> [N,Lq,C]."""
+        N, Lq, _ = query.shape
+        _, S, _ = input_flatten.shape
+        assert int(input_spatial_shapes.prod(1).sum()) == S                    # ms_deform_attn.py:107
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, S, M, self.d_model // M)
+        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 3)
+        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        if reference_points.shape[-1] != 3:
+            raise ValueError('Last dim of reference_points must be 3, but get {} instead.'.format(reference_points.shape[-1]))
+        normalizer = input_spatial_shapes.flip(-1)                             # (W,H,D): x,y,z order, ms_deform_attn.py:123-126
+        locations = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+        if not self.use_cuda:
+            raise RuntimeError("transoar_b200.MSDeformAttn only implements the use_cuda=True route; the reference's "
+                               "pure-PyTorch debug path (ms_deform_attn_core_pytorch) is not part of this package.")
+        sampled = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                             locations.contiguous(), weights, self.im2col_step)
+        return self.output_proj(sampled)
