@@ -49,6 +49,19 @@ def algorithmic_bytes(N, S, M, C, L, Lq, P, ev=4, eg=4):
     return fwd, bwd
 
 
+def volume_ids(step, rank, world, batch=BATCH):
+    """Volume sharding: global volume stream 0,1,2,...; step `step` hands `batch` consecutive volumes to every rank
+    (rank-major inside the step), so ranks never share a volume and the union over ranks is contiguous."""
+    base = (step * world + rank) * batch
+    return list(range(base, base + batch))
+
+
+def aggregate_throughput(local_ms, steps, world, batch=BATCH, all_reduce_max=None):
+    """Whole-job volumes/s: every rank did `steps` steps of `batch` volumes; time = max over ranks of the device time."""
+    ms = all_reduce_max(local_ms) if all_reduce_max is not None else local_ms
+    return world * batch * steps / (ms / 1e3), ms
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -224,7 +237,7 @@ def main():
     g = synth.GEOMETRIES[GEOM]
     N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
     # one buffer set per layer; every rank has its own volumes (seed depends on rank)
-    layers = [synth.make_inputs(g, N, args.dist, seed=1234 + 17 * rank + li, device=dev) for li in range(LAYERS)]
+    layers = [synth.make_inputs(g, N, args.dist, seed=1234 + 7919 * volume_ids(0, rank, world)[0] + li, device=dev) for li in range(LAYERS)]
 
     def step(record=None):
         for x in layers:
@@ -257,13 +270,14 @@ def main():
         stop.record()
         fence()
     launches = lib.msda3d_launch_count() - launches0
-    ms_total = start.elapsed_time(stop)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    value, ms_total = aggregate_throughput(start.elapsed_time(stop), args.steps, world, all_reduce_max=reduce_max)
     ms_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total / 1e3)
 
     # per-launch times (events sit between launches on the launching stream): [fwd, bwd(+zero-fill)] per layer
     fwd_ms, bwd_ms = [], []
@@ -275,8 +289,8 @@ def main():
     peak, peak_src = load_peaks()
     dom = "backward" if bwd_avg >= fwd_avg else "forward"
     dom_bytes, dom_ms = (bb, bwd_avg) if dom == "backward" else (bf, fwd_avg)
-    roofline = {"bound": "hbm", "kernel": f"msda3d {dom} (bwd_vec_kernel<float,16,1> incl. grad_value zero-fill)" if dom == "backward"
-                else "msda3d forward (fwd_vec_kernel<float,16,1>)",
+    roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_vec_kernel<float,16,1,3> + the cudaMemsetAsync zero-fill of grad_value" if dom == "backward"
+                else "msda3d forward: fwd_vec_kernel<float,16,1,4>",
                 "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes": dom_bytes,

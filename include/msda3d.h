@@ -93,6 +93,13 @@ void msda3d_host_release(void);
 int msda3d_debug_indices(void *stream, int dtype, const int64_t *spatial_shapes, const void *sampling_loc, int batch,
                          int num_heads, int num_levels, int num_query, int num_point, int32_t *idx, void *frac);
 
+/* Diagnostics / tuning knobs for profiling sessions; never needed for correct results.  Unknown keys return
+ * MSDA3D_EINVAL.  "nv" = 0|1|2: 16-byte vectors per lane in the vector kernels (0 = automatic);  "grid_mult" = CTAs
+ * per SM cap of the launch (0 = automatic);  "order" = 0 automatic | 1 linear | 2 brick unit order (brick needs
+ * num_query == spatial_size);  "diag_bwd_skip_red" = 1 drops the grad_value reductions
+ * (WRONG results; isolates their cost). */
+int msda3d_set_tuning(const char *key, int value);
+
 /* Number of kernel launches this library has issued in the calling process (bench.py's gpu_launches). */
 unsigned long long msda3d_launch_count(void);
 

@@ -1,0 +1,72 @@
+"""N > 1 host logic on CPU: two gloo ranks on 127.0.0.1 exercise bench.py's volume sharding, the max-over-ranks
+timing reduction and the whole-job aggregation (the data path itself has no collective: volumes are independent)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import bench
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ids = [bench.volume_ids(step, rank, world) for step in range(3)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ids)
+
+        def reduce_max(ms):
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        local_ms = 100.0 * (rank + 1)                 # rank 1 is the slow one
+        value, ms = bench.aggregate_throughput(local_ms, steps=5, world=world, all_reduce_max=reduce_max)
+        dist.barrier()
+        if rank == 0:
+            out.put((gathered, value, ms))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_max_over_ranks_timing():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, value, ms = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    flat = sorted(v for per_rank in gathered for step in per_rank for v in step)
+    assert flat == list(range(3 * world * bench.BATCH)), "ranks must cover a contiguous volume stream without overlap"
+    assert ms == 200.0                                 # max over ranks, not the mean
+    assert value == pytest.approx(world * bench.BATCH * 5 / 0.2)
+
+
+def test_algorithmic_bytes_match_survey_8d():
+    # VISCERAL fp32 N=1: B_f = 0.539 GB, B_b ~ 1.08 GB
+    bf, bb = bench.algorithmic_bytes(1, 117000, 6, 64, 4, 117000, 4)
+    assert bf == 4 * (117000 * 384 + 117000 * 384) + 16 * 117000 * 6 * 16 == 539136000
+    assert bb == 2 * bf
+    # decoder-style call (Lq = 300): the value term is capped by what 8 corners per sample can touch
+    bf300, _ = bench.algorithmic_bytes(1, 117000, 6, 64, 4, 300, 4)
+    assert bf300 == 4 * (8 * 300 * 6 * 16 * 64 + 300 * 384) + 16 * 300 * 6 * 16
+
+
+def test_cpu_arm_extrapolation():
+    # a full volume-layer pass (all S queries) taking 2 s -> a step of 2 volumes x 2 layers takes 8 s -> 0.25 volumes/s
+    assert bench.cpu_arm_value(2.0, 117000) == pytest.approx(0.25)
+    assert bench.cpu_arm_value(1.0, 58500) == pytest.approx(0.25)

@@ -311,7 +311,7 @@ def test_full_size_linearity_and_adjoint_identities(visceral, dist):
     fully = inside.all(-1).all(-1)                       # units whose every sample is interior
     o1 = _run_fwd(ones).view(1, -1, 6, 64)
     mass = x["aw"].sum((-1, -2))
-    assert fully.float().mean() > 0.05
+    assert fully.float().mean() > 0.005
     assert torch.allclose(o1[fully], mass[fully][:, None].expand(-1, 64), atol=2e-6)
 
 

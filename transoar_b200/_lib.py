@@ -6,7 +6,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsda3d.so")
+# MSDA3D_LIB lets profiling sessions load an experimental build of the same library; never a different implementation.
+LIB_PATH = os.environ.get("MSDA3D_LIB") or os.path.join(_HERE, "libmsda3d.so")
 _lib = None
 
 F32, F64, BF16, F16 = 0, 1, 2, 3
@@ -18,6 +19,7 @@ _SIGNATURES = {
     "msda3d_abi_version": (_ci, []),
     "msda3d_error_string": (ctypes.c_char_p, [_ci]),
     "msda3d_launch_count": (ctypes.c_ulonglong, []),
+    "msda3d_set_tuning": (_ci, [ctypes.c_char_p, _ci]),
     "msda3d_forward": (_ci, [_vp, _ci] + [_vp] * 5 + _DIMS + [_vp]),
     "msda3d_backward": (_ci, [_vp, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
     "msda3d_forward_host": (_ci, [_ci, _ci] + [_vp] * 5 + _DIMS + [_vp]),

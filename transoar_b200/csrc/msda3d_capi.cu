@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <string>
 
 #include "../../include/msda3d.h"
 
@@ -17,6 +18,7 @@ using namespace msda3d;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_diag_skip_red{0};   // diagnostics only (msda3d_set_tuning): drop the grad_value reductions
 
 struct Dims {
   int N, S, M, C, L, Lq, P;
@@ -45,15 +47,27 @@ int grid_for(long long units, int units_per_block)
   return (int)g;
 }
 
-// Vector-kernel eligibility: C = G * NV * VEC with G a power of two <= 32 (NV = 2 only on top of G = 32), <= 16 levels,
-// 16-byte aligned slabs and int32 element offsets inside one batch element.
+// Vector-kernel eligibility: C = G * NV * VEC with G a power of two <= 32, <= 16 levels, 16-byte aligned slabs and
+// 32-bit element offsets over the whole value tensor.  NV (16-byte vectors per lane) is 1 unless the channel count
+// needs 2 to fit a warp (measured on B200, profiles/r01_variants.txt: at C = 64 both are within 2 %, NV = 1 keeps
+// registers at 64 / 80 and four / three CTAs per SM resident).
+std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d_set_tuning "nv")
+std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
+std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
+
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
 {
   constexpr int VEC = Vec16<VT>::N;
   if (C % VEC) return false;
   const int q = C / VEC;
-  if (q <= 32 && (q & (q - 1)) == 0) { G = q; NV = 1; return true; }
-  if (q == 64) { G = 32; NV = 2; return true; }
+  const int forced = g_tune_nv.load();
+  for (int nv = (forced ? forced : 1); nv <= 2; ++nv) {
+    if (q % nv == 0) {
+      const int g = q / nv;
+      if (g <= 32 && (g & (g - 1)) == 0) { G = g; NV = nv; return true; }
+    }
+    if (forced) break;
+  }
   return false;
 }
 
@@ -62,22 +76,61 @@ bool vec_ok(const Dims &d, const void *a, const void *b, int &G, int &NV)
 {
   if (!vec_shape<VT>(d.C, G, NV)) return false;
   if (d.L > kMaxLevels) return false;
-  if ((long long)d.S * d.M * d.C >= (1LL << 31)) return false;
+  if ((long long)d.N * d.S * d.M * d.C >= (1LL << 31)) return false;
   if ((long long)d.L * d.P * 3 >= (1LL << 20)) return false;
   return aligned(a, 16) && aligned(b, 16);
 }
 
-#define VEC_DISPATCH(G_, NV_, ...)                        \
-  switch ((G_) * 4 + (NV_)) {                              \
-    case 1 * 4 + 1: { constexpr int G = 1, NV = 1; __VA_ARGS__; } break;   \
-    case 2 * 4 + 1: { constexpr int G = 2, NV = 1; __VA_ARGS__; } break;   \
-    case 4 * 4 + 1: { constexpr int G = 4, NV = 1; __VA_ARGS__; } break;   \
-    case 8 * 4 + 1: { constexpr int G = 8, NV = 1; __VA_ARGS__; } break;   \
-    case 16 * 4 + 1: { constexpr int G = 16, NV = 1; __VA_ARGS__; } break; \
-    case 32 * 4 + 1: { constexpr int G = 32, NV = 1; __VA_ARGS__; } break; \
-    case 32 * 4 + 2: { constexpr int G = 32, NV = 2; __VA_ARGS__; } break; \
-    default: return MSDA3D_EINVAL;                         \
+int use_brick(const Dims &d)
+{
+  const int o = g_tune_order.load();
+  return (o == 1) ? 0 : (d.Lq == d.S ? 1 : 0);
+}
+
+int sm_count()
+{
+  static int cached[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
+  return cached[dev];
+}
+
+// Grid: enough CTAs for every warp slot, capped at a multiple of the SM count (grid-stride loop covers the rest).
+int vec_grid(long long units, int G)
+{
+  const int upb = (kThreads / 32) * (32 / G);
+  long long g = (units + upb - 1) / upb;
+  const int mult = g_tune_grid_mult.load();
+  const long long cap = (long long)sm_count() * (mult > 0 ? mult : 64);
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+#define VEC_CASE(G_, NV_, ...) \
+  case (G_) * 4 + (NV_): { constexpr int G = G_, NV = NV_; __VA_ARGS__; } break;
+#define VEC_DISPATCH(g, nv, ...)                                                                              \
+  switch ((g) * 4 + (nv)) {                                                                                   \
+    VEC_CASE(1, 1, __VA_ARGS__) VEC_CASE(2, 1, __VA_ARGS__) VEC_CASE(4, 1, __VA_ARGS__) VEC_CASE(8, 1, __VA_ARGS__)   \
+    VEC_CASE(16, 1, __VA_ARGS__) VEC_CASE(32, 1, __VA_ARGS__)                                                 \
+    VEC_CASE(1, 2, __VA_ARGS__) VEC_CASE(2, 2, __VA_ARGS__) VEC_CASE(4, 2, __VA_ARGS__) VEC_CASE(8, 2, __VA_ARGS__)   \
+    VEC_CASE(16, 2, __VA_ARGS__) VEC_CASE(32, 2, __VA_ARGS__)                                                 \
+    default: return MSDA3D_EINVAL;                                                                            \
+  }
+
+// Resident CTAs per SM the kernels are compiled for (register caps 64 / 80 / 128 / 255 per thread).  Measured on B200
+// (profiles/r01_variants.txt): the fp32 forward gains 20 % going from 2-3 to 4 CTAs per SM (latency hiding), the
+// backward is bound by the reduction traffic into L2 and only needs 3.  Wider per-lane vectors get a looser cap so
+// that ptxas does not spill.
+template <typename VT, int NV> struct MinBlocks {
+  static constexpr bool wide = sizeof(VT) < 4;   // 16-bit storage: 8 channels per 16-byte vector
+  static constexpr int fwd = (!wide && NV == 1) ? 4 : (!wide || NV == 1) ? 3 : 2;
+  static constexpr int bwd = (!wide && NV == 1) ? 3 : (!wide || NV == 1) ? 2 : 1;
+};
+
 
 template <typename VT>
 int forward_half_or_float(cudaStream_t st, const Dims &d, const void *value, const int64_t *shapes, const int64_t *starts,
@@ -86,11 +139,10 @@ int forward_half_or_float(cudaStream_t st, const Dims &d, const void *value, con
   const long long units = (long long)d.N * d.Lq * d.M;
   int g_ = 0, nv_ = 0;
   if (vec_ok<VT>(d, value, out, g_, nv_)) {
-    const int upb = (kThreads / 32) * (32 / g_);
-    const int grid = grid_for(units, upb);
-    VEC_DISPATCH(g_, nv_, fwd_vec_kernel<VT, G, NV><<<grid, kThreads, 0, st>>>(
+    const int grid = vec_grid(units, g_);
+    VEC_DISPATCH(g_, nv_, fwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::fwd><<<grid, kThreads, 0, st>>>(
                               (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq,
-                              d.P, (VT *)out));
+                              d.P, (VT *)out, use_brick(d)));
   } else {
     fwd_generic_kernel<VT, float><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
         (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.C, d.L, d.Lq, d.P, (VT *)out);
@@ -108,11 +160,16 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
   if (e != cudaSuccess) return (int)e;
   int g_ = 0, nv_ = 0;
   if (vec_ok<VT>(d, value, gout, g_, nv_) && aligned(gv, 16)) {
-    const int upb = (kThreads / 32) * (32 / g_);
-    const int grid = grid_for(units, upb);
-    VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV><<<grid, kThreads, 0, st>>>(
-                              (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S,
-                              d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga));
+    const int grid = vec_grid(units, g_);
+    if (g_diag_skip_red.load()) {
+      VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd, true><<<grid, kThreads, 0, st>>>(
+                                (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
+                                d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d)));
+    } else {
+      VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd><<<grid, kThreads, 0, st>>>(
+                                (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
+                                d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d)));
+    }
   } else {
     bwd_generic_kernel<VT, float><<<grid_for(units, kThreads / 32), kThreads, 0, st>>>(
         (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.C, d.L, d.Lq,
@@ -129,6 +186,17 @@ extern "C" {
 int msda3d_abi_version(void) { return MSDA3D_ABI_VERSION; }
 
 unsigned long long msda3d_launch_count(void) { return g_launches.load(); }
+
+int msda3d_set_tuning(const char *key, int value)
+{
+  if (!key) return MSDA3D_EINVAL;
+  const std::string k(key);
+  if (k == "diag_bwd_skip_red") { g_diag_skip_red = value; return MSDA3D_OK; }
+  if (k == "nv" && value >= 0 && value <= 2) { g_tune_nv = value; return MSDA3D_OK; }
+  if (k == "grid_mult" && value >= 0) { g_tune_grid_mult = value; return MSDA3D_OK; }
+  if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
+  return MSDA3D_EINVAL;
+}
 
 const char *msda3d_error_string(int code)
 {

@@ -197,230 +197,335 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Vector kernels: C = G * NV * Vec16<VT>::N channels per unit, G lanes per unit (G | 32)
+// Vector kernels: C = G * NV * Vec16<VT>::N channels per unit, G lanes per unit (G | 32), 32/G units per warp.
+//
+// Control flow is warp-uniform (every lane runs every loop iteration, shuffles use the full mask); only the
+// "is this sample in range" test diverges, per group.  Per chunk of G samples, lane j of a group prepares sample j
+// (coordinates -> clamped corner offset, zero-padded axis weights, strides) and parks it in a per-warp shared-memory
+// slot; the group then walks the chunk reading each sample back with three broadcast LDS.128.
+//
+// Zero padding without predicated loads: the low corner is clamped into the volume and the stride along an axis is 0
+// when one of its two sides is outside, so all eight corner loads are unconditional and in bounds; the axis weight of
+// an outside side is forced to 0, which zeroes exactly the corner weights the reference zero-pads (cuh:60-107).  For
+// finite inputs the blend is bit-identical: fma(w, 0, acc) == fma(0, v, acc) == acc.
 // ---------------------------------------------------------------------------------------------------------------
-struct GroupSample {       // what lane j of a group prepares for sample (s0 + j) and the group then broadcasts
-  unsigned mask;
-  int off;                 // element offset of the (d_low,h_low,w_low) corner inside this batch element's value slab
-  float ld, lh, lw, aw;
+struct PreparedSample {
+  float4 a;   // {corner offset (uint bits), attention weight, hd_e, ld_e}
+  float4 b;   // {hh_e, lh_e, hw_e, lw_e}
+  int4 c;     // {stride d, stride h, stride w (elements; 0 when clamped), flags: bit0 in range, bits1..6 = dl,dh,hl,hh,wl,wh valid}
 };
 
-__device__ __forceinline__ GroupSample prepare_sample(const int4 *lv, const float *__restrict__ loc_u,
-                                                      const float *__restrict__ aw_u, int s, int LP, int P, int MC)
+struct UnitCoords {
+  bool active;
+  int m;
+  long long u, b;
+};
+
+// Work scheduling.  A "block slot" is the set of UPB = 8 * 32/G units one CTA processes together.  Slots are handed
+// out in contiguous runs (CTA i owns slots [i*per, (i+1)*per)), so what a CTA leaves in L1 is what it needs next.
+//   linear order : slot t = units [t*UPB, (t+1)*UPB) in memory order (head fastest, then query).
+//   brick order  : used when Lq == S, i.e. queries are the voxels of the level pyramid (the FPN refinement's
+//                  self-attention, decoder_blocks.py:107-131).  A slot is one head x one BDxBHxBW brick of
+//                  neighbouring query voxels: neighbouring queries sample neighbouring voxels, so the 8*32/G units of
+//                  a CTA share corner lines in L1 instead of each pulling its own from L2.  Pure scheduling: any
+//                  order gives the same results.
+struct BrickPlan {
+  int4 lvb[kMaxLevels];    // per level: bricks along d, h, w and index of the level's first brick
+  int nb;                  // bricks per (batch, head)
+};
+
+template <int UPB> struct BrickDims;    // UPB = BD * BH * BW, w fastest
+template <> struct BrickDims<8> { static constexpr int BD = 2, BH = 2, BW = 2; };
+template <> struct BrickDims<16> { static constexpr int BD = 2, BH = 2, BW = 4; };
+template <> struct BrickDims<32> { static constexpr int BD = 2, BH = 4, BW = 4; };
+template <> struct BrickDims<64> { static constexpr int BD = 4, BH = 4, BW = 4; };
+template <> struct BrickDims<128> { static constexpr int BD = 4, BH = 4, BW = 8; };
+template <> struct BrickDims<256> { static constexpr int BD = 4, BH = 8, BW = 8; };
+
+template <int UPB>
+__device__ __forceinline__ void make_brick_plan(BrickPlan &bp, const int4 *lv, int L)
 {
-  GroupSample g;
-  g.mask = 0; g.off = 0; g.ld = g.lh = g.lw = g.aw = 0.f;
-  if (s < LP) {
-    const int4 li = lv[s / P];
-    const float x = ldg_stream(loc_u + 3 * s), y = ldg_stream(loc_u + 3 * s + 1), z = ldg_stream(loc_u + 3 * s + 2);
-    g.aw = ldg_stream(aw_u + s);
-    const Sample<float> sm = locate<float>(x, y, z, li.x, li.y, li.z);
-    g.mask = sm.mask; g.ld = sm.ld; g.lh = sm.lh; g.lw = sm.lw;
-    g.off = (li.w + (sm.d_low * li.y + sm.h_low) * li.z + sm.w_low) * MC;
+  using B = BrickDims<UPB>;
+  int first = 0;
+  for (int l = 0; l < L; ++l) {
+    const int nd = (lv[l].x + B::BD - 1) / B::BD, nh = (lv[l].y + B::BH - 1) / B::BH, nw = (lv[l].z + B::BW - 1) / B::BW;
+    bp.lvb[l] = make_int4(nd, nh, nw, first);
+    first += nd * nh * nw;
   }
-  return g;
+  bp.nb = first;
 }
 
-template <typename VT, int G, int NV>
-__global__ void __launch_bounds__(kThreads)
+// unit of (slot t, unit-in-block ui)
+template <int UPB>
+__device__ __forceinline__ UnitCoords slot_unit(bool brick, long long t, int ui, long long total, const BrickPlan &bp,
+                                                const int4 *lv, int L, int M, int Lq)
+{
+  UnitCoords c;
+  if (!brick) {
+    const long long u = t * UPB + ui;
+    c.active = u < total;
+    c.u = c.active ? u : 0;
+    c.m = (int)(c.u % M);
+    c.b = c.u / ((long long)M * Lq);
+    return c;
+  }
+  using B = BrickDims<UPB>;
+  const long long per_batch = (long long)bp.nb * M;
+  c.b = t / per_batch;
+  const int r = (int)(t - c.b * per_batch);
+  c.m = r / bp.nb;
+  int br = r - c.m * bp.nb;
+  int l = 0;
+  while (l + 1 < L && br >= bp.lvb[l + 1].w) ++l;
+  const int4 nb = bp.lvb[l], li = lv[l];
+  br -= nb.w;
+  const int bw = br % nb.z, bh = (br / nb.z) % nb.y, bd = br / (nb.z * nb.y);
+  const int w = bw * B::BW + ui % B::BW, h = bh * B::BH + (ui / B::BW) % B::BH, d = bd * B::BD + ui / (B::BW * B::BH);
+  c.active = d < li.x && h < li.y && w < li.z;
+  const long long q = c.active ? (long long)li.w + ((long long)d * li.y + h) * li.z + w : 0;
+  c.u = (c.b * Lq + q) * M + c.m;
+  if (!c.active) { c.u = 0; c.m = 0; c.b = 0; }
+  return c;
+}
+
+// Lane-side preparation of sample s of unit uc (cuh:405-428 + cuh:36-46 + corner guards cuh:60-107).
+__device__ __forceinline__ PreparedSample prepare_sample(const int4 *lv, const float *__restrict__ loc, const float *__restrict__ aw,
+                                                         const UnitCoords &uc, int s, int LP, int P, int S, int MC, int C)
+{
+  PreparedSample ps;
+  ps.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.c = make_int4(0, 0, 0, 0);
+  if (uc.active && s < LP) {
+    const int4 li = lv[s / P];
+    const long long si = uc.u * LP + s;
+    const float x = ldg_stream(loc + 3 * si), y = ldg_stream(loc + 3 * si + 1), z = ldg_stream(loc + 3 * si + 2);
+    const Sample<float> sm = locate<float>(x, y, z, li.x, li.y, li.z);
+    if (sm.mask != 0) {
+      const bool vdl = sm.d_low >= 0, vdh = sm.d_low + 1 <= li.x - 1;
+      const bool vhl = sm.h_low >= 0, vhh = sm.h_low + 1 <= li.y - 1;
+      const bool vwl = sm.w_low >= 0, vwh = sm.w_low + 1 <= li.z - 1;
+      const int sW = MC, sH = li.z * MC, sD = li.y * sH;
+      const unsigned vox = (unsigned)((max(sm.d_low, 0) * li.y + max(sm.h_low, 0)) * li.z + max(sm.w_low, 0));
+      const unsigned off = ((unsigned)(uc.b * S) + (unsigned)li.w + vox) * (unsigned)MC + (unsigned)(uc.m * C);
+      ps.a = make_float4(__uint_as_float(off), ldg_stream(aw + si), vdl ? 1.f - sm.ld : 0.f, vdh ? sm.ld : 0.f);
+      ps.b = make_float4(vhl ? 1.f - sm.lh : 0.f, vhh ? sm.lh : 0.f, vwl ? 1.f - sm.lw : 0.f, vwh ? sm.lw : 0.f);
+      ps.c = make_int4((vdl && vdh) ? sD : 0, (vhl && vhh) ? sH : 0, (vwl && vwh) ? sW : 0,
+                       1 | (vdl << 1) | (vdh << 2) | (vhl << 3) | (vhh << 4) | (vwl << 5) | (vwh << 6));
+    }
+  }
+  return ps;
+}
+
+// cuh:109-110 from the (zero-padded) axis weights, products left to right: (d*h)*w.
+__device__ __forceinline__ void corner_weights_axes(float hd, float ld, float hh, float lh, float hw, float lw, float (&w)[8])
+{
+  const float a = __fmul_rn(hd, hh), b = __fmul_rn(hd, lh), c = __fmul_rn(ld, hh), d = __fmul_rn(ld, lh);
+  w[0] = __fmul_rn(a, hw); w[1] = __fmul_rn(a, lw); w[2] = __fmul_rn(b, hw); w[3] = __fmul_rn(b, lw);
+  w[4] = __fmul_rn(c, hw); w[5] = __fmul_rn(c, lw); w[6] = __fmul_rn(d, hw); w[7] = __fmul_rn(d, lw);
+}
+
+template <typename VT, int G, int NV, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
                const float *__restrict__ loc, const float *__restrict__ aw, int N, int S, int M, int L, int Lq, int P,
-               VT *__restrict__ out)
+               VT *__restrict__ out, int brick)
 {
   using V = Vec16<VT>;
-  constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL;
+  constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
   __shared__ int4 lv[kMaxLevels];
+  __shared__ BrickPlan bp;
+  __shared__ float4 sA[WARPS][32];
+  __shared__ float4 sB[WARPS][32];
+  __shared__ int4 sC[WARPS][32];
   if (threadIdx.x < L)
     lv[threadIdx.x] = make_int4((int)shapes[3 * threadIdx.x], (int)shapes[3 * threadIdx.x + 1],
                                 (int)shapes[3 * threadIdx.x + 2], (int)starts[threadIdx.x]);
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, g0 = lane - gl;
   const int MC = M * C, LP = L * P;
   const long long total = (long long)N * Lq * M;
-  const long long stride = (long long)gridDim.x * (kThreads / 32) * (32 / G);
-  for (long long u = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * (32 / G) + grp; u < total; u += stride) {
-    const int m = (int)(u % M);
-    const long long b = u / ((long long)M * Lq);
-    const VT *vbase = value + b * (long long)S * MC + m * C + gl * CPL;
-    const float *loc_u = loc + u * LP * 3;
-    const float *aw_u = aw + u * LP;
+  if (brick && threadIdx.x == 0) make_brick_plan<UPB>(bp, lv, L);
+  __syncthreads();
+  const long long slots = brick ? (long long)N * M * bp.nb : (total + UPB - 1) / UPB;
+  const long long per = (slots + gridDim.x - 1) / gridDim.x;
+  const long long t_end = min(slots, (blockIdx.x + 1) * per);
+  const unsigned lane_off = gl * VEC;                               // vector nv of this lane starts at nv*G*VEC + gl*VEC
+  for (long long t = blockIdx.x * per; t < t_end; ++t) {
+    const UnitCoords uc = slot_unit<UPB>(brick != 0, t, warp * UPW + lane / G, total, bp, lv, L, M, Lq);
     float acc[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
 
-    int l_cur = 0, p_cur = 0;
-    int4 li = lv[0];
     for (int s0 = 0; s0 < LP; s0 += G) {
-      const GroupSample mine = prepare_sample(lv, loc_u, aw_u, s0 + gl, LP, P, MC);
+      const PreparedSample mine = prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
+      __syncwarp();
+      sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
+      __syncwarp();
       const int cnt = min(G, LP - s0);
       for (int j = 0; j < cnt; ++j) {
-        const int sH = li.z * MC, sD = li.y * sH;
-        if (++p_cur == P) { p_cur = 0; ++l_cur; li = lv[min(l_cur, L - 1)]; }
-        const unsigned mask = __shfl_sync(gmask, mine.mask, j, G);
-        if (mask == 0) continue;                                  // cuh:428 -- uniform inside the group
-        const int off = __shfl_sync(gmask, mine.off, j, G);
-        const float ld = __shfl_sync(gmask, mine.ld, j, G);
-        const float lh = __shfl_sync(gmask, mine.lh, j, G);
-        const float lw = __shfl_sync(gmask, mine.lw, j, G);
-        const float wa = __shfl_sync(gmask, mine.aw, j, G);
+        const int4 pc = sC[warp][g0 + j];
+        if (pc.w == 0) continue;                                    // cuh:428 failed (or idle tail group)
+        const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
         float w[8];
-        corner_weights<float>(ld, lh, lw, w);
-        const VT *p0 = vbase + off;
+        corner_weights_axes(pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, w);
+        unsigned o[8];
+        o[0] = __float_as_uint(pa.x) + lane_off; o[1] = o[0] + pc.z; o[2] = o[0] + pc.y; o[3] = o[2] + pc.z;
+        o[4] = o[0] + pc.x; o[5] = o[4] + pc.z; o[6] = o[4] + pc.y; o[7] = o[6] + pc.z;
 #pragma unroll
         for (int nv = 0; nv < NV; ++nv) {
           float v[8][VEC];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (mask & (1u << k)) {
-              V::load(p0 + ((k & 4) ? sD : 0) + ((k & 2) ? sH : 0) + ((k & 1) ? MC : 0) + nv * VEC, v[k]);
-            } else {
-#pragma unroll
-              for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
-            }
-          }
+          for (int k = 0; k < 8; ++k) V::load(value + (o[k] + nv * (G * VEC)), v[k]);
 #pragma unroll
           for (int c = 0; c < VEC; ++c) {
             const float val = blend<float>(w, v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
-            acc[nv * VEC + c] = __fmaf_rn(wa, val, acc[nv * VEC + c]);   // cuh:430
+            acc[nv * VEC + c] = __fmaf_rn(pa.y, val, acc[nv * VEC + c]);   // cuh:430
           }
         }
       }
     }
-    VT *o = out + u * C + gl * CPL;
+    if (uc.active) {
+      VT *o = out + uc.u * C + lane_off;
 #pragma unroll
-    for (int nv = 0; nv < NV; ++nv) {
-      float t[VEC];
+      for (int nv = 0; nv < NV; ++nv) {
+        float tv[VEC];
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) t[c] = acc[nv * VEC + c];
-      V::store(o + nv * VEC, t);
+        for (int c = 0; c < VEC; ++c) tv[c] = acc[nv * VEC + c];
+        V::store(o + nv * (G * VEC), tv);
+      }
     }
   }
 }
 
-template <int G> __device__ __forceinline__ float group_sum(unsigned gmask, float v)
+template <int G> __device__ __forceinline__ float group_sum(float v)
 {
 #pragma unroll
-  for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(gmask, v, d, G);
+  for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
 }
 
-template <typename VT, int G, int NV>
-__global__ void __launch_bounds__(kThreads)
+// Backward.  With t_c = grad_output[c] and dot_k = sum_c t_c * v_k[c] (k = corner), every gradient of a sample is a
+// trilinear form in the eight dots:
+//   grad_attn_weight      = sum_k w_k dot_k                                   (cuh:236-237)
+//   grad_loc.{z,y,x}      = size * attn * sum_k d(w_k)/d{ld,lh,lw} dot_k      (cuh:159-231,238-240)
+// so the per-channel work is the eight dots (one FMA per corner and channel); the rest is ~40 scalar operations per
+// sample, evaluated separably (along w, then h, then d).  The reference spends 24 FMAs per channel on the same sums.
+// grad_value gets w_k * (t_c * attn) per corner as 128-bit reductions, skipped where the corner weight is zero.
+template <typename VT, int G, int NV, int MINB, bool SKIP_RED = false>
+__global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
                int M, int L, int Lq, int P, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-               float *__restrict__ grad_aw)
+               float *__restrict__ grad_aw, int brick)
 {
   using V = Vec16<VT>;
-  constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL;
+  constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
   __shared__ int4 lv[kMaxLevels];
+  __shared__ BrickPlan bp;
+  __shared__ float4 sA[WARPS][32];
+  __shared__ float4 sB[WARPS][32];
+  __shared__ int4 sC[WARPS][32];
   if (threadIdx.x < L)
     lv[threadIdx.x] = make_int4((int)shapes[3 * threadIdx.x], (int)shapes[3 * threadIdx.x + 1],
                                 (int)shapes[3 * threadIdx.x + 2], (int)starts[threadIdx.x]);
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, g0 = lane - gl;
   const int MC = M * C, LP = L * P;
   const long long total = (long long)N * Lq * M;
-  const long long stride = (long long)gridDim.x * (kThreads / 32) * (32 / G);
-  for (long long u = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * (32 / G) + grp; u < total; u += stride) {
-    const int m = (int)(u % M);
-    const long long b = u / ((long long)M * Lq);
-    const long long slab = b * (long long)S * MC + m * C + gl * CPL;
-    const VT *vbase = value + slab;
-    float *gbase = grad_value + slab;
-    const float *loc_u = loc + u * LP * 3;
-    const float *aw_u = aw + u * LP;
+  if (brick && threadIdx.x == 0) make_brick_plan<UPB>(bp, lv, L);
+  __syncthreads();
+  const long long slots = brick ? (long long)N * M * bp.nb : (total + UPB - 1) / UPB;
+  const long long per = (slots + gridDim.x - 1) / gridDim.x;
+  const long long t_end = min(slots, (blockIdx.x + 1) * per);
+  const unsigned lane_off = gl * VEC;                               // vector nv of this lane starts at nv*G*VEC + gl*VEC
+  for (long long t = blockIdx.x * per; t < t_end; ++t) {
+    const UnitCoords uc = slot_unit<UPB>(brick != 0, t, warp * UPW + lane / G, total, bp, lv, L, M, Lq);
     float top[CPL];
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv) {
-      float t[VEC];
-      V::load_stream(grad_out + u * C + gl * CPL + nv * VEC, t);
+      float tv[VEC];
+      V::load_stream(grad_out + uc.u * C + lane_off + nv * (G * VEC), tv);
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) top[nv * VEC + c] = t[c];
+      for (int c = 0; c < VEC; ++c) top[nv * VEC + c] = tv[c];
     }
 
-    int l_cur = 0, p_cur = 0;
-    int4 li = lv[0];
     for (int s0 = 0; s0 < LP; s0 += G) {
-      const GroupSample mine = prepare_sample(lv, loc_u, aw_u, s0 + gl, LP, P, MC);
-      float r_a = 0.f, r_w = 0.f, r_h = 0.f, r_d = 0.f;          // results of "my" sample (lane j keeps sample s0+j)
+      const PreparedSample mine = prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
+      __syncwarp();
+      sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
+      __syncwarp();
+      float r_a = 0.f, r_w = 0.f, r_h = 0.f, r_d = 0.f;            // lane j keeps the sums of sample s0 + j
       const int cnt = min(G, LP - s0);
       for (int j = 0; j < cnt; ++j) {
-        const int sH = li.z * MC, sD = li.y * sH;
-        const float fD = __int2float_rn(li.x), fH = __int2float_rn(li.y), fW = __int2float_rn(li.z);
-        if (++p_cur == P) { p_cur = 0; ++l_cur; li = lv[min(l_cur, L - 1)]; }
-        const unsigned mask = __shfl_sync(gmask, mine.mask, j, G);
-        if (mask == 0) continue;                                  // all four gradients of this sample stay 0 (cuh:618-621)
-        const int off = __shfl_sync(gmask, mine.off, j, G);
-        const float ld = __shfl_sync(gmask, mine.ld, j, G);
-        const float lh = __shfl_sync(gmask, mine.lh, j, G);
-        const float lw = __shfl_sync(gmask, mine.lw, j, G);
-        const float wa = __shfl_sync(gmask, mine.aw, j, G);
-        float w[8];
-        corner_weights<float>(ld, lh, lw, w);
-        const float hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
-        // d(weight)/d(frac) factors, cuh:159-231
-        const float d0 = hh * hw, d1 = hh * lw, d2 = lh * hw, d3 = lh * lw;
-        const float h0 = hd * hw, h1 = hd * lw, h2 = ld * hw, h3 = ld * lw;
-        const float w0 = hd * hh, w1 = hd * lh, w2 = ld * hh, w3 = ld * lh;
-        float pa = 0.f, pw = 0.f, ph = 0.f, pd = 0.f;
+        const int4 pc = sC[warp][g0 + j];
+        float qa = 0.f, qw = 0.f, qh = 0.f, qd = 0.f;
+        if (pc.w != 0) {
+          const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
+          float w[8];
+          corner_weights_axes(pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, w);
+          unsigned o[8];
+          o[0] = __float_as_uint(pa.x) + lane_off; o[1] = o[0] + pc.z; o[2] = o[0] + pc.y; o[3] = o[2] + pc.z;
+          o[4] = o[0] + pc.x; o[5] = o[4] + pc.z; o[6] = o[4] + pc.y; o[7] = o[6] + pc.z;
+          float dot[8];
 #pragma unroll
-        for (int nv = 0; nv < NV; ++nv) {
-          float v[8][VEC];
-          int koff[8];
+          for (int k = 0; k < 8; ++k) dot[k] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            koff[k] = off + ((k & 4) ? sD : 0) + ((k & 2) ? sH : 0) + ((k & 1) ? MC : 0) + nv * VEC;
-            if (mask & (1u << k)) {
-              V::load(vbase + koff[k], v[k]);
-            } else {
+          for (int nv = 0; nv < NV; ++nv) {
+            float v[8][VEC];
 #pragma unroll
-              for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+            for (int k = 0; k < 8; ++k) V::load(value + (o[k] + nv * (G * VEC)), v[k]);
+            float ta[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) ta[c] = top[nv * VEC + c] * pa.y;                 // cuh:151 top_grad * attn_weight
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+              for (int c = 0; c < VEC; ++c) dot[k] = fmaf(top[nv * VEC + c], v[k][c], dot[k]);
+              if (!SKIP_RED && w[k] != 0.f) {
+#pragma unroll
+                for (int c4 = 0; c4 < VEC; c4 += 4)
+                  red_add_v4(grad_value + (o[k] + nv * (G * VEC) + c4), w[k] * ta[c4], w[k] * ta[c4 + 1], w[k] * ta[c4 + 2], w[k] * ta[c4 + 3]);
+              }
             }
           }
-          float tgv[VEC];
+          // separable evaluation of the four trilinear forms; s?l / s?h = -1 / +1 where that side is inside, else 0
+          const float sdl = (pc.w & 2) ? -1.f : 0.f, sdh = (pc.w & 4) ? 1.f : 0.f;
+          const float shl = (pc.w & 8) ? -1.f : 0.f, shh = (pc.w & 16) ? 1.f : 0.f;
+          const float swl = (pc.w & 32) ? -1.f : 0.f, swh = (pc.w & 64) ? 1.f : 0.f;
+          float A[4], Bw[4];                                       // index = 2*kd + kh
 #pragma unroll
-          for (int c = 0; c < VEC; ++c) {
-            const float t = top[nv * VEC + c];
-            tgv[c] = t * wa;                                                           // cuh:151
-            const float val = blend<float>(w, v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
-            float gd = -d0 * v[0][c], gh = -h0 * v[0][c], gw = -w0 * v[0][c];          // cuh:159-231
-            gd -= d1 * v[1][c]; gh -= h1 * v[1][c]; gw += w0 * v[1][c];
-            gd -= d2 * v[2][c]; gh += h0 * v[2][c]; gw -= w1 * v[2][c];
-            gd -= d3 * v[3][c]; gh += h1 * v[3][c]; gw += w1 * v[3][c];
-            gd += d0 * v[4][c]; gh -= h2 * v[4][c]; gw -= w2 * v[4][c];
-            gd += d1 * v[5][c]; gh -= h3 * v[5][c]; gw += w2 * v[5][c];
-            gd += d2 * v[6][c]; gh += h2 * v[6][c]; gw -= w3 * v[6][c];
-            gd += d3 * v[7][c]; gh += h3 * v[7][c]; gw += w3 * v[7][c];
-            pa = fmaf(t, val, pa);                                                     // cuh:237
-            pw = fmaf(fW * gw, tgv[c], pw);                                            // cuh:238-240
-            ph = fmaf(fH * gh, tgv[c], ph);
-            pd = fmaf(fD * gd, tgv[c], pd);
+          for (int i = 0; i < 4; ++i) {
+            A[i] = pb.z * dot[2 * i] + pb.w * dot[2 * i + 1];
+            Bw[i] = swl * dot[2 * i] + swh * dot[2 * i + 1];
           }
+          float A2[2], Bh[2], Bw2[2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (mask & (1u << k)) {
-#pragma unroll
-              for (int c4 = 0; c4 < VEC; c4 += 4)
-                red_add_v4(gbase + koff[k] + c4, w[k] * tgv[c4], w[k] * tgv[c4 + 1], w[k] * tgv[c4 + 2], w[k] * tgv[c4 + 3]);
-            }
+          for (int i = 0; i < 2; ++i) {
+            A2[i] = pb.x * A[2 * i] + pb.y * A[2 * i + 1];
+            Bh[i] = shl * A[2 * i] + shh * A[2 * i + 1];
+            Bw2[i] = pb.x * Bw[2 * i] + pb.y * Bw[2 * i + 1];
           }
+          qa = pa.z * A2[0] + pa.w * A2[1];
+          qd = sdl * A2[0] + sdh * A2[1];
+          qh = pa.z * Bh[0] + pa.w * Bh[1];
+          qw = pa.z * Bw2[0] + pa.w * Bw2[1];
         }
-        pa = group_sum<G>(gmask, pa);
-        pw = group_sum<G>(gmask, pw);
-        ph = group_sum<G>(gmask, ph);
-        pd = group_sum<G>(gmask, pd);
-        if (gl == j) { r_a = pa; r_w = pw; r_h = ph; r_d = pd; }
+        qa = group_sum<G>(qa); qw = group_sum<G>(qw); qh = group_sum<G>(qh); qd = group_sum<G>(qd);
+        if (gl == j) { r_a = qa; r_w = qw; r_h = qh; r_d = qd; }
       }
       const int s = s0 + gl;
-      if (s < LP) {
-        float *gl_ = grad_loc + (u * LP + s) * 3;
-        gl_[0] = r_w; gl_[1] = r_h; gl_[2] = r_d;
-        grad_aw[u * LP + s] = r_a;
+      if (uc.active && s < LP) {
+        // my own sample: scale by attn * size (cuh:238-240); out-of-range samples carry exact zeros (cuh:618-621)
+        const int4 li = lv[s / P];
+        const float wa = __uint_as_float(__float_as_uint(mine.a.y));
+        float *gl_ = grad_loc + (uc.u * LP + s) * 3;
+        gl_[0] = __int2float_rn(li.z) * (r_w * wa);
+        gl_[1] = __int2float_rn(li.y) * (r_h * wa);
+        gl_[2] = __int2float_rn(li.x) * (r_d * wa);
+        grad_aw[uc.u * LP + s] = r_a;
       }
     }
   }

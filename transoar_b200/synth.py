@@ -8,6 +8,7 @@ Workload geometry follows the reference configs:
 
 Two sampling-location distributions:
   * dist "A": the reference test's own inputs (ops/test.py:54-57) -- uniform locations, worst-case locality.
+  * dist "B0": dist "B" without the jitter -- exactly what the freshly initialised model produces.
   * dist "B": what the model feeds the op -- reference point = the query's voxel centre at every level
     (backbones/decoder_blocks.py:107-131) plus offsets ``(dir_m * (p+1) + N(0,1)) / (W_l,H_l,D_l)`` where ``dir_m`` are
     the six axis directions MSDeformAttn initialises its offset bias with (ops/modules/ms_deform_attn.py:63-79).
@@ -101,13 +102,15 @@ def make_inputs(geom: Geometry, batch: int, dist: str = "A", seed: int = 1234, d
         loc = rnd(N, Lq, M, L, P, 3)
         aw = rnd(N, Lq, M, L, P) + 1e-5
         aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
-    elif dist == "B":
+    elif dist in ("B", "B0"):
         ref = reference_points(geom.shapes)                                      # [S,3]
         if Lq != S:
             ref = ref[torch.randint(0, S, (Lq,), generator=g)]
         dirs = head_directions(M)                                                # [M,3]
         steps = torch.arange(1, P + 1, dtype=torch.float32)                      # (p+1)
-        off = dirs[None, None, :, None, None, :] * steps[None, None, None, None, :, None] + rnd(N, Lq, M, L, P, 3, normal=True)
+        off = (dirs[None, None, :, None, None, :] * steps[None, None, None, None, :, None]).expand(N, Lq, M, L, P, 3)
+        if dist == "B":                 # "B0" = the untrained model: offsets are exactly the bias pattern, no jitter
+            off = off + rnd(N, Lq, M, L, P, 3, normal=True)
         norm = torch.tensor([[w, h, d] for d, h, w in geom.shapes], dtype=torch.float32)      # (W,H,D) per level
         loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
         aw = torch.softmax(rnd(N, Lq, M, L * P, normal=True), -1).reshape(N, Lq, M, L, P)
