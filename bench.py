@@ -62,6 +62,17 @@ def aggregate_throughput(local_ms, steps, world, batch=BATCH, all_reduce_max=Non
     return world * batch * steps / (ms / 1e3), ms
 
 
+def load_ncu_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[kind]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -292,7 +303,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_vec_kernel<float,16,1,3> + the cudaMemsetAsync zero-fill of grad_value" if dom == "backward"
                 else "msda3d forward: fwd_vec_kernel<float,16,1,4>",
                 "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": load_ncu_traffic(dom), "peak_source": peak_src,
                 "algorithmic_bytes": dom_bytes,
                 "forward": {"ms": fwd_avg, "bytes": bf, "gbs": bf / (fwd_avg * 1e-3) / 1e9, "frac": bf / (fwd_avg * 1e-3) / 1e9 / peak},
                 "backward": {"ms": bwd_avg, "bytes": bb, "gbs": bb / (bwd_avg * 1e-3) / 1e9, "frac": bb / (bwd_avg * 1e-3) / 1e9 / peak},
