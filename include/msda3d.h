@@ -96,8 +96,7 @@ int msda3d_debug_indices(void *stream, int dtype, const int64_t *spatial_shapes,
 /* Diagnostics / tuning knobs for profiling sessions; never needed for correct results.  Unknown keys return
  * MSDA3D_EINVAL.  "nv" = 0|1|2: 16-byte vectors per lane in the vector kernels (0 = automatic);  "grid_mult" = CTAs
  * per SM cap of the launch (0 = automatic);  "order" = 0 automatic | 1 linear | 2 brick unit order (brick needs
- * num_query == spatial_size);  "bwd_combine" = 1|0: combine grad_value contributions per query brick in shared
- * memory before reducing into global memory (brick order only; default 1);  "diag_bwd_skip_red" = 1 drops the grad_value reductions
+ * num_query == spatial_size);  "diag_bwd_skip_red" = 1 drops the grad_value reductions
  * (WRONG results; isolates their cost). */
 int msda3d_set_tuning(const char *key, int value);
 

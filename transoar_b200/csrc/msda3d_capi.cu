@@ -54,7 +54,6 @@ int grid_for(long long units, int units_per_block)
 std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d_set_tuning "nv")
 std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
 std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
-std::atomic<int> g_tune_combine{1};     // 1 = backward combines grad_value contributions per brick in shared memory
 
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
 {
@@ -126,13 +125,6 @@ int vec_grid(long long units, int G)
 // (profiles/r01_variants.txt): the fp32 forward gains 20 % going from 2-3 to 4 CTAs per SM (latency hiding), the
 // backward is bound by the reduction traffic into L2 and only needs 3.  Wider per-lane vectors get a looser cap so
 // that ptxas does not spill.
-#define VEC_DISPATCH_BRICK(g, nv, ...)                                                                        \
-  switch ((g) * 4 + (nv)) {                                                                                   \
-    VEC_CASE(4, 1, __VA_ARGS__) VEC_CASE(8, 1, __VA_ARGS__) VEC_CASE(16, 1, __VA_ARGS__) VEC_CASE(32, 1, __VA_ARGS__)  \
-    VEC_CASE(4, 2, __VA_ARGS__) VEC_CASE(8, 2, __VA_ARGS__) VEC_CASE(16, 2, __VA_ARGS__) VEC_CASE(32, 2, __VA_ARGS__)  \
-    default: return MSDA3D_EINVAL;                                                                            \
-  }
-
 template <typename VT, int NV> struct MinBlocks {
   static constexpr bool wide = sizeof(VT) < 4;   // 16-bit storage: 8 channels per 16-byte vector
   static constexpr int fwd = (!wide && NV == 1) ? 4 : (!wide || NV == 1) ? 3 : 2;
@@ -169,18 +161,7 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
   int g_ = 0, nv_ = 0;
   if (vec_ok<VT>(d, value, gout, g_, nv_) && aligned(gv, 16)) {
     const int grid = vec_grid(units, g_);
-    if (use_brick(d) && g_ >= 4 && g_tune_combine.load() && !g_diag_skip_red.load()) {
-      cudaError_t err = cudaSuccess;
-      VEC_DISPATCH_BRICK(g_, nv_, {
-        auto kern = bwd_brick_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd>;
-        constexpr size_t smem = bwd_brick_smem_bytes<VT, G, NV>();
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err == cudaSuccess)
-          kern<<<grid, kThreads, smem, st>>>((const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc,
-                                             (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga);
-      });
-      if (err != cudaSuccess) return (int)err;
-    } else if (g_diag_skip_red.load() == 2 && g_ == 16 && nv_ == 1) {
+    if (g_diag_skip_red.load() == 2 && g_ == 16 && nv_ == 1) {
       bwd_vec_kernel<VT, 16, 1, MinBlocks<VT, 1>::bwd, 2><<<grid, kThreads, 0, st>>>(
           (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P,
           (float *)gv, (float *)gl, (float *)ga, use_brick(d));
@@ -218,7 +199,6 @@ int msda3d_set_tuning(const char *key, int value)
   if (k == "nv" && value >= 0 && value <= 2) { g_tune_nv = value; return MSDA3D_OK; }
   if (k == "grid_mult" && value >= 0) { g_tune_grid_mult = value; return MSDA3D_OK; }
   if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
-  if (k == "bwd_combine" && (value == 0 || value == 1)) { g_tune_combine = value; return MSDA3D_OK; }
   return MSDA3D_EINVAL;
 }
 

@@ -463,8 +463,10 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
   return g;
 }
 
-// Backward, direct variant: grad_value gets w_k * (t_c * attn) per corner as 128-bit reductions (skipped where the corner
-// weight is zero).  Used when the queries have no spatial order to exploit (Lq != S) and for narrow heads.
+// grad_value gets w_k * (t_c * attn) per corner as 128-bit reductions (skipped where the corner weight is zero).  On
+// B200 these reductions are what bounds the kernel: the L2 atomic units take ~6.6 TB/s of fp32 payload
+// (tools/micro/red_bench.cu), the launch sends 8 corners x C floats per in-range sample.  Combining contributions of
+// neighbouring queries in shared memory first was tried and is slower (profiles/r01_experiments.md, section 4).
 template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
@@ -547,228 +549,6 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
       }
     }
   }
-}
-
-// Backward, combining variant (brick order, Lq == S).  On B200 the direct variant is bound by the L2 atomic units:
-// 8 corners x C floats of reductions per sample arrive at ~6.6 TB/s (tools/micro/red_bench.cu), half of the kernel's
-// time.  Neighbouring query voxels hit the same value voxels, so a CTA that owns a brick of K neighbouring queries of
-// one head first COMBINES their contributions in shared memory and sends one reduction per distinct voxel:
-//   phase 1  per (level, <=PC points): every sample is processed as in the direct variant, but instead of reducing
-//            into global memory it records 8 pairs (corner offset, w_k * attn) in a shared-memory list;
-//   phase 2  the pairs are grouped by voxel with an open-addressing hash table (integer atomicCAS on the tags, a
-//            counting sort on the slots); each group of G lanes then owns one distinct voxel at a time, accumulates
-//            sum_pairs coef * grad_output[query] in registers from a shared-memory copy of the brick's grad_output rows
-//            and issues ONE 128-bit reduction per lane.
-// With the model's sampling pattern (dist "B") a 2x4x4 brick merges 4.4 contributions per distinct voxel; the
-// reduction traffic into L2 drops by that factor.  Results differ from the direct variant only by summation order.
-template <int K> struct BrickK { static constexpr int value = K < 32 ? 32 : K; };
-
-template <typename VT, int G, int NV, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-bwd_brick_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-                 const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
-                 int M, int L, int Lq, int P, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                 float *__restrict__ grad_aw)
-{
-  using V = Vec16<VT>;
-  constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
-  constexpr int K = BrickK<UPB>::value, PASSES = K / UPB;          // units per brick
-  constexpr int NPAIR = 1024, PC = NPAIR / (8 * K);                // points per segment
-  constexpr int HT = 2 * NPAIR;                                    // hash slots (load factor <= 0.5)
-  constexpr unsigned kEmpty = 0xffffffffu;
-  static_assert(PC >= 1 && PC <= G && HT == 2048, "brick kernel: 2 <= G, 2048 hash slots");
-  __shared__ int4 lv[kMaxLevels];
-  __shared__ BrickPlan bp;
-  __shared__ float4 sA[WARPS][32];
-  __shared__ float4 sB[WARPS][32];
-  __shared__ int4 sC[WARPS][32];
-  __shared__ unsigned sWarpSum[WARPS];
-  __shared__ unsigned sNumUnique;
-  extern __shared__ __align__(16) unsigned char dyn[];
-  float *sTop = reinterpret_cast<float *>(dyn);                    // [K][C]
-  unsigned *sVox = reinterpret_cast<unsigned *>(sTop + K * C);     // [NPAIR] corner offset (without lane offset) or kEmpty
-  float *sCoef = reinterpret_cast<float *>(sVox + NPAIR);          // [NPAIR] w_k * attn
-  unsigned *sTag = reinterpret_cast<unsigned *>(sCoef + NPAIR);    // [HT]
-  unsigned *sCnt = sTag + HT;                                      // [HT] pairs per slot
-  unsigned *sFill = sCnt + HT;                                     // [HT] running write position of the slot's segment
-  unsigned short *sSlot = reinterpret_cast<unsigned short *>(sFill + HT);   // [NPAIR] slot of pair i
-  unsigned short *sIdx = sSlot + NPAIR;                            // [NPAIR] pair ids grouped by slot
-  unsigned short *sList = sIdx + NPAIR;                            // [NPAIR] non-empty slots
-
-  if (threadIdx.x < L)
-    lv[threadIdx.x] = make_int4((int)shapes[3 * threadIdx.x], (int)shapes[3 * threadIdx.x + 1],
-                                (int)shapes[3 * threadIdx.x + 2], (int)starts[threadIdx.x]);
-  __syncthreads();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, g0 = lane - gl;
-  const int MC = M * C, LP = L * P;
-  const long long total = (long long)N * Lq * M;
-  if (tid == 0) make_brick_plan<K>(bp, lv, L);
-  __syncthreads();
-  const long long slots = (long long)N * M * bp.nb;
-  const long long per = (slots + gridDim.x - 1) / gridDim.x;
-  const long long t_end = min(slots, (blockIdx.x + 1) * per);
-  const unsigned lane_off = gl * VEC;
-
-  for (long long t = blockIdx.x * per; t < t_end; ++t) {
-    // ---- brick prologue: grad_output rows of the K units -> shared memory (fp32), hash table reset
-    __syncthreads();
-#pragma unroll
-    for (int pass = 0; pass < PASSES; ++pass) {
-      const int ui = pass * UPB + warp * UPW + lane / G;
-      const UnitCoords uc = slot_unit<K>(true, t, ui, total, bp, lv, L, M, Lq);
-#pragma unroll
-      for (int nv = 0; nv < NV; ++nv) {
-        float tv[VEC];
-        V::load_stream(grad_out + uc.u * C + lane_off + nv * (G * VEC), tv);
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) sTop[ui * C + nv * (G * VEC) + lane_off + c] = uc.active ? tv[c] : 0.f;
-      }
-    }
-    for (int i = tid; i < HT; i += kThreads) { sTag[i] = kEmpty; sCnt[i] = 0; }
-    for (int i = tid; i < NPAIR; i += kThreads) sVox[i] = kEmpty;
-    __syncthreads();
-
-    for (int l = 0; l < L; ++l) {
-      for (int p0 = 0; p0 < P; p0 += PC) {
-        const int pcnt = min(PC, P - p0);
-        // ---- phase 1: per-sample gradients, pairs into shared memory
-#pragma unroll 1
-        for (int pass = 0; pass < PASSES; ++pass) {
-          const int ui = pass * UPB + warp * UPW + lane / G;
-          const UnitCoords uc = slot_unit<K>(true, t, ui, total, bp, lv, L, M, Lq);
-          float top[CPL];
-#pragma unroll
-          for (int nv = 0; nv < NV; ++nv) {
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) top[nv * VEC + c] = sTop[ui * C + nv * (G * VEC) + lane_off + c];
-          }
-          const int s_mine = l * P + p0 + gl;
-          const PreparedSample mine = prepare_sample(lv, loc, aw, uc, (gl < pcnt) ? s_mine : LP, LP, P, S, MC, C);
-          __syncwarp();
-          sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
-          __syncwarp();
-          float r_a = 0.f, r_w = 0.f, r_h = 0.f, r_d = 0.f;
-          for (int j = 0; j < pcnt; ++j) {
-            const int4 pc = sC[warp][g0 + j];
-            SampleGrads q = {0.f, 0.f, 0.f, 0.f};
-            if (pc.w != 0) {
-              const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
-              float w[8];
-              unsigned o[8];
-              q = sample_backward<VT, G, NV>(value, top, pa, pb, pc, lane_off, w, o);
-              const int pbase = (ui * PC + j) * 8;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (gl == (k % G) && w[k] != 0.f) { sVox[pbase + k] = o[k] - lane_off; sCoef[pbase + k] = w[k] * pa.y; }
-              }
-            }
-            q.a = group_sum<G>(q.a); q.w = group_sum<G>(q.w); q.h = group_sum<G>(q.h); q.d = group_sum<G>(q.d);
-            if (gl == j) { r_a = q.a; r_w = q.w; r_h = q.h; r_d = q.d; }
-          }
-          if (uc.active && gl < pcnt) {
-            const int4 li = lv[l];
-            float *gl_ = grad_loc + (uc.u * LP + s_mine) * 3;
-            gl_[0] = __int2float_rn(li.z) * (r_w * mine.a.y);
-            gl_[1] = __int2float_rn(li.y) * (r_h * mine.a.y);
-            gl_[2] = __int2float_rn(li.x) * (r_d * mine.a.y);
-            grad_aw[uc.u * LP + s_mine] = r_a;
-          }
-        }
-        __syncthreads();
-
-        // ---- phase 2a: hash every pair's voxel into a slot, count pairs per slot
-        for (int i = tid; i < NPAIR; i += kThreads) {
-          const unsigned vox = sVox[i];
-          if (vox != kEmpty) {
-            unsigned h = (vox * 2654435761u) >> 21;                 // HT = 2048 slots
-            while (true) {
-              const unsigned old = atomicCAS(&sTag[h], kEmpty, vox);
-              if (old == kEmpty || old == vox) break;
-              h = (h + 1) & (HT - 1);
-            }
-            sSlot[i] = (unsigned short)h;
-            atomicAdd(&sCnt[h], 1u);
-          }
-        }
-        __syncthreads();
-        // ---- phase 2b: exclusive scan of (pairs, non-empty) over the slots; thread owns HT/kThreads consecutive slots
-        {
-          constexpr int PER = HT / kThreads;
-          unsigned local = 0;
-#pragma unroll
-          for (int e = 0; e < PER; ++e) { const unsigned c = sCnt[tid * PER + e]; local += c | ((c != 0u) << 16); }
-          unsigned incl = local;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += n; }
-          if (lane == 31) sWarpSum[warp] = incl;
-          __syncthreads();
-          unsigned base = incl - local;
-          for (int wq = 0; wq < warp; ++wq) base += sWarpSum[wq];
-#pragma unroll
-          for (int e = 0; e < PER; ++e) {
-            const int s = tid * PER + e;
-            const unsigned c = sCnt[s];
-            sFill[s] = base & 0xffffu;
-            if (c != 0u) sList[base >> 16] = (unsigned short)s;
-            base += c | ((c != 0u) << 16);
-          }
-          if (tid == kThreads - 1) sNumUnique = base >> 16;
-        }
-        __syncthreads();
-        // ---- phase 2c: scatter pair ids into their slot's segment
-        for (int i = tid; i < NPAIR; i += kThreads) {
-          if (sVox[i] != kEmpty) sIdx[atomicAdd(&sFill[sSlot[i]], 1u)] = (unsigned short)i;
-        }
-        __syncthreads();
-        // ---- phase 2d: one group of G lanes per distinct voxel: accumulate in registers, one reduction per lane
-        {
-          const int nuniq = (int)sNumUnique;
-          for (int u = warp * UPW + lane / G; u < nuniq; u += UPB) {
-            const int s = sList[u];
-            const int end = (int)sFill[s], beg = end - (int)sCnt[s];
-            float acc[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
-            for (int e = beg; e < end; ++e) {
-              const int i = sIdx[e];
-              const float coef = sCoef[i];
-              const float *row = sTop + (i / (PC * 8)) * C + lane_off;
-#pragma unroll
-              for (int nv = 0; nv < NV; ++nv) {
-#pragma unroll
-                for (int c4 = 0; c4 < VEC; c4 += 4) {
-                  const float4 tv = *reinterpret_cast<const float4 *>(row + nv * (G * VEC) + c4);
-                  acc[nv * VEC + c4] = fmaf(coef, tv.x, acc[nv * VEC + c4]);
-                  acc[nv * VEC + c4 + 1] = fmaf(coef, tv.y, acc[nv * VEC + c4 + 1]);
-                  acc[nv * VEC + c4 + 2] = fmaf(coef, tv.z, acc[nv * VEC + c4 + 2]);
-                  acc[nv * VEC + c4 + 3] = fmaf(coef, tv.w, acc[nv * VEC + c4 + 3]);
-                }
-              }
-            }
-            float *dst = grad_value + (sTag[s] + lane_off);
-#pragma unroll
-            for (int nv = 0; nv < NV; ++nv) {
-#pragma unroll
-              for (int c4 = 0; c4 < VEC; c4 += 4)
-                red_add_v4(dst + nv * (G * VEC) + c4, acc[nv * VEC + c4], acc[nv * VEC + c4 + 1], acc[nv * VEC + c4 + 2],
-                           acc[nv * VEC + c4 + 3]);
-            }
-          }
-        }
-        __syncthreads();
-        // ---- reset the tables for the next segment
-        for (int i = tid; i < HT; i += kThreads) { sTag[i] = kEmpty; sCnt[i] = 0; }
-        for (int i = tid; i < NPAIR; i += kThreads) sVox[i] = kEmpty;
-        __syncthreads();
-      }
-    }
-  }
-}
-
-template <typename VT, int G, int NV> constexpr size_t bwd_brick_smem_bytes()
-{
-  constexpr int C = G * NV * Vec16<VT>::N, UPB = (kThreads / 32) * (32 / G), K = BrickK<UPB>::value;
-  return (size_t)K * C * 4 + 1024 * 4 * 2 + 2048 * 4 * 3 + 1024 * 2 * 3;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
