@@ -78,7 +78,7 @@ bool vec_ok(const Dims &d, const void *a, const void *b, int &G, int &NV)
   if (d.L > kMaxLevels) return false;
   if ((long long)d.N * d.S * d.M * d.C >= (1LL << 31)) return false;
   if ((long long)d.L * d.P * 3 >= (1LL << 20)) return false;
-  return aligned(a, 16) && aligned(b, 16);
+  return aligned(a, 4 * sizeof(VT)) && aligned(b, 4 * sizeof(VT));
 }
 
 int use_brick(const Dims &d)
@@ -126,9 +126,8 @@ int vec_grid(long long units, int G)
 // backward is bound by the reduction traffic into L2 and only needs 3.  Wider per-lane vectors get a looser cap so
 // that ptxas does not spill.
 template <typename VT, int NV> struct MinBlocks {
-  static constexpr bool wide = sizeof(VT) < 4;   // 16-bit storage: 8 channels per 16-byte vector
-  static constexpr int fwd = (!wide && NV == 1) ? 4 : (!wide || NV == 1) ? 3 : 2;
-  static constexpr int bwd = (!wide && NV == 1) ? 3 : (!wide || NV == 1) ? 2 : 1;
+  static constexpr int fwd = NV == 1 ? 4 : 3;
+  static constexpr int bwd = NV == 1 ? 3 : 2;
 };
 
 

@@ -130,7 +130,7 @@ template <> struct Cvt<__half> {
   static __device__ __forceinline__ __half down(float v) { return __float2half_rn(v); }
 };
 
-// 16-byte vectors of the storage type, widened to fp32 in registers.
+// Four-channel vectors of the storage type (16 bytes fp32, 8 bytes bf16 / fp16), widened to fp32 in registers.
 template <typename VT> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int N = 4;
@@ -150,34 +150,30 @@ template <> struct Vec16<float> {
     __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
 };
+// 16-bit storage uses 8-byte vectors so that a lane owns the same four channels as in fp32: the fp32 grad_value
+// reductions of neighbouring lanes then stay contiguous (one full sector per lane pair).  With 16-byte / 8-channel
+// vectors each lane's two reductions straddle half sectors and the L2 atomic units see twice the transactions
+// (measured: bf16 backward 11.1 ms vs 5.7 ms fp32, profiles/r01_sweep_before_bf16_fix.md).
 template <typename H2, typename H> struct Vec16Half {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void unpack(const uint4 t, float (&v)[8])
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint2 t, float (&v)[4])
   {
     const H2 *h = reinterpret_cast<const H2 *>(&t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = Cvt<H>::up(h[i].x);
-      v[2 * i + 1] = Cvt<H>::up(h[i].y);
-    }
+    v[0] = Cvt<H>::up(h[0].x); v[1] = Cvt<H>::up(h[0].y); v[2] = Cvt<H>::up(h[1].x); v[3] = Cvt<H>::up(h[1].y);
   }
-  static __device__ __forceinline__ void load(const H *p, float (&v)[8]) { unpack(__ldg(reinterpret_cast<const uint4 *>(p)), v); }
-  static __device__ __forceinline__ void load_stream(const H *p, float (&v)[8])
+  static __device__ __forceinline__ void load(const H *p, float (&v)[4]) { unpack(__ldg(reinterpret_cast<const uint2 *>(p)), v); }
+  static __device__ __forceinline__ void load_stream(const H *p, float (&v)[4])
   {
-    uint4 t;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+    uint2 t;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p));
     unpack(t, v);
   }
-  static __device__ __forceinline__ void store(H *p, const float (&v)[8])
+  static __device__ __forceinline__ void store(H *p, const float (&v)[4])
   {
-    uint4 t;
+    uint2 t;
     H2 *h = reinterpret_cast<H2 *>(&t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h[i].x = Cvt<H>::down(v[2 * i]);
-      h[i].y = Cvt<H>::down(v[2 * i + 1]);
-    }
-    __stcs(reinterpret_cast<uint4 *>(p), t);
+    h[0].x = Cvt<H>::down(v[0]); h[0].y = Cvt<H>::down(v[1]); h[1].x = Cvt<H>::down(v[2]); h[1].y = Cvt<H>::down(v[3]);
+    __stcs(reinterpret_cast<uint2 *>(p), t);
   }
 };
 template <> struct Vec16<__nv_bfloat16> : Vec16Half<__nv_bfloat162, __nv_bfloat16> {};
@@ -197,7 +193,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Vector kernels: C = G * NV * Vec16<VT>::N channels per unit, G lanes per unit (G | 32), 32/G units per warp.
+// Vector kernels: C = G * NV * 4 channels per unit, G lanes per unit (G | 32), 32/G units per warp.
 //
 // Control flow is warp-uniform (every lane runs every loop iteration, shuffles use the full mask); only the
 // "is this sample in range" test diverges, per group.  Per chunk of G samples, lane j of a group prepares sample j
