@@ -336,3 +336,46 @@ def test_batch_elements_are_independent_and_one_launch_covers_the_batch():
     for b in range(4):
         xb = {k: (v[b:b + 1].contiguous() if k in ("value", "loc", "aw", "grad_out") else v) for k, v in x.items()}
         assert torch.equal(_run_fwd(xb), out[b:b + 1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Module-level rows: mirrors loaded with the REFERENCE modules' weights vs the reference's outputs
+# (fixtures from tests/golden/make_golden_blocks.py, reference run on CPU through its use_cuda=False route)
+# ---------------------------------------------------------------------------------------------------------------
+def _load(name):
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def test_msdeformattn_module_against_reference_module_fixture():
+    z = _load("module_msdeformattn.npz")
+    m = MSDeformAttn(d_model=48, n_levels=2, n_heads=6, n_points=2).to(DEV).eval()
+    m.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    query, src = t("query").requires_grad_(True), t("src").requires_grad_(True)
+    out = m(query, t("ref"), src, t("shapes"), t("starts"))
+    out.backward(t("g"))
+    assert _relerr(_np(out), z["out"]) < 1e-4
+    assert _relerr(_np(query.grad), z["grad_query"]) < 1e-4 and _relerr(_np(src.grad), z["grad_src"]) < 1e-4
+    for k, p in m.named_parameters():
+        assert _relerr(_np(p.grad), z["pg." + k]) < 1e-4, k
+
+
+def test_refine_block_against_reference_block_fixture():
+    from transoar_b200.position_encoding import PositionEmbeddingSine3D
+    from transoar_b200.refine import DecoderDefAttnBlock
+    z = _load("block_defattn.npz")
+    blk = DecoderDefAttnBlock(d_model=48, nhead=6, num_layers=2, dim_feedforward=64, dropout=0.1,
+                              feature_levels=["P2", "P3", "P4"], n_points=2).to(DEV).eval()
+    blk.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    fmaps = [torch.from_numpy(z[f"fmap{i}"]).to(DEV).requires_grad_(True) for i in range(3)]
+    pe = PositionEmbeddingSine3D(channels=48)
+    outs = blk(fmaps, [pe(f) for f in fmaps])
+    sum((o * torch.from_numpy(z[f"g{i}"]).to(DEV)).sum() for i, o in enumerate(outs)).backward()
+    for i in range(3):
+        assert outs[i].shape == fmaps[i].shape
+        assert _relerr(_np(outs[i]), z[f"out{i}"]) < 1e-4
+        assert _relerr(_np(fmaps[i].grad), z[f"grad_fmap{i}"]) < 2e-4
+    for k, p in blk.named_parameters():
+        assert _relerr(_np(p.grad), z["pg." + k]) < 2e-4, k
