@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "msda3d.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(msda3d_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in ("msda3d.h", "roi_attn.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b((?:msda3d|roi_attn)_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_is_built_in_tree():
@@ -24,7 +27,7 @@ def test_library_is_built_in_tree():
 def test_every_declared_symbol_is_exported_and_bound():
     lib = _lib.lib()
     declared = _declared()
-    assert len(declared) >= 10
+    assert len(declared) >= 12 and "roi_attn_forward" in declared
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/msda3d.h but not exported"
     assert sorted(_lib.exported_symbols()) == declared, "python binding table out of sync with the header"

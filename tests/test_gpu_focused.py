@@ -1,0 +1,117 @@
+"""GPU parity for SURVEY 8 row a9: the fused RoI attention (include/roi_attn.h) against the dense oracle and against
+fixtures from the reference's FocusedAttn / FocusedDecoderLayer."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle.focused_attn_oracle import dense_masked_attention
+from transoar_b200 import focused
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _random_boxes(n_groups, per, grid, gen):
+    X, Y, Z = grid
+    out = []
+    for _ in range(n_groups):
+        lo = [int(torch.randint(0, s, (1,), generator=gen)) for s in grid]
+        hi = [int(torch.randint(l + 1, s + 1, (1,), generator=gen)) for l, s in zip(lo, grid)]
+        out += [lo + hi] * per
+    return torch.tensor(out, dtype=torch.int32)
+
+
+@pytest.mark.parametrize("hd,H,per,grid", [(48, 8, 27, (6, 7, 9)), (16, 2, 1, (3, 3, 3)), (32, 3, 7, (5, 4, 8)), (64, 2, 54, (4, 6, 5)),
+                                           (96, 1, 27, (3, 5, 7)), (128, 1, 5, (2, 3, 9))])
+def test_roi_attention_matches_dense_oracle(hd, H, per, grid):
+    gen = torch.Generator().manual_seed(hd + per)
+    boxes = _random_boxes(3, per, grid, gen)
+    boxes[0:per] = torch.tensor([0, 0, 0, *grid], dtype=torch.int32)                 # full grid (restrict_attn=False case)
+    boxes[per:2 * per] = torch.tensor([1, 1, 1, 2, 2, 2], dtype=torch.int32)        # a single voxel
+    Nq, Nkv, B = boxes.shape[0], grid[0] * grid[1] * grid[2], 2
+    mk = lambda *s: torch.randn(*s, generator=gen).to(DEV).requires_grad_(True)
+    q, k, v = mk(B, Nq, H, hd), mk(B, Nkv, H, hd), mk(B, Nkv, H, hd)
+    g = torch.randn(B, Nq, H * hd, generator=gen).to(DEV)
+    groups = focused.groups_from_boxes(boxes).to(DEV)
+    out = focused.RoIAttentionFunction.apply(q, k, v, groups, grid[1:])
+    out.backward(g)
+    got = [out.detach(), q.grad.clone(), k.grad.clone(), v.grad.clone()]
+    q.grad = k.grad = v.grad = None
+    want = dense_masked_attention(q, k, v, boxes, grid)
+    want.backward(g)
+    for a, b, tol in zip(got, [want.detach(), q.grad, k.grad, v.grad], (2e-5, 1e-4, 1e-4, 1e-4)):
+        assert _rel(a, b) < tol
+
+
+def test_empty_box_gives_nan_rows_like_softmax_of_all_minus_inf():
+    grid = (3, 3, 3)
+    boxes = torch.tensor([[0, 0, 0, 2, 2, 2], [1, 1, 1, 1, 2, 2]], dtype=torch.int32)  # second box is empty (x1 == x2)
+    q, k, v = (torch.randn(1, n, 2, 16, device=DEV) for n in (2, 27, 27))
+    out = focused.RoIAttentionFunction.apply(q, k, v, focused.groups_from_boxes(boxes).to(DEV), grid[1:])
+    want = dense_masked_attention(q, k, v, boxes, grid)
+    assert torch.isnan(out[0, 1]).all() and torch.isnan(want[0, 1]).all()
+    assert _rel(out[0, 0], want[0, 0]) < 2e-5
+
+
+def test_focused_attn_module_against_reference_fixture():
+    z = np.load(os.path.join(GOLDEN, "focused_attn.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    m = focused.FocusedAttn(96, 2, torch.from_numpy(z["mask"]), proj_drop=0.1, grid_shape=z["grid"]).to(DEV).eval()
+    m.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    q, k, v = (t(n).requires_grad_(True) for n in ("q", "k", "v"))
+    x, w = m(q, k, v, mask=None)
+    assert w is None                                                                 # dense weights only on request
+    x.backward(t("g"))
+    assert _rel(x.detach(), t("x")) < 1e-4
+    for got, name in ((q.grad, "grad_q"), (k.grad, "grad_k"), (v.grad, "grad_v")):
+        assert _rel(got, t(name)) < 2e-4, name
+    for name, p in m.named_parameters():
+        if bool(z["pg_none." + name]):
+            assert p.grad is None and name.startswith("q_proj")                      # q_proj never gets a gradient
+        else:
+            assert _rel(p.grad, t("pg." + name)) < 2e-4, name
+    m.materialize_weights = True
+    _, w = m(q.detach(), k.detach(), v.detach())
+    assert _rel(w, t("weights")) < 1e-4
+
+
+def test_focused_decoder_layer_against_reference_fixture():
+    z = np.load(os.path.join(GOLDEN, "focused_layer.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    cfg = {"num_queries": 14, "num_organs": 2, "input_levels": "P5", "restrict_attn": True}
+    props = {str(i): {"attn_area": z["props"][i].tolist()} for i in range(2)}
+    layer = focused.FocusedDecoderLayer(96, 64, 0.1, "relu", 2, cfg, props).to(DEV).eval()
+    layer.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    tgt, src = t("tgt").requires_grad_(True), t("src").requires_grad_(True)
+    out, _ = layer(tgt, t("qpos"), t("spos"), src)
+    out.backward(t("g"))
+    assert _rel(out.detach(), t("out")) < 1e-4
+    assert _rel(tgt.grad, t("grad_tgt")) < 2e-4 and _rel(src.grad, t("grad_src")) < 2e-4
+    for name, p in layer.named_parameters():
+        if p.grad is not None:
+            assert _rel(p.grad, t("pg." + name)) < 5e-4, name
+
+
+def test_visceral_shape_against_dense_path():
+    """540 queries = 20 organs x 27, P2 grid 40x40x64 = 102 400 tokens, 8 heads x 48 -- the dense path needs a 1.77 GB score tensor."""
+    gen = torch.Generator().manual_seed(5)
+    grid = (40, 40, 64)
+    props = {}
+    for o in range(20):
+        c = torch.rand(3, generator=gen) * 0.4 + 0.3
+        s = torch.rand(3, generator=gen) * 0.2 + 0.1
+        props[str(o)] = {"attn_area": torch.cat(((c - s / 2 - 0.05).clamp(0, 1), (c + s / 2 + 0.05).clamp(0, 1))).tolist()}
+    boxes = focused.boxes_from_bbox_props(props, 540, grid)
+    q = torch.randn(1, 540, 8, 48, generator=gen).to(DEV) * 0.3
+    k = torch.randn(1, 102400, 8, 48, generator=gen).to(DEV)
+    v = torch.randn(1, 102400, 8, 48, generator=gen).to(DEV)
+    out = focused.RoIAttentionFunction.apply(q, k, v, focused.groups_from_boxes(boxes).to(DEV), grid[1:])
+    want = dense_masked_attention(q, k, v, boxes, grid)
+    assert _rel(out, want) < 1e-4

@@ -27,6 +27,9 @@ _SIGNATURES = {
     "msda3d_forward_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 4),
     "msda3d_host_release": (None, []),
     "msda3d_debug_indices": (_ci, [_vp, _ci, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
+    # include/roi_attn.h
+    "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp]),
+    "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
 }
 
 

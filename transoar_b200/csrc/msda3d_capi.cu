@@ -15,9 +15,11 @@
 
 using namespace msda3d;
 
+std::atomic<unsigned long long> g_msda3d_launches{0};   // shared with roi_attn_capi.cu
+
 namespace {
 
-std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> &g_launches = g_msda3d_launches;
 std::atomic<int> g_diag_skip_red{0};   // diagnostics only (msda3d_set_tuning): drop the grad_value reductions
 
 struct Dims {

@@ -1,0 +1,90 @@
+// roi_attn_capi.cu -- C ABI of the fused RoI attention (include/roi_attn.h).
+#include "roi_attn_kernels.cuh"
+
+#include <atomic>
+
+#include "../../include/msda3d.h"
+#include "../../include/roi_attn.h"
+
+extern std::atomic<unsigned long long> g_msda3d_launches;
+
+namespace {
+
+template <int HD>
+int launch_fwd(cudaStream_t st, dim3 grid, const float *q, const float *k, const float *v, const int *groups, int Nq, int Nkv, int H,
+               int Y, int Z, float *out, float *lse)
+{
+  auto kern = roiattn::fwd_kernel<HD>;
+  constexpr size_t smem = roiattn::fwd_smem_bytes<HD>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, roiattn::kThreads, smem, st>>>(q, k, v, groups, Nq, Nkv, H, Y, Z, out, lse);
+  return (int)cudaGetLastError();
+}
+
+template <int HD>
+int launch_bwd(cudaStream_t st, dim3 grid, const float *q, const float *k, const float *v, const int *groups, const float *out,
+               const float *dout, const float *lse, int Nq, int Nkv, int H, int Y, int Z, float *dq, float *dk, float *dv)
+{
+  auto kern = roiattn::bwd_kernel<HD>;
+  constexpr size_t smem = roiattn::bwd_smem_bytes<HD>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, roiattn::kThreads, smem, st>>>(q, k, v, groups, out, dout, lse, Nq, Nkv, H, Y, Z, dq, dk, dv);
+  return (int)cudaGetLastError();
+}
+
+bool bad_dims(int G, int B, int Nq, int Nkv, int H, int Y, int Z)
+{
+  return G <= 0 || B <= 0 || Nq <= 0 || Nkv <= 0 || H <= 0 || Y <= 0 || Z <= 0 || Nkv % (Y * Z) != 0 || G > 65535 * 32 || H > 65535 ||
+         B > 65535;
+}
+
+}  // namespace
+
+#define HD_DISPATCH(hd, ...)                                  \
+  switch (hd) {                                               \
+    case 16: { constexpr int HD = 16; __VA_ARGS__; } break;   \
+    case 32: { constexpr int HD = 32; __VA_ARGS__; } break;   \
+    case 48: { constexpr int HD = 48; __VA_ARGS__; } break;   \
+    case 64: { constexpr int HD = 64; __VA_ARGS__; } break;   \
+    case 96: { constexpr int HD = 96; __VA_ARGS__; } break;   \
+    case 128: { constexpr int HD = 128; __VA_ARGS__; } break; \
+    default: return MSDA3D_EINVAL;                            \
+  }
+
+extern "C" {
+
+int roi_attn_forward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                     int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse)
+{
+  if (!q || !k || !v || !groups || !out || !lse) return MSDA3D_EINVAL;
+  if (bad_dims(num_groups, batch, num_query, num_kv, num_heads, grid_y, grid_z)) return MSDA3D_EINVAL;
+  const dim3 grid(num_groups, num_heads, batch);
+  int rc = 0;
+  HD_DISPATCH(head_dim, rc = launch_fwd<HD>((cudaStream_t)stream, grid, q, k, v, groups, num_query, num_kv, num_heads, grid_y, grid_z,
+                                            out, lse));
+  ++g_msda3d_launches;
+  return rc;
+}
+
+int roi_attn_backward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                      int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, const float *out,
+                      const float *dout, const float *lse, float *dq, float *dk, float *dv)
+{
+  if (!q || !k || !v || !groups || !out || !dout || !lse || !dq || !dk || !dv) return MSDA3D_EINVAL;
+  if (bad_dims(num_groups, batch, num_query, num_kv, num_heads, grid_y, grid_z)) return MSDA3D_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t kv_bytes = (size_t)batch * num_kv * num_heads * head_dim * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(dk, 0, kv_bytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dv, 0, kv_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  const dim3 grid(num_groups, num_heads, batch);
+  int rc = 0;
+  HD_DISPATCH(head_dim, rc = launch_bwd<HD>(st, grid, q, k, v, groups, out, dout, lse, num_query, num_kv, num_heads, grid_y, grid_z,
+                                            dq, dk, dv));
+  ++g_msda3d_launches;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// roi_attn_kernels.cuh -- fused RoI-restricted cross-attention (forward + gradient) for sm_100a.
+//
+// Replaces the attention core of the reference's FocusedAttn.forward, transoar/models/necks/focused_decoder.py:238-254:
+//     attn = q @ k^T ; attn += mask(-inf outside the query's RoI box) ; softmax(-1) ; x = attn @ v
+// The reference materialises attn as a dense fp32 [B, heads, Nq, Nkv] tensor (1.77 GB per sample and layer at the
+// VISCERAL shape) of which ~94 % is -inf.  generate_attn_masks (focused_decoder.py:138-159) only ever produces
+// axis-aligned boxes, shared by `num_queries_per_organ` consecutive queries, so a CTA owns one (batch, query group,
+// head), walks ONLY the key/value voxels inside the group's box in chunks of TK tokens and keeps the running softmax
+// statistics in registers (flash-attention style): no score tensor, no mask tensor.
+//
+// Shapes: q [B, Nq, H, HD] (already scaled), k / v [B, Nkv, H, HD], Nkv = X*Y*Z tokens in row-major (x, y, z) order
+// (= src.flatten(2) of a [B, C, X, Y, Z] map), groups int32 [Gn, 8] = {q0, nq (<= 32), x1, y1, z1, x2, y2, z2},
+// out [B, Nq, H*HD], lse [B, H, Nq] (log-sum-exp of the in-box scores, kept for the backward).
+// An empty box gives NaN rows, exactly as softmax over an all -inf row does in the reference.
+//
+// fp32 on the CUDA cores: inside the boxes the whole layer is ~10 GFLOP; the tensor-core work of this block is the
+// K/V projection over all tokens, which stays a cuBLAS GEMM in the module.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace roiattn {
+
+constexpr int TQ = 32;        // query rows per CTA (one RoI group, padded)
+constexpr int TK = 64;        // key/value tokens per chunk
+constexpr int kThreads = 128;
+
+struct Group {
+  int q0, nq, x1, y1, z1, x2, y2, z2;
+};
+
+// token id of the j-th voxel of the box (z fastest, then y, then x), or -1 past the end
+__device__ __forceinline__ int box_token(const Group &g, int j, int Y, int Z)
+{
+  const int bz = g.z2 - g.z1, by = g.y2 - g.y1, bx = g.x2 - g.x1;
+  if (bz <= 0 || by <= 0 || bx <= 0 || j >= bx * by * bz) return -1;
+  const int iz = j % bz, r = j / bz, iy = r % by, ix = r / by;
+  return ((g.x1 + ix) * Y + (g.y1 + iy)) * Z + (g.z1 + iz);
+}
+
+// Forward.  grid = (Gn, H, B).  Thread t owns score rows 4*(t/16)..+3 and columns (t%16) + 16*j (j < 4) of the TQ x TK tile
+// (consecutive lanes -> consecutive K rows: with a row stride of HD+4 floats the float4 reads are bank-conflict free), and
+// output rows 4*(t/16)..+3, columns (t%16) + 16*i (i < HD/16).
+template <int HD>
+__global__ void __launch_bounds__(kThreads)
+fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, const int *__restrict__ groups,
+           int Nq, int Nkv, int H, int Y, int Z, float *__restrict__ out, float *__restrict__ lse)
+{
+  static_assert(HD % 16 == 0 && HD <= 128, "head dim");
+  constexpr int OC = HD / 16;
+  extern __shared__ __align__(16) float smem_f[];
+  float (*sQ)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f);
+  float (*sK)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f + TQ * (HD + 4));
+  float (*sV)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f + (TQ + TK) * (HD + 4));
+  float (*sP)[TK + 4] = reinterpret_cast<float (*)[TK + 4]>(smem_f + (TQ + 2 * TK) * (HD + 4));
+  __shared__ int sTok[TK];
+
+  const int gi = blockIdx.x, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+  Group g;
+  {
+    const int *gp = groups + gi * 8;
+    g.q0 = gp[0]; g.nq = gp[1]; g.x1 = gp[2]; g.y1 = gp[3]; g.z1 = gp[4]; g.x2 = gp[5]; g.y2 = gp[6]; g.z2 = gp[7];
+  }
+  const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
+  const long long HHD = (long long)H * HD;
+
+  for (int i = t; i < TQ * (HD / 4); i += kThreads) {
+    const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < g.nq) val = *reinterpret_cast<const float4 *>(q + ((long long)b * Nq + g.q0 + r) * HHD + h * HD + c4);
+    *reinterpret_cast<float4 *>(&sQ[r][c4]) = val;
+  }
+
+  const int rg = t / 16, cg = t % 16;           // row group (4 rows), column group
+  float m_run[4], l_run[4], o[4][OC];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -CUDART_INF_F; l_run[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < OC; ++c) o[i][c] = 0.f;
+  }
+
+  for (int base = 0; base < ntok; base += TK) {
+    __syncthreads();
+    if (t < TK) sTok[t] = box_token(g, base + t, Y, Z);
+    __syncthreads();
+    for (int i = t; i < TK * (HD / 4); i += kThreads) {
+      const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+      const int tok = sTok[r];
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (tok >= 0) {
+        const long long off = ((long long)b * Nkv + tok) * HHD + h * HD + c4;
+        kv = __ldg(reinterpret_cast<const float4 *>(k + off));
+        vv = __ldg(reinterpret_cast<const float4 *>(v + off));
+      }
+      *reinterpret_cast<float4 *>(&sK[r][c4]) = kv;
+      *reinterpret_cast<float4 *>(&sV[r][c4]) = vv;
+    }
+    __syncthreads();
+
+    // S = Q K^T for my 4x4 tile
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < HD; d += 4) {
+      float4 qa[4], kb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4 *>(&sQ[rg * 4 + i][d]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kb[j] = *reinterpret_cast<const float4 *>(&sK[cg + 16 * j][d]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          s[i][j] += qa[i].x * kb[j].x + qa[i].y * kb[j].y + qa[i].z * kb[j].z + qa[i].w * kb[j].w;
+    }
+    // mask the tail of the last chunk, running max / sum per row (16 lanes share a row group)
+    float alpha[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (sTok[cg + 16 * j] < 0) s[i][j] = -CUDART_INF_F;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int dlt = 8; dlt > 0; dlt >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, dlt));
+      const float m_new = fmaxf(m_run[i], mx);
+      alpha[i] = (m_run[i] == -CUDART_INF_F) ? 0.f : __expf(m_run[i] - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = (s[i][j] == -CUDART_INF_F) ? 0.f : __expf(s[i][j] - m_new);
+        s[i][j] = p;
+        sum += p;
+      }
+#pragma unroll
+      for (int dlt = 8; dlt > 0; dlt >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dlt);
+      l_run[i] = l_run[i] * alpha[i] + sum;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sP[rg * 4 + i][cg + 16 * j] = s[i][j];
+    }
+    __syncthreads();
+    // O = O * alpha + P V
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < OC; ++c) o[i][c] *= alpha[i];
+#pragma unroll 4
+    for (int kk = 0; kk < TK; ++kk) {
+      float vv[OC];
+#pragma unroll
+      for (int c = 0; c < OC; ++c) vv[c] = sV[kk][cg + 16 * c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = sP[rg * 4 + i][kk];
+#pragma unroll
+        for (int c = 0; c < OC; ++c) o[i][c] = fmaf(p, vv[c], o[i][c]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = rg * 4 + i;
+    if (r < g.nq) {
+      const float inv = 1.f / l_run[i];          // empty box: 0 * inf = NaN, like softmax of an all -inf row
+      float *dst = out + ((long long)b * Nq + g.q0 + r) * HHD + h * HD;
+#pragma unroll
+      for (int c = 0; c < OC; ++c) dst[cg + 16 * c] = o[i][c] * inv;
+      if (cg == 0) lse[((long long)b * H + h) * Nq + g.q0 + r] = m_run[i] + __logf(l_run[i]);
+    }
+  }
+}
+
+// Backward.  grid = (Gn, H, B).  P = exp(S - lse), dV += P^T dO, dP = dO V^T, dS = P * (dP - D), D = rowsum(dO * O),
+// dQ += dS K, dK += dS^T Q.  dk / dv are accumulated with atomics (boxes of different organs overlap); dq is exclusive.
+template <int HD>
+__global__ void __launch_bounds__(kThreads)
+bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, const int *__restrict__ groups,
+           const float *__restrict__ out, const float *__restrict__ dout, const float *__restrict__ lse, int Nq, int Nkv, int H,
+           int Y, int Z, float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv)
+{
+  constexpr int OC = HD / 16;
+  extern __shared__ __align__(16) float smem_f[];
+  float (*sQ)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f);
+  float (*sdO)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f + TQ * (HD + 4));
+  float (*sK)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f + 2 * TQ * (HD + 4));
+  float (*sV)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem_f + (2 * TQ + TK) * (HD + 4));
+  float (*sP)[TK + 4] = reinterpret_cast<float (*)[TK + 4]>(smem_f + (2 * TQ + 2 * TK) * (HD + 4));   // P, then dS
+  __shared__ float sLse[TQ], sD[TQ];
+  __shared__ int sTok[TK];
+
+  const int gi = blockIdx.x, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+  Group g;
+  {
+    const int *gp = groups + gi * 8;
+    g.q0 = gp[0]; g.nq = gp[1]; g.x1 = gp[2]; g.y1 = gp[3]; g.z1 = gp[4]; g.x2 = gp[5]; g.y2 = gp[6]; g.z2 = gp[7];
+  }
+  const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
+  const long long HHD = (long long)H * HD;
+
+  for (int i = t; i < TQ * (HD / 4); i += kThreads) {
+    const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), da = qa;
+    if (r < g.nq) {
+      const long long off = ((long long)b * Nq + g.q0 + r) * HHD + h * HD + c4;
+      qa = *reinterpret_cast<const float4 *>(q + off);
+      da = *reinterpret_cast<const float4 *>(dout + off);
+    }
+    *reinterpret_cast<float4 *>(&sQ[r][c4]) = qa;
+    *reinterpret_cast<float4 *>(&sdO[r][c4]) = da;
+  }
+  if (t < TQ) {
+    float dsum = 0.f, l = 0.f;
+    if (t < g.nq) {
+      const long long off = ((long long)b * Nq + g.q0 + t) * HHD + h * HD;
+      for (int d = 0; d < HD; ++d) dsum += dout[off + d] * out[off + d];
+      l = lse[((long long)b * H + h) * Nq + g.q0 + t];
+    }
+    sD[t] = dsum; sLse[t] = l;
+  }
+
+  const int rg = t / 16, cg = t % 16;
+  float dqa[4][OC];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < OC; ++c) dqa[i][c] = 0.f;
+
+  for (int base = 0; base < ntok; base += TK) {
+    __syncthreads();
+    if (t < TK) sTok[t] = box_token(g, base + t, Y, Z);
+    __syncthreads();
+    for (int i = t; i < TK * (HD / 4); i += kThreads) {
+      const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+      const int tok = sTok[r];
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (tok >= 0) {
+        const long long off = ((long long)b * Nkv + tok) * HHD + h * HD + c4;
+        kv = __ldg(reinterpret_cast<const float4 *>(k + off));
+        vv = __ldg(reinterpret_cast<const float4 *>(v + off));
+      }
+      *reinterpret_cast<float4 *>(&sK[r][c4]) = kv;
+      *reinterpret_cast<float4 *>(&sV[r][c4]) = vv;
+    }
+    __syncthreads();
+
+    // S = Q K^T and dP = dO V^T for my 4x4 tile
+    float s[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+#pragma unroll 2
+    for (int d = 0; d < HD; d += 4) {
+      float4 qa[4], da[4], kb[4], vb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qa[i] = *reinterpret_cast<const float4 *>(&sQ[rg * 4 + i][d]);
+        da[i] = *reinterpret_cast<const float4 *>(&sdO[rg * 4 + i][d]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kb[j] = *reinterpret_cast<const float4 *>(&sK[cg + 16 * j][d]);
+        vb[j] = *reinterpret_cast<const float4 *>(&sV[cg + 16 * j][d]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] += qa[i].x * kb[j].x + qa[i].y * kb[j].y + qa[i].z * kb[j].z + qa[i].w * kb[j].w;
+          dp[i][j] += da[i].x * vb[j].x + da[i].y * vb[j].y + da[i].z * vb[j].z + da[i].w * vb[j].w;
+        }
+    }
+    // P and dS; P goes to smem first (dV needs it), dS replaces it afterwards
+    float ds[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      float pr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool valid = sTok[cg + 16 * j] >= 0 && r < g.nq;
+        pr[j] = valid ? __expf(s[i][j] - sLse[r]) : 0.f;
+        ds[i][j] = pr[j] * (dp[i][j] - sD[r]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sP[r][cg + 16 * j] = pr[j];
+    }
+    __syncthreads();
+    // dV[tok][c] += sum_r P[r][tok] * dO[r][c]
+    {
+      // 64 tokens x HD channels; thread handles tokens tg*4..+3 (tg = t/8 in 0..15) and channels (t%8) + 8*i (i < HD/8)
+      const int tg = t / 8, cl = t % 8;
+      float acc[4][HD / 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) acc[i][c] = 0.f;
+      for (int r = 0; r < TQ; ++r) {
+        float dv_[HD / 8];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) dv_[c] = sdO[r][cl + 8 * c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p = sP[r][tg * 4 + i];
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) acc[i][c] = fmaf(p, dv_[c], acc[i][c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = sTok[tg * 4 + i];
+        if (tok >= 0) {
+          float *dst = dv + ((long long)b * Nkv + tok) * HHD + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) atomicAdd(dst + cl + 8 * c, acc[i][c]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sP[rg * 4 + i][cg + 16 * j] = ds[i][j];
+    __syncthreads();
+    // dQ += dS K
+#pragma unroll 4
+    for (int kk = 0; kk < TK; ++kk) {
+      float kv[OC];
+#pragma unroll
+      for (int c = 0; c < OC; ++c) kv[c] = sK[kk][cg + 16 * c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d_ = sP[rg * 4 + i][kk];
+#pragma unroll
+        for (int c = 0; c < OC; ++c) dqa[i][c] = fmaf(d_, kv[c], dqa[i][c]);
+      }
+    }
+    // dK[tok][c] += sum_r dS[r][tok] * Q[r][c]
+    {
+      const int tg = t / 8, cl = t % 8;
+      float acc[4][HD / 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) acc[i][c] = 0.f;
+      for (int r = 0; r < TQ; ++r) {
+        float qv[HD / 8];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) qv[c] = sQ[r][cl + 8 * c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d_ = sP[r][tg * 4 + i];
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) acc[i][c] = fmaf(d_, qv[c], acc[i][c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = sTok[tg * 4 + i];
+        if (tok >= 0) {
+          float *dst = dk + ((long long)b * Nkv + tok) * HHD + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) atomicAdd(dst + cl + 8 * c, acc[i][c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = rg * 4 + i;
+    if (r < g.nq) {
+      float *dst = dq + ((long long)b * Nq + g.q0 + r) * HHD + h * HD;
+#pragma unroll
+      for (int c = 0; c < OC; ++c) dst[cg + 16 * c] = dqa[i][c];
+    }
+  }
+}
+
+template <int HD> constexpr size_t fwd_smem_bytes() { return sizeof(float) * ((TQ + 2 * TK) * (HD + 4) + TQ * (TK + 4)); }
+template <int HD> constexpr size_t bwd_smem_bytes() { return sizeof(float) * ((2 * TQ + 2 * TK) * (HD + 4) + TQ * (TK + 4)); }
+
+}  // namespace roiattn
