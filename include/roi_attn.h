@@ -23,11 +23,16 @@
 extern "C" {
 #endif
 
+/* The tokens of a box are split over several CTAs when (groups x heads x batch) would leave SMs idle; the partial softmax
+ * states live in `workspace` (device, fp32).  roi_attn_workspace_floats() says how many floats the best split needs
+ * (0 = no split); a NULL or smaller workspace only reduces the split, never the correctness. */
+long long roi_attn_workspace_floats(int num_groups, int batch, int num_query, int num_heads, int head_dim);
+
 int roi_attn_forward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups,
                      int batch, int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out,
-                     float *lse);
+                     float *lse, float *workspace, long long workspace_floats);
 
-/* dq is fully overwritten; dk and dv are zero-filled here (cudaMemsetAsync on `stream`) and then accumulated into with
+/* dq is fully overwritten (zero-filled + atomics when boxes are split); dk and dv are zero-filled here (cudaMemsetAsync on `stream`) and then accumulated into with
  * atomics, because the boxes of different groups overlap. */
 int roi_attn_backward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups,
                       int batch, int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z,

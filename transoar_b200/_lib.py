@@ -28,7 +28,8 @@ _SIGNATURES = {
     "msda3d_host_release": (None, []),
     "msda3d_debug_indices": (_ci, [_vp, _ci, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
     # include/roi_attn.h
-    "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp]),
+    "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
+    "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
     "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
 }
 

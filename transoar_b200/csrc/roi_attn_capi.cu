@@ -11,27 +11,39 @@ extern std::atomic<unsigned long long> g_msda3d_launches;
 namespace {
 
 template <int HD>
-int launch_fwd(cudaStream_t st, dim3 grid, const float *q, const float *k, const float *v, const int *groups, int Nq, int Nkv, int H,
-               int Y, int Z, float *out, float *lse)
+int launch_fwd(cudaStream_t st, int G, int B, const float *q, const float *k, const float *v, const int *groups, int Nq, int Nkv, int H,
+               int Y, int Z, float *out, float *lse, int S, float *part)
 {
   auto kern = roiattn::fwd_kernel<HD>;
   constexpr size_t smem = roiattn::fwd_smem_bytes<HD>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, roiattn::kThreads, smem, st>>>(q, k, v, groups, Nq, Nkv, H, Y, Z, out, lse);
+  kern<<<dim3(G * S, H, B), roiattn::kThreads, smem, st>>>(q, k, v, groups, Nq, Nkv, H, Y, Z, out, lse, S, part);
+  if (S > 1) {
+    const int rows = B * H * Nq;
+    roiattn::combine_kernel<HD><<<(rows + 3) / 4, 128, 0, st>>>(part, rows, Nq, H, S, out, lse);
+  }
   return (int)cudaGetLastError();
 }
 
 template <int HD>
-int launch_bwd(cudaStream_t st, dim3 grid, const float *q, const float *k, const float *v, const int *groups, const float *out,
-               const float *dout, const float *lse, int Nq, int Nkv, int H, int Y, int Z, float *dq, float *dk, float *dv)
+int launch_bwd(cudaStream_t st, int G, int B, const float *q, const float *k, const float *v, const int *groups, const float *out,
+               const float *dout, const float *lse, int Nq, int Nkv, int H, int Y, int Z, float *dq, float *dk, float *dv, int S)
 {
   auto kern = roiattn::bwd_kernel<HD>;
   constexpr size_t smem = roiattn::bwd_smem_bytes<HD>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, roiattn::kThreads, smem, st>>>(q, k, v, groups, out, dout, lse, Nq, Nkv, H, Y, Z, dq, dk, dv);
+  kern<<<dim3(G * S, H, B), roiattn::kThreads, smem, st>>>(q, k, v, groups, out, dout, lse, Nq, Nkv, H, Y, Z, dq, dk, dv, S);
   return (int)cudaGetLastError();
+}
+
+// Token splits per box: enough CTAs for ~4 per SM, at most 16 (each split re-reads Q and adds a partial state).
+int pick_splits(int G, int H, int B)
+{
+  const long long ctas = (long long)G * H * B;
+  long long s = (148LL * 4 + ctas - 1) / ctas;
+  return (int)(s < 1 ? 1 : s > 16 ? 16 : s);
 }
 
 bool bad_dims(int G, int B, int Nq, int Nkv, int H, int Y, int Z)
@@ -56,16 +68,26 @@ bool bad_dims(int G, int B, int Nq, int Nkv, int H, int Y, int Z)
 extern "C" {
 
 int roi_attn_forward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
-                     int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse)
+                     int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse,
+                     float *workspace, long long workspace_floats)
 {
   if (!q || !k || !v || !groups || !out || !lse) return MSDA3D_EINVAL;
   if (bad_dims(num_groups, batch, num_query, num_kv, num_heads, grid_y, grid_z)) return MSDA3D_EINVAL;
-  const dim3 grid(num_groups, num_heads, batch);
+  int S = pick_splits(num_groups, num_heads, batch);
+  const long long need = (long long)batch * num_heads * num_query * (head_dim + 2);
+  while (S > 1 && (!workspace || need * S > workspace_floats)) --S;       // no / small workspace: fewer splits, still correct
   int rc = 0;
-  HD_DISPATCH(head_dim, rc = launch_fwd<HD>((cudaStream_t)stream, grid, q, k, v, groups, num_query, num_kv, num_heads, grid_y, grid_z,
-                                            out, lse));
-  ++g_msda3d_launches;
+  HD_DISPATCH(head_dim, rc = launch_fwd<HD>((cudaStream_t)stream, num_groups, batch, q, k, v, groups, num_query, num_kv, num_heads,
+                                            grid_y, grid_z, out, lse, S, workspace));
+  g_msda3d_launches += (S > 1) ? 2 : 1;
   return rc;
+}
+
+long long roi_attn_workspace_floats(int num_groups, int batch, int num_query, int num_heads, int head_dim)
+{
+  if (num_groups <= 0 || batch <= 0 || num_query <= 0 || num_heads <= 0 || head_dim <= 0) return 0;
+  const int S = pick_splits(num_groups, num_heads, batch);
+  return S > 1 ? (long long)batch * num_heads * num_query * (head_dim + 2) * S : 0;
 }
 
 int roi_attn_backward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
@@ -76,13 +98,14 @@ int roi_attn_backward(void *stream, const float *q, const float *k, const float 
   if (bad_dims(num_groups, batch, num_query, num_kv, num_heads, grid_y, grid_z)) return MSDA3D_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t kv_bytes = (size_t)batch * num_kv * num_heads * head_dim * sizeof(float);
+  const int S = pick_splits(num_groups, num_heads, batch);
   cudaError_t e = cudaMemsetAsync(dk, 0, kv_bytes, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dv, 0, kv_bytes, st);
+  if (e == cudaSuccess && S > 1) e = cudaMemsetAsync(dq, 0, (size_t)batch * num_query * num_heads * head_dim * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  const dim3 grid(num_groups, num_heads, batch);
   int rc = 0;
-  HD_DISPATCH(head_dim, rc = launch_bwd<HD>(st, grid, q, k, v, groups, out, dout, lse, num_query, num_kv, num_heads, grid_y, grid_z,
-                                            dq, dk, dv));
+  HD_DISPATCH(head_dim, rc = launch_bwd<HD>(st, num_groups, batch, q, k, v, groups, out, dout, lse, num_query, num_kv, num_heads,
+                                            grid_y, grid_z, dq, dk, dv, S));
   ++g_msda3d_launches;
   return rc;
 }

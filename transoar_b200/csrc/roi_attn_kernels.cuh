@@ -40,13 +40,14 @@ __device__ __forceinline__ int box_token(const Group &g, int j, int Y, int Z)
   return ((g.x1 + ix) * Y + (g.y1 + iy)) * Z + (g.z1 + iz);
 }
 
-// Forward.  grid = (Gn, H, B).  Thread t owns score rows 4*(t/16)..+3 and columns (t%16) + 16*j (j < 4) of the TQ x TK tile
+// Forward.  grid = (Gn * S, H, B): S CTAs split the tokens of a box (flash-decoding style) so that 20 organs x 8 heads
+// still fill 148 SMs; S > 1 writes partial softmax states that combine_kernel merges.  Thread t owns score rows 4*(t/16)..+3 and columns (t%16) + 16*j (j < 4) of the TQ x TK tile
 // (consecutive lanes -> consecutive K rows: with a row stride of HD+4 floats the float4 reads are bank-conflict free), and
 // output rows 4*(t/16)..+3, columns (t%16) + 16*i (i < HD/16).
 template <int HD>
 __global__ void __launch_bounds__(kThreads)
 fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, const int *__restrict__ groups,
-           int Nq, int Nkv, int H, int Y, int Z, float *__restrict__ out, float *__restrict__ lse)
+           int Nq, int Nkv, int H, int Y, int Z, float *__restrict__ out, float *__restrict__ lse, int S, float *__restrict__ part)
 {
   static_assert(HD % 16 == 0 && HD <= 128, "head dim");
   constexpr int OC = HD / 16;
@@ -57,7 +58,7 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   float (*sP)[TK + 4] = reinterpret_cast<float (*)[TK + 4]>(smem_f + (TQ + 2 * TK) * (HD + 4));
   __shared__ int sTok[TK];
 
-  const int gi = blockIdx.x, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+  const int gi = blockIdx.x / S, split = blockIdx.x % S, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
   Group g;
   {
     const int *gp = groups + gi * 8;
@@ -65,6 +66,9 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   }
   const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
   const long long HHD = (long long)H * HD;
+  // this CTA's share of the box: chunks [c_beg, c_end) of TK tokens (S > 1: partial softmax state goes to `part`)
+  const int nchunk = (ntok + TK - 1) / TK, cps = (nchunk + S - 1) / S;
+  const int tok_beg = min(split * cps, nchunk) * TK, tok_end = min(min((split + 1) * cps, nchunk) * TK, ntok);
 
   for (int i = t; i < TQ * (HD / 4); i += kThreads) {
     const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
@@ -82,7 +86,7 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
     for (int c = 0; c < OC; ++c) o[i][c] = 0.f;
   }
 
-  for (int base = 0; base < ntok; base += TK) {
+  for (int base = tok_beg; base < tok_end; base += TK) {
     __syncthreads();
     if (t < TK) sTok[t] = box_token(g, base + t, Y, Z);
     __syncthreads();
@@ -167,6 +171,20 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
     }
   }
 
+  if (S > 1) {
+    // partial state of rows q0..q0+nq-1: part[b][h][q][split][HD + 2] = {o (unnormalised), m, l}
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      if (r < g.nq) {
+        float *dst = part + ((((long long)b * H + h) * Nq + g.q0 + r) * S + split) * (HD + 2);
+#pragma unroll
+        for (int c = 0; c < OC; ++c) dst[cg + 16 * c] = o[i][c];
+        if (cg == 0) { dst[HD] = m_run[i]; dst[HD + 1] = l_run[i]; }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = rg * 4 + i;
@@ -180,13 +198,42 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   }
 }
 
-// Backward.  grid = (Gn, H, B).  P = exp(S - lse), dV += P^T dO, dP = dO V^T, dS = P * (dP - D), D = rowsum(dO * O),
+// Merge the S partial softmax states of every (b, h, q) row: one warp per row.
+template <int HD>
+__global__ void __launch_bounds__(128)
+combine_kernel(const float *__restrict__ part, int rows, int Nq, int H, int S, float *__restrict__ out, float *__restrict__ lse)
+{
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // row = (b*H + h)*Nq + q
+  if (row >= rows) return;
+  const float *p = part + (long long)row * S * (HD + 2);
+  float M = -CUDART_INF_F;
+  for (int s_ = 0; s_ < S; ++s_) M = fmaxf(M, p[s_ * (HD + 2) + HD]);
+  float L = 0.f;
+  for (int s_ = 0; s_ < S; ++s_) {
+    const float m = p[s_ * (HD + 2) + HD];
+    L += (m == -CUDART_INF_F) ? 0.f : p[s_ * (HD + 2) + HD + 1] * __expf(m - M);
+  }
+  const int q_ = row % Nq, bh = row / Nq, h = bh % H, b = bh / H;
+  float *dst = out + ((long long)b * Nq + q_) * H * HD + h * HD;
+  const float inv = 1.f / L;
+  for (int c = lane; c < HD; c += 32) {
+    float acc = 0.f;
+    for (int s_ = 0; s_ < S; ++s_) {
+      const float m = p[s_ * (HD + 2) + HD];
+      if (m != -CUDART_INF_F) acc += p[s_ * (HD + 2) + c] * __expf(m - M);
+    }
+    dst[c] = acc * inv;
+  }
+  if (lane == 0) lse[row] = M + __logf(L);
+}
+
+// Backward.  grid = (Gn * S, H, B).  P = exp(S - lse), dV += P^T dO, dP = dO V^T, dS = P * (dP - D), D = rowsum(dO * O),
 // dQ += dS K, dK += dS^T Q.  dk / dv are accumulated with atomics (boxes of different organs overlap); dq is exclusive.
 template <int HD>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, const int *__restrict__ groups,
            const float *__restrict__ out, const float *__restrict__ dout, const float *__restrict__ lse, int Nq, int Nkv, int H,
-           int Y, int Z, float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv)
+           int Y, int Z, float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv, int S)
 {
   constexpr int OC = HD / 16;
   extern __shared__ __align__(16) float smem_f[];
@@ -198,7 +245,7 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   __shared__ float sLse[TQ], sD[TQ];
   __shared__ int sTok[TK];
 
-  const int gi = blockIdx.x, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+  const int gi = blockIdx.x / S, split = blockIdx.x % S, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
   Group g;
   {
     const int *gp = groups + gi * 8;
@@ -206,6 +253,8 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   }
   const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
   const long long HHD = (long long)H * HD;
+  const int nchunk = (ntok + TK - 1) / TK, cps = (nchunk + S - 1) / S;
+  const int tok_beg = min(split * cps, nchunk) * TK, tok_end = min(min((split + 1) * cps, nchunk) * TK, ntok);
 
   for (int i = t; i < TQ * (HD / 4); i += kThreads) {
     const int r = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
@@ -235,7 +284,7 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
 #pragma unroll
     for (int c = 0; c < OC; ++c) dqa[i][c] = 0.f;
 
-  for (int base = 0; base < ntok; base += TK) {
+  for (int base = tok_beg; base < tok_end; base += TK) {
     __syncthreads();
     if (t < TK) sTok[t] = box_token(g, base + t, Y, Z);
     __syncthreads();
@@ -381,7 +430,10 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
     if (r < g.nq) {
       float *dst = dq + ((long long)b * Nq + g.q0 + r) * HHD + h * HD;
 #pragma unroll
-      for (int c = 0; c < OC; ++c) dst[cg + 16 * c] = dqa[i][c];
+      for (int c = 0; c < OC; ++c) {
+        if (S > 1) atomicAdd(dst + cg + 16 * c, dqa[i][c]);     // dq zero-filled by the host wrapper when the box is split
+        else dst[cg + 16 * c] = dqa[i][c];
+      }
     }
   }
 }

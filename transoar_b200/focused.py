@@ -89,9 +89,12 @@ class RoIAttentionFunction(Function):
         Nkv = k.shape[1]
         out = torch.empty(B, Nq, H * HD, dtype=torch.float32, device=q.device)
         lse = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+        ws_n = _lib.lib().roi_attn_workspace_floats(groups.shape[0], B, Nq, H, HD)
+        ws = torch.empty(max(ws_n, 1), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
             rc = _lib.lib().roi_attn_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(q), _p(k), _p(v), _p(groups),
-                                             groups.shape[0], B, Nq, Nkv, H, HD, grid_yz[0], grid_yz[1], _p(out), _p(lse))
+                                             groups.shape[0], B, Nq, Nkv, H, HD, grid_yz[0], grid_yz[1], _p(out), _p(lse),
+                                             _p(ws), ws_n)
         _lib.check(rc, "roi_attn_forward")
         ctx.save_for_backward(q, k, v, groups, out, lse)
         ctx.grid_yz = grid_yz
