@@ -9,14 +9,20 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, "/root/reference")
-timm = types.ModuleType("timm"); timm.models = types.ModuleType("timm.models"); timm.models.layers = types.ModuleType("timm.models.layers")
-timm.models.layers.trunc_normal_ = torch.nn.init.trunc_normal_
-sys.modules.update({"timm": timm, "timm.models": timm.models, "timm.models.layers": timm.models.layers})
-torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+
+def _patch_environment():
+    """Only inside the generator process: reference on sys.path, timm shim, .cuda() -> no-op."""
+    sys.path.insert(0, "/root/reference")
+    timm = types.ModuleType("timm"); timm.models = types.ModuleType("timm.models"); timm.models.layers = types.ModuleType("timm.models.layers")
+    timm.models.layers.trunc_normal_ = torch.nn.init.trunc_normal_
+    sys.modules.update({"timm": timm, "timm.models": timm.models, "timm.models.layers": timm.models.layers})
+    torch.Tensor.cuda = lambda self, *a, **k: self
 
 
 def main():
+    _patch_environment()
     from transoar.models.necks.focused_decoder import FocusedAttn, FocusedDecoderLayer
 
     # ---- FocusedAttn on its own: 2 organs x 7 queries, grid (4,5,6), one box touching the border, one interior

@@ -115,3 +115,52 @@ def test_visceral_shape_against_dense_path():
     out = focused.RoIAttentionFunction.apply(q, k, v, focused.groups_from_boxes(boxes).to(DEV), grid[1:])
     want = dense_masked_attention(q, k, v, boxes, grid)
     assert _rel(out, want) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Backbone (a7) and whole-model assembly (a10) against fixtures from the reference modules (deterministic weights)
+# ---------------------------------------------------------------------------------------------------------------
+def _golden_cfgs():
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_golden_model as G
+    from detfill import det_fill_module, det_tensor
+    return G, det_fill_module, det_tensor
+
+
+def test_attn_fpn_against_reference_fixture():
+    from transoar_b200.attn_fpn import AttnFPN
+    G, det_fill_module, det_tensor = _golden_cfgs()
+    z = np.load(os.path.join(GOLDEN, "attn_fpn.npz"))
+    cfg5 = dict(G.BACKBONE, conv_kernels=[[3, 3, 3]] * 5, strides=[[1, 1, 1]] + [[2, 2, 2]] * 4, feature_levels=["P2", "P3", "P4"], use_cuda=True)
+    fpn = det_fill_module(AttnFPN(cfg5).eval()).to(DEV)
+    x = det_tensor((1, 1, 32, 32, 16), 7, scale=0.5, offset=0.5).to(DEV).requires_grad_(True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        out = fpn(x)
+        sum((out[k] * det_tensor(tuple(v.shape), 11 + i).to(DEV)).sum() for i, (k, v) in enumerate(out.items())).backward()
+    assert sorted(out) == ["P2", "P3", "P4"]
+    for k in out:
+        assert _rel(out[k].detach(), torch.from_numpy(z["out." + k]).to(DEV)) < 2e-4, k
+    assert _rel(x.grad, torch.from_numpy(z["grad_x"]).to(DEV)) < 1e-3
+    for k, p in fpn.named_parameters():
+        if "pg." + k in z.files:
+            assert _rel(p.grad, torch.from_numpy(z["pg." + k]).to(DEV)) < 2e-3, k
+
+
+def test_transoarnet_against_reference_fixture():
+    from transoar_b200.transoarnet import TransoarNet
+    G, det_fill_module, det_tensor = _golden_cfgs()
+    z = np.load(os.path.join(GOLDEN, "transoarnet.npz"))
+    cfg = {"backbone": dict(G.BACKBONE, start_channels=2, use_cuda=True), "neck": dict(G.NECK, nheads=3), "bbox_properties": G.PROPS}
+    net = det_fill_module(TransoarNet(cfg).eval()).to(DEV)
+    x = det_tensor((1, 1, 256, 256, 128), 3, scale=0.5, offset=0.5).to(DEV)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        out = net(x)
+        loss = out["pred_logits"].sum() + (out["pred_boxes"] * torch.arange(6., device=DEV)).sum() + sum(a["pred_boxes"].sum() for a in out["aux_outputs"])
+        loss.backward()
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    assert _rel(out["pred_logits"], t("pred_logits")) < 1e-3 and _rel(out["pred_boxes"], t("pred_boxes")) < 1e-3
+    assert _rel(out["aux_outputs"][0]["pred_boxes"], t("aux0_boxes")) < 1e-3
+    for k, p in net.named_parameters():
+        if "pg." + k in z.files and float(np.abs(z["pg." + k]).max()) > 1e-6:
+            assert _rel(p.grad, t("pg." + k)) < 5e-3, k

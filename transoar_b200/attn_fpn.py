@@ -1,0 +1,121 @@
+"""AttnFPN backbone -- mirror of transoar/models/backbones/attn_fpn.py (``AttnFPN`` :18-32, ``Decoder`` :34-145,
+``Encoder`` :148-213) and ``EncoderCnnBlock`` (transoar/models/backbones/encoder_blocks.py:14-54).
+
+Module / parameter names equal the reference's (``_encoder._stages.<i>._block.<k>``, ``_decoder._lateral/_up/_out/_refine``)
+so reference checkpoints load.  The 3D convolutions, transposed convolutions and InstanceNorm stay library calls
+(cuDNN / ATen) in this round; the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
+``transoar_b200.refine.DecoderDefAttnBlock``.  The Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) is
+not mirrored yet and raises."""
+import torch
+from torch import nn
+
+from .position_encoding import PositionEmbeddingSine3D
+from .refine import DecoderDefAttnBlock
+
+
+class EncoderCnnBlock(nn.Module):
+    """(Conv3d no-bias -> InstanceNorm3d(affine) -> ReLU) x 2; the first conv carries the stride (encoder_blocks.py:14-54)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding=1, bias=False, affine=True, eps=1e-05):
+        super().__init__()
+        layers = []
+        for cin, s in ((in_channels, stride), (out_channels, 1)):
+            layers += [nn.Conv3d(cin, out_channels, kernel_size=kernel_size, stride=s, padding=padding, bias=bias),
+                       nn.InstanceNorm3d(num_features=out_channels, affine=affine, eps=eps), nn.ReLU(inplace=True)]
+        self._block = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self._block(x)
+
+
+class Encoder(nn.Module):
+    """attn_fpn.py:148-213: one stage per entry of conv_kernels, channels start_channels * 2^stage."""
+
+    def __init__(self, config, debug=False):
+        super().__init__()
+        if config["use_encoder_attn"]:
+            raise NotImplementedError("the Swin encoder (use_encoder_attn, encoder_blocks.py:56-334) is not mirrored yet")
+        cin, cout = config["in_channels"], config["start_channels"]
+        self._stages = nn.ModuleList()
+        for kernel, stride in zip(config["conv_kernels"], config["strides"]):
+            self._stages.append(EncoderCnnBlock(cin, cout, kernel, stride))
+            cin, cout = cout, cout * 2
+
+    def forward(self, x):
+        outputs = {}
+        for i, stage in enumerate(self._stages):
+            x = stage(x)
+            outputs["C" + str(i)] = x
+        return outputs
+
+
+class Decoder(nn.Module):
+    """attn_fpn.py:34-145: 1x1 lateral convs, transposed-conv top-down path, 3x3x3 output convs, optional deformable refine."""
+
+    def __init__(self, config, debug=False):
+        super().__init__()
+        n_stages = len(config["conv_kernels"])
+        self._refine_fmaps = config["use_decoder_attn"]
+        self._refine_feature_levels = config["feature_levels"]
+        self._seg_proxy = config["use_seg_proxy_loss"]
+        enc_ch = [config["start_channels"] * 2 ** s for s in range(n_stages)]
+        wanted = config["out_fmaps"] + config["feature_levels"] if config["use_decoder_attn"] else config["out_fmaps"]
+        required = set(int(name[-1]) for name in wanted)                                   # :50-53 (a set, iterated ascending)
+        if self._seg_proxy:
+            required.add(0)
+        self._required_stages = required
+        first = min(required)
+        lat_in = enc_ch if self._seg_proxy else enc_ch[first:]
+        lat_out = [min(c, config["fpn_channels"]) for c in lat_in]                         # :57-58
+        self._lateral = nn.ModuleList(nn.Conv3d(i, o, kernel_size=1) for i, o in zip(lat_in, lat_out))
+        self._lateral_levels = len(self._lateral)
+        out_in = [lat_out[-n_stages + stage] for stage in required]                        # :67
+        out_out = [int(config["fpn_channels"])] * len(out_in)
+        out_out[0] = enc_ch[0] if self._seg_proxy else int(config["fpn_channels"])         # :69
+        self._out = nn.ModuleList(nn.Conv3d(i, o, kernel_size=3, padding=1) for i, o in zip(out_in, out_out))
+        rev_ch, rev_strides = lat_out[::-1], list(reversed(config["strides"]))
+        self._up = nn.ModuleList(nn.ConvTranspose3d(rev_ch[l], rev_ch[l + 1], kernel_size=rev_strides[l], stride=rev_strides[l])
+                                 for l in range(len(lat_out) - 1))                         # :76-83
+        if self._refine_fmaps:
+            if config["pos_encoding"] != "sine":
+                raise NotImplementedError("only the sine positional encoding is mirrored (the shipped configs use it)")
+            self._pos_enc = PositionEmbeddingSine3D(channels=config["hidden_dim"])
+            self._refine = DecoderDefAttnBlock(d_model=config["hidden_dim"], nhead=config["nheads"], num_layers=config["layers"],
+                                               dim_feedforward=config["dim_feedforward"], dropout=config["dropout"],
+                                               feature_levels=config["feature_levels"], n_points=config["n_points"],
+                                               use_cuda=config["use_cuda"])
+
+    def forward(self, x):
+        feats = list(x.values())[-self._lateral_levels:]
+        lateral = [conv(f) for conv, f in zip(self._lateral, feats)]
+        top_down, up = [], None
+        for idx, cur in enumerate(reversed(lateral)):                                     # coarsest first (:110-118)
+            if idx != 0:
+                cur = cur + up
+            if idx < self._lateral_levels - 1:
+                up = self._up[idx](cur)
+            top_down.append(cur)
+        fine_first = top_down[::-1]
+        if self._seg_proxy:
+            pairs = [(fine_first[stage], stage) for stage in self._required_stages]
+        else:
+            pairs = zip(fine_first, self._required_stages)                                # :124 (positional pairing, as the reference)
+        outputs = {"P" + str(stage): self._out[i](f) for i, (f, stage) in enumerate(pairs)}
+        if self._refine_fmaps:
+            fmaps = [outputs[name] for name in self._refine_feature_levels]
+            refined = self._refine(fmaps, [self._pos_enc(f) for f in fmaps])
+            outputs.update(zip(self._refine_feature_levels, refined))
+        return outputs
+
+
+class AttnFPN(nn.Module):
+    def __init__(self, fpn_config, debug=False):
+        super().__init__()
+        self._encoder = Encoder(fpn_config, debug)
+        self._decoder = Decoder(fpn_config, debug)
+
+    def forward(self, src):
+        return self._decoder(self._encoder(src))
+
+    def init_weights(self):
+        pass
