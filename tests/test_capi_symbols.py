@@ -13,10 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     names = set()
-    for header in ("msda3d.h", "roi_attn.h"):
+    for header in ("msda3d.h", "roi_attn.h", "instnorm.h"):
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names |= set(re.findall(r"\b((?:msda3d|roi_attn)_[a-z0-9_]+)\s*\(", text))
+        names |= set(re.findall(r"\b((?:msda3d|roi_attn|instnorm)_[a-z0-9_]+)\s*\(", text))
     return sorted(names)
 
 

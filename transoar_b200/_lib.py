@@ -27,6 +27,10 @@ _SIGNATURES = {
     "msda3d_forward_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 4),
     "msda3d_host_release": (None, []),
     "msda3d_debug_indices": (_ci, [_vp, _ci, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
+    # include/instnorm.h
+    "instnorm_workspace_floats": (ctypes.c_longlong, [_ci, _ci, _ci, ctypes.c_longlong]),
+    "instnorm_relu_forward": (_ci, [_vp, _ci, _vp, _vp, _vp, _ci, _ci, ctypes.c_longlong, ctypes.c_float, _vp, _vp, _vp, _vp]),
+    "instnorm_relu_backward": (_ci, [_vp, _ci] + [_vp] * 6 + [_ci, _ci, ctypes.c_longlong] + [_vp] * 4),
     # include/roi_attn.h
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),

@@ -2,13 +2,14 @@
 ``Encoder`` :148-213) and ``EncoderCnnBlock`` (transoar/models/backbones/encoder_blocks.py:14-54).
 
 Module / parameter names equal the reference's (``_encoder._stages.<i>._block.<k>``, ``_decoder._lateral/_up/_out/_refine``)
-so reference checkpoints load.  The 3D convolutions, transposed convolutions and InstanceNorm stay library calls
-(cuDNN / ATen) in this round; the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
+so reference checkpoints load.  The 3D convolutions and transposed convolutions stay library calls (cuDNN) in this round; every
+InstanceNorm3d -> ReLU pair runs as a fused sm_100a kernel (include/instnorm.h); the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
 ``transoar_b200.refine.DecoderDefAttnBlock``.  The Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) is
 not mirrored yet and raises."""
 import torch
 from torch import nn
 
+from .instnorm import instance_norm_relu
 from .position_encoding import PositionEmbeddingSine3D
 from .refine import DecoderDefAttnBlock
 
@@ -25,7 +26,11 @@ class EncoderCnnBlock(nn.Module):
         self._block = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self._block(x)
+        # same Sequential (so the reference's parameter names are kept), but each InstanceNorm3d -> ReLU pair runs as one
+        # fused sm_100a kernel (transoar_b200/instnorm.py) instead of cuDNN batch-norm + an elementwise ReLU
+        conv1, norm1, _, conv2, norm2, _ = self._block
+        x = instance_norm_relu(conv1(x), norm1.weight, norm1.bias, norm1.eps)
+        return instance_norm_relu(conv2(x), norm2.weight, norm2.bias, norm2.eps)
 
 
 class Encoder(nn.Module):

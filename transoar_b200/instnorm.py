@@ -1,0 +1,63 @@
+"""Fused InstanceNorm3d(affine) + ReLU on the sm_100a kernels (include/instnorm.h).
+
+Stands in for the ``nn.InstanceNorm3d(affine=True) -> nn.ReLU(inplace=True)`` pairs of the reference's ``EncoderCnnBlock``
+(transoar/models/backbones/encoder_blocks.py:28-46).  fp32 or bf16 activations, fp32 statistics and parameters."""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class InstanceNormReLUFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        if not x.is_cuda:
+            raise RuntimeError("instance_norm_relu: Not implemented on the CPU")
+        if x.dtype not in _DT:
+            x = x.float()
+        x = x.contiguous()
+        B, C = x.shape[:2]
+        V = x[0, 0].numel()
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty(B * C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        ws = torch.empty(_lib.lib().instnorm_workspace_floats(_DT[x.dtype], B, C, V), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().instnorm_relu_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _DT[x.dtype], _p(x), _p(w), _p(b),
+                                                  B, C, V, float(eps), _p(y), _p(mean), _p(rstd), _p(ws))
+        _lib.check(rc, "instnorm_relu_forward")
+        ctx.save_for_backward(x, y, w, mean, rstd)
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y, w, mean, rstd = ctx.saved_tensors
+        B, C = x.shape[:2]
+        V = x[0, 0].numel()
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=torch.float32, device=x.device)
+        db = torch.empty_like(dw)
+        ws = torch.empty(_lib.lib().instnorm_workspace_floats(_DT[x.dtype], B, C, V), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().instnorm_relu_backward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _DT[x.dtype], _p(dy), _p(x), _p(y),
+                                                   _p(w), _p(mean), _p(rstd), B, C, V, _p(dx), _p(dw), _p(db), _p(ws))
+        _lib.check(rc, "instnorm_relu_backward")
+        return dx, dw.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
+
+
+def instance_norm_relu(x, weight, bias, eps=1e-5):
+    """relu(instance_norm(x, weight, bias, eps)) for [N, C, *spatial] tensors."""
+    return InstanceNormReLUFunction.apply(x, weight, bias, eps)
