@@ -213,6 +213,133 @@ def workload_config():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Extras: the other hand-written kernels of the path and the whole model (reported beside the headline, never in it)
+# ---------------------------------------------------------------------------------------------------------------
+def _event_ms(fn, warm=2, reps=5):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_extras(dev, rank, world, dist):
+    import torch
+    import torch.nn.functional as F
+    from transoar_b200 import focused
+    from transoar_b200.configs import visceral_config
+    from transoar_b200.instnorm import instance_norm_relu
+    from transoar_b200.transoarnet import TransoarNet
+    peak, _ = load_peaks()
+    out = {}
+    gen = torch.Generator().manual_seed(7 + rank)
+    cfg = visceral_config()
+
+    # (a9) RoI-restricted cross-attention of one Focused-Decoder layer, B = 2, 540 queries, P2 grid 40x40x64, 8 heads x 48
+    grid = (40, 40, 64)
+    boxes = focused.boxes_from_bbox_props(cfg["bbox_properties"], 540, grid)
+    groups = focused.groups_from_boxes(boxes).to(dev)
+    q = (torch.randn(BATCH, 540, 8, 48, generator=gen) * 0.3).to(dev).requires_grad_(True)
+    k = torch.randn(BATCH, 102400, 8, 48, generator=gen).to(dev).requires_grad_(True)
+    v = torch.randn(BATCH, 102400, 8, 48, generator=gen).to(dev).requires_grad_(True)
+    g = torch.randn(BATCH, 540, 384, generator=gen).to(dev)
+
+    def roi_fb():
+        focused.RoIAttentionFunction.apply(q, k, v, groups, grid[1:]).backward(g)
+        q.grad = k.grad = v.grad = None
+
+    with torch.no_grad():
+        roi_f = _event_ms(lambda: focused.RoIAttentionFunction.apply(q, k, v, groups, grid[1:]))
+    vol = ((boxes[:, 3] - boxes[:, 0]) * (boxes[:, 4] - boxes[:, 1]) * (boxes[:, 5] - boxes[:, 2])).float()
+    out["roi_attention"] = {"fwd_ms": roi_f, "fwd_bwd_ms": _event_ms(roi_fb), "batch": BATCH, "queries": 540, "kv_tokens": 102400,
+                            "unmasked_kv_fraction": float(vol.mean()) / 102400,
+                            "dense_score_tensor_avoided_gb": BATCH * 8 * 540 * 102400 * 4 / 1e9}
+    del q, k, v, g
+
+    # (a7) fused InstanceNorm3d + ReLU on the first encoder activation (B x 24 x 160 x 160 x 256 fp32)
+    x = torch.randn(BATCH, 24, 160, 160, 256, device=dev, requires_grad=True)
+    w = torch.ones(24, device=dev, requires_grad=True)
+    b = torch.zeros(24, device=dev, requires_grad=True)
+    dy = torch.randn_like(x)
+
+    def in_fb():
+        instance_norm_relu(x, w, b).backward(dy)
+        x.grad = None
+
+    def aten_fb():
+        F.relu(F.instance_norm(x, weight=w, bias=b, eps=1e-5)).backward(dy)
+        x.grad = None
+
+    with torch.no_grad():
+        in_f = _event_ms(lambda: instance_norm_relu(x, w, b))
+    in_fbm, aten_fbm = _event_ms(in_fb), _event_ms(aten_fb, 1, 2)
+    nbytes = x.numel() * 4
+    out["instnorm_relu"] = {"fwd_ms": in_f, "fwd_bwd_ms": in_fbm, "aten_cudnn_fwd_bwd_ms": aten_fbm,
+                            "fwd_gbs": 3 * nbytes / in_f / 1e6, "fwd_frac_of_hbm_peak": 3 * nbytes / in_f / 1e6 / peak,
+                            "fwd_bwd_gbs": 8 * nbytes / in_fbm / 1e6, "fwd_bwd_frac_of_hbm_peak": 8 * nbytes / in_fbm / 1e6 / peak,
+                            "bytes_model": "fwd: 2 reads + 1 write of the activation; bwd: 4 reads + 1 write"}
+    del x, dy
+    torch.cuda.empty_cache()
+
+    # whole model: TransoarNet mirror (AttnFPN + deformable refine + Focused Decoder + heads), VISCERAL config, fwd + surrogate loss +
+    # bwd + AdamW; convolutions / linears are cuDNN / cuBLAS calls, the rest runs on this repo's kernels.  DDP over ranks.
+    torch.backends.cuda.matmul.allow_tf32 = True      # what the reference's pinned torch 1.10 does by default
+    torch.manual_seed(0)
+    net = TransoarNet(cfg).to(dev).train()
+    for name, p in net.named_parameters():
+        if ".q_proj." in name:
+            p.requires_grad_(False)                    # dead parameters: no gradient in the reference either
+    model = net
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4)
+    vol_in = torch.rand(BATCH, 1, 160, 160, 256, device=dev)
+    tgt = torch.rand(BATCH, 540, 6, device=dev)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        o = model(vol_in)
+        loss = F.l1_loss(o["pred_boxes"], tgt) + F.binary_cross_entropy_with_logits(o["pred_logits"], torch.zeros_like(o["pred_logits"]))
+        for a in o["aux_outputs"]:
+            loss = loss + F.l1_loss(a["pred_boxes"], tgt)
+        loss.backward()
+        opt.step()
+
+    for _ in range(3):
+        train_step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        train_step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / reps
+    out["whole_model"] = {"volumes_per_s": world * BATCH / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": BATCH, "n_gpus": world,
+                          "params": sum(p.numel() for p in net.parameters()),
+                          "what": "TransoarNet mirror, visceral yaml with use_decoder_attn/use_cuda on, fp32 (TF32 matmul/conv as torch 1.10), "
+                                  "fwd + surrogate L1/BCE loss (criterion + matcher are out of scope) + bwd + AdamW"
+                                  + ("; DDP, NCCL gradient all-reduce" if world > 1 else ""),
+                          "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 def main():
@@ -223,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the RoI-attention / InstanceNorm / whole-model extras")
     ap.add_argument("--dist", default=DIST, choices=["A", "B"])
     args = ap.parse_args()
     if args.impl == "reference":
@@ -378,6 +506,18 @@ def main():
                         "fwd_ms": rf, "bwd_ms": rb, "value": BATCH / (LAYERS * (rf + rb) * 1e-3), "unit": UNIT,
                         "speedup_fwd": rf / fwd_avg, "speedup_bwd": rb / bwd_avg}
 
+    # ---- the other kernels of the path and the whole model, as extra objects (not in `value`)
+    extras = {}
+    if not args.no_extras:
+        for x in layers:
+            x.clear()
+        layers.clear()
+        torch.cuda.empty_cache()
+        try:
+            extras = measure_extras(dev, rank, world, dist if world > 1 else None)
+        except Exception as exc:            # never lose the headline line because an extra failed
+            extras = {"extras_error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -386,7 +526,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "kernels": {"fwd_ms": fwd_avg, "bwd_ms": bwd_avg, "fwd_ms_min": min(fwd_ms), "bwd_ms_min": min(bwd_ms),
                         "share_fwd": fwd_avg / (fwd_avg + bwd_avg), "share_bwd": bwd_avg / (fwd_avg + bwd_avg)},
-            "ref_cuda_op": ref_cuda, "clocks": clocks.summary(),
+            "ref_cuda_op": ref_cuda, "clocks": clocks.summary(), **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
