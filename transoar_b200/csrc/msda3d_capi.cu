@@ -308,7 +308,8 @@ namespace {
 
 struct HostCtx {
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream_cmp = nullptr, stream_out = nullptr;   // H2D / compute / D2H
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr;
   // grow-only device scratch: 0 value, 1 loc, 2 aw, 3 gout, 4 out, 5 gv, 6 gloc, 7 gaw, 8 shapes, 9 starts
   void *buf[10] = {nullptr};
   size_t cap[10] = {0};
@@ -353,6 +354,10 @@ int host_run(int device, int dtype, bool do_fwd, bool do_bwd, const void *gout, 
   CU(cudaSetDevice(device));
   if (!c.stream) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.stream_cmp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.stream_out, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
     c.device = device;
   }
   const size_t es = elem_size(dtype), as = aux_size(dtype);
@@ -362,32 +367,48 @@ int host_run(int device, int dtype, bool do_fwd, bool do_bwd, const void *gout, 
   if ((rc = ensure(c, 0, n_val * es)) || (rc = ensure(c, 1, n_loc * as)) || (rc = ensure(c, 2, n_aw * as)) ||
       (rc = ensure(c, 8, (size_t)d.L * 3 * 8)) || (rc = ensure(c, 9, (size_t)d.L * 8)))
     return rc;
-  cudaStream_t st = c.stream;
-  CU(cudaMemcpyAsync(c.buf[8], shapes, (size_t)d.L * 3 * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c.buf[9], starts, (size_t)d.L * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c.buf[0], value, n_val * es, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c.buf[1], loc, n_loc * as, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c.buf[2], aw, n_aw * as, cudaMemcpyHostToDevice, st));
-  if (do_fwd) {
-    if ((rc = ensure(c, 4, n_out * es))) return rc;
-    rc = msda3d_forward(st, dtype, c.buf[0], (const int64_t *)c.buf[8], (const int64_t *)c.buf[9], c.buf[1], c.buf[2], d.N, d.S, d.M,
-                        d.C, d.L, d.Lq, d.P, c.buf[4]);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(out, c.buf[4], n_out * es, cudaMemcpyDeviceToHost, st));
+  if (do_fwd && (rc = ensure(c, 4, n_out * es))) return rc;
+  if (do_bwd && ((rc = ensure(c, 3, n_out * es)) || (rc = ensure(c, 5, n_val * as)) || (rc = ensure(c, 6, n_loc * as)) ||
+                 (rc = ensure(c, 7, n_aw * as))))
+    return rc;
+  // Three-stage pipeline over the batch elements (they are independent): H2D of element b+1 and D2H of element b-1 run on
+  // their own streams while element b computes, so the PCIe link is busy in both directions at once.
+  cudaStream_t s_in = c.stream, s_cmp = c.stream_cmp, s_out = c.stream_out;
+  CU(cudaMemcpyAsync(c.buf[8], shapes, (size_t)d.L * 3 * 8, cudaMemcpyHostToDevice, s_in));
+  CU(cudaMemcpyAsync(c.buf[9], starts, (size_t)d.L * 8, cudaMemcpyHostToDevice, s_in));
+  const size_t v1 = n_val / d.N, o1 = n_out / d.N, a1 = n_aw / d.N, l1 = n_loc / d.N;
+  auto at = [](const void *p, size_t bytes) { return (const void *)((const char *)p + bytes); };
+  auto atw = [](void *p, size_t bytes) { return (void *)((char *)p + bytes); };
+  for (int b = 0; b < d.N; ++b) {
+    CU(cudaMemcpyAsync(atw(c.buf[0], b * v1 * es), at(value, b * v1 * es), v1 * es, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(atw(c.buf[1], b * l1 * as), at(loc, b * l1 * as), l1 * as, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(atw(c.buf[2], b * a1 * as), at(aw, b * a1 * as), a1 * as, cudaMemcpyHostToDevice, s_in));
+    if (do_bwd) CU(cudaMemcpyAsync(atw(c.buf[3], b * o1 * es), at(gout, b * o1 * es), o1 * es, cudaMemcpyHostToDevice, s_in));
+    CU(cudaEventRecord(c.ev_in, s_in));
+    CU(cudaStreamWaitEvent(s_cmp, c.ev_in, 0));
+    if (do_fwd) {
+      rc = msda3d_forward(s_cmp, dtype, at(c.buf[0], b * v1 * es), (const int64_t *)c.buf[8], (const int64_t *)c.buf[9],
+                          at(c.buf[1], b * l1 * as), at(c.buf[2], b * a1 * as), 1, d.S, d.M, d.C, d.L, d.Lq, d.P, atw(c.buf[4], b * o1 * es));
+      if (rc) return rc;
+    }
+    if (do_bwd) {
+      rc = msda3d_backward(s_cmp, dtype, at(c.buf[3], b * o1 * es), at(c.buf[0], b * v1 * es), (const int64_t *)c.buf[8],
+                           (const int64_t *)c.buf[9], at(c.buf[1], b * l1 * as), at(c.buf[2], b * a1 * as), 1, d.S, d.M, d.C, d.L, d.Lq,
+                           d.P, atw(c.buf[5], b * v1 * as), atw(c.buf[6], b * l1 * as), atw(c.buf[7], b * a1 * as));
+      if (rc) return rc;
+    }
+    CU(cudaEventRecord(c.ev_done, s_cmp));
+    CU(cudaStreamWaitEvent(s_out, c.ev_done, 0));
+    if (do_fwd) CU(cudaMemcpyAsync(atw(out, b * o1 * es), at(c.buf[4], b * o1 * es), o1 * es, cudaMemcpyDeviceToHost, s_out));
+    if (do_bwd) {
+      CU(cudaMemcpyAsync(atw(gv, b * v1 * as), at(c.buf[5], b * v1 * as), v1 * as, cudaMemcpyDeviceToHost, s_out));
+      CU(cudaMemcpyAsync(atw(gl, b * l1 * as), at(c.buf[6], b * l1 * as), l1 * as, cudaMemcpyDeviceToHost, s_out));
+      CU(cudaMemcpyAsync(atw(ga, b * a1 * as), at(c.buf[7], b * a1 * as), a1 * as, cudaMemcpyDeviceToHost, s_out));
+    }
   }
-  if (do_bwd) {
-    if ((rc = ensure(c, 3, n_out * es)) || (rc = ensure(c, 5, n_val * as)) || (rc = ensure(c, 6, n_loc * as)) ||
-        (rc = ensure(c, 7, n_aw * as)))
-      return rc;
-    CU(cudaMemcpyAsync(c.buf[3], gout, n_out * es, cudaMemcpyHostToDevice, st));
-    rc = msda3d_backward(st, dtype, c.buf[3], c.buf[0], (const int64_t *)c.buf[8], (const int64_t *)c.buf[9], c.buf[1], c.buf[2], d.N,
-                         d.S, d.M, d.C, d.L, d.Lq, d.P, c.buf[5], c.buf[6], c.buf[7]);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(gv, c.buf[5], n_val * as, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(gl, c.buf[6], n_loc * as, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ga, c.buf[7], n_aw * as, cudaMemcpyDeviceToHost, st));
-  }
-  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(s_out));
+  CU(cudaStreamSynchronize(s_cmp));
+  CU(cudaStreamSynchronize(s_in));
   return 0;
 }
 
@@ -442,8 +463,10 @@ void msda3d_host_release(void)
       c.buf[i] = nullptr;
       c.cap[i] = 0;
     }
-    if (c.stream) cudaStreamDestroy(c.stream);
-    c.stream = nullptr;
+    if (c.stream) { cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream_cmp); cudaStreamDestroy(c.stream_out); }
+    if (c.ev_in) { cudaEventDestroy(c.ev_in); cudaEventDestroy(c.ev_done); }
+    c.stream = c.stream_cmp = c.stream_out = nullptr;
+    c.ev_in = c.ev_done = nullptr;
     c.device = -1;
     cudaSetDevice(prev);
   }
