@@ -1,0 +1,37 @@
+/*
+ * tc_gemm.h -- C ABI of the TF32 tensor-core GEMM in libmsda3d.so (sm_100a: tcgen05.mma + TMEM accumulators + TMA operand
+ * staging).  It carries the dense contractions of the hot path and their gradients:
+ *
+ *   torch.nn.Linear forward  (F.linear -> cuBLAS sgemm/tf32 in the reference) used by
+ *     MSDeformAttn.value_proj / sampling_offsets / attention_weights / output_proj  transoar/models/ops/modules/ms_deform_attn.py:58-61,109-140
+ *     DefAttnLayer.linear1 / linear2                                                transoar/models/backbones/decoder_blocks.py:156-160,172-175
+ *     FocusedAttn.k_proj / v_proj / proj                                            transoar/models/necks/focused_decoder.py:213-218,233-257
+ *     FocusedDecoderLayer.linear1 / linear2                                         transoar/models/necks/focused_decoder.py:131-135,186-187
+ *   and autograd's two gradient GEMMs of each of them (grad_input = grad_output W, grad_weight = grad_output^T input).
+ *
+ *   D[m, n] (+)= sum_{r < R} A(m, r) * B(n, r)   (+ bias[n])   (ReLU)          m < M, n < N, fp32 everywhere, TF32 multiply
+ *
+ *   a_mn_major == 0 : A(m, r) = A[m * lda + r]   ("K-major": the reduction index is contiguous, e.g. X[M, K], W[N, K])
+ *   a_mn_major == 1 : A(m, r) = A[r * lda + m]   ("MN-major": the m index is contiguous, e.g. grad_output^T)
+ *   b_mn_major likewise for B(n, r).  D is row-major with leading dimension ldd.
+ *   accumulate != 0 : D += result (red.global.add); required when split_k > 1.  split_k == 0 picks a split automatically
+ *                     (only when accumulate != 0; D must then hold the value to add to, e.g. zeros).
+ *
+ * Preconditions (TC_GEMM / MSDA3D_EINVAL otherwise): device pointers, A and B 16-byte aligned, lda % 4 == 0, ldb % 4 == 0
+ * (TMA global strides are multiples of 16 bytes); M, N, R > 0.  bias may be NULL.  Work is enqueued on `stream`; no
+ * allocation, no synchronisation.  Returns 0 / MSDA3D_E* / cudaError_t (msda3d_error_string explains all three).
+ */
+#ifndef TC_GEMM_H_
+#define TC_GEMM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
+                 float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TC_GEMM_H_ */

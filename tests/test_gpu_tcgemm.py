@@ -1,0 +1,101 @@
+"""GPU parity of the TF32 tcgen05 GEMM (include/tc_gemm.h) and of the Linear function built on it against fp64 matmul.
+Tolerance: TF32 keeps 10 mantissa bits of each operand (the tensor core reads the upper 19 bits of the fp32 word), so with
+|a|,|b| ~ 1 the error of a length-R dot product is ~ 2^-10 * sqrt(R) in absolute terms; the bound below is 4e-3 * sqrt(R) * max|a| max|b|,
+the same order torch's own TF32 matmul shows against fp64."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _operand(rows, red, mn_major, gen):
+    """Logical [rows, red] operand stored K-major ([rows, red]) or MN-major ([red, rows]); returns (storage, logical fp64, ld)."""
+    if mn_major:
+        st = torch.randn(red, rows, generator=gen).cuda()
+        return st, st.double().t(), rows
+    st = torch.randn(rows, red, generator=gen).cuda()
+    return st, st.double(), red
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("M,N,R", [(128, 128, 32), (256, 256, 64), (300, 200, 100), (1000, 384, 384), (516, 1024, 388), (64, 8, 16),
+                                   (2048, 1024, 1024)])
+def test_gemm_matches_fp64(a_mn, b_mn, M, N, R):
+    from transoar_b200.linear import gemm
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + R + a_mn * 2 + b_mn)
+    A, Ad, lda = _operand(M, R, a_mn, gen)
+    B, Bd, ldb = _operand(N, R, b_mn, gen)
+    bias = torch.randn(N, generator=gen).cuda()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=bias)
+    torch.cuda.synchronize()
+    want = Ad @ Bd.t() + bias.double()
+    err = float((D.double() - want).abs().max())
+    assert err < 4e-3 * math.sqrt(R) * 4.5 * 4.5 / 9, (err, M, N, R)
+    # ReLU epilogue + no bias
+    D2 = torch.empty(M, N, device="cuda")
+    gemm(A, a_mn, lda, B, b_mn, ldb, D2, M, N, R, relu=True)
+    assert float((D2.double() - (Ad @ Bd.t()).clamp_min(0)).abs().max()) < 4e-3 * math.sqrt(R) * 2.25
+
+
+@pytest.mark.parametrize("M,N,R,split", [(384, 1024, 20000, 0), (128, 128, 4096, 7), (200, 136, 1000, 3), (384, 384, 33000, 0)])
+def test_split_k_accumulates(M, N, R, split):
+    from transoar_b200.linear import gemm
+    gen = torch.Generator().manual_seed(R)
+    A, Ad, lda = _operand(M, R, 1, gen)
+    B, Bd, ldb = _operand(N, R, 1, gen)
+    D = torch.ones(M, N, device="cuda")
+    gemm(A, 1, lda, B, 1, ldb, D, M, N, R, accumulate=True, split_k=split)
+    torch.cuda.synchronize()
+    want = Ad @ Bd.t() + 1.0
+    assert float((D.double() - want).abs().max()) < 4e-3 * math.sqrt(R) * 2.25
+
+
+def test_exact_on_tf32_representable_inputs():
+    """Integers < 2^10 are exact in TF32 and the fp32 accumulation of their products is exact here: bit-identical to fp64."""
+    from transoar_b200.linear import gemm
+    gen = torch.Generator().manual_seed(5)
+    A = torch.randint(-8, 9, (384, 256), generator=gen).float().cuda()
+    B = torch.randint(-8, 9, (512, 256), generator=gen).float().cuda()
+    D = torch.empty(384, 512, device="cuda")
+    gemm(A, 0, 256, B, 0, 256, D, 384, 512, 256)
+    assert torch.equal(D.double(), A.double() @ B.double().t())
+    At, Bt = A.t().contiguous(), B.t().contiguous()
+    D2 = torch.empty(384, 512, device="cuda")
+    gemm(At, 1, 384, Bt, 1, 512, D2, 384, 512, 256)
+    assert torch.equal(D2, D)
+
+
+@pytest.mark.parametrize("shape,K,N,relu", [((2, 1000), 384, 1024, True), ((3, 7, 11), 384, 384, False), ((540,), 384, 8, False), ((234,), 1024, 384, False)])
+def test_linear_function_forward_backward(shape, K, N, relu):
+    from transoar_b200.linear import linear
+    gen = torch.Generator().manual_seed(K + N)
+    x = torch.randn(*shape, K, generator=gen).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=gen) / math.sqrt(K)).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=gen).cuda().requires_grad_(True)
+    g = torch.randn(*shape, N, generator=gen).cuda()
+    y = linear(x, w, b, relu)
+    y.backward(g)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    # take the ReLU mask from the kernel's own output so knife-edge activations do not count as errors
+    yd = yd * (y.detach() > 0) if relu else yd
+    yd.backward(g.double())
+    rows = x.numel() // K
+    tol = lambda red, scale: 4e-3 * math.sqrt(red) * scale
+    assert float((y.double() - yd).abs().max()) < tol(K, 4.5 * 4.5 / math.sqrt(K))
+    assert float((x.grad.double() - xd.grad).abs().max()) < tol(N, 4.5 * 4.5 / math.sqrt(K))
+    assert float((w.grad.double() - wd.grad).abs().max()) < tol(rows, 4.5 * 4.5)
+    assert float((b.grad.double() - bd.grad).abs().max()) < 1e-3 * math.sqrt(rows)
+
+
+def test_rejects_cpu_and_misaligned():
+    from transoar_b200.linear import gemm, linear
+    with pytest.raises(RuntimeError, match="CPU"):
+        linear(torch.randn(4, 8), torch.randn(8, 8))
+    A = torch.randn(16, 6).cuda()     # lda = 6 is not a multiple of 4
+    with pytest.raises(RuntimeError, match="aligned"):
+        gemm(A, 0, 6, A, 0, 6, torch.empty(16, 16).cuda(), 16, 16, 6)

@@ -33,7 +33,7 @@ print(f"B={B} {amp}: {ms:.1f} ms/step  {B / ms * 1e3:.2f} volumes/s  peak mem {t
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:14]
+rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:45]
 tot = sum(r.device_time_total for r in prof.key_averages())
 for r in rows:
     print(f"{r.device_time_total / 1e3:8.2f} ms {100 * r.device_time_total / tot:5.1f}%  x{r.count:<4d} {r.key[:110]}")

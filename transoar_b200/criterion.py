@@ -1,0 +1,176 @@
+"""Matcher + loss of the Focused-Decoder model, batched on the device -- mirrors of transoar/models/matcher.py:9-65
+(``Matcher``) and transoar/models/criterion.py:9-125 (``TransoarCriterion``), SURVEY 8(f) rank 2.
+
+The reference moves logits / boxes / targets to the CPU and loops over (batch, class) in Python with a ``topk`` per class
+(matcher.py:30-63: 2 x 20 iterations and four host syncs per training step at VISCERAL).  Here the per-class costs of all
+(batch, class) pairs are one [B, organs, queries-per-organ] tensor, the match is an ``argmin`` over its last axis and nothing
+leaves the device, so a training step has no host synchronisation before the optimiser.
+
+Behaviour kept from the reference on purpose:
+  * queries are statically split into ``num_organs`` groups; class c (1-based label) only competes inside group c-1;
+  * with ``anchor_matching`` the box costs use the ANCHORS, not the predictions (matcher.py:27-28);
+  * soft labels = GIoU cost of each query against the class's target, min-max normalised inside the group and clipped at 0
+    (matcher.py:59); a class absent from the sample gets soft label -1 and is dropped from the BCE (criterion.py:45-48);
+  * the auxiliary-layer losses re-run the matcher on the auxiliary logits but evaluate the losses on the FINAL layer's
+    predictions (criterion.py:118-119 pass ``outputs``, not ``aux_outputs``);
+  * box losses are normalised by the number of target boxes in the batch.
+Differences: ``num_top_queries`` is fixed at 1 (the only value the reference's criterion ever passes); on exact cost ties the
+first query wins (the reference inherits whatever CPU ``topk`` returns); targets whose labels repeat inside a sample keep the
+last box (the reference keeps the last one in its dict too, matcher.py:34)."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+def box_cxcyczwhd_to_xyzxyz(b):
+    c, s = b[..., :3], b[..., 3:]
+    return torch.cat((c - 0.5 * s, c + 0.5 * s), dim=-1)
+
+
+def paired_giou_3d(a, b):
+    """Generalised IoU of box pairs (xyzxyz, broadcastable leading dims) -- utils/bboxes.py:6-29,99-136 for matched pairs."""
+    vol = lambda x: (x[..., 3] - x[..., 0]) * (x[..., 4] - x[..., 1]) * (x[..., 5] - x[..., 2])
+    inter = (torch.minimum(a[..., 3:], b[..., 3:]) - torch.maximum(a[..., :3], b[..., :3])).clamp(min=0).prod(-1)
+    union = vol(a) + vol(b) - inter
+    hull = (torch.maximum(a[..., 3:], b[..., 3:]) - torch.minimum(a[..., :3], b[..., :3])).clamp(min=0).prod(-1)
+    return inter / union - (hull - union) / hull
+
+
+def dense_targets(targets, num_organs, device):
+    """List of {'boxes': [n,6], 'labels': [n] (1-based)} -> (boxes [B, organs, 6], valid [B, organs]); no host sync."""
+    B = len(targets)
+    boxes = torch.zeros(B, num_organs, 6, dtype=torch.float32, device=device)
+    valid = torch.zeros(B, num_organs, dtype=torch.bool, device=device)
+    for b, t in enumerate(targets):
+        idx = t["labels"].to(device=device, dtype=torch.long) - 1
+        boxes[b].index_copy_(0, idx, t["boxes"].to(device=device, dtype=torch.float32))
+        valid[b].index_fill_(0, idx, True)
+    return boxes, valid
+
+
+class Matcher(nn.Module):
+    """matcher.py:9-65.  ``forward`` returns (matched query index [B, organs] (long), soft_labels [B, organs, Q]) plus the
+    reference's dense 0/1 ``matches`` tensor on request."""
+
+    def __init__(self, cost_class=1, cost_bbox=1, cost_giou=1, anchor_matching=True, num_organs=None):
+        super().__init__()
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs can't be 0"
+        self.cost_class, self.cost_bbox, self.cost_giou = cost_class, cost_bbox, cost_giou
+        self.anchor_matching, self.num_organs = anchor_matching, num_organs
+
+    @torch.no_grad()
+    def forward(self, outputs, tgt_boxes, tgt_valid, anchors):
+        logits = outputs["pred_logits"]
+        B, Nq, _ = logits.shape
+        O = self.num_organs
+        Q = Nq // O
+        boxes = anchors[None].expand(B, -1, -1) if self.anchor_matching else outputs["pred_boxes"]
+        boxes = boxes.reshape(B, O, Q, -1).float()
+        logits = logits.reshape(B, O, Q).float()
+        tgt = tgt_boxes[:, :, None, :]                                                       # [B, O, 1, 6]
+        cost_class = -logits.sigmoid()
+        cost_bbox = (boxes - tgt).abs().sum(-1)                                              # cdist(p=1), matcher.py:50
+        cost_giou = -paired_giou_3d(box_cxcyczwhd_to_xyzxyz(boxes.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(tgt))
+        cost = self.cost_bbox * cost_bbox + self.cost_class * cost_class + self.cost_giou * cost_giou
+        best = cost.argmin(-1)                                                               # topk(C, 1, largest=False), matcher.py:54
+        if Q == 1:                                                                           # matcher.py:60-62 (0-dim topk result)
+            soft = torch.ones_like(cost_giou)
+        else:
+            hi, lo = cost_giou.amax(-1, keepdim=True), cost_giou.amin(-1, keepdim=True)
+            soft = ((cost_giou - hi) / (lo - hi)).clamp(min=0)                               # matcher.py:59
+        soft = torch.where(tgt_valid[:, :, None], soft, torch.full_like(soft, -1.0))         # matcher.py:44-45
+        return best, soft
+
+    @staticmethod
+    def dense_matches(best, tgt_valid, Q):
+        """The reference's [B, organs, Q] 0/1 tensor (matcher.py:40,57)."""
+        return (F.one_hot(best, Q) * tgt_valid[:, :, None]).long()
+
+
+class SoftDiceLoss(nn.Module):
+    """criterion.py:127-166 (batch dice, softmax non-linearity, background dropped)."""
+
+    def __init__(self, smooth_nom=1e-5, smooth_denom=1e-5):
+        super().__init__()
+        self.smooth_nom, self.smooth_denom = smooth_nom, smooth_denom
+
+    def forward(self, inp, target):
+        p = inp.softmax(1)
+        onehot = torch.zeros_like(p).scatter_(1, target[:, None].long(), 1)
+        axes = [0] + list(range(2, p.dim()))
+        tp = (p * onehot).sum(axes)
+        fp = (p * (1 - onehot)).sum(axes)
+        fn = ((1 - p) * onehot).sum(axes)
+        dc = (2 * tp + self.smooth_nom) / (2 * tp + fp + fn + self.smooth_denom)
+        return 1 - dc[1:].mean()
+
+
+class TransoarCriterion(nn.Module):
+    """criterion.py:9-125.  ``forward(outputs, targets, seg_targets, anchors)`` -> the reference's loss dict."""
+
+    def __init__(self, num_classes, matcher, seg_proxy, seg_fg_bg):
+        super().__init__()
+        self.num_classes, self.matcher = num_classes, matcher
+        self._seg_proxy, self._seg_fg_bg = seg_proxy, seg_fg_bg
+        if seg_proxy:
+            self._dice_loss = SoftDiceLoss()
+
+    def loss_class(self, outputs, soft_labels):
+        """BCE-with-logits over the queries of the classes present in the sample (criterion.py:40-49)."""
+        logits = outputs["pred_logits"].flatten().float()
+        labels = soft_labels.flatten()
+        keep = (labels != -1).float()
+        per = F.binary_cross_entropy_with_logits(logits, labels.clamp(min=0), reduction="none")
+        return (per * keep).sum() / keep.sum()
+
+    def loss_bboxes(self, outputs, tgt_boxes, tgt_valid, best, num_boxes):
+        """L1 + GIoU of the matched query of every present class against its target (criterion.py:52-77)."""
+        B, Nq, _ = outputs["pred_boxes"].shape
+        O = self.num_classes
+        preds = outputs["pred_boxes"].reshape(B, O, Nq // O, -1).float()
+        matched = torch.gather(preds, 2, best[:, :, None, None].expand(-1, -1, 1, preds.shape[-1])).squeeze(2)     # [B, O, 6]
+        w = tgt_valid.float()
+        loss_bbox = ((matched - tgt_boxes).abs().sum(-1) * w).sum() / num_boxes
+        giou = paired_giou_3d(box_cxcyczwhd_to_xyzxyz(matched.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(tgt_boxes))
+        # classes absent from a sample have a zero target box (0/0 GIoU): mask them out before they can poison the sum
+        loss_giou = (torch.where(tgt_valid, 1 - giou, torch.zeros_like(giou))).sum() / num_boxes
+        return loss_bbox, loss_giou
+
+    def loss_segmentation(self, outputs, targets):
+        if self._seg_fg_bg:
+            targets = (targets > 0).to(targets.dtype)
+        targets = targets.squeeze(1).long()
+        return F.cross_entropy(outputs["pred_seg"], targets), self._dice_loss(outputs["pred_seg"], targets)
+
+    def forward(self, outputs, targets, seg_targets, anchors):
+        dev = outputs["pred_logits"].device
+        tgt_boxes, tgt_valid = targets if isinstance(targets, tuple) else dense_targets(targets, self.num_classes, dev)
+        num_boxes = tgt_valid.sum().clamp(min=1).float()
+        best, soft = self.matcher(outputs, tgt_boxes, tgt_valid, anchors)
+        loss_bbox, loss_giou = self.loss_bboxes(outputs, tgt_boxes, tgt_valid, best, num_boxes)
+        zero = torch.zeros((), device=dev)
+        losses = {"bbox": loss_bbox, "giou": loss_giou, "cls": self.loss_class(outputs, soft), "segce": zero, "segdice": zero}
+        if self._seg_proxy:
+            losses["segce"], losses["segdice"] = self.loss_segmentation(outputs, seg_targets)
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            best, soft = self.matcher(aux, tgt_boxes, tgt_valid, anchors)
+            # the reference evaluates these on `outputs`, not on `aux` (criterion.py:118-119); kept for loss parity
+            losses[f"bbox_{i}"], losses[f"giou_{i}"] = self.loss_bboxes(outputs, tgt_boxes, tgt_valid, best, num_boxes)
+            losses[f"cls_{i}"] = self.loss_class(outputs, soft)
+        return losses
+
+
+def total_loss(loss_dict, loss_coefs):
+    """trainer.py:71-74: sum of loss * coefficient, coefficient looked up by the part of the key before '_'."""
+    return sum(v * loss_coefs[k.split("_")[0]] for k, v in loss_dict.items())
+
+
+VISCERAL_LOSS_COEFS = {"cls": 2, "bbox": 5, "giou": 2, "segce": 2, "segdice": 2}      # config/attn_fpn_foc_dec_visceral.yaml:36-41
+
+
+def build_criterion(config):
+    """models/build.py:32-48."""
+    matcher = Matcher(cost_class=config["set_cost_class"], cost_bbox=config["set_cost_bbox"], cost_giou=config["set_cost_giou"],
+                      anchor_matching=config["anchor_matching"], num_organs=config["neck"]["num_organs"])
+    return TransoarCriterion(num_classes=config["num_classes"], matcher=matcher, seg_proxy=config["backbone"]["use_seg_proxy_loss"],
+                             seg_fg_bg=config["backbone"]["fg_bg"])

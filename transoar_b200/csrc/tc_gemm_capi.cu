@@ -1,0 +1,120 @@
+// tc_gemm_capi.cu -- C ABI of the TF32 tcgen05 GEMM (include/tc_gemm.h): tensor-map construction, tile-shape choice, launch.
+#include "tc_gemm_kernels.cuh"
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/msda3d.h"
+#include "../../include/tc_gemm.h"
+
+extern std::atomic<unsigned long long> g_msda3d_launches;
+
+namespace {
+
+using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled lives in libcuda; fetched through the runtime so the library has no link-time driver dependency.
+EncodeTiled encode_fn()
+{
+  static EncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor [outer, inner] (inner contiguous, `ld` elements between outer rows), box = 32 inner elements (128 bytes,
+// one swizzle row) x box_outer rows; the swizzle form is the one the tensor core expects for that operand layout (kernels.cuh).  Out-of-bounds parts of a box are zero-filled, which is what makes ragged M / N / R work.
+int make_map(CUtensorMap *map, const float *ptr, long long inner, long long outer, long long ld, int box_outer, bool mn_major)
+{
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)tcgemm::BK, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
+}
+
+int sm_count()
+{
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, float *D, const float *bias, const tcgemm::Problem &p)
+{
+  using C = tcgemm::Cfg<BN>;
+  auto kern = tcgemm::gemm_tf32_kernel<BN, A_MN, B_MN>;
+  static std::once_flag once;                                    // one flag per instantiation
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  const long long work = (long long)((p.M + tcgemm::BM - 1) / tcgemm::BM) * ((p.N + BN - 1) / BN) * p.splits;
+  const int grid = (int)(work < sm_count() ? work : sm_count());
+  kern<<<grid, tcgemm::kThreads, C::SMEM_BYTES, st>>>(ma, mb, D, bias, p);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+template <int BN>
+int dispatch(cudaStream_t st, bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, float *D, const float *bias,
+             const tcgemm::Problem &p)
+{
+  if (!a_mn && !b_mn) return launch<BN, false, false>(st, ma, mb, D, bias, p);
+  if (!a_mn && b_mn) return launch<BN, false, true>(st, ma, mb, D, bias, p);
+  if (a_mn && !b_mn) return launch<BN, true, false>(st, ma, mb, D, bias, p);
+  return launch<BN, true, true>(st, ma, mb, D, bias, p);
+}
+
+}  // namespace
+
+extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
+                            float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k)
+{
+  if (A == nullptr || B == nullptr || D == nullptr || M <= 0 || N <= 0 || R <= 0 || lda <= 0 || ldb <= 0 || ldd < N) return MSDA3D_EINVAL;
+  if (lda % 4 != 0 || ldb % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+      (reinterpret_cast<uintptr_t>(D) & 3))
+    return MSDA3D_EALIGN;
+  if (split_k < 0 || (split_k != 1 && !accumulate)) return MSDA3D_EINVAL;
+
+  const int BN = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  const int m_tiles = (M + tcgemm::BM - 1) / tcgemm::BM, n_tiles = (N + BN - 1) / BN, r_blocks = (R + tcgemm::BK - 1) / tcgemm::BK;
+  int splits = split_k;
+  if (splits == 0) {                                             // fill the machine: one work item per SM where the reduction allows
+    const long long tiles = (long long)m_tiles * n_tiles;
+    splits = (int)(tiles >= sm_count() ? 1 : sm_count() / tiles);
+  }
+  if (splits > r_blocks) splits = r_blocks;
+  tcgemm::Problem p;
+  p.M = M; p.N = N; p.R = R; p.ldd = ldd; p.relu = relu; p.atomic = accumulate ? 1 : 0;
+  p.rb_per_split = (r_blocks + splits - 1) / splits;
+  p.splits = (r_blocks + p.rb_per_split - 1) / p.rb_per_split;   // no empty split
+
+  CUtensorMap ma, mb;
+  int rc = a_mn_major ? make_map(&ma, A, M, R, lda, tcgemm::BK, true) : make_map(&ma, A, R, M, lda, tcgemm::BM, false);
+  if (rc != 0) return rc;
+  rc = b_mn_major ? make_map(&mb, B, N, R, ldb, tcgemm::BK, true) : make_map(&mb, B, R, N, ldb, BN, false);
+  if (rc != 0) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return BN == 256 ? dispatch<256>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p)
+                   : dispatch<128>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
+}
