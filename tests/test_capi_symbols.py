@@ -13,10 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     names = set()
-    for header in ("msda3d.h", "roi_attn.h", "instnorm.h"):
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names |= set(re.findall(r"\b((?:msda3d|roi_attn|instnorm)_[a-z0-9_]+)\s*\(", text))
+        names |= set(re.findall(r"\b((?:msda3d|roi_attn|instnorm|tc_gemm|stem_conv)_[a-z0-9_]+)\s*\(", text))
     return sorted(names)
 
 
@@ -56,6 +56,9 @@ def test_null_and_bad_dimension_arguments_are_rejected_before_any_launch():
     odd = ctypes.c_void_p(p.value + 2)
     assert lib.msda3d_forward(None, 0, odd, p, p, p, p, *dims, p) == -3
     assert lib.msda3d_forward_host(99, 0, p, p, p, p, p, *dims, p) == -4
+    assert lib.tc_gemm_tf32(None, None, 0, 4, p, 0, 4, p, 4, None, 4, 4, 4, 0, 0, 1) == -1         # null operand
+    assert lib.tc_gemm_tf32(None, p, 0, 6, p, 0, 4, p, 4, None, 4, 4, 4, 0, 0, 1) == -3            # lda not a multiple of 4 (TMA stride)
+    assert lib.tc_gemm_tf32(None, p, 0, 4, p, 0, 4, p, 4, None, 4, 4, 4, 0, 0, 3) == -1            # split-K without accumulate
     assert lib.msda3d_launch_count() == before
 
 

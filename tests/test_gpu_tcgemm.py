@@ -99,3 +99,67 @@ def test_rejects_cpu_and_misaligned():
     A = torch.randn(16, 6).cuda()     # lda = 6 is not a multiple of 4
     with pytest.raises(RuntimeError, match="aligned"):
         gemm(A, 0, 6, A, 0, 6, torch.empty(16, 16).cuda(), 16, 16, 6)
+
+
+class _tf32:
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+def _rel(a, b):
+    b = torch.as_tensor(b, device=a.device)
+    return float((a.detach() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_refine_block_runs_its_linears_on_tcgen05_under_tf32():
+    """Same reference fixture as tests/test_gpu_parity.py::test_refine_block_against_reference_block_fixture, with TF32 requested:
+    all Linear GEMMs (forward and both gradients) go through tc_gemm_tf32; tolerance is TF32's (1e-2 of the tensor's max)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from transoar_b200 import _lib
+    from transoar_b200.position_encoding import PositionEmbeddingSine3D
+    from transoar_b200.refine import DecoderDefAttnBlock
+    z = np.load(os.path.join(GOLDEN, "block_defattn.npz"))
+    blk = DecoderDefAttnBlock(d_model=48, nhead=6, num_layers=2, dim_feedforward=64, dropout=0.1,
+                              feature_levels=["P2", "P3", "P4"], n_points=2).cuda().eval()
+    blk.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    fmaps = [torch.from_numpy(z[f"fmap{i}"]).cuda().requires_grad_(True) for i in range(3)]
+    pe = PositionEmbeddingSine3D(channels=48)
+    n0 = _lib.lib().msda3d_launch_count()
+    with _tf32():
+        outs = blk(fmaps, [pe(f) for f in fmaps])
+        sum((o * torch.from_numpy(z[f"g{i}"]).cuda()).sum() for i, o in enumerate(outs)).backward()
+    torch.cuda.synchronize()
+    # per layer: 6 Linear forwards + 6 x 2 gradient GEMMs + msda forward + backward = 20 launches of this library
+    assert _lib.lib().msda3d_launch_count() - n0 == 2 * 20
+    for i in range(3):
+        assert _rel(outs[i], z[f"out{i}"]) < 1e-2
+        assert _rel(fmaps[i].grad, z[f"grad_fmap{i}"]) < 2e-2
+    for k, p in blk.named_parameters():
+        assert _rel(p.grad, z["pg." + k]) < 2e-2, k
+
+
+def test_strict_fp32_request_bypasses_the_tf32_kernel():
+    from transoar_b200 import _lib
+    from transoar_b200.linear import TCLinear
+    lin = TCLinear(64, 32).cuda()
+    x = torch.randn(10, 64, device="cuda")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        n0 = _lib.lib().msda3d_launch_count()
+        y = lin(x, relu=True)
+        assert _lib.lib().msda3d_launch_count() == n0
+        assert torch.allclose(y, torch.relu(torch.nn.functional.linear(x, lin.weight, lin.bias)))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    with _tf32():
+        n0 = _lib.lib().msda3d_launch_count()
+        y2 = lin(x, relu=True)
+        assert _lib.lib().msda3d_launch_count() == n0 + 1
+    assert float((y - y2).abs().max()) < 2e-2

@@ -22,6 +22,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
+from .linear import TCLinear
 
 _QPG = 32     # query rows per CTA in the kernel (roiattn::TQ)
 
@@ -130,11 +131,11 @@ class FocusedAttn(nn.Module):
             raise ValueError("FocusedAttn needs grid_shape=(X, Y, Z) of the key/value feature map")
         self.dim, self.num_heads, self.ret_weights = dim, num_heads, return_weights
         self.scale = qk_scale or (dim // num_heads) ** -0.5
-        self.q_proj = nn.Linear(dim, dim, bias=bool(qkv_bias))       # dead parameter, kept for checkpoint compatibility (D10)
-        self.k_proj = nn.Linear(dim, dim, bias=bool(qkv_bias))
-        self.v_proj = nn.Linear(dim, dim, bias=bool(qkv_bias))
+        self.q_proj = TCLinear(dim, dim, bias=bool(qkv_bias))       # dead parameter, kept for checkpoint compatibility (D10)
+        self.k_proj = TCLinear(dim, dim, bias=bool(qkv_bias))
+        self.v_proj = TCLinear(dim, dim, bias=bool(qkv_bias))
         self.attn_drop = nn.Dropout(attn_drop)
-        self.proj = nn.Linear(dim, dim)
+        self.proj = TCLinear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         self.pos_bias = None
         self.grid_shape = tuple(int(s) for s in grid_shape)
@@ -196,10 +197,11 @@ class FocusedDecoderLayer(nn.Module):
         self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
-        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear1 = TCLinear(d_model, d_ffn)
         self.activation = _activation(activation)
+        self._fuse_relu = activation == "relu"
         self.dropout3 = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.linear2 = TCLinear(d_ffn, d_model)
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = nn.LayerNorm(d_model)
 
@@ -211,7 +213,8 @@ class FocusedDecoderLayer(nn.Module):
         k = src if src_pos is None else src + src_pos
         ca, weights = self.cross_attn(q, k, src)
         tgt = self.norm1(tgt + self.dropout1(ca))
-        ffn = self.linear2(self.dropout3(self.activation(self.linear1(tgt))))
+        hidden = self.linear1(tgt, relu=True) if self._fuse_relu else self.activation(self.linear1(tgt))
+        ffn = self.linear2(self.dropout3(hidden))
         return self.norm3(tgt + self.dropout4(ffn)), weights
 
 

@@ -9,6 +9,7 @@ fp32 tensors, TF32 multiply, fp32 accumulate: what torch 1.10 (the reference's p
 import ctypes
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -74,9 +75,21 @@ def linear(x, weight, bias=None, relu=False):
     return LinearFunction.apply(x, weight, bias, relu)
 
 
+def tc_eligible(x, weight):
+    """The tcgen05 kernel multiplies in TF32, so it runs exactly where torch itself would use TF32 tensor cores for an fp32
+    Linear: CUDA fp32 tensors with ``torch.backends.cuda.matmul.allow_tf32`` on (the default of the reference's torch 1.10;
+    off by default in torch >= 1.12).  Feature counts must be multiples of 4 (TMA strides are multiples of 16 bytes)."""
+    return (x.is_cuda and torch.backends.cuda.matmul.allow_tf32 and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and not torch.is_autocast_enabled() and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0)
+
+
 class TCLinear(nn.Linear):
-    """nn.Linear whose forward / backward GEMMs run on the tcgen05 kernel (fp32 CUDA tensors with 4-aligned feature counts);
-    anything else raises -- there is no fallback."""
+    """``nn.Linear`` (same parameters, same state_dict) whose forward / gradient GEMMs run on the tcgen05 kernel whenever TF32
+    is the requested precision (see ``tc_eligible``); with strict fp32 requested, under autocast or for the 1- / 6-wide heads
+    it is the plain library GEMM, exactly as in the reference.  ``relu=True`` fuses the activation into the GEMM epilogue."""
 
     def forward(self, x, relu=False):
-        return linear(x, self.weight, self.bias, relu)
+        if tc_eligible(x, self.weight):
+            return linear(x, self.weight, self.bias, relu)
+        y = F.linear(x, self.weight, self.bias)
+        return F.relu(y) if relu else y

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..functions import MSDeformAttnFunction
+from ...linear import TCLinear
 
 
 def _power_of_two(n):
@@ -43,10 +44,11 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64                                                  # ms_deform_attn.py:48
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.use_cuda = use_cuda
-        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 3)
-        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.output_proj = nn.Linear(d_model, d_model)
+        # nn.Linear subclasses (same parameter names): TF32 tcgen05 GEMMs when TF32 is the requested matmul precision
+        self.sampling_offsets = TCLinear(d_model, n_heads * n_levels * n_points * 3)
+        self.attention_weights = TCLinear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = TCLinear(d_model, d_model)
+        self.output_proj = TCLinear(d_model, d_model)
         self._reset_parameters()
 
     def _reset_parameters(self):

@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .linear import TCLinear
 from .ops.modules import MSDeformAttn
 
 
@@ -29,10 +30,11 @@ class DefAttnLayer(nn.Module):
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, use_cuda)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
-        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear1 = TCLinear(d_model, d_ffn)
         self.activation = _activation(activation)
+        self._fuse_relu = activation == "relu"                                  # ReLU runs in the GEMM epilogue
         self.dropout2 = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.linear2 = TCLinear(d_ffn, d_model)
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
 
@@ -40,7 +42,8 @@ class DefAttnLayer(nn.Module):
         query = src if pos is None else src + pos
         attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
         src = self.norm1(src + self.dropout1(attn))
-        ffn = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        hidden = self.linear1(src, relu=True) if self._fuse_relu else self.activation(self.linear1(src))
+        ffn = self.linear2(self.dropout2(hidden))
         return self.norm2(src + self.dropout3(ffn))
 
 
