@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
 
-Metric      : CT volumes/s through the 3D multi-scale deformable attention hot path (forward + gradient).
-Workload    : `visceral_refine_fwd_bwd` = configs[1]: the deformable FPN refinement of the Focused-Decoder model at
-              synthetic 160x160x256 volumes, fp32 -- per training step a batch of 2 volumes (yaml batch_size 2) passes
-              `layers: 2` DefAttnLayers, i.e. 2 x (MSDeformAttn3D forward + backward) at N=2, S=Lq=117000,
-              L=4 levels (40,40,64)..(5,5,8), M=6 heads x C=64, P=4 points.  Sampling locations follow the model's own
-              pattern (dist "B": voxel-centre reference points + directional offsets + N(0,1) voxels of jitter).
-Step        : one pass of that hot path over one batch (4 kernel launches + 2 grad_value zero-fills).
-Multi-GPU   : one process per GPU, each rank owns its own batch (volume sharding, weak scaling), no data-path collective.
+Metric      : CT volumes/s of a full training step at 160x160x256 (BASELINE.json `metric`, part 1), with the 3D multi-scale
+              deformable attention kernels' achieved HBM GB/s as the `roofline` object (part 2).
+Workload    : `visceral_train_step` = configs[1]: the Focused-Decoder model (AttnFPN backbone + deformable FPN refinement +
+              Focused Decoder + heads, config/attn_fpn_foc_dec_visceral.yaml with use_decoder_attn / use_cuda on) on synthetic
+              160x160x256 volumes, fp32 storage with TF32 tensor-core multiplies (the reference's torch 1.10 default), batch 2
+              per GPU (yaml batch_size).  One step = forward + matcher + losses + backward + AdamW, nothing skipped.
+Step        : one pass of the hot path over one batch, through `transoar_b200.engine.TrainStep.step`.
+Multi-GPU   : one process per GPU, volumes sharded by rank (weak scaling); the only collective is DDP's NCCL gradient all-reduce.
 
-Keys beyond the base contract: `roofline` (dominant kernel vs the measured HBM peak), `cpu_baseline` (the reference's
-use_cuda=False route restated on host cores), `e2e` (same metric through the host-buffer C-ABI entry point, copies
-inside the timed region), `kernels` (per-launch CUDA-event times), `clocks`.
-`--impl reference` runs the CPU arm: the reference's CPU implementation of this path (restated in oracle/) on the host.
+`value`     : inputs (volumes, targets) resident in HBM before the timed region.
+`e2e`       : the same call with the volumes in pinned HOST memory (H2D copy inside the step) and the loss read back every step.
+`roofline`  : the dominant kernel of the step (msda3d backward) -- algorithmic bytes / CUDA-event time of its launches inside
+              the timed region, against the measured HBM peak.
+`msda3d_op` : the operator alone (forward + gradient of both refinement layers) incl. the reference's own CUDA op on the same
+              inputs; `tc_gemm`, `roi_attention`, `instnorm_relu`: the other hand-written kernels of the path.
+`cpu_baseline` / `--impl reference`: the reference's CPU route of the same training step (oracle/model_oracle.py) on the
+              host cores, on a bounded sample (a smaller volume, time scaled by the voxel ratio).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import statistics
@@ -33,12 +36,14 @@ METRIC = "ct_volumes_per_sec"
 UNIT = "volumes/s"
 LAYERS = 2            # config/attn_fpn_foc_dec_visceral.yaml:83  `layers: 2`
 BATCH = 2             # config/attn_fpn_foc_dec_visceral.yaml:25  `batch_size: 2`
+VOLUME = (160, 160, 256)
 GEOM = "visceral_refine"
 DIST = "B"
+CPU_SAMPLE_SHAPES = [(32, 32, 64), (64, 64, 128), (96, 96, 160), (128, 128, 192), (160, 160, 256)]   # all divisible by 32 (five stride-2 stages)
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Algorithmic bytes (SURVEY.md 8d / DESIGN.md): compulsory HBM traffic of one launch
+# Algorithmic bytes (SURVEY.md 8d / DESIGN.md): compulsory HBM traffic of one msda3d launch
 # ---------------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(N, S, M, C, L, Lq, P, ev=4, eg=4):
     T = N * Lq * M * L * P
@@ -77,8 +82,10 @@ def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            j = json.load(f)
+        return {"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j.get("bf16_tflops", 1590.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -132,42 +139,57 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's CPU implementation of the path (restated in oracle/), bounded sample
-# ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(sample_queries, seed=1234, threads=None):
-    """One fwd+bwd of the use_cuda=False route (oracle.gridsample_path == func.py:41-65) for one volume, first
-    `sample_queries` queries, value over the full S.  Returns seconds."""
-    import torch
-    from oracle import msda3d_oracle as O
+def workload_config():
     from transoar_b200 import synth
-    if threads:
-        torch.set_num_threads(threads)
     g = synth.GEOMETRIES[GEOM]
-    gq = synth.Geometry(g.name, g.shapes, g.heads, g.channels, g.points, queries=sample_queries if sample_queries < g.spatial_size else 0)
-    x = synth.make_inputs(gq, 1, DIST, seed=seed)
-    v, loc, aw = (x[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
-    t0 = time.perf_counter()
-    out = O.gridsample_path(v, list(g.shapes), loc, aw)
-    out.backward(x["grad_out"])
-    return time.perf_counter() - t0
+    return {"workload": "visceral_train_step", "volume": "x".join(map(str, VOLUME)), "batch_per_gpu": BATCH,
+            "step": "forward + matcher + losses (cls/bbox/giou, aux layers) + backward + AdamW; nothing skipped",
+            "precision": "fp32 tensors, TF32 tensor-core multiplies for convolutions and linears (torch 1.10 default of the reference)",
+            "refine": {"layers": LAYERS, "levels": [list(s) for s in g.shapes], "S": g.spatial_size, "heads": g.heads,
+                       "channels_per_head": g.channels, "points": g.points},
+            "decoder": {"queries": 540, "organs": 20, "layers": 3, "kv_tokens": 102400},
+            "l2": "the step touches > 20 GB per batch (activations of 629 MB each at full resolution): every tensor is far larger than the 126 MB L2; no explicit flush",
+            "parallelism": "volume-sharded DDP, NCCL gradient all-reduce only"}
 
 
-def cpu_arm_value(seconds, sample_queries):
-    """volumes/s a host running only this sample's rate would reach on the full step (BATCH volumes x LAYERS passes)."""
-    from transoar_b200 import synth
-    frac = min(1.0, sample_queries / synth.GEOMETRIES[GEOM].spatial_size)        # fraction of one volume-layer pass
-    return frac / (LAYERS * seconds)
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU route of the training step (oracle/model_oracle.py), bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step_times(shape, steps, warmup, threads):
+    import torch
+    from oracle.model_oracle import CpuTrainStep
+    from transoar_b200.engine import synthetic_targets, visceral_train_config
+    cfg = visceral_train_config()
+    ts = CpuTrainStep(cfg, shape, threads=threads)
+    x = torch.rand(1, 1, *shape, generator=torch.Generator().manual_seed(1))
+    tg = synthetic_targets(cfg, 1, 0, "cpu")
+    times = [ts.step(x, tg)[0] for _ in range(warmup + steps)]
+    return times[warmup:]
 
 
-def calibrate_cpu_sample(budget_s):
-    """Pick the number of queries so one fwd+bwd costs about `budget_s` seconds (probe with 4096 queries first)."""
-    from transoar_b200 import synth
-    S = synth.GEOMETRIES[GEOM].spatial_size
-    cpu_reference_pass(1024)
-    t = cpu_reference_pass(4096)
-    per_q = max(t / 4096, 1e-9)
-    return int(max(4096, min(S, budget_s / per_q)))
+def cpu_sample_shape(budget_s, threads):
+    """Largest sample volume whose step is expected to fit `budget_s` (probe the smallest, scale by voxels)."""
+    vox = lambda s: s[0] * s[1] * s[2]
+    t = cpu_step_times(CPU_SAMPLE_SHAPES[1], 1, 1, threads)[0]
+    per_voxel = t / vox(CPU_SAMPLE_SHAPES[1])
+    best = CPU_SAMPLE_SHAPES[0]
+    for s in CPU_SAMPLE_SHAPES:
+        if per_voxel * vox(s) <= budget_s:
+            best = s
+    return best
+
+
+def cpu_value(shape, sec):
+    """volumes/s at full size: one sample step covers vox(shape)/vox(VOLUME) of a volume."""
+    frac = shape[0] * shape[1] * shape[2] / (VOLUME[0] * VOLUME[1] * VOLUME[2])
+    return frac / sec
+
+
+def cpu_sample_text(shape, sec, steps):
+    frac = shape[0] * shape[1] * shape[2] / (VOLUME[0] * VOLUME[1] * VOLUME[2])
+    return (f"whole training step (fwd + criterion + bwd + AdamW) of the same model through the reference's use_cuda=False route "
+            f"(F.grid_sample, nn.InstanceNorm3d, dense masked attention; oracle/model_oracle.py) on one {shape[0]}x{shape[1]}x{shape[2]} volume "
+            f"= {frac:.4f} of a 160x160x256 volume's voxels: {sec:.2f} s per step (mean of {steps}); time scaled linearly by voxels")
 
 
 def run_reference_arm(args):
@@ -177,24 +199,17 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    total_budget = 150.0
-    per_step = total_budget / max(1, args.steps + args.warmup)
-    q = calibrate_cpu_sample(min(per_step, 20.0))
-    for _ in range(args.warmup):
-        cpu_reference_pass(q)
-    times = [cpu_reference_pass(q) for _ in range(args.steps)]
-    t = sum(times) / len(times)
-    value = cpu_arm_value(t, q)
-    from transoar_b200 import synth
-    S = synth.GEOMETRIES[GEOM].spatial_size
+    per_step = 150.0 / max(1, args.steps + args.warmup)
+    shape = cpu_sample_shape(per_step, cores)
+    times = cpu_step_times(shape, args.steps, args.warmup, cores)
+    sec = sum(times) / len(times)
+    value = cpu_value(shape, sec)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{q} of {S} queries of one volume, one layer, fwd+bwd via the restated use_cuda=False route "
-                                   f"(F.grid_sample, func.py:41-65); {t:.2f} s per sample; step time extrapolated linearly"},
+                         "sample": cpu_sample_text(shape, sec, len(times))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,18 +217,8 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config():
-    from transoar_b200 import synth
-    g = synth.GEOMETRIES[GEOM]
-    return {"workload": "visceral_refine_fwd_bwd", "volume": "160x160x256", "batch_per_gpu": BATCH, "layers": LAYERS,
-            "levels": [list(s) for s in g.shapes], "S": g.spatial_size, "Lq": g.num_query, "heads": g.heads,
-            "channels_per_head": g.channels, "points": g.points, "loc_dist": "B (model-like: voxel-centre refs + directional offsets + N(0,1))",
-            "l2": "per-layer inputs (2.2 GB) exceed the 126 MB L2 and alternate between two buffer sets; no explicit flush",
-            "parallelism": "volume-sharded, no data-path collective"}
-
-
 # ---------------------------------------------------------------------------------------------------------------
-# Extras: the other hand-written kernels of the path and the whole model (reported beside the headline, never in it)
+# Extras: the hand-written kernels of the path one by one (reported beside the headline, never in it)
 # ---------------------------------------------------------------------------------------------------------------
 def _event_ms(fn, warm=2, reps=5):
     import torch
@@ -229,19 +234,99 @@ def _event_ms(fn, warm=2, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-def measure_extras(dev, rank, world, dist):
+def measure_msda_op(dev, rank, world, dist_name, with_ref):
+    """The operator alone on the refinement workload (N=2, S=Lq=117000, 4 levels, 6 heads x 64, 4 points): per-launch times, HBM
+    fractions, and the reference's own CUDA kernels (oracle/_ref) on the same inputs."""
+    import torch
+    from transoar_b200 import MultiScaleDeformableAttention as MSDA
+    from transoar_b200 import synth
+    g = synth.GEOMETRIES[GEOM]
+    N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
+    layers = [synth.make_inputs(g, N, dist_name, seed=1234 + 7919 * volume_ids(0, rank, world)[0] + li, device=dev) for li in range(LAYERS)]
+    ev = []
+
+    def step(record):
+        for x in layers:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], 64)
+            e[1].record()
+            MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], x["grad_out"], 64)
+            e[2].record()
+            if record:
+                ev.append(e)
+
+    for _ in range(3):
+        step(False)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    t0.record()
+    for _ in range(reps):
+        step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / len(ev)
+    bf, bb = algorithmic_bytes(N, S, M, C, L, Lq, P)
+    peak = load_peaks()["hbm_gbs"]
+    out = {"what": f"operator alone: {LAYERS} layers x (forward + gradient), N={N}, S=Lq={S}, L={L}, M={M}, C={C}, P={P}, dist {dist_name}",
+           "volumes_per_s": BATCH * reps / (t0.elapsed_time(t1) / 1e3), "ms_per_step": t0.elapsed_time(t1) / reps,
+           "fwd_ms": fwd, "bwd_ms": bwd, "fwd_gbs": bf / fwd / 1e6, "bwd_gbs": bb / bwd / 1e6,
+           "fwd_frac_of_hbm_peak": bf / fwd / 1e6 / peak, "bwd_frac_of_hbm_peak": bb / bwd / 1e6 / peak,
+           "algorithmic_bytes": {"fwd": bf, "bwd": bb}}
+    if with_ref:
+        from oracle import msda3d_oracle as O
+        if O.refcuda_available():
+            x = layers[0]
+            zeros = (torch.zeros_like(x["value"]), torch.zeros_like(x["loc"]), torch.zeros_like(x["aw"]))
+            rf = _event_ms(lambda: O.refcuda_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"]), 2, 3)
+
+            def ref_b():
+                for z in zeros:
+                    z.zero_()
+                O.refcuda_backward(x["grad_out"], x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], out=zeros)
+
+            rb = _event_ms(ref_b, 1, 3)
+            out["ref_cuda_op"] = {"what": "the reference's own CUDA kernels (oracle/_ref, compiled from /root/reference for sm_100a), same inputs",
+                                  "fwd_ms": rf, "bwd_ms": rb, "volumes_per_s": BATCH / (LAYERS * (rf + rb) * 1e-3),
+                                  "speedup_fwd": rf / fwd, "speedup_bwd": rb / bwd}
+    return out
+
+
+def measure_kernels(dev, rank):
     import torch
     import torch.nn.functional as F
     from transoar_b200 import focused
     from transoar_b200.configs import visceral_config
     from transoar_b200.instnorm import instance_norm_relu
-    from transoar_b200.transoarnet import TransoarNet
-    peak, _ = load_peaks()
+    from transoar_b200.linear import gemm
+    peaks = load_peaks()
     out = {}
     gen = torch.Generator().manual_seed(7 + rank)
     cfg = visceral_config()
 
-    # (a9) RoI-restricted cross-attention of one Focused-Decoder layer, B = 2, 540 queries, P2 grid 40x40x64, 8 heads x 48
+    # dense contractions: the FFN / projection GEMMs of one refinement layer at 2 x 117000 tokens (TF32 tcgen05 kernel vs cuBLAS TF32)
+    T = BATCH * 117000
+    tf32_peak = peaks["bf16_tflops"] / 2          # TF32 dense is half the bf16 rate on this part (1.1 vs 2.25 PFLOP/s nominal)
+    rows = []
+    for K, N in ((384, 384), (384, 1024), (1024, 384)):
+        x = torch.randn(T, K, device=dev)
+        w = torch.randn(N, K, device=dev) / K ** 0.5
+        b = torch.randn(N, device=dev)
+        dy = torch.randn(T, N, device=dev)
+        y, dx, dw = torch.empty(T, N, device=dev), torch.empty(T, K, device=dev), torch.zeros(N, K, device=dev)
+        fl = 2.0 * T * K * N / 1e12
+        for name, ours, lib in (("fwd", lambda: gemm(x, 0, K, w, 0, K, y, T, N, K, bias=b), lambda: torch.addmm(b, x, w.t(), out=y)),
+                                ("dgrad", lambda: gemm(dy, 0, N, w, 1, K, dx, T, K, N), lambda: torch.mm(dy, w, out=dx)),
+                                ("wgrad", lambda: gemm(dy, 1, N, x, 1, K, dw, N, K, T, accumulate=True, split_k=0), lambda: torch.mm(dy.t(), x, out=dw))):
+            a, c = _event_ms(ours, 2, 5), _event_ms(lib, 2, 5)
+            rows.append({"gemm": f"{name} tokens={T} in={K} out={N}", "ms": a, "tflops": fl / a * 1e3, "frac_of_tf32_peak": fl / a * 1e3 / tf32_peak,
+                         "cublas_tf32_ms": c})
+        del x, w, dy, y, dx, dw
+    out["tc_gemm"] = {"bound": "tensor", "peak_tflops": tf32_peak, "peak_source": peaks["source"] + ", bf16_tflops / 2 for TF32", "cases": rows}
+
+    # RoI-restricted cross-attention of one Focused-Decoder layer, B = 2, 540 queries, P2 grid 40x40x64, 8 heads x 48
     grid = (40, 40, 64)
     boxes = focused.boxes_from_bbox_props(cfg["bbox_properties"], 540, grid)
     groups = focused.groups_from_boxes(boxes).to(dev)
@@ -262,7 +347,7 @@ def measure_extras(dev, rank, world, dist):
                             "dense_score_tensor_avoided_gb": BATCH * 8 * 540 * 102400 * 4 / 1e9}
     del q, k, v, g
 
-    # (a7) fused InstanceNorm3d + ReLU on the first encoder activation (B x 24 x 160 x 160 x 256 fp32)
+    # fused InstanceNorm3d + ReLU on the first encoder activation (B x 24 x 160 x 160 x 256 fp32)
     x = torch.randn(BATCH, 24, 160, 160, 256, device=dev, requires_grad=True)
     w = torch.ones(24, device=dev, requires_grad=True)
     b = torch.zeros(24, device=dev, requires_grad=True)
@@ -281,61 +366,11 @@ def measure_extras(dev, rank, world, dist):
     in_fbm, aten_fbm = _event_ms(in_fb), _event_ms(aten_fb, 1, 2)
     nbytes = x.numel() * 4
     out["instnorm_relu"] = {"fwd_ms": in_f, "fwd_bwd_ms": in_fbm, "aten_cudnn_fwd_bwd_ms": aten_fbm,
-                            "fwd_gbs": 3 * nbytes / in_f / 1e6, "fwd_frac_of_hbm_peak": 3 * nbytes / in_f / 1e6 / peak,
-                            "fwd_bwd_gbs": 8 * nbytes / in_fbm / 1e6, "fwd_bwd_frac_of_hbm_peak": 8 * nbytes / in_fbm / 1e6 / peak,
+                            "fwd_gbs": 3 * nbytes / in_f / 1e6, "fwd_frac_of_hbm_peak": 3 * nbytes / in_f / 1e6 / peaks["hbm_gbs"],
+                            "fwd_bwd_gbs": 8 * nbytes / in_fbm / 1e6, "fwd_bwd_frac_of_hbm_peak": 8 * nbytes / in_fbm / 1e6 / peaks["hbm_gbs"],
                             "bytes_model": "fwd: 2 reads + 1 write of the activation; bwd: 4 reads + 1 write"}
     del x, dy
     torch.cuda.empty_cache()
-
-    # whole model: TransoarNet mirror (AttnFPN + deformable refine + Focused Decoder + heads), VISCERAL config, fwd + surrogate loss +
-    # bwd + AdamW; convolutions / linears are cuDNN / cuBLAS calls, the rest runs on this repo's kernels.  DDP over ranks.
-    torch.backends.cuda.matmul.allow_tf32 = True      # what the reference's pinned torch 1.10 does by default
-    torch.manual_seed(0)
-    net = TransoarNet(cfg).to(dev).train()
-    for name, p in net.named_parameters():
-        if ".q_proj." in name:
-            p.requires_grad_(False)                    # dead parameters: no gradient in the reference either
-    model = net
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(net, device_ids=[dev.index], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4)
-    vol_in = torch.rand(BATCH, 1, 160, 160, 256, device=dev)
-    tgt = torch.rand(BATCH, 540, 6, device=dev)
-
-    def train_step():
-        opt.zero_grad(set_to_none=True)
-        o = model(vol_in)
-        loss = F.l1_loss(o["pred_boxes"], tgt) + F.binary_cross_entropy_with_logits(o["pred_logits"], torch.zeros_like(o["pred_logits"]))
-        for a in o["aux_outputs"]:
-            loss = loss + F.l1_loss(a["pred_boxes"], tgt)
-        loss.backward()
-        opt.step()
-
-    for _ in range(3):
-        train_step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        train_step()
-    e1.record()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / reps
-    out["whole_model"] = {"volumes_per_s": world * BATCH / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": BATCH, "n_gpus": world,
-                          "params": sum(p.numel() for p in net.parameters()),
-                          "what": "TransoarNet mirror, visceral yaml with use_decoder_attn/use_cuda on, fp32 (TF32 matmul/conv as torch 1.10), "
-                                  "fwd + surrogate L1/BCE loss (criterion + matcher are out of scope) + bwd + AdamW"
-                                  + ("; DDP, NCCL gradient all-reduce" if world > 1 else ""),
-                          "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
     return out
 
 
@@ -350,8 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the RoI-attention / InstanceNorm / whole-model extras")
-    ap.add_argument("--dist", default=DIST, choices=["A", "B"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (operator alone, GEMM, RoI attention, InstanceNorm)")
+    ap.add_argument("--dist", default=DIST, choices=["A", "B"], help="sampling-location distribution of the operator-alone extra")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -360,6 +395,7 @@ def main():
     import torch.distributed as dist
     from transoar_b200 import MultiScaleDeformableAttention as MSDA
     from transoar_b200 import _lib, synth
+    from transoar_b200.engine import TrainStep, synthetic_targets, visceral_train_config
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: transoar_b200 has no CPU path")
@@ -373,160 +409,122 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
-    g = synth.GEOMETRIES[GEOM]
-    N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
-    # one buffer set per layer; every rank has its own volumes (seed depends on rank)
-    layers = [synth.make_inputs(g, N, args.dist, seed=1234 + 7919 * volume_ids(0, rank, world)[0] + li, device=dev) for li in range(LAYERS)]
-
-    def step(record=None):
-        for x in layers:
-            if record is not None:
-                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
-            out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], 64)
-            if record is not None:
-                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
-            grads = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], x["grad_out"], 64)
-            if record is not None:
-                record.append(torch.cuda.Event(enable_timing=True)); record[-1].record()
-        return out, grads
-
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    fence()
-    launches0 = lib.msda3d_launch_count()
-    ev = []
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        fence()
-        start.record()
-        for _ in range(args.steps):
-            step(ev)
-        stop.record()
-        fence()
-    launches = lib.msda3d_launch_count() - launches0
-    def reduce_max(ms):
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- the headline: whole training step, inputs resident on the device
+    cfg = visceral_train_config()
+    torch.manual_seed(0)                                   # identical initial weights on every rank (DDP also broadcasts rank 0's)
+    ts = TrainStep(cfg, dev, world=world)
+    gen = torch.Generator().manual_seed(100 + volume_ids(0, rank, world)[0])
+    n_sets = 2                                             # alternate between two resident batches
+    vols_host = [torch.rand(BATCH, 1, *VOLUME, generator=gen).pin_memory() for _ in range(n_sets)]
+    vols_dev = [v.to(dev) for v in vols_host]
+    targets = [synthetic_targets(cfg, BATCH, 1000 * rank + i, dev) for i in range(n_sets)]
+    warm = max(3, args.warmup)
+    for i in range(warm):
+        ts.step(vols_dev[i % n_sets], targets[i % n_sets])
+    fence()
+    ev_log = []
+    MSDA.set_event_log(ev_log)
+    launches0 = lib.msda3d_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        fence()
+        start.record()
+        for i in range(args.steps):
+            loss = ts.step(vols_dev[i % n_sets], targets[i % n_sets])
+        stop.record()
+        fence()
+    launches = lib.msda3d_launch_count() - launches0
+    MSDA.set_event_log(None)
     value, ms_total = aggregate_throughput(start.elapsed_time(stop), args.steps, world, all_reduce_max=reduce_max)
     ms_step = ms_total / args.steps
+    final_loss = float(loss.item())
 
-    # per-launch times (events sit between launches on the launching stream): [fwd, bwd(+zero-fill)] per layer
-    fwd_ms, bwd_ms = [], []
-    for i in range(0, len(ev), 3):
-        fwd_ms.append(ev[i].elapsed_time(ev[i + 1]))
-        bwd_ms.append(ev[i + 1].elapsed_time(ev[i + 2]))
-    fwd_avg, bwd_avg = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    # per-launch times of the msda3d kernels inside the timed region (events on the launching stream)
+    fwd_ms = [a.elapsed_time(b) for k, a, b in ev_log if k == "fwd"]
+    bwd_ms = [a.elapsed_time(b) for k, a, b in ev_log if k == "bwd"]
+    g = synth.GEOMETRIES[GEOM]
+    N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
     bf, bb = algorithmic_bytes(N, S, M, C, L, Lq, P)
-    peak, peak_src = load_peaks()
-    dom = "backward" if bwd_avg >= fwd_avg else "forward"
-    dom_bytes, dom_ms = (bb, bwd_avg) if dom == "backward" else (bf, fwd_avg)
-    roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_vec_kernel<float,16,1,3> + the cudaMemsetAsync zero-fill of grad_value" if dom == "backward"
-                else "msda3d forward: fwd_vec_kernel<float,16,1,4>",
-                "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": load_ncu_traffic(dom), "peak_source": peak_src,
-                "algorithmic_bytes": dom_bytes,
-                "forward": {"ms": fwd_avg, "bytes": bf, "gbs": bf / (fwd_avg * 1e-3) / 1e9, "frac": bf / (fwd_avg * 1e-3) / 1e9 / peak},
-                "backward": {"ms": bwd_avg, "bytes": bb, "gbs": bb / (bwd_avg * 1e-3) / 1e9, "frac": bb / (bwd_avg * 1e-3) / 1e9 / peak},
-                "note": "gather path: 8 corner reads per sample go through L1/L2, requested bytes = "
-                        f"{8 * N * Lq * M * L * P * C * 4 / 1e9:.1f} GB per launch vs {bf / 1e9:.2f} GB compulsory; see DESIGN.md"}
+    peaks = load_peaks()
+    peak = peaks["hbm_gbs"]
+    fwd_avg, bwd_avg = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_vec_kernel<float,16,1,3> + the cudaMemsetAsync zero-fill of grad_value "
+                                          f"({LAYERS} launches per step, the largest single kernel of the step)",
+                "achieved": bb / bwd_avg / 1e6, "peak": peak, "unit": "GB/s", "frac": bb / bwd_avg / 1e6 / peak,
+                "traffic": load_ncu_traffic("backward"), "peak_source": peaks["source"], "algorithmic_bytes": bb,
+                "launches_timed": len(bwd_ms), "share_of_step": LAYERS * bwd_avg / ms_step,
+                "forward": {"ms": fwd_avg, "bytes": bf, "gbs": bf / fwd_avg / 1e6, "frac": bf / fwd_avg / 1e6 / peak,
+                            "traffic": load_ncu_traffic("forward"), "share_of_step": LAYERS * fwd_avg / ms_step},
+                "backward": {"ms": bwd_avg, "bytes": bb, "gbs": bb / bwd_avg / 1e6, "frac": bb / bwd_avg / 1e6 / peak},
+                "note": "gather / scatter path: 8 corner reads (and 8 reductions) per sample go through L1/L2, requested bytes = "
+                        f"{8 * N * Lq * M * L * P * C * 4 / 1e9:.1f} GB per launch vs {bf / 1e9:.2f} GB compulsory; the binding resources are the "
+                        "L1 data pipe (forward) and the L2 atomic units (backward), not HBM -- see DESIGN.md"}
 
-    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)
+    # ---- end to end: same call, volumes in pinned host memory (H2D inside the step), loss read back every step
     e2e = None
     if not args.no_e2e:
-        host = [{k: v.cpu().pin_memory() for k, v in x.items()} for x in layers]
-        res = [{"out": torch.empty(N, Lq, M * C).pin_memory(), "gv": torch.empty(N, S, M, C).pin_memory(),
-                "gl": torch.empty(N, Lq, M, L, P, 3).pin_memory(), "ga": torch.empty(N, Lq, M, L, P).pin_memory()} for _ in layers]
-        p = lambda t_: ctypes.c_void_p(t_.data_ptr())
-
-        def e2e_step():
-            for h, r in zip(host, res):
-                rc = lib.msda3d_forward_backward_host(local, _lib.F32, p(h["grad_out"]), p(h["value"]), p(h["shapes"]), p(h["starts"]),
-                                                      p(h["loc"]), p(h["aw"]), N, S, M, C, L, Lq, P, p(r["out"]), p(r["gv"]), p(r["gl"]), p(r["ga"]))
-                _lib.check(rc, "msda3d_forward_backward_host")
-
-        e2e_steps = max(3, min(args.steps, 8))
-        e2e_step(); e2e_step()
+        e2e_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            float(ts.step(vols_host[i % n_sets], targets[i % n_sets]).item())
         fence()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for i in range(e2e_steps):
+            float(ts.step(vols_host[i % n_sets], targets[i % n_sets]).item())
         fence()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = LAYERS * sum(host[0][k].numel() * host[0][k].element_size() for k in ("value", "loc", "aw", "grad_out", "shapes", "starts"))
-        d2h = LAYERS * sum(v.numel() * v.element_size() for v in res[0].values())
-        e2e = {"value": world * BATCH * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "ms_per_step": 1e3 * float(tt.item()) / e2e_steps,
-               "api": "msda3d_forward_backward_host (include/msda3d.h), pinned host tensors, synchronous return"}
-        lib.msda3d_host_release()
-        del host, res
+        dt = reduce_max(time.perf_counter() - t0)
+        e2e = {"value": world * BATCH * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": vols_host[0].numel() * 4, "d2h_bytes_per_step": 4,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "transoar_b200.engine.TrainStep.step(volumes_in_pinned_host_memory, targets) -> loss; float(loss) on the host every step"}
+    params = sum(p.numel() for p in ts.net.parameters())
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    del ts, vols_dev, vols_host
+    torch.cuda.empty_cache()
 
-    # ---- baselines (rank 0, single-GPU runs only): reference CPU route + the reference's own compiled CUDA op
-    cpu_baseline, ref_cuda = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import msda3d_oracle as O
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        q = calibrate_cpu_sample(15.0)
-        tsec = cpu_reference_pass(q)
-        cpu_baseline = {"value": cpu_arm_value(tsec, q), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{q} of {S} queries of one volume, one layer, fwd+bwd via the restated use_cuda=False route "
-                                  f"(F.grid_sample, func.py:41-65): {tsec:.2f} s; step time extrapolated linearly"}
-        if O.refcuda_available():
-            x = layers[0]
-            for _ in range(2):
-                O.refcuda_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"])
-            zeros = (torch.zeros_like(x["value"]), torch.zeros_like(x["loc"]), torch.zeros_like(x["aw"]))
-            O.refcuda_backward(x["grad_out"], x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], out=zeros)
-            torch.cuda.synchronize()
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            reps = 3
-            e[0].record()
-            for _ in range(reps):
-                O.refcuda_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"])
-            e[1].record()
-            for _ in range(reps):
-                for z in zeros:
-                    z.zero_()
-                O.refcuda_backward(x["grad_out"], x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], out=zeros)
-            e[2].record()
-            torch.cuda.synchronize()
-            rf, rb = e[0].elapsed_time(e[1]) / reps, e[1].elapsed_time(e[2]) / reps
-            ref_cuda = {"what": "the reference's own CUDA kernels (oracle/_ref, compiled from /root/reference for sm_100a) on layer-0 inputs, N=2",
-                        "fwd_ms": rf, "bwd_ms": rb, "value": BATCH / (LAYERS * (rf + rb) * 1e-3), "unit": UNIT,
-                        "speedup_fwd": rf / fwd_avg, "speedup_bwd": rb / bwd_avg}
-
-    # ---- the other kernels of the path and the whole model, as extra objects (not in `value`)
+    # ---- the kernels of the path one by one
     extras = {}
     if not args.no_extras:
-        for x in layers:
-            x.clear()
-        layers.clear()
-        torch.cuda.empty_cache()
         try:
-            extras = measure_extras(dev, rank, world, dist if world > 1 else None)
+            extras["msda3d_op"] = measure_msda_op(dev, rank, world, args.dist, with_ref=(rank == 0 and world == 1))
+            torch.cuda.empty_cache()
+            if rank == 0:
+                extras.update(measure_kernels(dev, rank))
         except Exception as exc:            # never lose the headline line because an extra failed
-            extras = {"extras_error": f"{type(exc).__name__}: {exc}"[:300]}
+            extras["extras_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    if world > 1:
+        dist.barrier()
+
+    # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU route of the same step, bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        shape = cpu_sample_shape(12.0, cores)
+        times = cpu_step_times(shape, 2, 1, cores)
+        sec = sum(times) / len(times)
+        cpu_baseline = {"value": cpu_value(shape, sec), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": cpu_sample_text(shape, sec, len(times))}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(workload_config(), loc_dist=args.dist),
+            "data": "synthetic", "config": workload_config(),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "kernels": {"fwd_ms": fwd_avg, "bwd_ms": bwd_avg, "fwd_ms_min": min(fwd_ms), "bwd_ms_min": min(bwd_ms),
-                        "share_fwd": fwd_avg / (fwd_avg + bwd_avg), "share_bwd": bwd_avg / (fwd_avg + bwd_avg)},
-            "ref_cuda_op": ref_cuda, "clocks": clocks.summary(), **extras,
+            "kernels": {"msda3d_fwd_ms": fwd_avg, "msda3d_bwd_ms": bwd_avg, "msda3d_fwd_ms_min": min(fwd_ms), "msda3d_bwd_ms_min": min(bwd_ms),
+                        "launches_of_this_library_per_step": launches / args.steps},
+            "model": {"params": params, "peak_mem_gib": peak_mem, "final_loss": final_loss},
+            "clocks": clocks.summary(), **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -67,6 +67,21 @@ def test_algorithmic_bytes_match_survey_8d():
 
 
 def test_cpu_arm_extrapolation():
-    # a full volume-layer pass (all S queries) taking 2 s -> a step of 2 volumes x 2 layers takes 8 s -> 0.25 volumes/s
-    assert bench.cpu_arm_value(2.0, 117000) == pytest.approx(0.25)
-    assert bench.cpu_arm_value(1.0, 58500) == pytest.approx(0.25)
+    # a whole step on a full-size volume taking 40 s -> 0.025 volumes/s; a 64x64x128 sample (0.08 of the voxels) taking 4 s -> 0.02
+    assert bench.cpu_value((160, 160, 256), 40.0) == pytest.approx(0.025)
+    assert bench.cpu_value((64, 64, 128), 4.0) == pytest.approx(0.02)
+    assert all(d % 32 == 0 for s in bench.CPU_SAMPLE_SHAPES for d in s)      # five stride-2 stages
+
+
+def test_cpu_reference_route_of_the_train_step_runs_and_learns():
+    """oracle/model_oracle.py (the CPU arm of bench.py): two steps on the smallest sample volume, loss finite and decreasing."""
+    times = []
+    import torch
+    from oracle.model_oracle import CpuTrainStep
+    from transoar_b200.engine import synthetic_targets, visceral_train_config
+    cfg = visceral_train_config()
+    ts = CpuTrainStep(cfg, (32, 32, 64))
+    x = torch.rand(1, 1, 32, 32, 64, generator=torch.Generator().manual_seed(1))
+    tg = synthetic_targets(cfg, 1, 0, "cpu")
+    losses = [ts.step(x, tg)[1] for _ in range(2)]
+    assert all(l == l and l < 1e3 for l in losses) and losses[1] < losses[0]

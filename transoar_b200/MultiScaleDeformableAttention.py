@@ -20,6 +20,33 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
 
+# Optional per-launch timing (bench.py): when a list is installed, each forward / backward appends
+# (kind, start_event, stop_event) recorded on the launching stream.  None (the default) costs nothing.
+_EVENT_LOG = None
+
+
+def set_event_log(log):
+    """Install (or with None remove) the list that receives ("fwd"|"bwd", start, stop) CUDA-event triples per launch."""
+    global _EVENT_LOG
+    _EVENT_LOG = log
+
+
+class _timed:
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        if _EVENT_LOG is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _EVENT_LOG is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _EVENT_LOG.append((self.kind, self.e0, e1))
+
+
 def _p(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
@@ -67,7 +94,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         sampling_loc, attn_weight = sampling_loc.to(aux), attn_weight.to(aux)
     N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_loc)
     out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _timed("fwd"):
         rc = _lib.lib().msda3d_forward(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(value), _p(spatial_shapes),
             _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P, _p(out))
@@ -89,7 +116,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty(value.shape, dtype=aux, device=value.device)       # zero-filled by the library
     grad_loc = torch.empty_like(sampling_loc)
     grad_aw = torch.empty_like(attn_weight)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _timed("bwd"):
         rc = _lib.lib().msda3d_backward(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(grad_output), _p(value), _p(spatial_shapes),
             _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P,

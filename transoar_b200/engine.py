@@ -1,0 +1,84 @@
+"""One training step of the Focused-Decoder model on one GPU (or one DDP rank) -- the public call of this package.
+
+Mirrors what ``scripts/train.py:38-63`` builds and what ``Trainer._train_one_epoch`` (transoar/trainer.py:50-87) does per
+batch: model forward -> criterion (matcher + losses) -> weighted total loss -> backward -> AdamW step, with the reference's two
+parameter groups (backbone at ``lr_backbone``, everything else at ``lr``).  Differences, all in DESIGN.md: fp32 without the
+trainer's fp16 autocast (the reference's own CUDA op cannot run under it); TF32 tensor-core multiplies requested
+explicitly (torch 1.10, the reference's pin, has them on by default); the three dead ``q_proj`` parameters are frozen so DDP
+needs no ``find_unused_parameters``; no host synchronisation inside the step (the criterion stays on the device).
+
+    ts = TrainStep(visceral_train_config(), device)
+    loss = ts.step(volumes, targets)          # volumes: [B,1,160,160,256] on the host (pinned) or on the device
+
+Multi-GPU: one process per GPU, ``world > 1`` wraps the model in DistributedDataParallel (NCCL gradient all-reduce overlapped
+with the backward); volumes are sharded by rank, nothing else crosses GPUs."""
+import copy
+
+import torch
+
+from .configs import visceral_config
+from .criterion import VISCERAL_LOSS_COEFS, build_criterion, dense_targets, total_loss
+from .transoarnet import TransoarNet
+
+
+def visceral_train_config(seed=0):
+    """config/attn_fpn_foc_dec_visceral.yaml: model part from ``configs.visceral_config`` + the training keys (:11-41)."""
+    cfg = visceral_config(seed)
+    cfg.update(lr=2e-4, lr_backbone=2e-5, weight_decay=1e-4, clip_max_norm=-1, batch_size=2, anchor_matching=True,
+               set_cost_class=1, set_cost_bbox=0, set_cost_giou=0, loss_coefs=copy.deepcopy(VISCERAL_LOSS_COEFS), num_classes=20)
+    return cfg
+
+
+def synthetic_targets(config, batch, seed, device):
+    """One box per organ = the atlas median jittered by a few percent, labels 1..num_organs; dense form."""
+    g = torch.Generator().manual_seed(seed)
+    med = torch.tensor([p["median"] for p in config["bbox_properties"].values()], dtype=torch.float32)
+    targets = []
+    for _ in range(batch):
+        boxes = (med + (torch.rand(med.shape, generator=g) - 0.5) * 0.04).clamp(0.01, 0.99)
+        targets.append({"boxes": boxes, "labels": torch.arange(1, med.shape[0] + 1)})
+    return dense_targets(targets, med.shape[0], device)
+
+
+class TrainStep:
+    def __init__(self, config, device, world=1, tf32=True):
+        self.config, self.device = config, torch.device(device)
+        if tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        self.net = TransoarNet(config).to(self.device).train()
+        for name, p in self.net.named_parameters():
+            if ".q_proj." in name:
+                p.requires_grad_(False)
+        self.model = self.net
+        if world > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            self.model = DDP(self.net, device_ids=[self.device.index], gradient_as_bucket_view=True, static_graph=True)
+        self.criterion = build_criterion(config).to(self.device)
+        named = [(n, p) for n, p in self.net.named_parameters() if p.requires_grad]
+        groups = [{"params": [p for n, p in named if "_backbone" in n]},
+                  {"params": [p for n, p in named if "_backbone" not in n], "lr": float(config["lr"])}]
+        self.optim = torch.optim.AdamW(groups, lr=float(config["lr_backbone"]), weight_decay=float(config["weight_decay"]))
+        self._staging = None
+
+    def to_device(self, volumes):
+        """Host volumes (ideally pinned) -> a reused device buffer, asynchronously on the current stream."""
+        if volumes.is_cuda:
+            return volumes
+        if self._staging is None or self._staging.shape != volumes.shape:
+            self._staging = torch.empty(volumes.shape, dtype=torch.float32, device=self.device)
+        self._staging.copy_(volumes, non_blocking=True)
+        return self._staging
+
+    def step(self, volumes, targets, seg_targets=None):
+        """targets: the reference's list of {'boxes','labels'} dicts or the dense (boxes [B,O,6], valid [B,O]) pair.  Returns the total loss (device scalar)."""
+        x = self.to_device(volumes)
+        self.optim.zero_grad(set_to_none=True)
+        out = self.model(x)
+        losses = self.criterion(out, targets, seg_targets, self.net._anchors)
+        loss = total_loss(losses, self.config["loss_coefs"])
+        loss.backward()
+        if self.config.get("clip_max_norm", -1) > 0:
+            torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.config["clip_max_norm"])
+        self.optim.step()
+        return loss.detach()
