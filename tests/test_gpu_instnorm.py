@@ -49,3 +49,36 @@ def test_visceral_first_stage_shape_and_statistics():
 def test_cpu_tensor_raises():
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         instance_norm_relu(torch.zeros(1, 2, 2, 2, 2), torch.ones(2), torch.zeros(2))
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 16, 16, 32), (1, 48, 9, 7, 13), (2, 96, 5, 6, 7), (1, 768, 5, 5, 8), (3, 384, 2, 3, 5), (2, 192, 1, 1, 3),
+                                   (1, 24, 40, 41, 67)])
+def test_channels_last_layout_matches_torch_and_keeps_the_layout(shape):
+    """NDHWC kernels (include/instnorm.h, *_ndhwc): same numbers as the NCDHW path, output and gradient stay channels-last."""
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = (torch.randn(*shape, generator=g) * 2 + 3).to(DEV)
+    w = (torch.rand(shape[1], generator=g) + 0.5).to(DEV)
+    b = (torch.randn(shape[1], generator=g) * 0.3).to(DEV)
+    dy = torch.randn(*shape, generator=g).to(DEV)
+    xs = x.contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    ws, bs = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    from transoar_b200 import _lib
+    n0 = _lib.lib().msda3d_launch_count()
+    y = instance_norm_relu(xs, ws, bs, 1e-5)
+    y.backward(dy)
+    assert _lib.lib().msda3d_launch_count() - n0 == 7
+    assert y.is_contiguous(memory_format=torch.channels_last_3d) and xs.grad.is_contiguous(memory_format=torch.channels_last_3d)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.relu(F.instance_norm(xr, weight=wr, bias=br, eps=1e-5))
+    yr.backward(dy.double())
+    assert _rel(y, yr) < 1e-5 and _rel(xs.grad, xr.grad) < 2e-4
+    assert _rel(ws.grad, wr.grad) < 1e-4 and _rel(bs.grad, br.grad) < 1e-4
+
+
+def test_channels_last_first_stage_statistics_at_full_size():
+    x = (torch.randn(1, 24, 160, 160, 256, device=DEV) * 5 + 100).contiguous(memory_format=torch.channels_last_3d)
+    w, b = torch.ones(24, device=DEV), torch.zeros(24, device=DEV)
+    y = instance_norm_relu(x, w, b)
+    ref = F.relu(F.instance_norm(x, weight=w, bias=b, eps=1e-5))
+    assert _rel(y, ref) < 1e-4

@@ -115,33 +115,64 @@ def _rel(a, b):
     return float((a.detach() - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def test_refine_block_runs_its_linears_on_tcgen05_under_tf32():
-    """Same reference fixture as tests/test_gpu_parity.py::test_refine_block_against_reference_block_fixture, with TF32 requested:
-    all Linear GEMMs (forward and both gradients) go through tc_gemm_tf32; tolerance is TF32's (1e-2 of the tensor's max)."""
-    import os
-    import numpy as np
-    from conftest import GOLDEN
-    from transoar_b200 import _lib
+def _refine_block_errors(z):
     from transoar_b200.position_encoding import PositionEmbeddingSine3D
     from transoar_b200.refine import DecoderDefAttnBlock
-    z = np.load(os.path.join(GOLDEN, "block_defattn.npz"))
     blk = DecoderDefAttnBlock(d_model=48, nhead=6, num_layers=2, dim_feedforward=64, dropout=0.1,
                               feature_levels=["P2", "P3", "P4"], n_points=2).cuda().eval()
     blk.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
     fmaps = [torch.from_numpy(z[f"fmap{i}"]).cuda().requires_grad_(True) for i in range(3)]
     pe = PositionEmbeddingSine3D(channels=48)
-    n0 = _lib.lib().msda3d_launch_count()
-    with _tf32():
-        outs = blk(fmaps, [pe(f) for f in fmaps])
-        sum((o * torch.from_numpy(z[f"g{i}"]).cuda()).sum() for i, o in enumerate(outs)).backward()
+    outs = blk(fmaps, [pe(f) for f in fmaps])
+    sum((o * torch.from_numpy(z[f"g{i}"]).cuda()).sum() for i, o in enumerate(outs)).backward()
     torch.cuda.synchronize()
-    # per layer: 6 Linear forwards + 6 x 2 gradient GEMMs + msda forward + backward = 20 launches of this library
-    assert _lib.lib().msda3d_launch_count() - n0 == 2 * 20
+    errs = {}
     for i in range(3):
-        assert _rel(outs[i], z[f"out{i}"]) < 1e-2
-        assert _rel(fmaps[i].grad, z[f"grad_fmap{i}"]) < 2e-2
+        errs[f"out{i}"] = _rel(outs[i], z[f"out{i}"])
+        errs[f"grad_fmap{i}"] = _rel(fmaps[i].grad, z[f"grad_fmap{i}"])
     for k, p in blk.named_parameters():
-        assert _rel(p.grad, z["pg." + k]) < 2e-2, k
+        errs["pg." + k] = _rel(p.grad, z["pg." + k])
+    return errs
+
+
+def test_refine_block_runs_its_linears_on_tcgen05_under_tf32(monkeypatch):
+    """Same reference fixture as tests/test_gpu_parity.py::test_refine_block_against_reference_block_fixture, with TF32 requested:
+    all Linear GEMMs (forward and both gradients) go through tc_gemm_tf32.  TF32 perturbs the sampling offsets by ~1e-3, a few
+    samples change voxel cell and their piecewise-constant location gradients jump, so the yardstick is the error the library's
+    own TF32 GEMMs (cuBLAS, same flag) make on the same fixture: ours must stay within 2x of it (+1e-3)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from transoar_b200 import _lib, linear
+    z = np.load(os.path.join(GOLDEN, "block_defattn.npz"))
+    with _tf32():
+        n0 = _lib.lib().msda3d_launch_count()
+        ours = _refine_block_errors(z)
+        # per layer: 6 Linear forwards + 6 x 2 gradient GEMMs + msda forward + backward = 20 launches of this library
+        assert _lib.lib().msda3d_launch_count() - n0 == 2 * 20
+        monkeypatch.setattr(linear, "tc_eligible", lambda x, w: False)
+        n0 = _lib.lib().msda3d_launch_count()
+        cublas = _refine_block_errors(z)
+        assert _lib.lib().msda3d_launch_count() - n0 == 2 * 2
+    print("max rel err  ours %.3e  cublas-tf32 %.3e" % (max(ours.values()), max(cublas.values())))
+    assert max(ours[k] for k in ours if k.startswith("out")) < 1e-2
+    bad = {k: (ours[k], cublas[k]) for k in ours if not ours[k] <= 2 * cublas[k] + 1e-3}
+    assert not bad, bad
+
+
+def test_tma_rounding_beats_truncation():
+    """Operands are rounded to TF32 by the copy engine (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32): unbiased, ~half the error of
+    truncation.  Checked against fp64 on a GEMM with positive operands, where truncation shows as a systematic -2^-11 bias."""
+    from transoar_b200.linear import gemm
+    gen = torch.Generator().manual_seed(3)
+    A = (torch.rand(512, 1024, generator=gen) + 0.5).cuda()
+    B = (torch.rand(256, 1024, generator=gen) + 0.5).cuda()
+    D = torch.empty(512, 256, device="cuda")
+    gemm(A, 0, 1024, B, 0, 1024, D, 512, 256, 1024)
+    want = A.double() @ B.double().t()
+    rel = (D.double() - want) / want
+    assert abs(float(rel.mean())) < 1e-4, float(rel.mean())          # truncation would give about -5e-4
+    assert float(rel.abs().max()) < 1e-3
 
 
 def test_strict_fp32_request_bypasses_the_tf32_kernel():

@@ -31,6 +31,9 @@ _SIGNATURES = {
     "instnorm_workspace_floats": (ctypes.c_longlong, [_ci, _ci, _ci, ctypes.c_longlong]),
     "instnorm_relu_forward": (_ci, [_vp, _ci, _vp, _vp, _vp, _ci, _ci, ctypes.c_longlong, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "instnorm_relu_backward": (_ci, [_vp, _ci] + [_vp] * 6 + [_ci, _ci, ctypes.c_longlong] + [_vp] * 4),
+    "instnorm_ndhwc_workspace_floats": (ctypes.c_longlong, [_ci, _ci, ctypes.c_longlong]),
+    "instnorm_relu_forward_ndhwc": (_ci, [_vp] * 4 + [_ci, _ci, ctypes.c_longlong, ctypes.c_float] + [_vp] * 4),
+    "instnorm_relu_backward_ndhwc": (_ci, [_vp] * 7 + [_ci, _ci, ctypes.c_longlong] + [_vp] * 4),
     # include/roi_attn.h
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),

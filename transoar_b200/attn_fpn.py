@@ -29,7 +29,11 @@ class EncoderCnnBlock(nn.Module):
         # same Sequential (so the reference's parameter names are kept), but each InstanceNorm3d -> ReLU pair runs as one
         # fused sm_100a kernel (transoar_b200/instnorm.py) instead of cuDNN batch-norm + an elementwise ReLU
         conv1, norm1, _, conv2, norm2, _ = self._block
-        x = instance_norm_relu(conv1(x), norm1.weight, norm1.bias, norm1.eps)
+        x = conv1(x)
+        if conv1.in_channels == 1 and conv2.weight.is_contiguous(memory_format=torch.channels_last_3d) and not x.is_contiguous(memory_format=torch.channels_last_3d):
+            # a 1-channel input / weight is layout-ambiguous and cuDNN answers NCDHW: move to NDHWC once, here
+            x = x.contiguous(memory_format=torch.channels_last_3d)
+        x = instance_norm_relu(x, norm1.weight, norm1.bias, norm1.eps)
         return instance_norm_relu(conv2(x), norm2.weight, norm2.bias, norm2.eps)
 
 
@@ -48,6 +52,10 @@ class Encoder(nn.Module):
 
     def forward(self, x):
         outputs = {}
+        if x.is_cuda and self._stages[0]._block[3].weight.is_contiguous(memory_format=torch.channels_last_3d):
+            # channels-last model (TransoarNet.to(memory_format=torch.channels_last_3d)): hand the first convolution an NDHWC
+            # input so that every activation of the backbone is produced and consumed in the tensor-core convolutions' own layout
+            x = x.contiguous(memory_format=torch.channels_last_3d)
         for i, stage in enumerate(self._stages):
             x = stage(x)
             outputs["C" + str(i)] = x

@@ -47,6 +47,26 @@ int bwd(cudaStream_t st, const void *dy, const void *x, const void *y, const flo
   return (int)cudaGetLastError();
 }
 
+// channels-last: chunks per sample chosen so that the grid holds ~8 CTAs per SM; every chunk is a whole number of voxel rows
+struct ClPlan { int chunks; long long chunk_vox; };
+ClPlan cl_plan(int B, int C, long long V)
+{
+  const int rows = instnorm::kClThreads / (C / 4);
+  const long long min_vox = (long long)rows * instnorm::kClUnroll;
+  long long chunks = (V + min_vox - 1) / min_vox;
+  const long long target = (148 * 8 + B - 1) / B;
+  if (chunks > target) chunks = target;
+  if (chunks < 1) chunks = 1;
+  long long cv = (V + chunks - 1) / chunks;
+  cv = (cv + rows - 1) / rows * rows;
+  ClPlan p;
+  p.chunk_vox = cv;
+  p.chunks = (int)((V + cv - 1) / cv);
+  return p;
+}
+
+bool cl_bad(int B, int C, long long V) { return B <= 0 || V <= 0 || !instnorm::cl_supported(C) || (long long)B * C > 65535; }
+
 bool bad(int dtype, int B, int C, long long V) { return (dtype != MSDA3D_F32 && dtype != MSDA3D_BF16) || B <= 0 || C <= 0 || V <= 0 || (long long)B * C > 65535; }
 
 }  // namespace
@@ -79,6 +99,49 @@ int instnorm_relu_backward(void *stream, int dtype, const void *dy, const void *
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == MSDA3D_F32 ? bwd<float>(st, dy, x, y, gamma, mean, rstd, batch, channels, voxels, dx, dgamma, dbeta, workspace)
                              : bwd<__nv_bfloat16>(st, dy, x, y, gamma, mean, rstd, batch, channels, voxels, dx, dgamma, dbeta, workspace);
+}
+
+long long instnorm_ndhwc_workspace_floats(int batch, int channels, long long voxels)
+{
+  if (cl_bad(batch, channels, voxels)) return 0;
+  return (long long)batch * channels * (3LL * cl_plan(batch, channels, voxels).chunks + 2);
+}
+
+int instnorm_relu_forward_ndhwc(void *stream, const float *x, const float *gamma, const float *beta, int batch, int channels, long long voxels,
+                                float eps, float *y, float *mean, float *rstd, float *workspace)
+{
+  if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace || cl_bad(batch, channels, voxels)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ClPlan p = cl_plan(batch, channels, voxels);
+  const int I = batch * channels;
+  const dim3 grid(p.chunks, batch);
+  instnorm::cl_stats_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(x, voxels, channels, p.chunks, p.chunk_vox, workspace);
+  instnorm::stats_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, eps, mean, rstd);
+  instnorm::cl_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(x, gamma, beta, mean, rstd, voxels, channels, p.chunk_vox, y);
+  g_msda3d_launches += 3;
+  return (int)cudaGetLastError();
+}
+
+int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *y, const float *gamma, const float *mean,
+                                 const float *rstd, int batch, int channels, long long voxels, float *dx, float *dgamma, float *dbeta,
+                                 float *workspace)
+{
+  if (!dy || !x || !y || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !workspace || cl_bad(batch, channels, voxels))
+    return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ClPlan p = cl_plan(batch, channels, voxels);
+  const int I = batch * channels;
+  const dim3 grid(p.chunks, batch);
+  float *sums = workspace + (long long)I * p.chunks * 2;
+  instnorm::cl_bwd_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, y, mean, rstd, voxels, channels, p.chunks, p.chunk_vox, workspace);
+  instnorm::bwd_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, sums);
+  instnorm::bwd_param_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, batch, channels, dgamma, dbeta);
+  instnorm::cl_bwd_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, y, gamma, mean, rstd, sums, voxels, channels, p.chunk_vox, dx);
+  g_msda3d_launches += 4;
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

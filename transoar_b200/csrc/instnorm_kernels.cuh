@@ -281,4 +281,189 @@ bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const T *__r
   }
 }
 
+// =====================================================================================================================
+// Channels-last (NDHWC) variants, fp32.  x, y [B][V][C]: what cuDNN's tensor-core convolutions produce and consume, so a
+// channels-last encoder needs no NCDHW <-> NDHWC transposes around every convolution (14 ms of the 126 ms VISCERAL step).
+// A CTA streams a run of voxels of one sample; thread t owns the float4 channel group t % (C/4) of voxel rows t / (C/4),
+// so a warp still reads whole 128-byte lines.  Per-channel sums are reduced over the voxel rows of the CTA in shared memory.
+// Statistics use the shifted single-pass form (shift = the chunk's first voxel) and the same fp64 merge as above.
+// Requires C % 4 == 0 and (C/4) | 192 -- every channel count of the reference's encoders (24 ... 768).
+// =====================================================================================================================
+constexpr int kClThreads = 192;
+constexpr int kClUnroll = 8;
+
+__host__ __device__ inline bool cl_supported(int C) { return C > 0 && C % 4 == 0 && kClThreads % (C / 4) == 0; }
+
+// sum NV float4-wide values over the voxel rows of the CTA; result valid in the threads of row 0 (t < cg)
+template <int NV>
+__device__ __forceinline__ void cl_reduce_rows(float (&v)[NV][4], int cg, int rows, float *red /* [kClThreads][NV * 4] */)
+{
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[t * (NV * 4) + i * 4 + j] = v[i][j];
+  for (int s = rows >> 1; s > 0; s >>= 1) {
+    __syncthreads();
+    if (t < s * cg) {
+#pragma unroll
+      for (int k = 0; k < NV * 4; ++k) red[t * (NV * 4) + k] += red[(t + s * cg) * (NV * 4) + k];
+    }
+  }
+  __syncthreads();
+  if (t < cg) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = red[t * (NV * 4) + i * 4 + j];
+  }
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_stats_partial_kernel(const float *__restrict__ x, long long V, int C, int chunks, long long chunk_vox, float *__restrict__ part)
+{
+  __shared__ float red[kClThreads * 8];
+  const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const long long v0 = (long long)ch * chunk_vox, v1 = min(V, v0 + chunk_vox);
+  const float *base = x + (long long)b * V * C + g * 4;
+  const float4 K = __ldg(reinterpret_cast<const float4 *>(base + v0 * C));
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (long long v = v0 + r; v < v1; v += (long long)rows * kClUnroll) {
+    float4 q[kClUnroll];
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const long long vv = v + (long long)u * rows;
+      q[u] = vv < v1 ? __ldg(reinterpret_cast<const float4 *>(base + vv * C)) : K;
+    }
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const float d0 = q[u].x - K.x, d1 = q[u].y - K.y, d2 = q[u].z - K.z, d3 = q[u].w - K.w;
+      acc[0][0] += d0; acc[0][1] += d1; acc[0][2] += d2; acc[0][3] += d3;
+      acc[1][0] = fmaf(d0, d0, acc[1][0]); acc[1][1] = fmaf(d1, d1, acc[1][1]);
+      acc[1][2] = fmaf(d2, d2, acc[1][2]); acc[1][3] = fmaf(d3, d3, acc[1][3]);
+    }
+  }
+  cl_reduce_rows<2>(acc, cg, rows, red);
+  if (threadIdx.x < cg) {
+    const float n = (float)(v1 - v0);
+    const float k4[4] = {K.x, K.y, K.z, K.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float *p = part + (((long long)b * C + g * 4 + j) * chunks + ch) * 3;
+      p[0] = n; p[1] = k4[j] + acc[0][j] / n; p[2] = fmaxf(acc[1][j] - acc[0][j] * acc[0][j] / n, 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ mean,
+                const float *__restrict__ rstd, long long V, int C, long long chunk_vox, float *__restrict__ y)
+{
+  const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int b = blockIdx.y;
+  const long long v0 = (long long)blockIdx.x * chunk_vox, v1 = min(V, v0 + chunk_vox);
+  float a[4], o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = g * 4 + j;
+    a[j] = rstd[b * C + c] * gamma[c];
+    o[j] = beta[c] - mean[b * C + c] * a[j];
+  }
+  const long long off = (long long)b * V * C + g * 4;
+  for (long long v = v0 + r; v < v1; v += (long long)rows * kClUnroll) {
+    float4 q[kClUnroll];
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1) q[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+    }
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1)
+        *reinterpret_cast<float4 *>(y + off + vv * C) = make_float4(fmaxf(fmaf(q[u].x, a[0], o[0]), 0.f), fmaxf(fmaf(q[u].y, a[1], o[1]), 0.f),
+                                                                     fmaxf(fmaf(q[u].z, a[2], o[2]), 0.f), fmaxf(fmaf(q[u].w, a[3], o[3]), 0.f));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ mean,
+                      const float *__restrict__ rstd, long long V, int C, int chunks, long long chunk_vox, float *__restrict__ part)
+{
+  __shared__ float red[kClThreads * 8];
+  const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const long long v0 = (long long)ch * chunk_vox, v1 = min(V, v0 + chunk_vox);
+  float mu[4], rs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { mu[j] = mean[b * C + g * 4 + j]; rs[j] = rstd[b * C + g * 4 + j]; }
+  const long long off = (long long)b * V * C + g * 4;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (long long v = v0 + r; v < v1; v += (long long)rows * (kClUnroll / 2)) {
+#pragma unroll
+    for (int u = 0; u < kClUnroll / 2; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1) {
+        const float4 gq = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
+        const float4 xq = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+        const float4 yq = __ldg(reinterpret_cast<const float4 *>(y + off + vv * C));
+        const float gg[4] = {gq.x, gq.y, gq.z, gq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w}, yy[4] = {yq.x, yq.y, yq.z, yq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dz = yy[j] > 0.f ? gg[j] : 0.f;
+          acc[0][j] += dz;
+          acc[1][j] = fmaf(dz, (xx[j] - mu[j]) * rs[j], acc[1][j]);
+        }
+      }
+    }
+  }
+  cl_reduce_rows<2>(acc, cg, rows, red);
+  if (threadIdx.x < cg) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float *p = part + (((long long)b * C + g * 4 + j) * chunks + ch) * 2;
+      p[0] = acc[0][j]; p[1] = acc[1][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ gamma,
+                    const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ sums, long long V, int C,
+                    long long chunk_vox, float *__restrict__ dx)
+{
+  const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int b = blockIdx.y;
+  const long long v0 = (long long)blockIdx.x * chunk_vox, v1 = min(V, v0 + chunk_vox);
+  float mu[4], rs[4], a[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = g * 4 + j, i = b * C + c;
+    mu[j] = mean[i]; rs[j] = rstd[i]; a[j] = gamma[c] * rs[j];
+    m1[j] = sums[2 * i] / (float)V; m2[j] = sums[2 * i + 1] / (float)V;
+  }
+  const long long off = (long long)b * V * C + g * 4;
+  for (long long v = v0 + r; v < v1; v += (long long)rows * (kClUnroll / 2)) {
+#pragma unroll
+    for (int u = 0; u < kClUnroll / 2; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1) {
+        const float4 gq = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
+        const float4 xq = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+        const float4 yq = __ldg(reinterpret_cast<const float4 *>(y + off + vv * C));
+        const float gg[4] = {gq.x, gq.y, gq.z, gq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w}, yy[4] = {yq.x, yq.y, yq.z, yq.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dz = yy[j] > 0.f ? gg[j] : 0.f;
+          o[j] = a[j] * (dz - m1[j] - (xx[j] - mu[j]) * rs[j] * m2[j]);
+        }
+        *reinterpret_cast<float4 *>(dx + off + vv * C) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 }  // namespace instnorm

@@ -2,6 +2,7 @@
 #include "tc_gemm_kernels.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/msda3d.h"
@@ -39,7 +40,10 @@ int make_map(CUtensorMap *map, const float *ptr, long long inner, long long oute
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)tcgemm::BK, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstride, box, estr,
+  // TFLOAT32: the copy engine rounds each fp32 value to TF32 (nearest) on its way into shared memory, so the tensor core's
+  // read of the upper 19 bits is a rounding, not a truncation (TC_GEMM_TMA_ROUND=0 keeps raw fp32 words: diagnostics only).
+  static const bool round_tf32 = [] { const char *e = getenv("TC_GEMM_TMA_ROUND"); return e == nullptr || e[0] != '0'; }();
+  const CUresult r = enc(map, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -41,12 +41,16 @@ def synthetic_targets(config, batch, seed, device):
 
 
 class TrainStep:
-    def __init__(self, config, device, world=1, tf32=True):
+    def __init__(self, config, device, world=1, tf32=True, channels_last=True):
         self.config, self.device = config, torch.device(device)
         if tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
         self.net = TransoarNet(config).to(self.device).train()
+        if channels_last:
+            # conv weights NDHWC: the backbone's activations then stay in the layout the tensor-core convolutions use, the fused
+            # InstanceNorm kernels follow it, and flatten(2).transpose(1, 2) of a feature map is a view
+            self.net = self.net.to(memory_format=torch.channels_last_3d)
         for name, p in self.net.named_parameters():
             if ".q_proj." in name:
                 p.requires_grad_(False)

@@ -250,7 +250,7 @@ class FocusedDecoder(nn.Module):
 
     def forward(self, src, query_embed, pos):
         assert query_embed is not None
-        src = src.flatten(2).transpose(1, 2)
+        src = src.flatten(2).transpose(1, 2).contiguous()          # a view + one plain copy when the backbone is channels-last
         pos = pos.flatten(2).transpose(1, 2)
         bs, _, c = src.shape
         query_pos, tgt = torch.split(query_embed, c, dim=1)
