@@ -38,6 +38,10 @@ _SIGNATURES = {
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
     "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
+    # include/stem_conv.h
+    "stem_conv3d_workspace_floats": (ctypes.c_longlong, [_ci]),
+    "stem_conv3d_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp]),
+    "stem_conv3d_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
     # include/tc_gemm.h
     "tc_gemm_tf32": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6),
 }

@@ -2,7 +2,8 @@
 ``Encoder`` :148-213) and ``EncoderCnnBlock`` (transoar/models/backbones/encoder_blocks.py:14-54).
 
 Module / parameter names equal the reference's (``_encoder._stages.<i>._block.<k>``, ``_decoder._lateral/_up/_out/_refine``)
-so reference checkpoints load.  The 3D convolutions and transposed convolutions stay library calls (cuDNN) in this round; every
+so reference checkpoints load.  The encoder's first convolution (1 input channel) is a direct sm_100a stencil (include/stem_conv.h) when the model is
+channels-last; the other 3D convolutions and transposed convolutions stay library calls (cuDNN tensor-core kernels); every
 InstanceNorm3d -> ReLU pair runs as a fused sm_100a kernel (include/instnorm.h); the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
 ``transoar_b200.refine.DecoderDefAttnBlock``.  The Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) is
 not mirrored yet and raises."""
@@ -12,6 +13,7 @@ from torch import nn
 from .instnorm import instance_norm_relu
 from .position_encoding import PositionEmbeddingSine3D
 from .refine import DecoderDefAttnBlock
+from .stem_conv import stem_conv3d, stem_eligible
 
 
 class EncoderCnnBlock(nn.Module):
@@ -29,10 +31,14 @@ class EncoderCnnBlock(nn.Module):
         # same Sequential (so the reference's parameter names are kept), but each InstanceNorm3d -> ReLU pair runs as one
         # fused sm_100a kernel (transoar_b200/instnorm.py) instead of cuDNN batch-norm + an elementwise ReLU
         conv1, norm1, _, conv2, norm2, _ = self._block
-        x = conv1(x)
-        if conv1.in_channels == 1 and conv2.weight.is_contiguous(memory_format=torch.channels_last_3d) and not x.is_contiguous(memory_format=torch.channels_last_3d):
-            # a 1-channel input / weight is layout-ambiguous and cuDNN answers NCDHW: move to NDHWC once, here
-            x = x.contiguous(memory_format=torch.channels_last_3d)
+        cl_model = conv2.weight.is_contiguous(memory_format=torch.channels_last_3d) and not conv2.weight.is_contiguous()
+        if cl_model and stem_eligible(conv1, x):
+            x = stem_conv3d(x, conv1.weight)                    # 1 -> C direct stencil, writes NDHWC (include/stem_conv.h)
+        else:
+            x = conv1(x)
+            if cl_model and conv1.in_channels == 1 and not x.is_contiguous(memory_format=torch.channels_last_3d):
+                # a 1-channel input / weight is layout-ambiguous and cuDNN answers NCDHW: move to NDHWC once, here
+                x = x.contiguous(memory_format=torch.channels_last_3d)
         x = instance_norm_relu(x, norm1.weight, norm1.bias, norm1.eps)
         return instance_norm_relu(conv2(x), norm2.weight, norm2.bias, norm2.eps)
 
