@@ -38,6 +38,10 @@ _SIGNATURES = {
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
     "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
+    # include/fused_ln.h
+    "fused_ln_workspace_floats": (ctypes.c_longlong, [_ci]),
+    "fused_ln_forward": (_ci, [_vp] * 5 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 4),
+    "fused_ln_backward": (_ci, [_vp] * 6 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 5),
     # include/stem_conv.h
     "stem_conv3d_workspace_floats": (ctypes.c_longlong, [_ci]),
     "stem_conv3d_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp]),

@@ -1,0 +1,97 @@
+// fused_ln_capi.cu -- C ABI of the fused residual + dropout + LayerNorm (include/fused_ln.h).
+#include "fused_ln_kernels.cuh"
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/fused_ln.h"
+#include "../../include/msda3d.h"
+
+extern std::atomic<unsigned long long> g_msda3d_launches;
+
+namespace {
+
+constexpr int kCtas = 148 * 6;
+
+bool bad(long long rows, int C) { return rows <= 0 || C <= 0 || C % 4 != 0 || C > 4 * 32 * fusedln::kMaxNV; }
+int nv_of(int C) { return (C / 4 + 31) / 32; }
+uint32_t thresh_of(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.f + 0.5f); }
+int grid_of(long long rows) { const long long need = (rows + fusedln::kWarps - 1) / fusedln::kWarps; return (int)(need < kCtas ? need : kCtas); }
+
+template <int NV>
+int fwd(cudaStream_t st, const float *a, const float *b, const float *gamma, const float *beta, long long rows, int C, float eps, float p,
+        unsigned long long seed, float *z, float *y, float *mean, float *rstd)
+{
+  fusedln::fwd_kernel<NV><<<grid_of(rows), fusedln::kThreads, 0, st>>>(a, b, gamma, beta, rows, C, eps, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f,
+                                                                        seed, z, y, mean, rstd);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+template <int NV>
+int bwd(cudaStream_t st, const float *dy, const float *z, const float *gamma, const float *mean, const float *rstd, long long rows, int C, float p,
+        unsigned long long seed, float *da, float *db, float *dgamma, float *dbeta, float *ws)
+{
+  const int grid = grid_of(rows);
+  const size_t smem = (size_t)fusedln::kWarps * 2 * C * sizeof(float);
+  auto kern = fusedln::bwd_kernel<NV>;
+  static std::once_flag once;                                      // C = 1024: 64 KB of reduction scratch
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fusedln::kWarps * 2 * 4 * 32 * fusedln::kMaxNV * (int)sizeof(float)); });
+  if (err != cudaSuccess) return (int)err;
+  kern<<<grid, fusedln::kThreads, smem, st>>>(dy, z, gamma, mean, rstd, rows, C, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed, da, db, ws);
+  fusedln::bwd_finalize_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(ws, grid, C, dgamma, dbeta);
+  g_msda3d_launches += 2;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+long long fused_ln_workspace_floats(int channels) { return channels > 0 ? (long long)kCtas * 2 * channels : 0; }
+
+int fused_ln_forward(void *stream, const float *a, const float *b, const float *gamma, const float *beta, long long rows, int channels,
+                     float eps, float p_drop, unsigned long long seed, float *z, float *y, float *mean, float *rstd)
+{
+  if (!a || !gamma || !beta || !y || !mean || !rstd || bad(rows, channels) || p_drop < 0.f || p_drop >= 1.f) return MSDA3D_EINVAL;
+  if (b != nullptr && z == nullptr) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(y) |
+       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15)
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+#define FWD_CALL(NV) fwd<NV>(st, a, b, gamma, beta, rows, channels, eps, b ? p_drop : 0.f, seed, z, y, mean, rstd)
+  switch (nv_of(channels)) {
+    case 1: return FWD_CALL(1);
+    case 2: return FWD_CALL(2);
+    case 3: return FWD_CALL(3);
+    case 4: return FWD_CALL(4);
+    case 5: case 6: return FWD_CALL(6);
+    default: return FWD_CALL(8);
+  }
+#undef FWD_CALL
+}
+
+int fused_ln_backward(void *stream, const float *dy, const float *z, const float *gamma, const float *mean, const float *rstd, long long rows,
+                      int channels, float p_drop, unsigned long long seed, float *da, float *db, float *dgamma, float *dbeta, float *workspace)
+{
+  if (!dy || !z || !gamma || !mean || !rstd || !da || !dgamma || !dbeta || !workspace || bad(rows, channels) || p_drop < 0.f || p_drop >= 1.f)
+    return MSDA3D_EINVAL;
+  if (db != nullptr && p_drop <= 0.f) return MSDA3D_EINVAL;          // without dropout db == da: pass NULL
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db) |
+       reinterpret_cast<uintptr_t>(gamma)) & 15)
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+#define BWD_CALL(NV) bwd<NV>(st, dy, z, gamma, mean, rstd, rows, channels, db ? p_drop : 0.f, seed, da, db, dgamma, dbeta, workspace)
+  switch (nv_of(channels)) {
+    case 1: return BWD_CALL(1);
+    case 2: return BWD_CALL(2);
+    case 3: return BWD_CALL(3);
+    case 4: return BWD_CALL(4);
+    case 5: case 6: return BWD_CALL(6);
+    default: return BWD_CALL(8);
+  }
+#undef BWD_CALL
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
+from .fused_ln import add_dropout_layer_norm
 from .linear import TCLinear
 
 _QPG = 32     # query rows per CTA in the kernel (roiattn::TQ)
@@ -208,14 +209,14 @@ class FocusedDecoderLayer(nn.Module):
     def forward(self, tgt, query_pos, src_pos, src):
         qk = tgt if query_pos is None else tgt + query_pos
         sa = self.self_attn(qk.transpose(0, 1), qk.transpose(0, 1), tgt.transpose(0, 1))[0].transpose(0, 1)
-        tgt = self.norm2(tgt + self.dropout2(sa))
+        tgt = add_dropout_layer_norm(tgt, sa, self.norm2, self.dropout2.p, self.training)
         q = tgt if query_pos is None else tgt + query_pos
         k = src if src_pos is None else src + src_pos
         ca, weights = self.cross_attn(q, k, src)
-        tgt = self.norm1(tgt + self.dropout1(ca))
+        tgt = add_dropout_layer_norm(tgt, ca, self.norm1, self.dropout1.p, self.training)
         hidden = self.linear1(tgt, relu=True) if self._fuse_relu else self.activation(self.linear1(tgt))
         ffn = self.linear2(self.dropout3(hidden))
-        return self.norm3(tgt + self.dropout4(ffn)), weights
+        return add_dropout_layer_norm(tgt, ffn, self.norm3, self.dropout4.p, self.training), weights
 
 
 class FocusedDecoderModel(nn.Module):

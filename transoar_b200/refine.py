@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .fused_ln import add_dropout_layer_norm
 from .linear import TCLinear
 from .ops.modules import MSDeformAttn
 
@@ -41,10 +42,10 @@ class DefAttnLayer(nn.Module):
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         query = src if pos is None else src + pos
         attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        src = self.norm1(src + self.dropout1(attn))
+        src = add_dropout_layer_norm(src, attn, self.norm1, self.dropout1.p, self.training)       # norm1(src + dropout1(attn)), one kernel
         hidden = self.linear1(src, relu=True) if self._fuse_relu else self.activation(self.linear1(src))
         ffn = self.linear2(self.dropout2(hidden))
-        return self.norm2(src + self.dropout3(ffn))
+        return add_dropout_layer_norm(src, ffn, self.norm2, self.dropout3.p, self.training)       # norm2(src + dropout3(ffn))
 
 
 class DefAttnTransformer(nn.Module):
