@@ -386,6 +386,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (operator alone, GEMM, RoI attention, InstanceNorm)")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="for ncu --profile-from-start off: warm up, bracket ONE training step with cudaProfilerStart/Stop, exit")
     ap.add_argument("--dist", default=DIST, choices=["A", "B"], help="sampling-location distribution of the operator-alone extra")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -433,6 +435,12 @@ def main():
     for i in range(warm):
         ts.step(vols_dev[i % n_sets], targets[i % n_sets])
     fence()
+    if args.profile_one_step:
+        torch.cuda.profiler.start()
+        ts.step(vols_dev[0], targets[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
     ev_log = []
     MSDA.set_event_log(ev_log)
     launches0 = lib.msda3d_launch_count()

@@ -9,6 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cl = (sys.argv[2] if len(sys.argv) > 2 else "cl") == "cl"
 tf32 = (sys.argv[3] if len(sys.argv) > 3 else "tf32") == "tf32"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+torch.backends.cudnn.benchmark = (sys.argv[5] == "bench") if len(sys.argv) > 5 else False
 torch.manual_seed(0)
 cfg = visceral_train_config()
 ts = TrainStep(cfg, dev, tf32=tf32, channels_last=cl)
@@ -16,7 +17,7 @@ if not tf32:
     torch.backends.cuda.matmul.allow_tf32 = False
 x = torch.rand(B, 1, 160, 160, 256, device=dev)
 tg = synthetic_targets(cfg, B, 0, dev)
-for _ in range(3): ts.step(x, tg)
+for _ in range(4): ts.step(x, tg)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -100,7 +100,15 @@ extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long l
     return MSDA3D_EALIGN;
   if (split_k < 0 || (split_k != 1 && !accumulate)) return MSDA3D_EINVAL;
 
-  const int BN = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  // tile width: fewest column tiles first (every extra one re-reads the whole A operand), then least padding
+  int BN = 128;
+  {
+    int best_tiles = 1 << 30, best_pad = 1 << 30;
+    for (int cand : {128, 192, 256}) {
+      const int tiles = (N + cand - 1) / cand, pad = tiles * cand - N;
+      if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best_tiles = tiles; best_pad = pad; BN = cand; }
+    }
+  }
   const int m_tiles = (M + tcgemm::BM - 1) / tcgemm::BM, n_tiles = (N + BN - 1) / BN, r_blocks = (R + tcgemm::BK - 1) / tcgemm::BK;
   int splits = split_k;
   if (splits == 0) {                                             // fill the machine: one work item per SM where the reduction allows
@@ -119,6 +127,7 @@ extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long l
   rc = b_mn_major ? make_map(&mb, B, N, R, ldb, tcgemm::BK, true) : make_map(&mb, B, R, N, ldb, BN, false);
   if (rc != 0) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return BN == 256 ? dispatch<256>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p)
-                   : dispatch<128>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
+  if (BN == 256) return dispatch<256>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
+  if (BN == 192) return dispatch<192>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
+  return dispatch<128>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
 }

@@ -37,8 +37,8 @@ template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;            // 6 (BN=128) / 4 (BN=256)
-  static constexpr int TMEM_COLS = 2 * BN;                             // 256 / 512: power of two
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;            // 6 (BN=128) / 5 (BN=192) / 4 (BN=256)
+  static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;              // two accumulators of BN columns, rounded to a power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
