@@ -31,6 +31,11 @@ extern "C" {
 int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
                  float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k);
 
+/* Diagnostics: while a device buffer of 12 x 296 uint64 is installed, every launch writes per CTA the cycles its three roles spent
+ * waiting: [0] producer on "empty", [1] producer total, [2] MMA on "full", [3] MMA on "tmem empty", [4] MMA total, [5] epilogue on
+ * "tmem full", [6] epilogue total; then at 8 * 296 + 4 * cta: epilogue cycles in TMEM load / shared-memory stage / store.  NULL (the default) removes it.  Not thread-safe; tools/exp_gemm_roles.py uses it. */
+void tc_gemm_debug_profile(unsigned long long *device_counters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""Swin encoder stages on the GPU: the reference fixture again (strict fp32), the tcgen05 route of their Linear layers under TF32,
+and the whole Swin-FPN backbone (configs[3] family) forward + backward at a small volume."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    b = torch.as_tensor(b, device=a.device)
+    return float((a.detach() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _run_stages(z, G, swin):
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    cur, feats = x, []
+    for i, st in enumerate(G.STAGES):
+        m = swin.EncoderSwinBlock(dim=st["dim"], depth=st["depth"], num_heads=st["heads"], window_size=G.WINDOW, mlp_ratio=4, qkv_bias=True,
+                                  qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=[0.0, 0.1], downsample=swin.PatchMerging).eval()
+        m.load_state_dict({k[len(f"sd{i}."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"sd{i}.")}, strict=True)
+        cur = m.to(DEV)(cur)
+        feats.append(cur)
+    sys.path.insert(0, GOLDEN)
+    from detfill import det_tensor
+    sum((f * det_tensor(tuple(f.shape), 90 + i).to(DEV)).sum() for i, f in enumerate(feats)).backward()
+    return x, feats
+
+
+@pytest.mark.parametrize("tf32,tol", [(False, 1e-4), (True, 2e-2)])
+def test_stages_against_reference_fixture(tf32, tol):
+    sys.path.insert(0, GOLDEN)
+    import make_golden_swin as G
+    from transoar_b200 import _lib, swin
+    z = np.load(os.path.join(GOLDEN, "swin.npz"))
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    try:
+        n0 = _lib.lib().msda3d_launch_count()
+        x, feats = _run_stages(z, G, swin)
+        launched = _lib.lib().msda3d_launch_count() - n0
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    # 3 stages x (2 blocks x 4 Linear + 1 merging Linear) x (forward + 2 gradient GEMMs) on the tcgen05 kernel, none with strict fp32
+    assert launched == (3 * 9 * 3 if tf32 else 0)
+    for i, f in enumerate(feats):
+        assert _rel(f, z[f"out{i}"]) < tol, i
+    assert _rel(x.grad, z["grad_x"]) < 5 * tol
+
+
+def test_swin_fpn_backbone_runs_forward_and_backward():
+    from transoar_b200.attn_fpn import AttnFPN
+    from transoar_b200.configs import VISCERAL_BACKBONE
+    cfg = dict(VISCERAL_BACKBONE, use_encoder_attn=True, start_channels=12, fpn_channels=96, hidden_dim=96, dim_feedforward=128)
+    torch.manual_seed(0)
+    fpn = AttnFPN(cfg).to(DEV).to(memory_format=torch.channels_last_3d).train()
+    x = torch.rand(1, 1, 64, 64, 96, device=DEV)
+    out = fpn(x)
+    assert sorted(out) == ["P2", "P3", "P4", "P5"] and out["P2"].shape == (1, 96, 16, 16, 24)
+    sum(v.square().mean() for v in out.values()).backward()
+    grads = [p.grad for p in fpn.parameters() if p.requires_grad]
+    assert all(g is not None and torch.isfinite(g).all() for g in grads)

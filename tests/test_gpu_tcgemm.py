@@ -41,6 +41,28 @@ def test_gemm_matches_fp64(a_mn, b_mn, M, N, R):
     assert float((D2.double() - (Ad @ Bd.t()).clamp_min(0)).abs().max()) < 4e-3 * math.sqrt(R) * 2.25
 
 
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("M,N,R", [(20000, 384, 384), (20076, 200, 100), (40000, 1024, 96), (19000, 96, 384)])
+def test_cta_pair_kernel_matches_fp64_and_the_single_cta_kernel(a_mn, b_mn, M, N, R):
+    """Enough 256-row tiles to fill the machine with CTA pairs: the cta_group::2 kernel runs (each CTA stages half of the B tile).
+    Checked against fp64 and bit-for-bit against a row block computed by the single-CTA kernel (same K order, same arithmetic)."""
+    from transoar_b200.linear import gemm
+    gen = torch.Generator().manual_seed(M + N + R + a_mn * 2 + b_mn)
+    A, Ad, lda = _operand(M, R, a_mn, gen)
+    B, Bd, ldb = _operand(N, R, b_mn, gen)
+    bias = torch.randn(N, generator=gen).cuda()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=bias, relu=True)
+    torch.cuda.synchronize()
+    want = (Ad @ Bd.t() + bias.double()).clamp_min(0)
+    assert float((D.double() - want).abs().max()) < 4e-3 * math.sqrt(R) * 2.25
+    if not a_mn:                                                   # 1024 rows alone are too few tiles for pairs: single-CTA kernel
+        D1 = torch.empty(1024, N, device="cuda")
+        gemm(A[:1024], 0, lda, B, b_mn, ldb, D1, 1024, N, R, bias=bias, relu=True)
+        assert torch.equal(D1, D[:1024])
+
+
 @pytest.mark.parametrize("M,N,R,split", [(384, 1024, 20000, 0), (128, 128, 4096, 7), (200, 136, 1000, 3), (384, 384, 33000, 0)])
 def test_split_k_accumulates(M, N, R, split):
     from transoar_b200.linear import gemm

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "stem_conv3d_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp]),
     "stem_conv3d_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
     # include/tc_gemm.h
+    "tc_gemm_debug_profile": (None, [_vp]),
     "tc_gemm_tf32": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6),
 }
 

@@ -5,8 +5,8 @@ Module / parameter names equal the reference's (``_encoder._stages.<i>._block.<k
 so reference checkpoints load.  The encoder's first convolution (1 input channel) is a direct sm_100a stencil (include/stem_conv.h) when the model is
 channels-last; the other 3D convolutions and transposed convolutions stay library calls (cuDNN tensor-core kernels); every
 InstanceNorm3d -> ReLU pair runs as a fused sm_100a kernel (include/instnorm.h); the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
-``transoar_b200.refine.DecoderDefAttnBlock``.  The Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) is
-not mirrored yet and raises."""
+``transoar_b200.refine.DecoderDefAttnBlock``; the Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) through
+``transoar_b200.swin``."""
 import torch
 from torch import nn
 
@@ -14,6 +14,7 @@ from .instnorm import instance_norm_relu
 from .position_encoding import PositionEmbeddingSine3D
 from .refine import DecoderDefAttnBlock
 from .stem_conv import stem_conv3d, stem_eligible
+from .swin import ConvPatchMerging, EncoderSwinBlock, PatchMerging
 
 
 class EncoderCnnBlock(nn.Module):
@@ -48,12 +49,21 @@ class Encoder(nn.Module):
 
     def __init__(self, config, debug=False):
         super().__init__()
-        if config["use_encoder_attn"]:
-            raise NotImplementedError("the Swin encoder (use_encoder_attn, encoder_blocks.py:56-334) is not mirrored yet")
         cin, cout = config["in_channels"], config["start_channels"]
+        depths = config["depths"]
+        drop_path = [v.item() for v in torch.linspace(0, config["drop_path_rate"], sum(depths))]       # stochastic-depth schedule (:160-161)
+        merging = ConvPatchMerging if config["conv_merging"] else PatchMerging
         self._stages = nn.ModuleList()
-        for kernel, stride in zip(config["conv_kernels"], config["strides"]):
-            self._stages.append(EncoderCnnBlock(cin, cout, kernel, stride))
+        for stage, (kernel, stride) in enumerate(zip(config["conv_kernels"], config["strides"])):
+            if config["use_encoder_attn"] and stage > 1:                                               # stages 0-1 stay convolutional (:172)
+                k = stage - 2
+                self._stages.append(EncoderSwinBlock(dim=cin, depth=depths[k], num_heads=config["num_heads"][k],
+                                                     window_size=config["window_size"], mlp_ratio=config["mlp_ratio"],
+                                                     qkv_bias=config["qkv_bias"], qk_scale=config["qk_scale"], drop=config["drop_rate"],
+                                                     attn_drop=config["attn_drop_rate"],
+                                                     drop_path=drop_path[sum(depths[:k]):sum(depths[:k + 1])], downsample=merging))
+            else:
+                self._stages.append(EncoderCnnBlock(cin, cout, kernel, stride))
             cin, cout = cout, cout * 2
 
     def forward(self, x):

@@ -12,6 +12,8 @@ extern std::atomic<unsigned long long> g_msda3d_launches;
 
 namespace {
 
+std::atomic<unsigned long long *> g_prof{nullptr};          // diagnostics only (tc_gemm_debug_profile)
+
 using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -63,10 +65,52 @@ int sm_count()
   return sms[dev];
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, float *D, const float *bias, const tcgemm::Problem &p)
+// co-resident CTA pairs (clusters of 2) of the pair kernel on the current device; 0 if clusters cannot be scheduled
+template <int BN, bool A_MN, bool B_MN> int max_pairs()
 {
-  using C = tcgemm::Cfg<BN>;
+  static int pairs[64];
+  static bool known[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!known[dev]) {
+    using C = tcgemm::Cfg<BN, 2>;
+    auto kern = tcgemm::gemm_tf32_pair_kernel<BN, A_MN, B_MN>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * sm_count());
+      cfg.blockDim = dim3(tcgemm::kThreads);
+      cfg.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    pairs[dev] = n;
+    known[dev] = true;
+  }
+  return pairs[dev];
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, float *D, const float *bias, const tcgemm::Problem &p, bool pair)
+{
+  if (pair) {
+    const int pairs = max_pairs<BN, A_MN, B_MN>();
+    if (pairs > 0) {
+      using C = tcgemm::Cfg<BN, 2>;
+      const long long work = (long long)((p.M + 2 * tcgemm::BM - 1) / (2 * tcgemm::BM)) * ((p.N + BN - 1) / BN) * p.splits;
+      const int grid = 2 * (int)(work < pairs ? work : pairs);
+      tcgemm::gemm_tf32_pair_kernel<BN, A_MN, B_MN><<<grid, tcgemm::kThreads, C::SMEM_BYTES, st>>>(ma, mb, D, bias, p);
+      ++g_msda3d_launches;
+      return (int)cudaGetLastError();
+    }
+    return MSDA3D_ENODEV;                                          // the B tensor map was built for half tiles: no silent switch
+  }
+  using C = tcgemm::Cfg<BN, 1>;
   auto kern = tcgemm::gemm_tf32_kernel<BN, A_MN, B_MN>;
   static std::once_flag once;                                    // one flag per instantiation
   static cudaError_t attr_err = cudaSuccess;
@@ -81,15 +125,17 @@ int launch(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, float 
 
 template <int BN>
 int dispatch(cudaStream_t st, bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, float *D, const float *bias,
-             const tcgemm::Problem &p)
+             const tcgemm::Problem &p, bool pair)
 {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(st, ma, mb, D, bias, p);
-  if (!a_mn && b_mn) return launch<BN, false, true>(st, ma, mb, D, bias, p);
-  if (a_mn && !b_mn) return launch<BN, true, false>(st, ma, mb, D, bias, p);
-  return launch<BN, true, true>(st, ma, mb, D, bias, p);
+  if (!a_mn && !b_mn) return launch<BN, false, false>(st, ma, mb, D, bias, p, pair);
+  if (!a_mn && b_mn) return launch<BN, false, true>(st, ma, mb, D, bias, p, pair);
+  if (a_mn && !b_mn) return launch<BN, true, false>(st, ma, mb, D, bias, p, pair);
+  return launch<BN, true, true>(st, ma, mb, D, bias, p, pair);
 }
 
 }  // namespace
+
+extern "C" void tc_gemm_debug_profile(unsigned long long *device_counters) { g_prof.store(device_counters); }
 
 extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
                             float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k)
@@ -118,16 +164,21 @@ extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long l
   if (splits > r_blocks) splits = r_blocks;
   tcgemm::Problem p;
   p.M = M; p.N = N; p.R = R; p.ldd = ldd; p.relu = relu; p.atomic = accumulate ? 1 : 0;
+  p.prof = g_prof.load();
   p.rb_per_split = (r_blocks + splits - 1) / splits;
   p.splits = (r_blocks + p.rb_per_split - 1) / p.rb_per_split;   // no empty split
 
+  // CTA pairs (256-row tiles, B tile split over the pair) when there are enough row tiles to fill the machine with pairs;
+  // TC_GEMM_PAIR=0 forces the single-CTA kernel (diagnostics).
+  static const bool pair_enabled = [] { const char *e = getenv("TC_GEMM_PAIR"); return e == nullptr || e[0] != '0'; }();
+  const bool pair = pair_enabled && !accumulate && splits == 1 && (long long)(M / 256) * n_tiles >= sm_count() / 2;
   CUtensorMap ma, mb;
   int rc = a_mn_major ? make_map(&ma, A, M, R, lda, tcgemm::BK, true) : make_map(&ma, A, R, M, lda, tcgemm::BM, false);
   if (rc != 0) return rc;
-  rc = b_mn_major ? make_map(&mb, B, N, R, ldb, tcgemm::BK, true) : make_map(&mb, B, R, N, ldb, BN, false);
+  rc = b_mn_major ? make_map(&mb, B, N, R, ldb, tcgemm::BK, true) : make_map(&mb, B, R, N, ldb, pair ? BN / 2 : BN, false);
   if (rc != 0) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch<256>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
-  if (BN == 192) return dispatch<192>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
-  return dispatch<128>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p);
+  if (BN == 256) return dispatch<256>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p, pair);
+  if (BN == 192) return dispatch<192>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p, pair);
+  return dispatch<128>(st, a_mn_major != 0, b_mn_major != 0, ma, mb, D, bias, p, pair);
 }

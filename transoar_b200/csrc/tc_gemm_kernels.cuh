@@ -33,13 +33,18 @@ constexpr int kThreads = 192;
 constexpr int kSlabBytes = BK * 128;  // MN-major operands: one 32(mn) x BK(r) slab per TMA box
 constexpr unsigned kSpinLimit = 1u << 28;
 
-template <int BN> struct Cfg {
+// CTAS = 1: one CTA computes a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so the operand bytes an SM pulls
+// from L2 per flop drop by (128 + BN/2) / (128 + BN) (0.7 at BN = 192).
+template <int BN, int CTAS> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;            // 6 (BN=128) / 5 (BN=192) / 4 (BN=256)
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;      // 1 CTA: 6 / 5 / 4 (BN = 128 / 192 / 256); pair: 8 / 7 / 6
   static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;              // two accumulators of BN columns, rounded to a power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                    // per epilogue warp: a 32 x 32 fp32 chunk, rows padded to 36 floats
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,6 +83,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// Pair variant: the copy lands in this CTA's shared memory, its bytes are counted on the LEADER CTA's mbarrier (same offset,
+// CTA-rank bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
+{
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(bar), "r"(rank) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -86,10 +115,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Pair variant: arrives on the barrier at this offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
+{
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
@@ -124,11 +163,11 @@ template <bool MN> __device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
 }
 template <bool MN> __device__ __forceinline__ uint32_t kstep_bytes() { return MN ? 1024u : (uint32_t)(UMMA_K * 4); }
 
-template <int BN, bool A_MN, bool B_MN> __host__ __device__ constexpr uint32_t instr_desc()
+template <int BN, bool A_MN, bool B_MN, int CTAS> __host__ __device__ constexpr uint32_t instr_desc()
 {
   // c_format F32 (bits 4-5 = 1), a/b format TF32 (bits 7-9 / 10-12 = 2), a/b major (bits 15 / 16), N >> 3 (bits 17-22), M >> 4 (24-28)
   return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)((BM * CTAS) >> 4) << 24);
 }
 
 struct Problem {
@@ -136,156 +175,238 @@ struct Problem {
   long long ldd;
   int splits, rb_per_split;    // split-K: split s reduces r-blocks [s * rb_per_split, ...)
   int relu, atomic;            // atomic: D += (split-K or accumulate into an existing gradient)
+  unsigned long long *prof;    // diagnostics (tc_gemm_debug_profile): per CTA 8 cycle counters of the three roles' waits, or NULL
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ D,
+// wait + (diagnostics only) the cycles it took
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, const unsigned long long *prof, unsigned long long &acc)
+{
+  if (prof == nullptr) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+
+template <int BN, bool A_MN, bool B_MN, int CTAS>
+__device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUtensorMap &tmB, float *__restrict__ D,
                  const float *__restrict__ bias, const Problem p)
 {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // 128-byte swizzle atoms are 1024-byte aligned
-  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t epi_base = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bars = epi_base + C::EPI_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
   auto tempty = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;          // rank 0 = leader: owns the "full" / "tmem empty" barriers, issues the MMAs
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128 * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (p.N + BN - 1) / BN;      // a tile is 128 * CTAS rows
   const int r_blocks = (p.R + BK - 1) / BK;
   const long long work = (long long)m_tiles * n_tiles * p.splits;
+  const long long w_first = blockIdx.x / CTAS, w_step = gridDim.x / CTAS;                     // both CTAs of a pair walk the same tiles
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      unsigned long long t_wait = 0;
+      const long long t_begin = clock64();
+      for (long long w = w_first; w < work; w += w_step) {
         const int nt = (int)(w % n_tiles), mt = (int)((w / n_tiles) % m_tiles), sp = (int)(w / ((long long)n_tiles * m_tiles));
         const int kb0 = sp * p.rb_per_split, kb1 = min(r_blocks, kb0 + p.rb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty(stage), phase ^ 1u);
-          mbar_expect_tx(full(stage), C::STAGE_BYTES);
+          mbar_wait_timed(empty(stage), phase ^ 1u, p.prof, t_wait);
+          if (rank == 0) mbar_expect_tx(full(stage), C::STAGE_BYTES * CTAS);            // the leader's barrier counts both CTAs' bytes
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const int m0 = (mt * CTAS + (int)rank) * BM, n0 = nt * BN + (int)rank * (BN / CTAS);
+          auto load = [&](uint32_t dst, const CUtensorMap *map, int c0, int c1) {
+            if (CTAS == 2) tma_load_2d_pair(dst, map, full(stage), c0, c1);
+            else tma_load_2d(dst, map, full(stage), c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, full(stage), kb * BK, mt * BM);
+            load(sa, &tmA, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * kSlabBytes, &tmA, full(stage), mt * BM + 32 * i, kb * BK);
+            for (int i = 0; i < BM / 32; ++i) load(sa + i * kSlabBytes, &tmA, m0 + 32 * i, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, full(stage), kb * BK, nt * BN);
+            load(sb, &tmB, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * kSlabBytes, &tmB, full(stage), nt * BN + 32 * i, kb * BK);
+            for (int i = 0; i < BN / CTAS / 32; ++i) load(sb + i * kSlabBytes, &tmB, n0 + 32 * i, kb * BK);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.prof != nullptr) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc<BN, A_MN, B_MN>();
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = instr_desc<BN, A_MN, B_MN, CTAS>();
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      unsigned long long t_full = 0, t_tempty = 0;
+      const long long t_begin = clock64();
+      for (long long w = w_first; w < work; w += w_step) {
         const int sp = (int)(w / ((long long)n_tiles * m_tiles));
         const int kb0 = sp * p.rb_per_split, kb1 = min(r_blocks, kb0 + p.rb_per_split);
-        mbar_wait(tempty(as), aphase ^ 1u);                       // the epilogue has drained this accumulator
+        mbar_wait_timed(tempty(as), aphase ^ 1u, p.prof, t_tempty);   // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full(stage), phase);
+          mbar_wait_timed(full(stage), phase, p.prof, t_full);
           tc_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(acc, smem_desc<A_MN>(sa + k * kstep_bytes<A_MN>()), smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>()), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(empty(stage));                              // smem slot free once these MMAs have read it
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = smem_desc<A_MN>(sa + k * kstep_bytes<A_MN>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
+            if (CTAS == 2) umma_tf32_pair(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (CTAS == 2) umma_commit_pair(empty(stage)); else umma_commit(empty(stage));   // smem slot(s) free once these MMAs have read them
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull(as));                                   // accumulator complete
+        if (CTAS == 2) umma_commit_pair(tfull(as)); else umma_commit(tfull(as));           // accumulator complete (in both CTAs)
         if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+      if (p.prof != nullptr) {
+        p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty;
+        p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
       }
     }
   } else {
     const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-    const int row_in_tile = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+    unsigned long long t_tfull = 0, t_ph[3] = {0, 0, 0};
+    const long long t_begin = clock64();
+    for (long long w = w_first; w < work; w += w_step) {
       const int nt = (int)(w % n_tiles), mt = (int)((w / n_tiles) % m_tiles);
-      mbar_wait(tfull(as), aphase);
+      mbar_wait_timed(tfull(as), aphase, p.prof, t_tfull);
       tc_fence_after();
-      const int m = mt * BM + row_in_tile;
-      float *drow = D + (long long)m * p.ldd;
+      // The accumulator comes out of TMEM one row per thread; a row-per-thread store would touch 32 different lines per
+      // instruction.  Each warp therefore turns its 32 x 32 chunk around in shared memory (rows padded to 36 floats: the
+      // 16-byte accesses of both phases are conflict-free) and stores 4 full 128-byte row segments per instruction.
+      const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * (32 * 36 * 4);
+      const int sub_row = lane >> 3, quad = lane & 7;
       const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+      const bool timed = p.prof != nullptr && warp == 2 && lane == 0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const long long tp0 = timed ? clock64() : 0;
         float v[32];
         tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(q * 32) << 16), v);
         const int n0 = nt * BN + c0;
-        if (m < p.M && n0 < p.N) {
-          if (bias != nullptr) {
+        if (n0 >= p.N) continue;                                  // warp-uniform
+        const long long tp1 = timed ? clock64() : 0;
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += (n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my_epi + (uint32_t)(lane * 36 + 4 * i) * 4), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                       "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+        __syncwarp();
+        const long long tp2 = timed ? clock64() : 0;
+        // bias / ReLU on the store side: a lane owns the same four columns for all rows of the chunk
+        const int n = n0 + 4 * quad;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) {
+          if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+            b4 = __ldg(reinterpret_cast<const float4 *>(bias + n));
+          } else {
+            b4.x = n < p.N ? __ldg(bias + n) : 0.f; b4.y = n + 1 < p.N ? __ldg(bias + n + 1) : 0.f;
+            b4.z = n + 2 < p.N ? __ldg(bias + n + 2) : 0.f; b4.w = n + 3 < p.N ? __ldg(bias + n + 3) : 0.f;
           }
-          if (p.relu) {
+        }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          const int r = r0 + sub_row;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(my_epi + (uint32_t)(r * 36 + 4 * quad) * 4) : "memory");
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          const int m = (mt * CTAS + (int)rank) * BM + q * 32 + r;
+          if (m >= p.M || n >= p.N) continue;
+          float *dst = D + (long long)m * p.ldd + n;
+          if (vec_ok && n + 3 < p.N) {
+            if (p.atomic)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            else
+              *reinterpret_cast<float4 *>(dst) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int n = n0 + i;
-            if (vec_ok && n + 3 < p.N) {
-              if (p.atomic)
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(drow + n), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
-                             "f"(v[i + 3]) : "memory");
-              else
-                *reinterpret_cast<float4 *>(drow + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (n + j < p.N) {
-                  if (p.atomic) atomicAdd(drow + n + j, v[i + j]);
-                  else drow[n + j] = v[i + j];
-                }
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < p.N) {
+                if (p.atomic) atomicAdd(dst + j, ov[j]);
+                else dst[j] = ov[j];
               }
             }
           }
         }
+        if (timed) {
+          const long long tp3 = clock64();
+          t_ph[0] += (unsigned long long)(tp1 - tp0); t_ph[1] += (unsigned long long)(tp2 - tp1); t_ph[2] += (unsigned long long)(tp3 - tp2);
+        }
       }
       tc_fence_before();
-      mbar_arrive(tempty(as));
+      if (CTAS == 2) mbar_arrive_cluster(tempty(as), 0u); else mbar_arrive(tempty(as));     // the leader's MMA warp waits for both CTAs' epilogues
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (p.prof != nullptr && warp == 2 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin);
+      p.prof[296 * 8 + blockIdx.x * 4 + 0] = t_ph[0]; p.prof[296 * 8 + blockIdx.x * 4 + 1] = t_ph[1]; p.prof[296 * 8 + blockIdx.x * 4 + 2] = t_ph[2];
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();         // nobody touches the peer's barriers / TMEM after this point
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ D,
+                 const float *__restrict__ bias, const Problem p)
+{
+  gemm_tf32_body<BN, A_MN, B_MN, 1>(tmA, tmB, D, bias, p);
+}
+
+// CTA-pair variant: cluster of two CTAs on one TPC, 256 x BN tiles, tcgen05.mma.cta_group::2.
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ D,
+                      const float *__restrict__ bias, const Problem p)
+{
+  gemm_tf32_body<BN, A_MN, B_MN, 2>(tmA, tmB, D, bias, p);
 }
 
 }  // namespace tcgemm
