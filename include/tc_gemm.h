@@ -31,6 +31,18 @@ extern "C" {
 int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
                  float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k);
 
+/* Same GEMM with two more epilogue stages, for the FFN of DefAttnLayer / FocusedDecoderLayer (linear2(dropout(relu(linear1(x)))),
+ * decoder_blocks.py:172-175, focused_decoder.py:186-187):
+ *   p_drop > 0 : after bias / ReLU, element (m, n) is dropped with probability p_drop (kept values scaled by 1 / (1 - p_drop)); the keep
+ *                decision is the counter-based hash of (seed, m * N + n) also used by fused_ln.h -- no mask tensor is stored.
+ *   gate       : D = result * (gate[m, n] > 0 ? gate_scale : 0), gate laid out like D: the backward of ReLU + dropout taken from the
+ *                saved activation h = dropout(relu(.)) (h > 0 exactly where the unit was active and kept), fused into the
+ *                grad_input GEMM of the second Linear.
+ * Both need N % 4 == 0, ldd % 4 == 0, 16-byte aligned D / gate and accumulate == 0. */
+int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
+                    float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k,
+                    const float *gate, float gate_scale, float p_drop, unsigned long long seed);
+
 /* Diagnostics: while a device buffer of 12 x 296 uint64 is installed, every launch writes per CTA the cycles its three roles spent
  * waiting: [0] producer on "empty", [1] producer total, [2] MMA on "full", [3] MMA on "tmem empty", [4] MMA total, [5] epilogue on
  * "tmem full", [6] epilogue total; then at 8 * 296 + 4 * cta: epilogue cycles in TMEM load / shared-memory stage / store.  NULL (the default) removes it.  Not thread-safe; tools/exp_gemm_roles.py uses it. */

@@ -216,3 +216,36 @@ def test_strict_fp32_request_bypasses_the_tf32_kernel():
         y2 = lin(x, relu=True)
         assert _lib.lib().msda3d_launch_count() == n0 + 1
     assert float((y - y2).abs().max()) < 2e-2
+
+
+def test_ffn_function_matches_fp64_and_its_dropout_is_consistent():
+    """FFNFunction (bias + ReLU + dropout in the first GEMM's epilogue, the gate in the grad_input GEMM of the second) against fp64
+    autograd with the very mask the kernel drew (recovered from the saved activation: h == 0 where relu(pre) > 0 means dropped)."""
+    from transoar_b200.linear import FFNFunction
+    gen = torch.Generator().manual_seed(11)
+    M, K, Hd, N, p = 3000, 384, 1024, 384, 0.1
+    x = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    w1 = (torch.randn(Hd, K, generator=gen) / math.sqrt(K)).cuda().requires_grad_(True)
+    b1 = (torch.randn(Hd, generator=gen) * 0.1).cuda().requires_grad_(True)
+    w2 = (torch.randn(N, Hd, generator=gen) / math.sqrt(Hd)).cuda().requires_grad_(True)
+    b2 = (torch.randn(N, generator=gen) * 0.1).cuda().requires_grad_(True)
+    g = torch.randn(M, N, generator=gen).cuda()
+    for pp in (0.0, p):
+        for t in (x, w1, b1, w2, b2):
+            t.grad = None
+        y = FFNFunction.apply(x, w1, b1, w2, b2, pp, 77)
+        h = [t for t in y.grad_fn.saved_tensors if t.shape == (M, Hd)][0]
+        y.backward(g)
+        xd, w1d, b1d, w2d, b2d = (t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2))
+        pre = torch.relu(xd @ w1d.t() + b1d)
+        keep = ((h > 0) | (pre.detach() <= 1e-4)).double()                    # kernel's mask where it matters (active units)
+        if pp > 0:
+            rate = 1 - float(((h > 0) & (pre.detach() > 1e-4)).sum() / (pre.detach() > 1e-4).sum())
+            assert abs(rate - pp) < 5e-3, rate
+        hd = pre * keep / (1 - pp)
+        yd = hd @ w2d.t() + b2d
+        yd.backward(g.double())
+        tol = 2e-2
+        assert float((y.double() - yd).abs().max()) < tol * float(yd.abs().max())
+        for a, b_ in ((x, xd), (w1, w1d), (b1, b1d), (w2, w2d), (b2, b2d)):
+            assert float((a.grad.double() - b_.grad).abs().max()) < tol * float(b_.grad.abs().max()), a.shape

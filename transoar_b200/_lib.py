@@ -48,6 +48,8 @@ _SIGNATURES = {
     "stem_conv3d_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
     # include/tc_gemm.h
     "tc_gemm_debug_profile": (None, [_vp]),
+    "tc_gemm_tf32_ex": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6
+                        + [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong]),
     "tc_gemm_tf32": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6),
 }
 

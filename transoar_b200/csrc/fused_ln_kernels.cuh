@@ -16,28 +16,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "hash_rng.cuh"
+
 namespace fusedln {
+
+using hashrng::keep4;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxNV = 8;                     // float4 groups per lane: C <= 4 * 32 * 8 = 1024
-
-// splitmix64 finaliser over (seed, index of the float4): four 16-bit uniforms per call, one per element of the float4
-__device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx)
-{
-  uint64_t x = idx * 0x9E3779B97F4A7C15ull + seed;
-  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27; x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return x;
-}
-// keep element j (0..3) of float4 number `idx` iff its 16-bit uniform >= thresh (thresh = round(p * 65536))
-__device__ __forceinline__ void keep4(uint64_t seed, uint64_t idx, uint32_t thresh, float scale, float (&m)[4])
-{
-  const uint64_t r = mix64(seed, idx);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) m[j] = ((uint32_t)(r >> (16 * j)) & 0xFFFFu) >= thresh ? scale : 0.f;
-}
 
 __device__ __forceinline__ float warp_sum(float v)
 {

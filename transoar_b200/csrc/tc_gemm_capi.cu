@@ -140,11 +140,22 @@ extern "C" void tc_gemm_debug_profile(unsigned long long *device_counters) { g_p
 extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
                             float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k)
 {
+  return tc_gemm_tf32_ex(stream, A, a_mn_major, lda, B, b_mn_major, ldb, D, ldd, bias, M, N, R, relu, accumulate, split_k, nullptr, 1.f, 0.f, 0ull);
+}
+
+extern "C" int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,
+                               float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k,
+                               const float *gate, float gate_scale, float p_drop, unsigned long long seed)
+{
   if (A == nullptr || B == nullptr || D == nullptr || M <= 0 || N <= 0 || R <= 0 || lda <= 0 || ldb <= 0 || ldd < N) return MSDA3D_EINVAL;
   if (lda % 4 != 0 || ldb % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
       (reinterpret_cast<uintptr_t>(D) & 3))
     return MSDA3D_EALIGN;
   if (split_k < 0 || (split_k != 1 && !accumulate)) return MSDA3D_EINVAL;
+  if (gate != nullptr || p_drop > 0.f) {                         // fused gate / dropout: vector epilogue only, never with accumulation
+    if (accumulate || p_drop < 0.f || p_drop >= 1.f || N % 4 != 0 || ldd % 4 != 0) return MSDA3D_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(D) & 15) || (reinterpret_cast<uintptr_t>(gate) & 15)) return MSDA3D_EALIGN;
+  }
 
   // tile width: fewest column tiles first (every extra one re-reads the whole A operand), then least padding
   int BN = 128;
@@ -164,6 +175,9 @@ extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long l
   if (splits > r_blocks) splits = r_blocks;
   tcgemm::Problem p;
   p.M = M; p.N = N; p.R = R; p.ldd = ldd; p.relu = relu; p.atomic = accumulate ? 1 : 0;
+  p.gate = gate; p.gate_scale = gate_scale; p.seed = seed;
+  p.drop_thresh = p_drop > 0.f ? (unsigned int)(p_drop * 65536.f + 0.5f) : 0u;
+  p.drop_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.prof = g_prof.load();
   p.rb_per_split = (r_blocks + splits - 1) / splits;
   p.splits = (r_blocks + p.rb_per_split - 1) / p.rb_per_split;   // no empty split

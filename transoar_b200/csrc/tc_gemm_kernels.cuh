@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "hash_rng.cuh"
+
 namespace tcgemm {
 
 constexpr int BM = 128;               // rows of D per tile = TMEM lanes
@@ -175,6 +177,12 @@ struct Problem {
   long long ldd;
   int splits, rb_per_split;    // split-K: split s reduces r-blocks [s * rb_per_split, ...)
   int relu, atomic;            // atomic: D += (split-K or accumulate into an existing gradient)
+  // fused epilogue extras (NULL / 0 = off); both need the vector path (ldd % 4 == 0, N % 4 == 0, 16-byte aligned D / gate)
+  const float *gate;           // D = result * (gate[m, n] > 0 ? gate_scale : 0): gradient of ReLU (+ dropout) taken from the saved activation
+  float gate_scale;
+  unsigned int drop_thresh;    // dropout after bias / ReLU: keep iff 16-bit hash(seed, element) >= drop_thresh, kept values * drop_scale
+  float drop_scale;
+  unsigned long long seed;
   unsigned long long *prof;    // diagnostics (tc_gemm_debug_profile): per CTA 8 cycle counters of the three roles' waits, or NULL
 };
 
@@ -352,11 +360,21 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
           const int m = (mt * CTAS + (int)rank) * BM + q * 32 + r;
           if (m >= p.M || n >= p.N) continue;
           float *dst = D + (long long)m * p.ldd + n;
+          if (p.drop_thresh != 0u) {                              // host guarantees the vector path: N % 4 == 0
+            float keep[4];
+            hashrng::keep4(p.seed, ((unsigned long long)m * p.N + n) >> 2, p.drop_thresh, p.drop_scale, keep);
+            o.x *= keep[0]; o.y *= keep[1]; o.z *= keep[2]; o.w *= keep[3];
+          }
+          if (p.gate != nullptr) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gate + (long long)m * p.ldd + n));
+            o.x = g4.x > 0.f ? o.x * p.gate_scale : 0.f; o.y = g4.y > 0.f ? o.y * p.gate_scale : 0.f;
+            o.z = g4.z > 0.f ? o.z * p.gate_scale : 0.f; o.w = g4.w > 0.f ? o.w * p.gate_scale : 0.f;
+          }
           if (vec_ok && n + 3 < p.N) {
             if (p.atomic)
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             else
-              *reinterpret_cast<float4 *>(dst) = o;
+              __stcs(reinterpret_cast<float4 *>(dst), o);               // write-once stream: evict-first keeps the operands in L2
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll

@@ -23,7 +23,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .fused_ln import add_dropout_layer_norm
-from .linear import TCLinear
+from .linear import TCLinear, ffn
 
 _QPG = 32     # query rows per CTA in the kernel (roiattn::TQ)
 
@@ -214,9 +214,11 @@ class FocusedDecoderLayer(nn.Module):
         k = src if src_pos is None else src + src_pos
         ca, weights = self.cross_attn(q, k, src)
         tgt = add_dropout_layer_norm(tgt, ca, self.norm1, self.dropout1.p, self.training)
-        hidden = self.linear1(tgt, relu=True) if self._fuse_relu else self.activation(self.linear1(tgt))
-        ffn = self.linear2(self.dropout3(hidden))
-        return add_dropout_layer_norm(tgt, ffn, self.norm3, self.dropout4.p, self.training), weights
+        if self._fuse_relu:
+            out = ffn(tgt, self.linear1, self.linear2, self.dropout3.p, self.training)
+        else:
+            out = self.linear2(self.dropout3(self.activation(self.linear1(tgt))))
+        return add_dropout_layer_norm(tgt, out, self.norm3, self.dropout4.p, self.training), weights
 
 
 class FocusedDecoderModel(nn.Module):

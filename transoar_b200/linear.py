@@ -21,15 +21,17 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=None, relu=False, accumulate=False, split_k=1):
-    """D[M,N] (+)= sum_r A(m,r) B(n,r) (+bias)(relu) on the current stream; see include/tc_gemm.h for the operand forms."""
+def gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=None, relu=False, accumulate=False, split_k=1, gate=None, gate_scale=1.0,
+         p_drop=0.0, seed=0):
+    """D[M,N] (+)= sum_r A(m,r) B(n,r) (+bias)(relu)(dropout)(gate) on the current stream; see include/tc_gemm.h."""
     if not (A.is_cuda and B.is_cuda and D.is_cuda):
         raise RuntimeError("tc_gemm: Not implemented on the CPU")
     if A.dtype != torch.float32 or B.dtype != torch.float32 or D.dtype != torch.float32:
         raise RuntimeError("tc_gemm: fp32 tensors only")
     with torch.cuda.device(D.device):
-        rc = _lib.lib().tc_gemm_tf32(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(A), int(a_mn), lda, _p(B), int(b_mn), ldb,
-                                     _p(D), D.stride(0), _p(bias), M, N, R, int(relu), int(accumulate), split_k)
+        rc = _lib.lib().tc_gemm_tf32_ex(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(A), int(a_mn), lda, _p(B), int(b_mn), ldb,
+                                        _p(D), D.stride(0), _p(bias), M, N, R, int(relu), int(accumulate), split_k,
+                                        _p(gate), float(gate_scale), float(p_drop), int(seed))
     _lib.check(rc, "tc_gemm_tf32")
     return D
 
@@ -69,6 +71,57 @@ class LinearFunction(Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
         return dx, dw, db, None
+
+
+class FFNFunction(Function):
+    """y = W2 dropout(relu(W1 x + b1)) + b2 -- the feed-forward block of DefAttnLayer / FocusedDecoderLayer (decoder_blocks.py:172-175,
+    focused_decoder.py:186-187) as two GEMMs forward and four backward, with everything elementwise in their epilogues: bias + ReLU +
+    dropout in the first GEMM (hash mask, never stored), and the ReLU / dropout gradient in the grad_input GEMM of the second
+    Linear, gated by the saved activation h (h > 0 exactly where a unit was active and kept)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p, seed):
+        K, Hd, N = x.shape[-1], w1.shape[0], w2.shape[0]
+        x2 = x.reshape(-1, K).contiguous()
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        M = x2.shape[0]
+        h = torch.empty(M, Hd, dtype=torch.float32, device=x.device)
+        gemm(x2, 0, K, w1c, 0, K, h, M, Hd, K, bias=b1.contiguous(), relu=True, p_drop=p, seed=seed)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        gemm(h, 0, Hd, w2c, 0, Hd, y, M, N, Hd, bias=b2.contiguous())
+        ctx.save_for_backward(x2, w1c, w2c, h)
+        ctx.p, ctx.in_shape = float(p), x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w1, w2, h = ctx.saved_tensors
+        M, K = x2.shape
+        Hd, N = w1.shape[0], w2.shape[0]
+        dy2 = dy.reshape(M, N).contiguous()
+        dh = torch.empty(M, Hd, dtype=torch.float32, device=dy.device)
+        gemm(dy2, 0, N, w2, 1, Hd, dh, M, Hd, N, gate=h, gate_scale=1.0 / (1.0 - ctx.p))          # (dY W2) * relu'/dropout gate
+        dw2 = torch.zeros(N, Hd, dtype=torch.float32, device=dy.device)
+        gemm(dy2, 1, N, h, 1, Hd, dw2, N, Hd, M, accumulate=True, split_k=0)
+        dw1 = torch.zeros(Hd, K, dtype=torch.float32, device=dy.device)
+        gemm(dh, 1, Hd, x2, 1, K, dw1, Hd, K, M, accumulate=True, split_k=0)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+            gemm(dh, 0, Hd, w1, 1, K, dx, M, K, Hd)
+            dx = dx.reshape(ctx.in_shape)
+        return dx, dw1, dh.sum(0), dw2, dy2.sum(0), None, None
+
+
+def ffn(x, linear1, linear2, p, training):
+    """``linear2(dropout(relu(linear1(x)), p))``: the fused two-GEMM form when both layers are tcgen05-eligible, else the composition."""
+    if (tc_eligible(x, linear1.weight) and tc_eligible(x, linear2.weight) and linear1.bias is not None and linear2.bias is not None
+            and x.shape[-1] == linear1.weight.shape[1]):
+        p = float(p) if training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        return FFNFunction.apply(x, linear1.weight, linear1.bias, linear2.weight, linear2.bias, p, seed)
+    return linear2(F.dropout(F.relu(linear1(x)), p, training))
 
 
 def linear(x, weight, bias=None, relu=False):

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .fused_ln import add_dropout_layer_norm
-from .linear import TCLinear
+from .linear import TCLinear, ffn
 from .ops.modules import MSDeformAttn
 
 
@@ -43,9 +43,11 @@ class DefAttnLayer(nn.Module):
         query = src if pos is None else src + pos
         attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
         src = add_dropout_layer_norm(src, attn, self.norm1, self.dropout1.p, self.training)       # norm1(src + dropout1(attn)), one kernel
-        hidden = self.linear1(src, relu=True) if self._fuse_relu else self.activation(self.linear1(src))
-        ffn = self.linear2(self.dropout2(hidden))
-        return add_dropout_layer_norm(src, ffn, self.norm2, self.dropout3.p, self.training)       # norm2(src + dropout3(ffn))
+        if self._fuse_relu:      # linear2(dropout2(relu(linear1(src)))): bias + ReLU + dropout live in the first GEMM's epilogue
+            out = ffn(src, self.linear1, self.linear2, self.dropout2.p, self.training)
+        else:
+            out = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        return add_dropout_layer_norm(src, out, self.norm2, self.dropout3.p, self.training)       # norm2(src + dropout3(ffn))
 
 
 class DefAttnTransformer(nn.Module):
