@@ -87,6 +87,31 @@ int msda3d_forward_backward_host(int device, int dtype, const void *grad_output,
                                  void *output, void *grad_value, void *grad_sampling_loc, void *grad_attn_weight);
 void msda3d_host_release(void);
 
+/* Fused prologue: the part of MSDeformAttn.forward between the two small Linear layers and the op
+ * (transoar/models/ops/modules/ms_deform_attn.py:115-126)
+ *     attention_weights = softmax(logits.view(N, Lq, M, L*P), -1)
+ *     sampling_locations = reference_points[:, :, None, :, None, :] + sampling_offsets / (W, H, D)_l
+ * is done inside the kernels: they read the RAW sampling offsets [N, Lq, M, L, P, 3] and attention logits [N, Lq, M, L, P] (the
+ * outputs of the sampling_offsets / attention_weights Linear layers) plus reference_points [ref_batch (1 or N), Lq, L, 3], and the
+ * backward returns the gradients with respect to the raw offsets and logits (softmax backward and the 1 / (W, H, D) scale applied
+ * in-kernel).  sampling_loc and attn_weight -- 540 MB per layer at VISCERAL -- never exist in HBM, and six ATen kernels per layer
+ * (softmax, div, add and their gradients) disappear.  The location is computed as fadd(ref, fdiv(offset, size)) -- the two fp32
+ * roundings ATen performs -- so the sampled voxels are the same as on the unfused route; the softmax differs from ATen's in the
+ * last ulp.  fp32 only; requires the vector kernels and L * P <= C / 4 lanes (msda3d_fused_supported says so), e.g. C = 64,
+ * L * P <= 16: the reference's configuration.  Otherwise MSDA3D_EINVAL -- callers use the unfused entry points. */
+int msda3d_fused_supported(int channels, int num_levels, int num_point);
+
+int msda3d_forward_fused(void *stream, const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                         const float *reference_points, int ref_batch, const float *sampling_offsets, const float *attn_logits,
+                         int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                         float *output);
+
+int msda3d_backward_fused(void *stream, const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start_index, const float *reference_points, int ref_batch,
+                          const float *sampling_offsets, const float *attn_logits, int batch, int spatial_size, int num_heads,
+                          int channels, int num_levels, int num_query, int num_point, float *grad_value,
+                          float *grad_sampling_offsets, float *grad_attn_logits);
+
 /* Test hook: the sampling-index arithmetic of the production kernels, one record per sample (N*Lq*M*L*P):
  * idx int32[4] = {in_range, d_low, h_low, w_low}, frac[3] = {ld, lh, lw} (fp32 for F32/BF16/F16, fp64 for F64).
  * Device pointers.  Compared bit-for-bit with the oracle in tests/. */

@@ -379,3 +379,64 @@ def test_refine_block_against_reference_block_fixture():
         assert _relerr(_np(fmaps[i].grad), z[f"grad_fmap{i}"]) < 2e-4
     for k, p in blk.named_parameters():
         assert _relerr(_np(p.grad), z["pg." + k]) < 2e-4, k
+
+
+@pytest.mark.parametrize("geom", [((8, 8, 16), (4, 4, 8), (2, 2, 4), (1, 1, 2)), ((6, 5, 7), (3, 3, 4)), ((4, 4, 4),)])
+@pytest.mark.parametrize("ref_batch", [1, 2])
+def test_fused_prologue_equals_the_three_step_prologue_plus_op(geom, ref_batch):
+    """msda3d_*_fused against softmax -> ref + off / (W,H,D) -> MSDeformAttnFunction on the same raw offsets / logits:
+    the sampled voxels are the same (identical location arithmetic), the softmax differs in the last ulp."""
+    from transoar_b200.ops.functions import MSDeformAttnFusedFunction
+    N, M, C, P = 2, 6, 64, 16 // len(geom) if len(geom) != 3 else 5
+    L = len(geom)
+    P = 16 // L
+    gen = torch.Generator().manual_seed(L * 10 + ref_batch)
+    shapes = torch.tensor(geom, dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    starts = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    Lq = S
+    value = (torch.randn(N, S, M, C, generator=gen)).to(DEV).requires_grad_(True)
+    ref = torch.rand(ref_batch, Lq, L, 3, generator=gen).to(DEV)
+    off = (torch.randn(N, Lq, M, L, P, 3, generator=gen) * 2.0).to(DEV).requires_grad_(True)       # in voxels: some samples leave the volume
+    logit = torch.randn(N, Lq, M, L, P, generator=gen).to(DEV).requires_grad_(True)
+    g = torch.randn(N, Lq, M * C, generator=gen).to(DEV)
+    shapes_d, starts_d = shapes.to(DEV), starts.to(DEV)
+    out = MSDeformAttnFusedFunction.apply(value, shapes_d, starts_d, ref, off, logit)
+    out.backward(g)
+    got = (out.detach(), value.grad.clone(), off.grad.clone(), logit.grad.clone())
+    value.grad = off.grad = logit.grad = None
+    aw = torch.softmax(logit.view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+    loc = ref[:, :, None, :, None, :] + off / shapes_d.flip(-1)[None, None, None, :, None, :]
+    want = MSDeformAttnFunction.apply(value, shapes_d, starts_d, loc.contiguous(), aw, 64)
+    want.backward(g)
+    assert _relerr(_np(got[0]), _np(want)) < 2e-6
+    assert _relerr(_np(got[1]), _np(value.grad)) < 1e-5
+    assert _relerr(_np(got[2]), _np(off.grad)) < 2e-5
+    assert _relerr(_np(got[3]), _np(logit.grad)) < 2e-5
+
+
+def test_module_takes_the_fused_route_and_matches_the_unfused_one():
+    from transoar_b200 import _lib
+    torch.manual_seed(3)
+    m = MSDeformAttn(d_model=384, n_levels=4, n_heads=6, n_points=4).to(DEV)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.05)
+    shapes = torch.tensor(((8, 8, 12), (4, 4, 6), (2, 2, 3), (1, 1, 2)), dtype=torch.long, device=DEV)
+    starts = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    x = torch.randn(2, S, 384, device=DEV)
+    ref = torch.rand(1, S, 4, 3, device=DEV)
+    outs = []
+    for fused in (True, False):
+        m.fuse_prologue = fused
+        m.zero_grad()
+        xq = x.clone().requires_grad_(True)
+        n0 = _lib.lib().msda3d_launch_count()
+        y = m(xq, ref, xq, shapes, starts)
+        y.square().mean().backward()
+        outs.append((y.detach(), xq.grad.clone(), m.sampling_offsets.weight.grad.clone(), m.attention_weights.bias.grad.clone(),
+                     _lib.lib().msda3d_launch_count() - n0))
+    assert outs[0][4] == outs[1][4] == 2                                      # one forward + one backward launch of this library either way
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert _relerr(_np(a), _np(b)) < 5e-5

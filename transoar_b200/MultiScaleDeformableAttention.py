@@ -123,3 +123,45 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
             _p(grad_value), _p(grad_loc), _p(grad_aw))
     _lib.check(rc, "ms_deform_attn_backward")
     return [grad_value.to(value.dtype), grad_loc.to(loc_dtype), grad_aw.to(aw_dtype)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused prologue (include/msda3d.h, msda3d_*_fused): softmax over the unit's L*P logits and ref + offset / (W, H, D) inside the op
+# ---------------------------------------------------------------------------------------------------------------
+def fused_supported(value, reference_points, sampling_offsets, attn_logits):
+    """fp32 CUDA tensors, vector kernels, L * P <= C / 4 (C = 64, L * P <= 16: the reference's configuration), 3-D reference points."""
+    if not (value.is_cuda and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32 and attn_logits.dtype == torch.float32
+            and reference_points.dtype == torch.float32 and reference_points.shape[-1] == 3 and not torch.is_autocast_enabled()):
+        return False
+    L, P = sampling_offsets.shape[3], sampling_offsets.shape[4]
+    return bool(_lib.lib().msda3d_fused_supported(value.shape[3], L, P)) and reference_points.shape[0] in (1, value.shape[0])
+
+
+def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits):
+    """-> output [N, Lq, M*C] from raw offsets [N,Lq,M,L,P,3], logits [N,Lq,M,L,P] and reference points [1|N, Lq, L, 3]."""
+    _check([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+            ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits)], 1)
+    N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_offsets)
+    out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device), _timed("fwd"):
+        rc = _lib.lib().msda3d_forward_fused(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(value), _p(spatial_shapes), _p(level_start_index),
+            _p(reference_points), reference_points.shape[0], _p(sampling_offsets), _p(attn_logits), N, S, M, C, L, Lq, P, _p(out))
+    _lib.check(rc, "ms_deform_attn_forward_fused")
+    return out
+
+
+def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits, grad_output):
+    """-> [grad_value, grad_sampling_offsets, grad_attn_logits]."""
+    _check([("value", value), ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+            ("grad_output", grad_output)], 1)
+    N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_offsets)
+    grad_value = torch.empty_like(value)                                         # zero-filled by the library
+    grad_off, grad_logit = torch.empty_like(sampling_offsets), torch.empty_like(attn_logits)
+    with torch.cuda.device(value.device), _timed("bwd"):
+        rc = _lib.lib().msda3d_backward_fused(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(grad_output), _p(value), _p(spatial_shapes), _p(level_start_index),
+            _p(reference_points), reference_points.shape[0], _p(sampling_offsets), _p(attn_logits), N, S, M, C, L, Lq, P,
+            _p(grad_value), _p(grad_off), _p(grad_logit))
+    _lib.check(rc, "ms_deform_attn_backward_fused")
+    return [grad_value, grad_off, grad_logit]

@@ -22,6 +22,9 @@ _SIGNATURES = {
     "msda3d_set_tuning": (_ci, [ctypes.c_char_p, _ci]),
     "msda3d_forward": (_ci, [_vp, _ci] + [_vp] * 5 + _DIMS + [_vp]),
     "msda3d_backward": (_ci, [_vp, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
+    "msda3d_fused_supported": (_ci, [_ci, _ci, _ci]),
+    "msda3d_forward_fused": (_ci, [_vp] * 5 + [_ci] + [_vp] * 2 + _DIMS + [_vp]),
+    "msda3d_backward_fused": (_ci, [_vp] * 6 + [_ci] + [_vp] * 2 + _DIMS + [_vp] * 3),
     "msda3d_forward_host": (_ci, [_ci, _ci] + [_vp] * 5 + _DIMS + [_vp]),
     "msda3d_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
     "msda3d_forward_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 4),

@@ -285,6 +285,72 @@ int msda3d_backward(void *stream, int dtype, const void *grad_output, const void
   }
 }
 
+// Fused prologue variants (fp32, vector kernels only, L * P <= G lanes of a unit): see include/msda3d.h.
+static int fused_shape(const Dims &d, const void *value, const void *other, int &G, int &NV)
+{
+  if (!vec_ok<float>(d, value, other, G, NV)) return MSDA3D_EINVAL;
+  if (d.L * d.P > G) return MSDA3D_EINVAL;
+  return MSDA3D_OK;
+}
+
+int msda3d_fused_supported(int channels, int num_levels, int num_point)
+{
+  int G = 0, NV = 0;
+  if (channels <= 0 || num_levels <= 0 || num_point <= 0 || num_levels > kMaxLevels) return 0;
+  return vec_shape<float>(channels, G, NV) && num_levels * num_point <= G;
+}
+
+int msda3d_forward_fused(void *stream, const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                         const float *reference_points, int ref_batch, const float *sampling_offsets, const float *attn_logits, int batch,
+                         int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point, float *output)
+{
+  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output) return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int rc = check_dims(d)) return rc;
+  if (ref_batch != 1 && ref_batch != batch) return MSDA3D_EINVAL;
+  if (!aligned(reference_points, 4) || !aligned(sampling_offsets, 4) || !aligned(attn_logits, 4) || !aligned(spatial_shapes, 8) ||
+      !aligned(level_start_index, 8))
+    return MSDA3D_EALIGN;
+  int g_ = 0, nv_ = 0;
+  if (int rc = fused_shape(d, value, output, g_, nv_)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
+  const int grid = vec_grid(units, g_);
+  VEC_DISPATCH(g_, nv_, fwd_vec_kernel<float, G, NV, MinBlocks<float, NV>::fwd, 1><<<grid, kThreads, 0, st>>>(
+                            value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d.N, d.S, d.M, d.L, d.Lq, d.P, output,
+                            use_brick(d), reference_points, rb));
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
+int msda3d_backward_fused(void *stream, const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start_index, const float *reference_points, int ref_batch, const float *sampling_offsets,
+                          const float *attn_logits, int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, float *grad_value, float *grad_sampling_offsets, float *grad_attn_logits)
+{
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !grad_value ||
+      !grad_sampling_offsets || !grad_attn_logits)
+    return MSDA3D_EINVAL;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int rc = check_dims(d)) return rc;
+  if (ref_batch != 1 && ref_batch != batch) return MSDA3D_EINVAL;
+  if (!aligned(grad_value, 16) || !aligned(grad_sampling_offsets, 4) || !aligned(grad_attn_logits, 4) || !aligned(reference_points, 4) ||
+      !aligned(sampling_offsets, 4) || !aligned(attn_logits, 4))
+    return MSDA3D_EALIGN;
+  int g_ = 0, nv_ = 0;
+  if (int rc = fused_shape(d, value, grad_output, g_, nv_)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, (size_t)d.N * d.S * d.M * d.C * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
+  const int grid = vec_grid(units, g_);
+  VEC_DISPATCH(g_, nv_, bwd_vec_kernel<float, G, NV, MinBlocks<float, NV>::bwd, 0, 1><<<grid, kThreads, 0, st>>>(
+                            grad_output, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d.N, d.S, d.M, d.L, d.Lq,
+                            d.P, grad_value, grad_sampling_offsets, grad_attn_logits, use_brick(d), reference_points, rb));
+  ++g_launches;
+  return (int)cudaGetLastError();
+}
+
 int msda3d_debug_indices(void *stream, int dtype, const int64_t *spatial_shapes, const void *sampling_loc, int batch, int num_heads,
                          int num_levels, int num_query, int num_point, int32_t *idx, void *frac)
 {

@@ -284,32 +284,90 @@ __device__ __forceinline__ UnitCoords slot_unit(bool brick, long long t, int ui,
   return c;
 }
 
-// Lane-side preparation of sample s of unit uc (cuh:405-428 + cuh:36-46 + corner guards cuh:60-107).
-__device__ __forceinline__ PreparedSample prepare_sample(const int4 *lv, const float *__restrict__ loc, const float *__restrict__ aw,
-                                                         const UnitCoords &uc, int s, int LP, int P, int S, int MC, int C)
+// Lane-side preparation of one sample given its normalised location (x, y, z) and attention weight
+// (cuh:424-428 + cuh:36-46 + corner guards cuh:60-107).
+__device__ __forceinline__ PreparedSample prepare_located(const int4 li, float x, float y, float z, float w, const UnitCoords &uc, int S, int MC, int C)
 {
   PreparedSample ps;
   ps.a = make_float4(0.f, 0.f, 0.f, 0.f);
   ps.b = make_float4(0.f, 0.f, 0.f, 0.f);
   ps.c = make_int4(0, 0, 0, 0);
+  const Sample<float> sm = locate<float>(x, y, z, li.x, li.y, li.z);
+  if (sm.mask != 0) {
+    const bool vdl = sm.d_low >= 0, vdh = sm.d_low + 1 <= li.x - 1;
+    const bool vhl = sm.h_low >= 0, vhh = sm.h_low + 1 <= li.y - 1;
+    const bool vwl = sm.w_low >= 0, vwh = sm.w_low + 1 <= li.z - 1;
+    const int sW = MC, sH = li.z * MC, sD = li.y * sH;
+    const unsigned vox = (unsigned)((max(sm.d_low, 0) * li.y + max(sm.h_low, 0)) * li.z + max(sm.w_low, 0));
+    const unsigned off = ((unsigned)(uc.b * S) + (unsigned)li.w + vox) * (unsigned)MC + (unsigned)(uc.m * C);
+    ps.a = make_float4(__uint_as_float(off), w, vdl ? 1.f - sm.ld : 0.f, vdh ? sm.ld : 0.f);
+    ps.b = make_float4(vhl ? 1.f - sm.lh : 0.f, vhh ? sm.lh : 0.f, vwl ? 1.f - sm.lw : 0.f, vwh ? sm.lw : 0.f);
+    ps.c = make_int4((vdl && vdh) ? sD : 0, (vhl && vhh) ? sH : 0, (vwl && vwh) ? sW : 0,
+                     1 | (vdl << 1) | (vdh << 2) | (vhl << 3) | (vhh << 4) | (vwl << 5) | (vwh << 6));
+  }
+  return ps;
+}
+
+// Sample s of unit uc from the op's own inputs: sampling_loc / attn_weight (cuh:405-423).
+__device__ __forceinline__ PreparedSample prepare_sample(const int4 *lv, const float *__restrict__ loc, const float *__restrict__ aw,
+                                                         const UnitCoords &uc, int s, int LP, int P, int S, int MC, int C)
+{
   if (uc.active && s < LP) {
-    const int4 li = lv[s / P];
     const long long si = uc.u * LP + s;
     const float x = ldg_stream(loc + 3 * si), y = ldg_stream(loc + 3 * si + 1), z = ldg_stream(loc + 3 * si + 2);
-    const Sample<float> sm = locate<float>(x, y, z, li.x, li.y, li.z);
-    if (sm.mask != 0) {
-      const bool vdl = sm.d_low >= 0, vdh = sm.d_low + 1 <= li.x - 1;
-      const bool vhl = sm.h_low >= 0, vhh = sm.h_low + 1 <= li.y - 1;
-      const bool vwl = sm.w_low >= 0, vwh = sm.w_low + 1 <= li.z - 1;
-      const int sW = MC, sH = li.z * MC, sD = li.y * sH;
-      const unsigned vox = (unsigned)((max(sm.d_low, 0) * li.y + max(sm.h_low, 0)) * li.z + max(sm.w_low, 0));
-      const unsigned off = ((unsigned)(uc.b * S) + (unsigned)li.w + vox) * (unsigned)MC + (unsigned)(uc.m * C);
-      ps.a = make_float4(__uint_as_float(off), ldg_stream(aw + si), vdl ? 1.f - sm.ld : 0.f, vdh ? sm.ld : 0.f);
-      ps.b = make_float4(vhl ? 1.f - sm.lh : 0.f, vhh ? sm.lh : 0.f, vwl ? 1.f - sm.lw : 0.f, vwh ? sm.lw : 0.f);
-      ps.c = make_int4((vdl && vdh) ? sD : 0, (vhl && vhh) ? sH : 0, (vwl && vwh) ? sW : 0,
-                       1 | (vdl << 1) | (vdh << 2) | (vhl << 3) | (vhh << 4) | (vwl << 5) | (vwh << 6));
-    }
+    return prepare_located(lv[s / P], x, y, z, ldg_stream(aw + si), uc, S, MC, C);
   }
+  PreparedSample ps;
+  ps.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.c = make_int4(0, 0, 0, 0);
+  return ps;
+}
+
+template <int G> __device__ __forceinline__ float group_max(float v)
+{
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+template <int G> __device__ __forceinline__ float group_sum_f(float v)
+{
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Fused prologue (MSDeformAttn.forward, transoar/models/ops/modules/ms_deform_attn.py:115-126): the op reads the RAW outputs of the
+// sampling_offsets / attention_weights Linear layers and does, for the L*P <= G samples of its unit,
+//     attn = softmax(logits)                   (over the unit's L*P samples; lanes of the group hold one sample each)
+//     loc  = ref[q, l] + offset / (W, H, D)_l  (division then addition, each rounded once -- the same two fp32 operations ATen runs)
+// so sampling_loc and attn_weight are never written to or read from HBM.  `weight` returns the lane's softmax value (0 for idle lanes).
+template <int G>
+__device__ __forceinline__ PreparedSample prepare_sample_fused(const int4 *lv, const float *__restrict__ off, const float *__restrict__ logit,
+                                                               const float *__restrict__ ref, long long ref_bstride, const UnitCoords &uc, int s,
+                                                               int LP, int P, int L, int M, int Lq, int S, int MC, int C, float &weight)
+{
+  const bool mine = uc.active && s < LP;
+  const long long si = uc.u * LP + s;
+  const float lg = mine ? ldg_stream(logit + si) : -INFINITY;
+  const float mx = group_max<G>(lg);
+  const float e = mine ? expf(lg - mx) : 0.f;
+  const float sum = group_sum_f<G>(e);
+  weight = mine ? __fdiv_rn(e, sum) : 0.f;
+  if (mine) {
+    const int l = s / P;
+    const int4 li = lv[l];
+    const long long q = (uc.u / M) % Lq;
+    const float *r = ref + uc.b * ref_bstride + (q * L + l) * 3;
+    const float x = __fadd_rn(__ldg(r), __fdiv_rn(ldg_stream(off + 3 * si), __int2float_rn(li.z)));
+    const float y = __fadd_rn(__ldg(r + 1), __fdiv_rn(ldg_stream(off + 3 * si + 1), __int2float_rn(li.y)));
+    const float z = __fadd_rn(__ldg(r + 2), __fdiv_rn(ldg_stream(off + 3 * si + 2), __int2float_rn(li.x)));
+    return prepare_located(li, x, y, z, weight, uc, S, MC, C);
+  }
+  PreparedSample ps;
+  ps.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  ps.c = make_int4(0, 0, 0, 0);
   return ps;
 }
 
@@ -321,11 +379,13 @@ __device__ __forceinline__ void corner_weights_axes(float hd, float ld, float hh
   w[4] = __fmul_rn(c, hw); w[5] = __fmul_rn(c, lw); w[6] = __fmul_rn(d, hw); w[7] = __fmul_rn(d, lw);
 }
 
-template <typename VT, int G, int NV, int MINB>
+// FUSED = 1: `loc` / `aw` are the raw sampling offsets / attention logits and `ref` [N|1, Lq, L, 3] the reference points
+// (prepare_sample_fused); requires L * P <= G.
+template <typename VT, int G, int NV, int MINB, int FUSED = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
                const float *__restrict__ loc, const float *__restrict__ aw, int N, int S, int M, int L, int Lq, int P,
-               VT *__restrict__ out, int brick)
+               VT *__restrict__ out, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0)
 {
   using V = Vec16<VT>;
   constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
@@ -355,7 +415,9 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
 
     for (int s0 = 0; s0 < LP; s0 += G) {
-      const PreparedSample mine = prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
+      float w_unused;
+      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc, aw, ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_unused)
+                                        : prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
       __syncwarp();
       sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
       __syncwarp();
@@ -463,12 +525,14 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
 // B200 these reductions are what bounds the kernel: the L2 atomic units take ~6.6 TB/s of fp32 payload
 // (tools/micro/red_bench.cu), the launch sends 8 corners x C floats per in-range sample.  Combining contributions of
 // neighbouring queries in shared memory first was tried and is slower (profiles/r01_experiments.md, section 4).
-template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0>
+// FUSED = 1 (see fwd_vec_kernel): grad_loc / grad_aw receive the gradients with respect to the raw offsets / logits:
+//   d/d offset = d/d loc / (W, H, D)      d/d logit_j = attn_j * (g_j - sum_k attn_k g_k)   (softmax backward inside the group)
+template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
                int M, int L, int Lq, int P, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-               float *__restrict__ grad_aw, int brick)
+               float *__restrict__ grad_aw, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0)
 {
   using V = Vec16<VT>;
   constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
@@ -503,7 +567,9 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
     }
 
     for (int s0 = 0; s0 < LP; s0 += G) {
-      const PreparedSample mine = prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
+      float w_mine = 0.f;
+      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc, aw, ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_mine)
+                                        : prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
       __syncwarp();
       sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
       __syncwarp();
@@ -534,7 +600,18 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
         if (gl == j) { r_a = q.a; r_w = q.w; r_h = q.h; r_d = q.d; }
       }
       const int s = s0 + gl;
-      if (uc.active && s < LP) {
+      if (FUSED) {
+        const float dot = group_sum_f<G>(w_mine * r_a);             // softmax backward needs the whole unit: every lane takes part
+        if (uc.active && s < LP) {
+          const int4 li = lv[s / P];
+          const float fw = __int2float_rn(li.z), fh = __int2float_rn(li.y), fd = __int2float_rn(li.x);
+          float *gl_ = grad_loc + (uc.u * LP + s) * 3;
+          gl_[0] = __fdiv_rn(fw * (r_w * mine.a.y), fw);            // d loc (cuh:238-240), then the gradient of offset / W
+          gl_[1] = __fdiv_rn(fh * (r_h * mine.a.y), fh);
+          gl_[2] = __fdiv_rn(fd * (r_d * mine.a.y), fd);
+          grad_aw[uc.u * LP + s] = w_mine * (r_a - dot);
+        }
+      } else if (uc.active && s < LP) {
         // my own sample: scale by attn * size (cuh:238-240); out-of-range samples carry exact zeros (cuh:618-621)
         const int4 li = lv[s / P];
         float *gl_ = grad_loc + (uc.u * LP + s) * 3;

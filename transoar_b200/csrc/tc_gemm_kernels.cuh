@@ -374,7 +374,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
             if (p.atomic)
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             else
-              __stcs(reinterpret_cast<float4 *>(dst), o);               // write-once stream: evict-first keeps the operands in L2
+              *reinterpret_cast<float4 *>(dst) = o;                   // (evict-first .cs stores measured 20 % slower here)
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll

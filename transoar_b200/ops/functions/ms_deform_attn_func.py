@@ -27,3 +27,22 @@ class MSDeformAttnFunction(Function):
         saved = ctx.saved_tensors
         g_value, g_loc, g_attn = MSDA.ms_deform_attn_backward(*saved, grad_output.contiguous(), ctx.im2col_step)
         return g_value, None, None, g_loc, g_attn, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """The op with its prologue fused: ``apply(value, spatial_shapes, level_start_index, reference_points,
+    sampling_offsets, attention_logits)`` equals ``MSDeformAttnFunction.apply(value, shapes, starts, reference_points[:, :, None, :, None, :]
+    + sampling_offsets / (W, H, D), softmax(attention_logits over L*P), 64)`` (ms_deform_attn.py:115-136) without materialising the
+    locations or the attention weights; gradients flow to value, the raw offsets and the raw logits."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+        reference_points, sampling_offsets, attention_logits = (t.contiguous() for t in (reference_points, sampling_offsets, attention_logits))
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits)
+        return MSDA.ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        g_value, g_off, g_logit = MSDA.ms_deform_attn_backward_fused(*ctx.saved_tensors, grad_output.contiguous())
+        return g_value, None, None, None, g_off, g_logit

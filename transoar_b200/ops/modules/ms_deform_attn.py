@@ -12,7 +12,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions import MSDeformAttnFunction
+from ... import MultiScaleDeformableAttention as MSDA
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 from ...linear import TCLinear
 
 
@@ -44,6 +45,7 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64                                                  # ms_deform_attn.py:48
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.use_cuda = use_cuda
+        self.fuse_prologue = True                                              # False: always the reference's three-step prologue + plain op
         # nn.Linear subclasses (same parameter names): TF32 tcgen05 GEMMs when TF32 is the requested matmul precision
         self.sampling_offsets = TCLinear(d_model, n_heads * n_levels * n_points * 3)
         self.attention_weights = TCLinear(d_model, n_heads * n_levels * n_points)
@@ -78,9 +80,14 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, S, M, self.d_model // M)
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 3)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        logits = self.attention_weights(query).view(N, Lq, M, L, P)
         if reference_points.shape[-1] != 3:
             raise ValueError('Last dim of reference_points must be 3, but get {} instead.'.format(reference_points.shape[-1]))
+        if self.use_cuda and self.fuse_prologue and MSDA.fused_supported(value, reference_points, offsets, logits):
+            # softmax over the unit's L*P logits and ref + offset / (W, H, D) happen inside the kernels (include/msda3d.h, *_fused)
+            sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, reference_points, offsets, logits)
+            return self.output_proj(sampled)
+        weights = F.softmax(logits.view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         normalizer = input_spatial_shapes.flip(-1)                             # (W,H,D): x,y,z order, ms_deform_attn.py:123-126
         locations = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
         if not self.use_cuda:
