@@ -112,6 +112,22 @@ int msda3d_backward_fused(void *stream, const float *grad_output, const float *v
                           int channels, int num_levels, int num_query, int num_point, float *grad_value,
                           float *grad_sampling_offsets, float *grad_attn_logits);
 
+/* Same, with offsets and logits taken from ONE row-major tensor [N*Lq, merged_ld] (merged_ld >= 4*M*L*P): columns [0, 3*M*L*P) are the
+ * offsets of a query laid out [M][L][P][3], columns [3*M*L*P, 4*M*L*P) its logits [M][L][P] -- the output of a single Linear layer
+ * whose weight is the concatenation of sampling_offsets.weight and attention_weights.weight (one GEMM instead of two).  `merged`
+ * replaces both pointers; the backward writes both gradients into `grad_merged` of the same shape (columns past 4*M*L*P untouched).
+ * merged_ld == 0 means the dense two-array form above (attn_logits / grad_attn_logits are then used). */
+int msda3d_forward_fused_ld(void *stream, const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *reference_points, int ref_batch, const float *sampling_offsets_or_merged,
+                            const float *attn_logits, long long merged_ld, int batch, int spatial_size, int num_heads, int channels,
+                            int num_levels, int num_query, int num_point, float *output);
+
+int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *reference_points, int ref_batch,
+                             const float *sampling_offsets_or_merged, const float *attn_logits, long long merged_ld, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                             float *grad_value, float *grad_sampling_offsets_or_merged, float *grad_attn_logits);
+
 /* Test hook: the sampling-index arithmetic of the production kernels, one record per sample (N*Lq*M*L*P):
  * idx int32[4] = {in_range, d_low, h_low, w_low}, frac[3] = {ld, lh, lw} (fp32 for F32/BF16/F16, fp64 for F64).
  * Device pointers.  Compared bit-for-bit with the oracle in tests/. */

@@ -428,15 +428,23 @@ def test_module_takes_the_fused_route_and_matches_the_unfused_one():
     x = torch.randn(2, S, 384, device=DEV)
     ref = torch.rand(1, S, 4, 3, device=DEV)
     outs = []
-    for fused in (True, False):
-        m.fuse_prologue = fused
-        m.zero_grad()
-        xq = x.clone().requires_grad_(True)
-        n0 = _lib.lib().msda3d_launch_count()
-        y = m(xq, ref, xq, shapes, starts)
-        y.square().mean().backward()
-        outs.append((y.detach(), xq.grad.clone(), m.sampling_offsets.weight.grad.clone(), m.attention_weights.bias.grad.clone(),
-                     _lib.lib().msda3d_launch_count() - n0))
-    assert outs[0][4] == outs[1][4] == 2                                      # one forward + one backward launch of this library either way
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for fused, tf32 in ((True, False), (False, False), (True, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            m.fuse_prologue = fused
+            m.zero_grad()
+            xq = x.clone().requires_grad_(True)
+            n0 = _lib.lib().msda3d_launch_count()
+            y = m(xq, ref, xq, shapes, starts)
+            y.square().mean().backward()
+            outs.append((y.detach(), xq.grad.clone(), m.sampling_offsets.weight.grad.clone(), m.attention_weights.bias.grad.clone(),
+                         _lib.lib().msda3d_launch_count() - n0))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert outs[0][4] == outs[1][4] == 2                                      # strict fp32: op forward + backward only, fused or not
+    assert outs[2][4] == 2 + 3 * 3                                            # TF32: value / merged offsets+logits / output projections x (fwd + 2 grads)
     for a, b in zip(outs[0][:4], outs[1][:4]):
         assert _relerr(_np(a), _np(b)) < 5e-5
+    for a, b in zip(outs[2][:4], outs[1][:4]):                                # merged-projection route, TF32 tolerance
+        assert _relerr(_np(a), _np(b)) < 3e-2

@@ -170,8 +170,9 @@ def test_refine_block_runs_its_linears_on_tcgen05_under_tf32(monkeypatch):
     with _tf32():
         n0 = _lib.lib().msda3d_launch_count()
         ours = _refine_block_errors(z)
-        # per layer: 6 Linear forwards + 6 x 2 gradient GEMMs + msda forward + backward + 2 fused LayerNorms (1 + 2 kernels) = 26 launches
-        assert _lib.lib().msda3d_launch_count() - n0 == 2 * 26
+        # per layer: 3 projection GEMMs (value, merged offsets+logits, output) x 3 + the FFN's 2 forward + 4 backward GEMMs + msda forward +
+        # backward + 2 fused LayerNorms (1 + 2 kernels) = 23 launches
+        assert _lib.lib().msda3d_launch_count() - n0 == 2 * 23
         monkeypatch.setattr(linear, "tc_eligible", lambda x, w: False)
         n0 = _lib.lib().msda3d_launch_count()
         cublas = _refine_block_errors(z)
@@ -237,12 +238,14 @@ def test_ffn_function_matches_fp64_and_its_dropout_is_consistent():
         h = [t for t in y.grad_fn.saved_tensors if t.shape == (M, Hd)][0]
         y.backward(g)
         xd, w1d, b1d, w2d, b2d = (t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2))
-        pre = torch.relu(xd @ w1d.t() + b1d)
-        keep = ((h > 0) | (pre.detach() <= 1e-4)).double()                    # kernel's mask where it matters (active units)
+        lin = xd @ w1d.t() + b1d
+        # the reference takes the kernel's own ReLU / dropout decisions (h > 0), so knife-edge units (|pre-activation| below TF32's
+        # error) count the same way on both sides instead of showing up as O(dh * w) outliers in the gradients
         if pp > 0:
-            rate = 1 - float(((h > 0) & (pre.detach() > 1e-4)).sum() / (pre.detach() > 1e-4).sum())
+            clearly_on = lin.detach() > 1e-2
+            rate = 1 - float(((h > 0) & clearly_on).sum() / clearly_on.sum())
             assert abs(rate - pp) < 5e-3, rate
-        hd = pre * keep / (1 - pp)
+        hd = lin * (h > 0).double() / (1 - pp)
         yd = hd @ w2d.t() + b2d
         yd.backward(g.double())
         tol = 2e-2

@@ -128,13 +128,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
 # ---------------------------------------------------------------------------------------------------------------
 # Fused prologue (include/msda3d.h, msda3d_*_fused): softmax over the unit's L*P logits and ref + offset / (W, H, D) inside the op
 # ---------------------------------------------------------------------------------------------------------------
-def fused_supported(value, reference_points, sampling_offsets, attn_logits):
+def fused_supported(value, reference_points, n_levels, n_points):
     """fp32 CUDA tensors, vector kernels, L * P <= C / 4 (C = 64, L * P <= 16: the reference's configuration), 3-D reference points."""
-    if not (value.is_cuda and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32 and attn_logits.dtype == torch.float32
-            and reference_points.dtype == torch.float32 and reference_points.shape[-1] == 3 and not torch.is_autocast_enabled()):
+    if not (value.is_cuda and value.dtype == torch.float32 and reference_points.dtype == torch.float32 and reference_points.shape[-1] == 3
+            and not torch.is_autocast_enabled()):
         return False
-    L, P = sampling_offsets.shape[3], sampling_offsets.shape[4]
-    return bool(_lib.lib().msda3d_fused_supported(value.shape[3], L, P)) and reference_points.shape[0] in (1, value.shape[0])
+    return bool(_lib.lib().msda3d_fused_supported(value.shape[3], n_levels, n_points)) and reference_points.shape[0] in (1, value.shape[0])
 
 
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits):
@@ -165,3 +164,34 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, refe
             _p(grad_value), _p(grad_off), _p(grad_logit))
     _lib.check(rc, "ms_deform_attn_backward_fused")
     return [grad_value, grad_off, grad_logit]
+
+
+def ms_deform_attn_forward_merged(value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points):
+    """Fused prologue with offsets and logits in one tensor ``merged`` [N, Lq, ld]: columns [0, 3*M*L*P) offsets, then M*L*P logits."""
+    _check([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+            ("reference_points", reference_points), ("merged", merged)], 1)
+    N, S, M, C = value.shape
+    Lq, ld = merged.shape[1], merged.shape[2]
+    out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device), _timed("fwd"):
+        rc = _lib.lib().msda3d_forward_fused_ld(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(value), _p(spatial_shapes), _p(level_start_index),
+            _p(reference_points), reference_points.shape[0], _p(merged), None, ld, N, S, M, C, n_levels, Lq, n_points, _p(out))
+    _lib.check(rc, "ms_deform_attn_forward_merged")
+    return out
+
+
+def ms_deform_attn_backward_merged(value, spatial_shapes, level_start_index, reference_points, merged, grad_output, n_levels, n_points):
+    """-> [grad_value, grad_merged]."""
+    _check([("value", value), ("reference_points", reference_points), ("merged", merged), ("grad_output", grad_output)], 1)
+    N, S, M, C = value.shape
+    Lq, ld = merged.shape[1], merged.shape[2]
+    grad_value = torch.empty_like(value)
+    grad_merged = torch.empty_like(merged) if ld == 4 * M * n_levels * n_points else torch.zeros_like(merged)
+    with torch.cuda.device(value.device), _timed("bwd"):
+        rc = _lib.lib().msda3d_backward_fused_ld(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(grad_output), _p(value), _p(spatial_shapes), _p(level_start_index),
+            _p(reference_points), reference_points.shape[0], _p(merged), None, ld, N, S, M, C, n_levels, Lq, n_points,
+            _p(grad_value), _p(grad_merged), None)
+    _lib.check(rc, "ms_deform_attn_backward_merged")
+    return [grad_value, grad_merged]

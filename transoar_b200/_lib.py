@@ -25,6 +25,8 @@ _SIGNATURES = {
     "msda3d_fused_supported": (_ci, [_ci, _ci, _ci]),
     "msda3d_forward_fused": (_ci, [_vp] * 5 + [_ci] + [_vp] * 2 + _DIMS + [_vp]),
     "msda3d_backward_fused": (_ci, [_vp] * 6 + [_ci] + [_vp] * 2 + _DIMS + [_vp] * 3),
+    "msda3d_forward_fused_ld": (_ci, [_vp] * 5 + [_ci] + [_vp] * 2 + [ctypes.c_longlong] + _DIMS + [_vp]),
+    "msda3d_backward_fused_ld": (_ci, [_vp] * 6 + [_ci] + [_vp] * 2 + [ctypes.c_longlong] + _DIMS + [_vp] * 3),
     "msda3d_forward_host": (_ci, [_ci, _ci] + [_vp] * 5 + _DIMS + [_vp]),
     "msda3d_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 3),
     "msda3d_forward_backward_host": (_ci, [_ci, _ci] + [_vp] * 6 + _DIMS + [_vp] * 4),

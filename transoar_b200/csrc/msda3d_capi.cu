@@ -300,14 +300,27 @@ int msda3d_fused_supported(int channels, int num_levels, int num_point)
   return vec_shape<float>(channels, G, NV) && num_levels * num_point <= G;
 }
 
+// merged_ld > 0: offsets and logits are columns [0, 3*M*L*P) and [3*M*L*P, 4*M*L*P) of one row-major [N*Lq, merged_ld] tensor
+static int merged_ok(const Dims &d, long long merged_ld) { return merged_ld == 0 || merged_ld >= 4LL * d.M * d.L * d.P; }
+
 int msda3d_forward_fused(void *stream, const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                          const float *reference_points, int ref_batch, const float *sampling_offsets, const float *attn_logits, int batch,
                          int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point, float *output)
+{
+  return msda3d_forward_fused_ld(stream, value, spatial_shapes, level_start_index, reference_points, ref_batch, sampling_offsets, attn_logits, 0,
+                                 batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, output);
+}
+
+int msda3d_forward_fused_ld(void *stream, const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *reference_points, int ref_batch, const float *sampling_offsets, const float *attn_logits,
+                            long long merged_ld, int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                            int num_point, float *output)
 {
   if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output) return MSDA3D_EINVAL;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int rc = check_dims(d)) return rc;
   if (ref_batch != 1 && ref_batch != batch) return MSDA3D_EINVAL;
+  if (!merged_ok(d, merged_ld)) return MSDA3D_EINVAL;
   if (!aligned(reference_points, 4) || !aligned(sampling_offsets, 4) || !aligned(attn_logits, 4) || !aligned(spatial_shapes, 8) ||
       !aligned(level_start_index, 8))
     return MSDA3D_EALIGN;
@@ -317,8 +330,8 @@ int msda3d_forward_fused(void *stream, const float *value, const int64_t *spatia
   const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
   const int grid = vec_grid(units, g_);
   VEC_DISPATCH(g_, nv_, fwd_vec_kernel<float, G, NV, MinBlocks<float, NV>::fwd, 1><<<grid, kThreads, 0, st>>>(
-                            value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d.N, d.S, d.M, d.L, d.Lq, d.P, output,
-                            use_brick(d), reference_points, rb));
+                            value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M,
+                            d.L, d.Lq, d.P, output, use_brick(d), reference_points, rb, merged_ld, 3 * d.M * d.L * d.P));
   ++g_launches;
   return (int)cudaGetLastError();
 }
@@ -328,12 +341,24 @@ int msda3d_backward_fused(void *stream, const float *grad_output, const float *v
                           const float *attn_logits, int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                           int num_point, float *grad_value, float *grad_sampling_offsets, float *grad_attn_logits)
 {
+  return msda3d_backward_fused_ld(stream, grad_output, value, spatial_shapes, level_start_index, reference_points, ref_batch, sampling_offsets,
+                                  attn_logits, 0, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, grad_value,
+                                  grad_sampling_offsets, grad_attn_logits);
+}
+
+int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *reference_points, int ref_batch, const float *sampling_offsets,
+                             const float *attn_logits, long long merged_ld, int batch, int spatial_size, int num_heads, int channels,
+                             int num_levels, int num_query, int num_point, float *grad_value, float *grad_sampling_offsets,
+                             float *grad_attn_logits)
+{
   if (!grad_output || !value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !grad_value ||
       !grad_sampling_offsets || !grad_attn_logits)
     return MSDA3D_EINVAL;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int rc = check_dims(d)) return rc;
   if (ref_batch != 1 && ref_batch != batch) return MSDA3D_EINVAL;
+  if (!merged_ok(d, merged_ld)) return MSDA3D_EINVAL;
   if (!aligned(grad_value, 16) || !aligned(grad_sampling_offsets, 4) || !aligned(grad_attn_logits, 4) || !aligned(reference_points, 4) ||
       !aligned(sampling_offsets, 4) || !aligned(attn_logits, 4))
     return MSDA3D_EALIGN;
@@ -345,8 +370,10 @@ int msda3d_backward_fused(void *stream, const float *grad_output, const float *v
   const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
   const int grid = vec_grid(units, g_);
   VEC_DISPATCH(g_, nv_, bwd_vec_kernel<float, G, NV, MinBlocks<float, NV>::bwd, 0, 1><<<grid, kThreads, 0, st>>>(
-                            grad_output, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d.N, d.S, d.M, d.L, d.Lq,
-                            d.P, grad_value, grad_sampling_offsets, grad_attn_logits, use_brick(d), reference_points, rb));
+                            grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits,
+                            d.N, d.S, d.M, d.L, d.Lq, d.P, grad_value, grad_sampling_offsets,
+                            merged_ld ? grad_sampling_offsets : grad_attn_logits, use_brick(d), reference_points, rb, merged_ld,
+                            3 * d.M * d.L * d.P));
   ++g_launches;
   return (int)cudaGetLastError();
 }

@@ -342,13 +342,26 @@ template <int G> __device__ __forceinline__ float group_sum_f(float v)
 //     attn = softmax(logits)                   (over the unit's L*P samples; lanes of the group hold one sample each)
 //     loc  = ref[q, l] + offset / (W, H, D)_l  (division then addition, each rounded once -- the same two fp32 operations ATen runs)
 // so sampling_loc and attn_weight are never written to or read from HBM.  `weight` returns the lane's softmax value (0 for idle lanes).
+// Where unit u keeps its L*P offsets / logits: dense arrays [units][L*P][3] / [units][L*P] (ld == 0), or both inside one row-major
+// [N*Lq, ld] tensor -- the output of ONE Linear layer that computes offsets (columns [0, 3*M*L*P)) and logits (columns from
+// logit_col) together -- so that the two small projections are a single GEMM and their gradients arrive in one tensor.
+__device__ __forceinline__ long long fused_off_base(const UnitCoords &uc, int LP, int M, long long ld)
+{
+  return ld ? (uc.u / M) * ld + (long long)uc.m * LP * 3 : uc.u * LP * 3;
+}
+__device__ __forceinline__ long long fused_logit_base(const UnitCoords &uc, int LP, int M, long long ld, int logit_col)
+{
+  return ld ? (uc.u / M) * ld + logit_col + (long long)uc.m * LP : uc.u * LP;
+}
+
 template <int G>
 __device__ __forceinline__ PreparedSample prepare_sample_fused(const int4 *lv, const float *__restrict__ off, const float *__restrict__ logit,
                                                                const float *__restrict__ ref, long long ref_bstride, const UnitCoords &uc, int s,
                                                                int LP, int P, int L, int M, int Lq, int S, int MC, int C, float &weight)
 {
+  // `off` / `logit` already point at this unit's first sample (fused_off_base / fused_logit_base)
   const bool mine = uc.active && s < LP;
-  const long long si = uc.u * LP + s;
+  const long long si = s;
   const float lg = mine ? ldg_stream(logit + si) : -INFINITY;
   const float mx = group_max<G>(lg);
   const float e = mine ? expf(lg - mx) : 0.f;
@@ -385,7 +398,8 @@ template <typename VT, int G, int NV, int MINB, int FUSED = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
                const float *__restrict__ loc, const float *__restrict__ aw, int N, int S, int M, int L, int Lq, int P,
-               VT *__restrict__ out, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0)
+               VT *__restrict__ out, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0, long long fused_ld = 0,
+               int logit_col = 0)
 {
   using V = Vec16<VT>;
   constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
@@ -416,7 +430,8 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 
     for (int s0 = 0; s0 < LP; s0 += G) {
       float w_unused;
-      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc, aw, ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_unused)
+      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc + fused_off_base(uc, LP, M, fused_ld), aw + fused_logit_base(uc, LP, M, fused_ld, logit_col),
+                                                                  ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_unused)
                                         : prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
       __syncwarp();
       sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
@@ -532,7 +547,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
                int M, int L, int Lq, int P, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-               float *__restrict__ grad_aw, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0)
+               float *__restrict__ grad_aw, int brick, const float *__restrict__ ref = nullptr, long long ref_bstride = 0,
+               long long fused_ld = 0, int logit_col = 0)
 {
   using V = Vec16<VT>;
   constexpr int VEC = V::N, CPL = VEC * NV, C = G * CPL, UPW = 32 / G, WARPS = kThreads / 32, UPB = WARPS * UPW;
@@ -568,7 +584,8 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
 
     for (int s0 = 0; s0 < LP; s0 += G) {
       float w_mine = 0.f;
-      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc, aw, ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_mine)
+      const PreparedSample mine = FUSED ? prepare_sample_fused<G>(lv, loc + fused_off_base(uc, LP, M, fused_ld), aw + fused_logit_base(uc, LP, M, fused_ld, logit_col),
+                                                                  ref, ref_bstride, uc, s0 + gl, LP, P, L, M, Lq, S, MC, C, w_mine)
                                         : prepare_sample(lv, loc, aw, uc, s0 + gl, LP, P, S, MC, C);
       __syncwarp();
       sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
@@ -605,11 +622,11 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
         if (uc.active && s < LP) {
           const int4 li = lv[s / P];
           const float fw = __int2float_rn(li.z), fh = __int2float_rn(li.y), fd = __int2float_rn(li.x);
-          float *gl_ = grad_loc + (uc.u * LP + s) * 3;
+          float *gl_ = grad_loc + fused_off_base(uc, LP, M, fused_ld) + 3 * s;
           gl_[0] = __fdiv_rn(fw * (r_w * mine.a.y), fw);            // d loc (cuh:238-240), then the gradient of offset / W
           gl_[1] = __fdiv_rn(fh * (r_h * mine.a.y), fh);
           gl_[2] = __fdiv_rn(fd * (r_d * mine.a.y), fd);
-          grad_aw[uc.u * LP + s] = w_mine * (r_a - dot);
+          grad_aw[fused_logit_base(uc, LP, M, fused_ld, logit_col) + s] = w_mine * (r_a - dot);
         }
       } else if (uc.active && s < LP) {
         // my own sample: scale by attn * size (cuh:238-240); out-of-range samples carry exact zeros (cuh:618-621)

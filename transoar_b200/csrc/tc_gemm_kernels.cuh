@@ -327,6 +327,16 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const long long tp0 = timed ? clock64() : 0;
+        // gate values of this lane's eight (row, 4-column) pieces: loaded first so that their latency hides behind the TMEM read
+        float4 g4[8];
+        if (p.gate != nullptr) {
+          const int ng = nt * BN + c0 + 4 * quad;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int mg = (mt * CTAS + (int)rank) * BM + q * 32 + 4 * i + sub_row;
+            g4[i] = (mg < p.M && ng + 3 < p.N) ? __ldg(reinterpret_cast<const float4 *>(p.gate + (long long)mg * p.ldd + ng)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         float v[32];
         tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(q * 32) << 16), v);
         const int n0 = nt * BN + c0;
@@ -366,9 +376,9 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
             o.x *= keep[0]; o.y *= keep[1]; o.z *= keep[2]; o.w *= keep[3];
           }
           if (p.gate != nullptr) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gate + (long long)m * p.ldd + n));
-            o.x = g4.x > 0.f ? o.x * p.gate_scale : 0.f; o.y = g4.y > 0.f ? o.y * p.gate_scale : 0.f;
-            o.z = g4.z > 0.f ? o.z * p.gate_scale : 0.f; o.w = g4.w > 0.f ? o.w * p.gate_scale : 0.f;
+            const float4 gq = g4[r0 >> 2];
+            o.x = gq.x > 0.f ? o.x * p.gate_scale : 0.f; o.y = gq.y > 0.f ? o.y * p.gate_scale : 0.f;
+            o.z = gq.z > 0.f ? o.z * p.gate_scale : 0.f; o.w = gq.w > 0.f ? o.w * p.gate_scale : 0.f;
           }
           if (vec_ok && n + 3 < p.N) {
             if (p.atomic)

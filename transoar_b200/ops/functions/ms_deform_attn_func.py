@@ -46,3 +46,21 @@ class MSDeformAttnFusedFunction(Function):
     def backward(ctx, grad_output):
         g_value, g_off, g_logit = MSDA.ms_deform_attn_backward_fused(*ctx.saved_tensors, grad_output.contiguous())
         return g_value, None, None, None, g_off, g_logit
+
+
+class MSDeformAttnMergedFunction(Function):
+    """``MSDeformAttnFusedFunction`` with the raw offsets and logits in one tensor ``merged`` [N, Lq, 4*M*L*P] -- the output of a single
+    Linear layer over the concatenated sampling_offsets / attention_weights weights; the gradient comes back in the same layout."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points):
+        reference_points, merged = reference_points.contiguous(), merged.contiguous()
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, merged)
+        ctx.lp = (n_levels, n_points)
+        return MSDA.ms_deform_attn_forward_merged(value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        g_value, g_merged = MSDA.ms_deform_attn_backward_merged(*ctx.saved_tensors, grad_output.contiguous(), *ctx.lp)
+        return g_value, None, None, None, g_merged, None, None

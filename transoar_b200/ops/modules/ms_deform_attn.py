@@ -13,8 +13,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from ... import MultiScaleDeformableAttention as MSDA
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
-from ...linear import TCLinear
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction
+from ...linear import TCLinear, linear, tc_eligible
 
 
 def _power_of_two(n):
@@ -79,11 +79,20 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, S, M, self.d_model // M)
-        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 3)
-        logits = self.attention_weights(query).view(N, Lq, M, L, P)
         if reference_points.shape[-1] != 3:
             raise ValueError('Last dim of reference_points must be 3, but get {} instead.'.format(reference_points.shape[-1]))
-        if self.use_cuda and self.fuse_prologue and MSDA.fused_supported(value, reference_points, offsets, logits):
+        if (self.use_cuda and self.fuse_prologue and tc_eligible(query, self.sampling_offsets.weight)
+                and MSDA.fused_supported(value, reference_points, L, P)):
+            # both small projections as ONE GEMM over the concatenated weights (N = 4*M*L*P = 384 columns); its output feeds the op
+            # directly and the op's backward returns one gradient tensor for one pair of gradient GEMMs
+            w_cat = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
+            b_cat = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
+            merged = linear(query, w_cat, b_cat)
+            sampled = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index, reference_points, merged, L, P)
+            return self.output_proj(sampled)
+        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 3)
+        logits = self.attention_weights(query).view(N, Lq, M, L, P)
+        if self.use_cuda and self.fuse_prologue and MSDA.fused_supported(value, reference_points, L, P):
             # softmax over the unit's L*P logits and ref + offset / (W, H, D) happen inside the kernels (include/msda3d.h, *_fused)
             sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, reference_points, offsets, logits)
             return self.output_proj(sampled)
