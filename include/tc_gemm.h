@@ -43,6 +43,12 @@ int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, long long lda,
                     float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k,
                     const float *gate, float gate_scale, float p_drop, unsigned long long seed);
 
+/* Column sums out[c] = sum_rows x[row * ld + c] of a row-major fp32 matrix: the bias gradient of a Linear layer (autograd's
+ * grad_output.sum(0), an ATen reduce kernel in the reference).  channels % 4 == 0, channels <= 1024, ld % 4 == 0, x and workspace
+ * 16-byte aligned; workspace holds tc_colsum_workspace_floats(channels) floats.  One HBM pass + a tiny finalize kernel. */
+long long tc_colsum_workspace_floats(int channels);
+int tc_colsum(void *stream, const float *x, long long rows, int channels, long long ld, float *out, float *workspace);
+
 /* Diagnostics: while a device buffer of 12 x 296 uint64 is installed, every launch writes per CTA the cycles its three roles spent
  * waiting: [0] producer on "empty", [1] producer total, [2] MMA on "full", [3] MMA on "tmem empty", [4] MMA total, [5] epilogue on
  * "tmem full", [6] epilogue total; then at 8 * 296 + 4 * cta: epilogue cycles in TMEM load / shared-memory stage / store.  NULL (the default) removes it.  Not thread-safe; tools/exp_gemm_roles.py uses it. */

@@ -252,3 +252,15 @@ def test_ffn_function_matches_fp64_and_its_dropout_is_consistent():
         assert float((y.double() - yd).abs().max()) < tol * float(yd.abs().max())
         for a, b_ in ((x, xd), (w1, w1d), (b1, b1d), (w2, w2d), (b2, b2d)):
             assert float((a.grad.double() - b_.grad).abs().max()) < tol * float(b_.grad.abs().max()), a.shape
+
+
+@pytest.mark.parametrize("rows,C", [(234000, 384), (5000, 1024), (1024, 4), (70001, 96), (2049, 288)])
+def test_colsum_matches_fp64(rows, C):
+    from transoar_b200 import _lib
+    from transoar_b200.linear import colsum
+    x = torch.randn(rows, C, generator=torch.Generator().manual_seed(rows + C)).cuda() + 0.5
+    n0 = _lib.lib().msda3d_launch_count()
+    got = colsum(x)
+    assert _lib.lib().msda3d_launch_count() - n0 == 2
+    want = x.double().sum(0)
+    assert float((got.double() - want).abs().max()) < 1e-5 * float(want.abs().max()) + 1e-3

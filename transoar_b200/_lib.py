@@ -52,6 +52,8 @@ _SIGNATURES = {
     "stem_conv3d_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp]),
     "stem_conv3d_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp, _vp]),
     # include/tc_gemm.h
+    "tc_colsum_workspace_floats": (ctypes.c_longlong, [_ci]),
+    "tc_colsum": (_ci, [_vp, _vp, ctypes.c_longlong, _ci, ctypes.c_longlong, _vp, _vp]),
     "tc_gemm_debug_profile": (None, [_vp]),
     "tc_gemm_tf32_ex": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6
                         + [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong]),

@@ -316,7 +316,8 @@ int msda3d_forward_fused_ld(void *stream, const float *value, const int64_t *spa
                             long long merged_ld, int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                             int num_point, float *output)
 {
-  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output) return MSDA3D_EINVAL;
+  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || (!attn_logits && merged_ld == 0) || !output)
+    return MSDA3D_EINVAL;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int rc = check_dims(d)) return rc;
   if (ref_batch != 1 && ref_batch != batch) return MSDA3D_EINVAL;
@@ -352,8 +353,8 @@ int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float
                              int num_levels, int num_query, int num_point, float *grad_value, float *grad_sampling_offsets,
                              float *grad_attn_logits)
 {
-  if (!grad_output || !value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !grad_value ||
-      !grad_sampling_offsets || !grad_attn_logits)
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !grad_value ||
+      !grad_sampling_offsets || (merged_ld == 0 && (!attn_logits || !grad_attn_logits)))
     return MSDA3D_EINVAL;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int rc = check_dims(d)) return rc;

@@ -135,6 +135,24 @@ int dispatch(cudaStream_t st, bool a_mn, bool b_mn, const CUtensorMap &ma, const
 
 }  // namespace
 
+constexpr int kColsumCtas = 148 * 4;
+
+extern "C" long long tc_colsum_workspace_floats(int channels) { return channels > 0 ? (long long)kColsumCtas * channels : 0; }
+
+extern "C" int tc_colsum(void *stream, const float *x, long long rows, int channels, long long ld, float *out, float *workspace)
+{
+  if (!x || !out || !workspace || rows <= 0 || channels <= 0 || channels % 4 != 0 || channels > 1024 || ld < channels || ld % 4 != 0) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(workspace)) & 15) return MSDA3D_EALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int lanes = tcgemm::kColsumThreads / (channels / 4);
+  const long long need = (rows + lanes - 1) / lanes;
+  const int grid = (int)(need < kColsumCtas ? need : kColsumCtas);
+  tcgemm::colsum_partial_kernel<<<grid, tcgemm::kColsumThreads, 0, st>>>(x, rows, channels, ld, workspace);
+  tcgemm::colsum_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(workspace, grid, channels, out);
+  g_msda3d_launches += 2;
+  return (int)cudaGetLastError();
+}
+
 extern "C" void tc_gemm_debug_profile(unsigned long long *device_counters) { g_prof.store(device_counters); }
 
 extern "C" int tc_gemm_tf32(void *stream, const float *A, int a_mn_major, long long lda, const float *B, int b_mn_major, long long ldb,

@@ -437,4 +437,55 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   gemm_tf32_body<BN, A_MN, B_MN, 2>(tmA, tmB, D, bias, p);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Column sums of a row-major [rows, C] matrix: the bias gradient of a Linear layer (grad_bias = sum over tokens of grad_output).
+// HBM-bound single pass: thread t owns the float4 column group t % (C/4) and walks rows t / (C/4), t / (C/4) + rows_per_pass, ...;
+// the row lanes of a CTA are combined in shared memory, one partial per CTA, summed by colsum_finalize_kernel.  C % 4 == 0, C <= 1024.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kColsumThreads = 256;
+
+__global__ void __launch_bounds__(kColsumThreads)
+colsum_partial_kernel(const float *__restrict__ x, long long rows, int C, long long ld, float *__restrict__ part)
+{
+  __shared__ float4 red[kColsumThreads];
+  const int cg = C >> 2, lanes = kColsumThreads / cg, t = threadIdx.x;
+  const int g = t % cg, r = t / cg;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < lanes) {
+    const long long step = (long long)gridDim.x * lanes;
+    long long row = (long long)blockIdx.x * lanes + r;
+    for (; row + 3 * step < rows; row += 4 * step) {               // four independent loads in flight
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + g);
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(x + (row + step) * ld) + g);
+      const float4 c = __ldg(reinterpret_cast<const float4 *>(x + (row + 2 * step) * ld) + g);
+      const float4 d = __ldg(reinterpret_cast<const float4 *>(x + (row + 3 * step) * ld) + g);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; row < rows; row += step) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + g);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  red[t] = acc;
+  __syncthreads();
+  if (t < cg) {
+    float4 s = red[t];
+    for (int k = 1; k < lanes; ++k) {
+      const float4 o = red[t + k * cg];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    reinterpret_cast<float4 *>(part + (long long)blockIdx.x * C)[t] = s;
+  }
+}
+
+__global__ void colsum_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ out)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < ctas; ++b) s += part[(long long)b * C + c];
+  out[c] = (float)s;
+}
+
 }  // namespace tcgemm

@@ -36,6 +36,19 @@ def gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=None, relu=False, accumula
     return D
 
 
+def colsum(x2):
+    """Column sums of a contiguous fp32 CUDA matrix [rows, C] (bias gradient); ATen's reduction where the kernel's shape limits do not hold."""
+    rows, C = x2.shape
+    if not (x2.is_cuda and x2.dtype == torch.float32 and x2.is_contiguous() and C % 4 == 0 and C <= 1024 and rows >= 1024):
+        return x2.sum(0)
+    out = torch.empty(C, dtype=torch.float32, device=x2.device)
+    ws = torch.empty(_lib.lib().tc_colsum_workspace_floats(C), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        rc = _lib.lib().tc_colsum(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(x2), rows, C, C, _p(out), _p(ws))
+    _lib.check(rc, "tc_colsum")
+    return out
+
+
 class LinearFunction(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
@@ -69,7 +82,7 @@ class LinearFunction(Function):
             dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
             gemm(dy2, 1, N, x2, 1, K, dw, N, K, M, accumulate=True, split_k=0)           # dW = dY^T X      (both MN-major, split-K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(0)
+            db = colsum(dy2)
         return dx, dw, db, None
 
 
@@ -111,7 +124,7 @@ class FFNFunction(Function):
             dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
             gemm(dh, 0, Hd, w1, 1, K, dx, M, K, Hd)
             dx = dx.reshape(ctx.in_shape)
-        return dx, dw1, dh.sum(0), dw2, dy2.sum(0), None, None
+        return dx, dw1, colsum(dh), dw2, colsum(dy2), None, None
 
 
 def ffn(x, linear1, linear2, p, training):
