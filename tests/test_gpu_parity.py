@@ -443,7 +443,8 @@ def test_module_takes_the_fused_route_and_matches_the_unfused_one():
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     assert outs[0][4] == outs[1][4] == 2                                      # strict fp32: op forward + backward only, fused or not
-    assert outs[2][4] == 2 + 3 * 3                                            # TF32: value / merged offsets+logits / output projections x (fwd + 2 grads)
+    # TF32: value / merged offsets+logits / output projections x (fwd + 2 gradient GEMMs), + 2 column-sum kernels per bias gradient
+    assert outs[2][4] == 2 + 3 * 3 + 3 * 2, outs[2][4]
     for a, b in zip(outs[0][:4], outs[1][:4]):
         assert _relerr(_np(a), _np(b)) < 5e-5
     for a, b in zip(outs[2][:4], outs[1][:4]):                                # merged-projection route, TF32 tolerance

@@ -8,6 +8,7 @@
 #include "msda3d_kernels.cuh"
 
 #include <atomic>
+#include <type_traits>
 #include <mutex>
 #include <string>
 
@@ -56,6 +57,7 @@ int grid_for(long long units, int units_per_block)
 std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d_set_tuning "nv")
 std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
 std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
+std::atomic<int> g_tune_pair{0};        // 0 = automatic (pair-combining backward in brick order for 16-lane fp32 units), 1 = off
 
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
 {
@@ -170,6 +172,11 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd, 1><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
                                 d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d)));
+    } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 0) {
+      // w-neighbouring units of a warp combine their grad_value contributions before the reductions (kernels.cuh, PAIR)
+      bwd_vec_kernel<float, 16, 1, 2, 0, 0, 1><<<grid, kThreads, 0, st>>>(
+          (const float *)gout, (const float *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P,
+          (float *)gv, (float *)gl, (float *)ga, 1);
     } else {
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
@@ -200,6 +207,7 @@ int msda3d_set_tuning(const char *key, int value)
   if (k == "nv" && value >= 0 && value <= 2) { g_tune_nv = value; return MSDA3D_OK; }
   if (k == "grid_mult" && value >= 0) { g_tune_grid_mult = value; return MSDA3D_OK; }
   if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
+  if (k == "pair" && value >= 0 && value <= 1) { g_tune_pair = value; return MSDA3D_OK; }
   return MSDA3D_EINVAL;
 }
 
@@ -370,6 +378,14 @@ int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float
   if (e != cudaSuccess) return (int)e;
   const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
   const int grid = vec_grid(units, g_);
+  if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 0) {
+    bwd_vec_kernel<float, 16, 1, 2, 0, 1, 1><<<grid, kThreads, 0, st>>>(
+        grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M, d.L,
+        d.Lq, d.P, grad_value, grad_sampling_offsets, merged_ld ? grad_sampling_offsets : grad_attn_logits, 1, reference_points, rb, merged_ld,
+        3 * d.M * d.L * d.P);
+    ++g_launches;
+    return (int)cudaGetLastError();
+  }
   VEC_DISPATCH(g_, nv_, bwd_vec_kernel<float, G, NV, MinBlocks<float, NV>::bwd, 0, 1><<<grid, kThreads, 0, st>>>(
                             grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits,
                             d.N, d.S, d.M, d.L, d.Lq, d.P, grad_value, grad_sampling_offsets,

@@ -542,7 +542,13 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
 // neighbouring queries in shared memory first was tried and is slower (profiles/r01_experiments.md, section 4).
 // FUSED = 1 (see fwd_vec_kernel): grad_loc / grad_aw receive the gradients with respect to the raw offsets / logits:
 //   d/d offset = d/d loc / (W, H, D)      d/d logit_j = attn_j * (g_j - sum_k attn_k g_k)   (softmax backward inside the group)
-template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0>
+// PAIR = 1 (G = 16, NV = 1, brick order): the two units of a warp are w-neighbouring query voxels of one head.  Their samples of a
+// level land in the same cell or in w-adjacent cells whenever their offsets agree (always at initialisation, mostly in a trained
+// model: the offsets come from one Linear layer applied to neighbouring voxels), so up to all eight grad_value reductions of the
+// second unit hit addresses the first unit reduces into as well.  The half-warps compare corner offsets, the first unit adds the
+// second unit's contributions with warp shuffles and issues ONE reduction per shared address: 25-47 % fewer L2 atomics (the
+// resource that bounds this kernel) at the price of ~35 shuffles per sample.  Only the order of the fp32 sums changes.
+template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0, int PAIR = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
@@ -595,7 +601,65 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
       for (int j = 0; j < cnt; ++j) {
         const int4 pc = sC[warp][g0 + j];
         SampleGrads q = {0.f, 0.f, 0.f, 0.f};
-        if (pc.w != 0) {
+        if constexpr (PAIR != 0) {
+          static_assert(PAIR == 0 || (G == 16 && NV == 1), "pair combining is written for 16 lanes x one 16-byte vector per unit");
+          const bool act = pc.w != 0;
+          float w[8], ay = 0.f;
+          unsigned o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { w[k] = 0.f; o[k] = 0u; }
+          if (act) {
+            const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
+            q = sample_backward<VT, G, NV>(value, top, pa, pb, pc, lane_off, w, o);
+            ay = pa.y;
+          }
+          // what the partner unit (other half-warp, same lane offset) is doing with this sample
+          const unsigned po0 = __shfl_xor_sync(0xffffffffu, o[0], 16), po1 = __shfl_xor_sync(0xffffffffu, o[1], 16);
+          const int px = __shfl_xor_sync(0xffffffffu, pc.x, 16), py = __shfl_xor_sync(0xffffffffu, pc.y, 16), pz = __shfl_xor_sync(0xffffffffu, pc.z, 16);
+          const int pact = __shfl_xor_sync(0xffffffffu, (int)act, 16);
+          const bool second = lane >= 16;                                         // this lane belongs to the unit that hands its sums over
+          const bool geom = act && pact != 0 && pc.x == px && pc.y == py && pc.z == pz;
+          const bool same = geom && o[0] == po0;                                  // same cell: all eight corners coincide
+          const bool shift = geom && !same && pc.z != 0 && (second ? o[0] == po1 : po0 == o[1]);   // second unit one cell further in w
+          unsigned need = 0;
+          float c[8][4];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float wk = w[k] * ay;
+            if (w[k] != 0.f) need |= 1u << k;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[k][i] = wk * top[i];
+          }
+          if (same || shift) {                                                    // uniform over the warp's two units
+            const unsigned pneed = __shfl_xor_sync(0xffffffffu, need, 16);
+            if (same) {                                                           // corner k of the second unit lands on corner k of the first
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float got = __shfl_xor_sync(0xffffffffu, c[k][i], 16);
+                  if (!second) c[k][i] += got;
+                }
+              }
+              need = second ? 0u : (need | pneed);
+            } else {                                                              // its w-low corner k - 1 lands on the first unit's w-high corner k
+#pragma unroll
+              for (int k = 1; k < 8; k += 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float got = __shfl_xor_sync(0xffffffffu, c[k - 1][i], 16);
+                  if (!second) c[k][i] += got;
+                }
+              }
+              need = second ? (need & 0xAAu) : (need | ((pneed & 0x55u) << 1));
+            }
+          }
+          if (SKIP_RED == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (need >> k & 1u) red_add_v4(grad_value + o[k], c[k][0], c[k][1], c[k][2], c[k][3]);
+          }
+        } else if (pc.w != 0) {
           const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
           float w[8];
           unsigned o[8];
