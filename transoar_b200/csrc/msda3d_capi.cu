@@ -57,7 +57,7 @@ int grid_for(long long units, int units_per_block)
 std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d_set_tuning "nv")
 std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
 std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
-std::atomic<int> g_tune_pair{0};        // 0 = automatic (pair-combining backward in brick order for 16-lane fp32 units), 1 = off
+std::atomic<int> g_tune_pair{0};        // 1 = pair-combining backward (kernels.cuh, PAIR) in brick order for 16-lane fp32 units; measured slower, off by default
 
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
 {
@@ -172,7 +172,7 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd, 1><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
                                 d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d)));
-    } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 0) {
+    } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 1) {
       // w-neighbouring units of a warp combine their grad_value contributions before the reductions (kernels.cuh, PAIR)
       bwd_vec_kernel<float, 16, 1, 2, 0, 0, 1><<<grid, kThreads, 0, st>>>(
           (const float *)gout, (const float *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P,
@@ -378,7 +378,7 @@ int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float
   if (e != cudaSuccess) return (int)e;
   const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
   const int grid = vec_grid(units, g_);
-  if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 0) {
+  if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 1) {
     bwd_vec_kernel<float, 16, 1, 2, 0, 1, 1><<<grid, kThreads, 0, st>>>(
         grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M, d.L,
         d.Lq, d.P, grad_value, grad_sampling_offsets, merged_ld ? grad_sampling_offsets : grad_attn_logits, 1, reference_points, rb, merged_ld,

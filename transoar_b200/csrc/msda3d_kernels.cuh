@@ -546,8 +546,10 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
 // level land in the same cell or in w-adjacent cells whenever their offsets agree (always at initialisation, mostly in a trained
 // model: the offsets come from one Linear layer applied to neighbouring voxels), so up to all eight grad_value reductions of the
 // second unit hit addresses the first unit reduces into as well.  The half-warps compare corner offsets, the first unit adds the
-// second unit's contributions with warp shuffles and issues ONE reduction per shared address: 25-47 % fewer L2 atomics (the
-// resource that bounds this kernel) at the price of ~35 shuffles per sample.  Only the order of the fp32 sums changes.
+// second unit's contributions with warp shuffles and issues ONE reduction per shared address: 25-47 % fewer L2 atomics at the
+// price of ~35 shuffles per sample and 122 registers (2 CTAs per SM).  Only the order of the fp32 sums changes.  MEASURED SLOWER on
+// B200 (5.16 -> 5.98 ms without jitter, 5.69 -> 6.96 ms with; profiles/r01_experiments.md section 8), so it is off unless
+// msda3d_set_tuning("pair", 1) asks for it.
 template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0, int PAIR = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
