@@ -29,13 +29,14 @@ int instnorm_relu_backward(void *stream, int dtype, const void *dy, const void *
 
 /* Channels-last variants: x, y, dy, dx are [N, D, H, W, C] in memory (torch.channels_last_3d), fp32, 16-byte aligned; channels must be
  * a multiple of 4 with (channels / 4) dividing 192 (24, 48, 96, 192, 384, 768, ...).  Same statistics, same outputs; they let the
- * encoder stay in the layout cuDNN's / this library's tensor-core convolutions use, with no NCDHW <-> NDHWC transposes. */
+ * encoder stay in the layout cuDNN's / this library's tensor-core convolutions use, with no NCDHW <-> NDHWC transposes.  The backward
+ * takes beta instead of y: it recomputes the ReLU mask from x with the forward's arithmetic (two tensor reads per pass, not three). */
 long long instnorm_ndhwc_workspace_floats(int batch, int channels, long long voxels);
 
 int instnorm_relu_forward_ndhwc(void *stream, const float *x, const float *gamma, const float *beta, int batch, int channels,
                                 long long voxels, float eps, float *y, float *mean, float *rstd, float *workspace);
 
-int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *y, const float *gamma, const float *mean,
+int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *gamma, const float *beta, const float *mean,
                                  const float *rstd, int batch, int channels, long long voxels, float *dx, float *dgamma, float *dbeta,
                                  float *workspace);
 

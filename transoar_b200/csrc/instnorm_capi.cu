@@ -123,23 +123,23 @@ int instnorm_relu_forward_ndhwc(void *stream, const float *x, const float *gamma
   return (int)cudaGetLastError();
 }
 
-int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *y, const float *gamma, const float *mean,
+int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *gamma, const float *beta, const float *mean,
                                  const float *rstd, int batch, int channels, long long voxels, float *dx, float *dgamma, float *dbeta,
                                  float *workspace)
 {
-  if (!dy || !x || !y || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !workspace || cl_bad(batch, channels, voxels))
+  if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !workspace || cl_bad(batch, channels, voxels))
     return MSDA3D_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
     return MSDA3D_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const ClPlan p = cl_plan(batch, channels, voxels);
   const int I = batch * channels;
   const dim3 grid(p.chunks, batch);
   float *sums = workspace + (long long)I * p.chunks * 2;
-  instnorm::cl_bwd_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, y, mean, rstd, voxels, channels, p.chunks, p.chunk_vox, workspace);
+  instnorm::cl_bwd_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, voxels, channels, p.chunks, p.chunk_vox, workspace);
   instnorm::bwd_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, sums);
   instnorm::bwd_param_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, batch, channels, dgamma, dbeta);
-  instnorm::cl_bwd_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, y, gamma, mean, rstd, sums, voxels, channels, p.chunk_vox, dx);
+  instnorm::cl_bwd_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, sums, voxels, channels, p.chunk_vox, dx);
   g_msda3d_launches += 4;
   return (int)cudaGetLastError();
 }

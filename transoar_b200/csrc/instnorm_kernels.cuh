@@ -388,31 +388,44 @@ cl_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, co
   }
 }
 
+// The ReLU mask is recomputed from x with the forward's own arithmetic (fmaf(x, rstd * gamma, beta - mean * rstd * gamma) > 0), so the
+// backward reads two tensors per pass (dy, x) instead of three (dy, x, y): 5 instead of 7 passes over the activation in total.
 __global__ void __launch_bounds__(kClThreads)
-cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ mean,
-                      const float *__restrict__ rstd, long long V, int C, int chunks, long long chunk_vox, float *__restrict__ part)
+cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                      const float *__restrict__ mean, const float *__restrict__ rstd, long long V, int C, int chunks, long long chunk_vox,
+                      float *__restrict__ part)
 {
   __shared__ float red[kClThreads * 8];
   const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int b = blockIdx.y, ch = blockIdx.x;
   const long long v0 = (long long)ch * chunk_vox, v1 = min(V, v0 + chunk_vox);
-  float mu[4], rs[4];
+  float mu[4], rs[4], fa[4], fo[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { mu[j] = mean[b * C + g * 4 + j]; rs[j] = rstd[b * C + g * 4 + j]; }
+  for (int j = 0; j < 4; ++j) {
+    const int c = g * 4 + j;
+    mu[j] = mean[b * C + c]; rs[j] = rstd[b * C + c];
+    fa[j] = rs[j] * gamma[c]; fo[j] = beta[c] - mu[j] * fa[j];                 // exactly cl_apply_kernel's a / o
+  }
   const long long off = (long long)b * V * C + g * 4;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (long long v = v0 + r; v < v1; v += (long long)rows * (kClUnroll / 2)) {
+  for (long long v = v0 + r; v < v1; v += (long long)rows * kClUnroll) {
+    float4 gq[kClUnroll], xq[kClUnroll];
 #pragma unroll
-    for (int u = 0; u < kClUnroll / 2; ++u) {
+    for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
       if (vv < v1) {
-        const float4 gq = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
-        const float4 xq = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
-        const float4 yq = __ldg(reinterpret_cast<const float4 *>(y + off + vv * C));
-        const float gg[4] = {gq.x, gq.y, gq.z, gq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w}, yy[4] = {yq.x, yq.y, yq.z, yq.w};
+        gq[u] = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
+        xq[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1) {
+        const float gg[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w}, xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float dz = yy[j] > 0.f ? gg[j] : 0.f;
+          const float dz = fmaf(xx[j], fa[j], fo[j]) > 0.f ? gg[j] : 0.f;
           acc[0][j] += dz;
           acc[1][j] = fmaf(dz, (xx[j] - mu[j]) * rs[j], acc[1][j]);
         }
@@ -430,34 +443,40 @@ cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x,
 }
 
 __global__ void __launch_bounds__(kClThreads)
-cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ gamma,
+cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ sums, long long V, int C,
                     long long chunk_vox, float *__restrict__ dx)
 {
   const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int b = blockIdx.y;
   const long long v0 = (long long)blockIdx.x * chunk_vox, v1 = min(V, v0 + chunk_vox);
-  float mu[4], rs[4], a[4], m1[4], m2[4];
+  float mu[4], rs[4], a[4], fo[4], m1[4], m2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = g * 4 + j, i = b * C + c;
-    mu[j] = mean[i]; rs[j] = rstd[i]; a[j] = gamma[c] * rs[j];
+    mu[j] = mean[i]; rs[j] = rstd[i]; a[j] = rs[j] * gamma[c]; fo[j] = beta[c] - mu[j] * a[j];
     m1[j] = sums[2 * i] / (float)V; m2[j] = sums[2 * i + 1] / (float)V;
   }
   const long long off = (long long)b * V * C + g * 4;
-  for (long long v = v0 + r; v < v1; v += (long long)rows * (kClUnroll / 2)) {
+  for (long long v = v0 + r; v < v1; v += (long long)rows * kClUnroll) {
+    float4 gq[kClUnroll], xq[kClUnroll];
 #pragma unroll
-    for (int u = 0; u < kClUnroll / 2; ++u) {
+    for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
       if (vv < v1) {
-        const float4 gq = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
-        const float4 xq = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
-        const float4 yq = __ldg(reinterpret_cast<const float4 *>(y + off + vv * C));
-        const float gg[4] = {gq.x, gq.y, gq.z, gq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w}, yy[4] = {yq.x, yq.y, yq.z, yq.w};
+        gq[u] = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
+        xq[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kClUnroll; ++u) {
+      const long long vv = v + (long long)u * rows;
+      if (vv < v1) {
+        const float gg[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w}, xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float dz = yy[j] > 0.f ? gg[j] : 0.f;
+          const float dz = fmaf(xx[j], a[j], fo[j]) > 0.f ? gg[j] : 0.f;
           o[j] = a[j] * (dz - m1[j] - (xx[j] - mu[j]) * rs[j] * m2[j]);
         }
         *reinterpret_cast<float4 *>(dx + off + vv * C) = make_float4(o[0], o[1], o[2], o[3]);

@@ -50,7 +50,7 @@ class InstanceNormReLUFunction(Function):
                 rc = _lib.lib().instnorm_relu_forward_ndhwc(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(x), _p(w), _p(b),
                                                             B, C, V, float(eps), _p(y), _p(mean), _p(rstd), _p(ws))
             _lib.check(rc, "instnorm_relu_forward_ndhwc")
-            ctx.save_for_backward(x, y, w, mean, rstd)
+            ctx.save_for_backward(x, b, w, mean, rstd)            # the NDHWC backward recomputes the ReLU mask from x: y is not kept
             ctx.param_dtypes = (weight.dtype, bias.dtype)
             return y
         ws = torch.empty(_lib.lib().instnorm_workspace_floats(_DT[x.dtype], B, C, V), dtype=torch.float32, device=x.device)
@@ -65,7 +65,7 @@ class InstanceNormReLUFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, y, w, mean, rstd = ctx.saved_tensors
+        x, y, w, mean, rstd = ctx.saved_tensors                  # channels-last: the second entry is beta, not y (mask recomputed from x)
         B, C = x.shape[:2]
         V = x[0, 0].numel()
         dy = dy.to(x.dtype)
@@ -76,8 +76,8 @@ class InstanceNormReLUFunction(Function):
         if ctx.channels_last:
             ws = torch.empty(_lib.lib().instnorm_ndhwc_workspace_floats(B, C, V), dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):
-                rc = _lib.lib().instnorm_relu_backward_ndhwc(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy), _p(x), _p(y),
-                                                             _p(w), _p(mean), _p(rstd), B, C, V, _p(dx), _p(dw), _p(db), _p(ws))
+                rc = _lib.lib().instnorm_relu_backward_ndhwc(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy), _p(x), _p(w),
+                                                             _p(y), _p(mean), _p(rstd), B, C, V, _p(dx), _p(dw), _p(db), _p(ws))
             _lib.check(rc, "instnorm_relu_backward_ndhwc")
             return dx, dw.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
         ws = torch.empty(_lib.lib().instnorm_workspace_floats(_DT[x.dtype], B, C, V), dtype=torch.float32, device=x.device)
