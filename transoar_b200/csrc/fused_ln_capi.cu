@@ -40,7 +40,7 @@ int bwd(cudaStream_t st, const float *dy, const float *z, const float *gamma, co
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fusedln::kWarps * 2 * 4 * 32 * fusedln::kMaxNV * (int)sizeof(float)); });
   if (err != cudaSuccess) return (int)err;
   kern<<<grid, fusedln::kThreads, smem, st>>>(dy, z, gamma, mean, rstd, rows, C, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed, da, db, ws);
-  fusedln::bwd_finalize_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(ws, grid, C, dgamma, dbeta);
+  fusedln::bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(ws, grid, C, dgamma, dbeta);
   g_msda3d_launches += 2;
   return (int)cudaGetLastError();
 }

@@ -183,14 +183,23 @@ bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const floa
   }
 }
 
-__global__ void bwd_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ dgamma, float *__restrict__ dbeta)
+// 256 threads per 32 entries of [dgamma | dbeta]: warp w sums partials w, w + 8, ..., combined in shared memory
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ dgamma,
+                                                          float *__restrict__ dbeta)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int b = 0; b < ctas; ++b) s += part[(long long)b * 2 * C + i];
-  if (i < C) dgamma[i] = (float)s;
-  else dbeta[i - C] = (float)s;
+  if (i < 2 * C)
+    for (int b = w; b < ctas; b += 8) s += part[(long long)b * 2 * C + i];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < 2 * C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][lane];
+    if (i < C) dgamma[i] = (float)s;
+    else dbeta[i - C] = (float)s;
+  }
 }
 
 }  // namespace fusedln

@@ -215,6 +215,8 @@ struct UnitCoords {
   bool active;
   int m;
   long long u, b;
+  long long row;   // b * Lq + q = u / M: the unit's (batch, query) row (fused prologue: row of the reference points / merged projection)
+  int q;           // query index inside the batch element
 };
 
 // Work scheduling.  A "block slot" is the set of UPB = 8 * 32/G units one CTA processes together.  Slots are handed
@@ -261,8 +263,10 @@ __device__ __forceinline__ UnitCoords slot_unit(bool brick, long long t, int ui,
     const long long u = t * UPB + ui;
     c.active = u < total;
     c.u = c.active ? u : 0;
-    c.m = (int)(c.u % M);
-    c.b = c.u / ((long long)M * Lq);
+    c.row = c.u / M;
+    c.m = (int)(c.u - c.row * M);
+    c.b = c.row / Lq;
+    c.q = (int)(c.row - c.b * Lq);
     return c;
   }
   using B = BrickDims<UPB>;
@@ -279,8 +283,10 @@ __device__ __forceinline__ UnitCoords slot_unit(bool brick, long long t, int ui,
   const int w = bw * B::BW + ui % B::BW, h = bh * B::BH + (ui / B::BW) % B::BH, d = bd * B::BD + ui / (B::BW * B::BH);
   c.active = d < li.x && h < li.y && w < li.z;
   const long long q = c.active ? (long long)li.w + ((long long)d * li.y + h) * li.z + w : 0;
-  c.u = (c.b * Lq + q) * M + c.m;
-  if (!c.active) { c.u = 0; c.m = 0; c.b = 0; }
+  c.row = c.b * Lq + q;
+  c.q = (int)q;
+  c.u = c.row * M + c.m;
+  if (!c.active) { c.u = 0; c.m = 0; c.b = 0; c.row = 0; c.q = 0; }
   return c;
 }
 
@@ -347,11 +353,11 @@ template <int G> __device__ __forceinline__ float group_sum_f(float v)
 // logit_col) together -- so that the two small projections are a single GEMM and their gradients arrive in one tensor.
 __device__ __forceinline__ long long fused_off_base(const UnitCoords &uc, int LP, int M, long long ld)
 {
-  return ld ? (uc.u / M) * ld + (long long)uc.m * LP * 3 : uc.u * LP * 3;
+  return ld ? uc.row * ld + (long long)uc.m * LP * 3 : uc.u * LP * 3;
 }
 __device__ __forceinline__ long long fused_logit_base(const UnitCoords &uc, int LP, int M, long long ld, int logit_col)
 {
-  return ld ? (uc.u / M) * ld + logit_col + (long long)uc.m * LP : uc.u * LP;
+  return ld ? uc.row * ld + logit_col + (long long)uc.m * LP : uc.u * LP;
 }
 
 template <int G>
@@ -370,8 +376,7 @@ __device__ __forceinline__ PreparedSample prepare_sample_fused(const int4 *lv, c
   if (mine) {
     const int l = s / P;
     const int4 li = lv[l];
-    const long long q = (uc.u / M) % Lq;
-    const float *r = ref + uc.b * ref_bstride + (q * L + l) * 3;
+    const float *r = ref + uc.b * ref_bstride + ((long long)uc.q * L + l) * 3;
     const float x = __fadd_rn(__ldg(r), __fdiv_rn(ldg_stream(off + 3 * si), __int2float_rn(li.z)));
     const float y = __fadd_rn(__ldg(r + 1), __fdiv_rn(ldg_stream(off + 3 * si + 1), __int2float_rn(li.y)));
     const float z = __fadd_rn(__ldg(r + 2), __fdiv_rn(ldg_stream(off + 3 * si + 2), __int2float_rn(li.x)));

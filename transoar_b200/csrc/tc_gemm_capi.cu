@@ -148,7 +148,7 @@ extern "C" int tc_colsum(void *stream, const float *x, long long rows, int chann
   const long long need = (rows + lanes - 1) / lanes;
   const int grid = (int)(need < kColsumCtas ? need : kColsumCtas);
   tcgemm::colsum_partial_kernel<<<grid, tcgemm::kColsumThreads, 0, st>>>(x, rows, channels, ld, workspace);
-  tcgemm::colsum_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(workspace, grid, channels, out);
+  tcgemm::colsum_finalize_kernel<<<(channels + 31) / 32, 256, 0, st>>>(workspace, grid, channels, out);
   g_msda3d_launches += 2;
   return (int)cudaGetLastError();
 }

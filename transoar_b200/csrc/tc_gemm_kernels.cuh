@@ -10,12 +10,13 @@
 // m / n index is contiguous: what the gradient GEMMs dX = dY W and dW = dY^T X need) -- the tensor cores read both
 // layouts from shared memory, so no operand is ever transposed in HBM.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer: one elected lane issues cp.async.bulk.tensor boxes (128-byte swizzle) into a ring of stages,
 //               completion counted on the stage's "full" mbarrier
 //   warp 1      owns TMEM (tcgen05.alloc / dealloc); lane 0 issues tcgen05.mma.kind::tf32 128 x BN x 8, four per stage, and
 //               tcgen05.commit's the stage back to the producer ("empty") and the finished tile to the epilogue ("tmem full")
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias / ReLU -> global (or red.add for split-K)
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld 32 lanes x 32 columns ->
+//               registers -> shared-memory turn-around -> bias / ReLU / dropout / gate -> global (or red.add for split-K)
 //   The accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
 // fp32 operands are fed to the tensor cores as they are: kind::tf32 reads the upper 19 bits.
 #pragma once
@@ -31,7 +32,8 @@ namespace tcgemm {
 constexpr int BM = 128;               // rows of D per tile = TMEM lanes
 constexpr int BK = 32;                // reduction elements per stage = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;             // tf32
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;           // two epilogue warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSlabBytes = BK * 128;  // MN-major operands: one 32(mn) x BK(r) slab per TMA box
 constexpr unsigned kSpinLimit = 1u << 28;
 
@@ -42,10 +44,10 @@ template <int BN, int CTAS> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;      // 1 CTA: 6 / 5 / 4 (BN = 128 / 192 / 256); pair: 8 / 7 / 6
+  static constexpr int STAGES_RAW = (184 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;      // 1 CTA: 5 / 4 / 3 (BN = 128 / 192 / 256); pair: 7 / 6 / 5
   static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;              // two accumulators of BN columns, rounded to a power of two
-  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                    // per epilogue warp: a 32 x 32 fp32 chunk, rows padded to 36 floats
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * 36 * 4;            // per epilogue warp: a 32 x 32 fp32 chunk, rows padded to 36 floats
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -214,7 +216,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128 * CTAS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kEpiWarps * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -325,7 +327,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
       const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
       const bool timed = p.prof != nullptr && warp == 2 && lane == 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {   // the quarter's warps take alternating chunks
         const long long tp0 = timed ? clock64() : 0;
         // gate values of this lane's eight (row, 4-column) pieces: loaded first so that their latency hides behind the TMEM read
         float4 g4[8];
@@ -479,13 +481,22 @@ colsum_partial_kernel(const float *__restrict__ x, long long rows, int C, long l
   }
 }
 
-__global__ void colsum_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ out)
+// 256 threads per 32 columns: warp w sums partials w, w + 8, ... of its columns, the eight warps are combined in shared memory
+// (a single thread per column walking all CTAs' partials is latency-bound: 45 us for 592 partials)
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ out)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int b = 0; b < ctas; ++b) s += part[(long long)b * C + c];
-  out[c] = (float)s;
+  if (c < C)
+    for (int b = w; b < ctas; b += 8) s += part[(long long)b * C + c];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][lane];
+    out[c] = (float)s;
+  }
 }
 
 }  // namespace tcgemm
