@@ -512,6 +512,25 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- the other shipped yaml (attn_fpn_foc_dec_amos.yaml: refinement over P3..P5, 405 queries / 15 organs) on the same volumes
+    if not args.no_extras and "extras_error" not in extras:
+        try:
+            from transoar_b200.engine import amos_train_config
+            acfg = amos_train_config(volume=VOLUME)
+            torch.manual_seed(0)
+            ats = TrainStep(acfg, dev, world=1)
+            av = torch.rand(BATCH, 1, *VOLUME, device=dev)
+            atg = synthetic_targets(acfg, BATCH, 5, dev)
+            a_ms = _event_ms(lambda: ats.step(av, atg), 4, 8)
+            extras["amos_yaml_train_step"] = {"what": "config/attn_fpn_foc_dec_amos.yaml (feature_levels P3-P5, 405 queries, 15 organs) on 160x160x256 volumes, "
+                                                      "same step, this rank only", "volumes_per_s_per_gpu": BATCH / (a_ms / 1e3), "ms_per_step": a_ms}
+            del ats, av
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            extras["amos_yaml_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    if world > 1:
+        dist.barrier()
+
     # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU route of the same step, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -38,3 +38,14 @@ def synthetic_atlas(num_organs=20, seed=0):
 def visceral_config(seed=0):
     return {"backbone": copy.deepcopy(VISCERAL_BACKBONE), "neck": copy.deepcopy(VISCERAL_NECK),
             "bbox_properties": synthetic_atlas(20, seed)}
+
+
+def amos_config(seed=0, volume=(256, 256, 128)):
+    """config/attn_fpn_foc_dec_amos.yaml: as the VISCERAL file except out_fmaps [P3], feature_levels [P3, P4, P5], input_levels P3,
+    405 queries for 15 organs, 256x256x128 patches (diff of the two yamls: lines 73, 77, 93, 114-115, 121).  The RoI grid follows
+    the P3 feature map of ``volume`` (the reference hard-codes 256x256x128 for 15 organs, focused_decoder.py:108-117)."""
+    bb = copy.deepcopy(VISCERAL_BACKBONE)
+    bb.update(out_fmaps=["P3"], feature_levels=["P3", "P4", "P5"])
+    neck = copy.deepcopy(VISCERAL_NECK)
+    neck.update(input_levels="P3", num_queries=405, num_organs=15)
+    return {"backbone": bb, "neck": neck, "bbox_properties": synthetic_atlas(15, seed), "neck_input_shape": tuple(v // 8 for v in volume)}

@@ -29,6 +29,15 @@ def visceral_train_config(seed=0):
     return cfg
 
 
+def amos_train_config(seed=0, volume=(256, 256, 128)):
+    """config/attn_fpn_foc_dec_amos.yaml (same training keys as the VISCERAL file, 15 classes)."""
+    from .configs import amos_config
+    cfg = amos_config(seed, volume)
+    cfg.update(lr=2e-4, lr_backbone=2e-5, weight_decay=1e-4, clip_max_norm=-1, batch_size=2, anchor_matching=True,
+               set_cost_class=1, set_cost_bbox=0, set_cost_giou=0, loss_coefs=copy.deepcopy(VISCERAL_LOSS_COEFS), num_classes=15)
+    return cfg
+
+
 def synthetic_targets(config, batch, seed, device):
     """One box per organ = the atlas median jittered by a few percent, labels 1..num_organs; dense form."""
     g = torch.Generator().manual_seed(seed)
