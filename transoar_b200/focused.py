@@ -13,7 +13,6 @@ when ``materialize_weights`` is set (scripts/test.py:78-80 reads it for visualis
 """
 import copy
 import ctypes
-import math
 
 import torch
 import torch.nn.functional as F

@@ -5,7 +5,6 @@ reference checkpoints load unchanged), initialisation and forward semantics; the
 sm_100a kernels behind ``MSDeformAttnFunction``.  ``use_cuda=False`` selected the pure-PyTorch debug route in the
 reference (ms_deform_attn.py:137-138); this package has no such route and raises instead of silently falling back.
 """
-import math
 import warnings
 
 import torch

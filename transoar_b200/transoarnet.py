@@ -3,7 +3,6 @@
 ``_cls_head``, ``_reg_head``, ``_query_embed``, ``_seg_head``) and the same output dict.  Anchors / restrictions are
 registered as (non-persistent) buffers instead of being ``.cuda()``-ed in the constructor, so the model can be built on
 any device and moved with ``.to()``; the RoI grid is derived from the feature map."""
-from collections import defaultdict
 
 import torch
 import torch.nn.functional as F
