@@ -1,0 +1,44 @@
+"""GPU parity of the tcgen05 implicit-GEMM 3x3x3 convolution (include/conv3d_tc.h) against torch's conv3d in fp64 on the same
+inputs (TF32 tolerance), forward and input gradient, ragged shapes included."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _err(a, b):
+    return float((a.double() - b.double()).abs().max())
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 16, 8), (2, 5, 32, 24), (1, 4, 20, 13), (1, 2, 7, 5), (1, 9, 48, 40)])
+@pytest.mark.parametrize("c", [24, 8, 32])
+def test_forward_and_input_gradient_match_conv3d(shape, c):
+    from transoar_b200.conv3d_tc import conv3d_k3
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(N + D + H + W + c)
+    x = torch.randn(N, c, D, H, W, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    w = (torch.randn(c, c, 3, 3, 3, generator=g) / math.sqrt(27 * c)).to(DEV).requires_grad_(True)
+    dy = torch.randn(N, c, D, H, W, generator=g).to(DEV)
+    y = conv3d_k3(x, w)
+    y.backward(dy)
+    assert y.is_contiguous(memory_format=torch.channels_last_3d) and x.grad.shape == x.shape
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    yd = F.conv3d(xd, wd, None, 1, 1)
+    yd.backward(dy.double())
+    tol = 4e-3 * math.sqrt(27 * c) * 4.5 * 4.5 / math.sqrt(27 * c)            # TF32: ~2^-10 relative per product, |x|, |dy| up to ~4.5
+    assert _err(y, yd) < tol, (_err(y, yd), tol)
+    assert _err(x.grad, xd.grad) < tol
+    assert _err(w.grad, wd.grad) < 4e-3 * math.sqrt(N * D * H * W) * 4.5 * 4.5 / 9
+
+
+def test_exact_on_tf32_representable_inputs():
+    """Small integers are exact in TF32 and their sums exact in fp32: the convolution must equal torch's bit for bit."""
+    from transoar_b200.conv3d_tc import conv3d_k3
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(-4, 5, (1, 24, 6, 20, 11), generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randint(-3, 4, (24, 24, 3, 3, 3), generator=g).float().to(DEV)
+    assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1))

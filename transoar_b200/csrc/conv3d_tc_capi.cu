@@ -1,0 +1,85 @@
+// conv3d_tc_capi.cu -- C ABI of the tcgen05 3x3x3 convolution (include/conv3d_tc.h): 5-D tensor map over the NDHWC input, launch.
+#include "conv3d_tc_kernels.cuh"
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/conv3d_tc.h"
+#include "../../include/msda3d.h"
+
+extern std::atomic<unsigned long long> g_msda3d_launches;
+
+namespace {
+
+using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled encode_fn()
+{
+  static EncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiled>(p);
+  });
+  return fn;
+}
+
+bool ci_ok(int ci) { return ci == 8 || ci == 16 || ci == 24 || ci == 32 || ci == 48; }
+
+template <int CI>
+int launch(cudaStream_t st, const CUtensorMap &mx, const float *w, float *y, int N, int D, int H, int W, int CO)
+{
+  using C = convtc::ConvCfg<CI>;
+  auto kern = convtc::conv3d_k3_kernel<CI>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
+  if (err != cudaSuccess) return (int)err;
+  const long long tiles = (long long)N * D * ((H + convtc::TH - 1) / convtc::TH) * ((W + convtc::TW - 1) / convtc::TW);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  kern<<<grid, convtc::kThreadsConv, C::SMEM_BYTES, st>>>(mx, w, y, N, D, H, W, CO);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int conv3d_tc_supported(int in_channels, int out_channels)
+{
+  return ci_ok(in_channels) && out_channels > 0 && out_channels % 4 == 0 && out_channels <= convtc::NPAD &&
+         convtc::ConvCfg<48>::SMEM_BYTES * (in_channels == 48) <= 227 * 1024;
+}
+
+extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w_taps, int batch, int depth, int height, int width,
+                                    int in_channels, int out_channels, float *y)
+{
+  if (!x || !w_taps || !y || batch <= 0 || depth <= 0 || height <= 0 || width <= 0) return MSDA3D_EINVAL;
+  if (!conv3d_tc_supported(in_channels, out_channels)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w_taps)) & 15) return MSDA3D_EALIGN;
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t C = (cuuint64_t)in_channels, W = (cuuint64_t)width, H = (cuuint64_t)height, D = (cuuint64_t)depth;
+  const cuuint64_t gdim[5] = {C, W, H, D, (cuuint64_t)batch};
+  const cuuint64_t gstride[4] = {C * 4, W * C * 4, H * W * C * 4, D * H * W * C * 4};
+  const cuuint32_t box[5] = {4, (cuuint32_t)convtc::HW, (cuuint32_t)convtc::HH, 3, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap mx;
+  // TFLOAT32: the copy engine rounds the activations to TF32; out-of-bounds voxels of the halo box are zero-filled (= padding 1)
+  if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return MSDA3D_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (in_channels) {
+    case 8: return launch<8>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+    case 16: return launch<16>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+    case 24: return launch<24>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+    case 32: return launch<32>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+    default: return launch<48>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+  }
+}

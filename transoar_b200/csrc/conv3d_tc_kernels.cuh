@@ -1,0 +1,182 @@
+// conv3d_tc_kernels.cuh -- 3x3x3 / stride 1 / padding 1 convolution of a channels-last (NDHWC) fp32 volume on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands by TMA), for the narrow full-resolution stages of the AttnFPN
+// encoder (EncoderCnnBlock stage 0, second convolution: 24 -> 24 channels at 160x160x256, transoar/models/backbones/encoder_blocks.py:
+// 34-40 via attn_fpn.py:170-182), forward and -- called with the flipped / transposed weights -- the gradient with respect to the input.
+// cuDNN's choice for that input gradient on B200 is a "strided dgrad" kernel that takes 4.1 ms per step; the forward takes 1.5 ms.
+//
+// Implicit GEMM without an im2col copy.  One CTA tile = 1 x 16 x 8 output voxels (d, h, w) = the 128 rows of the MMA.  The input
+// halo tile (3 x 18 x 10 voxels) is loaded ONCE per tile by TMA as CI/4 "channel-chunk planes" [chunk][d][h][w][4 floats] (5-D tensor
+// map over N, D, H, W, C with a 4-channel box; out-of-bounds parts are zero-filled, which is the convolution's padding).  In that form
+// the A operand of every filter tap (kd, kh, kw) is the no-swizzle K-major canonical layout of the tensor core -- rows (voxels) 16
+// bytes apart inside a plane, the tile's h rows one halo row pitch (160 bytes) apart, the next four channels one plane further -- so a
+// tap is nothing but a START-ADDRESS OFFSET of ((kd * 18 + kh) * 10 + kw) * 16 bytes in the shared-memory descriptor: 27 taps x CI/8
+// k-steps = 81 MMAs (128 x 32 x 8) read the same tile.  The weights of all 27 taps live in shared memory for the whole (persistent)
+// kernel, rounded to TF32 when they are staged.  Pipeline as in tc_gemm_kernels.cuh: TMA producer warp, single-thread MMA issuer,
+// four epilogue warps (TMEM -> registers -> one contiguous CO * 4-byte row per voxel), two tile stages, two TMEM accumulators.
+#pragma once
+
+#include "tc_gemm_kernels.cuh"
+
+namespace convtc {
+
+using namespace tcgemm;
+
+constexpr int TH = 16, TW = 8;                 // tile: 1 x TH x TW voxels = 128 MMA rows
+constexpr int HH = TH + 2, HW = TW + 2;        // halo tile: 3 x HH x HW voxels
+constexpr int kPlaneBytes = 3 * HH * HW * 16;  // one 4-channel chunk of the halo tile
+constexpr int kThreadsConv = 192;
+constexpr int NPAD = 32;                       // MMA N (output channels padded to a multiple of 16)
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
+{
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// no-swizzle shared-memory descriptor: start, leading-dimension byte offset, stride byte offset (all in 16-byte units), sm_100 version 1
+__device__ __forceinline__ uint64_t desc_noswizzle(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ float to_tf32(float x)
+{
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int CI> struct ConvCfg {
+  static constexpr int CHUNKS = CI / 4;
+  static constexpr int STAGE_BYTES = CHUNKS * kPlaneBytes;                   // 51840 for CI = 24
+  static constexpr int W_TAP_BYTES = CHUNKS * NPAD * 16;                     // one tap of B: [k-chunk][n (32)][4 floats]
+  static constexpr int W_BYTES = 27 * W_TAP_BYTES;                           // 82944 for CI = 24
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 128 + 128;
+};
+
+// x [N, D, H, W, CI] through the tensor map; wg [27][CO][CI] (tap-major; for the input gradient: flipped taps, transposed channels);
+// y [N, D, H, W, CO].  CI % 8 == 0, CO % 4 == 0, CO <= 32.
+template <int CI>
+__global__ void __launch_bounds__(kThreadsConv, 1)
+conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restrict__ wg, float *__restrict__ y, int N, int D, int H, int W, int CO)
+{
+  using C = ConvCfg<CI>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t wbase = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bars = wbase + C::W_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (2 + s); };
+  auto tfull = [&](int a) { return bars + 8u * (4 + a); };
+  auto tempty = [&](int a) { return bars + 8u * (6 + a); };
+  const uint32_t tmem_slot = bars + 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // weights -> shared memory, B operand of tap t: [k-chunk kc][n][4 floats] = wg[t][n][4 kc .. 4 kc + 3], rows n >= CO zero
+  for (int i = threadIdx.x; i < 27 * C::CHUNKS * NPAD; i += kThreadsConv) {
+    const int n = i % NPAD, kc = (i / NPAD) % C::CHUNKS, t = i / (NPAD * C::CHUNKS);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < CO) {
+      const float4 g = __ldg(reinterpret_cast<const float4 *>(wg + ((long long)t * CO + n) * CI + 4 * kc));
+      v = make_float4(to_tf32(g.x), to_tf32(g.y), to_tf32(g.z), to_tf32(g.w));
+    }
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * NPAD) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy weight stores must be visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int th = (H + TH - 1) / TH, tw = (W + TW - 1) / TW;
+  const long long tiles = (long long)N * D * th * tw;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
+        mbar_wait(empty(stage), phase ^ 1u);
+        mbar_expect_tx(full(stage), C::STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::CHUNKS; ++c)
+          tma_load_5d(base + stage * C::STAGE_BYTES + c * kPlaneBytes, &tmX, full(stage), 4 * c, iw * TW - 1, ih * TH - 1, d - 1, n);
+        if (++stage == 2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128, N = 32, both operands K-major, TF32 in, fp32 out
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty(as), aphase ^ 1u);
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * C::STAGE_BYTES, acc = tmem_base + (uint32_t)(as * NPAD);
+        uint32_t first = 0;
+#pragma unroll 1
+        for (int tap = 0; tap < 27; ++tap) {
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          const uint32_t a_tap = sa + (uint32_t)(((kd * HH + kh) * HW + kw) * 16);
+          const uint32_t b_tap = wbase + (uint32_t)tap * C::W_TAP_BYTES;
+#pragma unroll
+          for (int s = 0; s < CI / 8; ++s) {
+            // A: rows (w) 16 B apart, 8-row groups (tile rows h) one halo row pitch apart, second 4-channel chunk one plane further
+            const uint64_t da = desc_noswizzle(a_tap + (uint32_t)(2 * s) * kPlaneBytes, kPlaneBytes, HW * 16);
+            // B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NPAD * 16 B further
+            const uint64_t db = desc_noswizzle(b_tap + (uint32_t)(2 * s) * (NPAD * 16), NPAD * 16, 128);
+            umma_tf32(acc, da, db, idesc, first);
+            first = 1u;
+          }
+        }
+        umma_commit(empty(stage));
+        umma_commit(tfull(as));
+        if (++stage == 2) { stage = 0; phase ^= 1u; }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane, hh = row / TW, ww = row % TW;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t)(as * NPAD) + ((uint32_t)(q * 32) << 16), v);
+      tc_fence_before();
+      mbar_arrive(tempty(as));                                   // the accumulator is in registers: the next tile may overwrite it
+      const int h = ih * TH + hh, w = iw * TW + ww;
+      if (h < H && w < W) {
+        float *dst = y + ((((long long)n * D + d) * H + h) * W + w) * CO;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          if (c < CO) __stcs(reinterpret_cast<float4 *>(dst + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NPAD) : "memory");
+  }
+}
+
+}  // namespace convtc

@@ -446,7 +446,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kColsumThreads = 256;
 
-__global__ void __launch_bounds__(kColsumThreads)
+static __global__ void __launch_bounds__(kColsumThreads)
 colsum_partial_kernel(const float *__restrict__ x, long long rows, int C, long long ld, float *__restrict__ part)
 {
   __shared__ float4 red[kColsumThreads];
@@ -483,7 +483,7 @@ colsum_partial_kernel(const float *__restrict__ x, long long rows, int C, long l
 
 // 256 threads per 32 columns: warp w sums partials w, w + 8, ... of its columns, the eight warps are combined in shared memory
 // (a single thread per column walking all CTAs' partials is latency-bound: 45 us for 592 partials)
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ out)
+static __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *__restrict__ part, int ctas, int C, float *__restrict__ out)
 {
   __shared__ double red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
