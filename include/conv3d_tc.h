@@ -5,7 +5,7 @@
  * attn_fpn.py:170-182: 24 -> 24 channels at 160x160x256) -- cuDNN implicit-GEMM kernels in the reference -- and, called with the
  * flipped / transposed weights, autograd's gradient with respect to the input (cudnn_convolution_backward_input).
  *
- *   x       fp32 [N, D, H, W, CI]   channels-last (torch.channels_last_3d), 16-byte aligned; CI in {8, 16, 24, 32, 48}
+ *   x       fp32 [N, D, H, W, CI]   channels-last (torch.channels_last_3d), 16-byte aligned; CI in {8, 16, 24}
  *   w_taps  fp32 [27, CO, CI]       tap-major weights: w_taps[(kd*3 + kh)*3 + kw][co][ci] = weight[co][ci][kd][kh][kw]
  *                                   (input gradient: w_taps[t][ci][co] = weight[co][ci][2-kd][2-kh][2-kw], channel roles swapped)
  *   y       fp32 [N, D, H, W, CO]   channels-last; CO % 4 == 0, CO <= 32

@@ -15,7 +15,7 @@ def _err(a, b):
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 16, 8), (2, 5, 32, 24), (1, 4, 20, 13), (1, 2, 7, 5), (1, 9, 48, 40)])
-@pytest.mark.parametrize("c", [24, 8, 32])
+@pytest.mark.parametrize("c", [24, 8, 16])
 def test_forward_and_input_gradient_match_conv3d(shape, c):
     from transoar_b200.conv3d_tc import conv3d_k3
     N, D, H, W = shape
@@ -36,9 +36,10 @@ def test_forward_and_input_gradient_match_conv3d(shape, c):
 
 
 def test_exact_on_tf32_representable_inputs():
-    """Small integers are exact in TF32 and their sums exact in fp32: the convolution must equal torch's bit for bit."""
+    """Small integers are exact in TF32 and their sums exact in fp32: the result must be the exact integer convolution (torch's fp64
+    GPU convolution itself is off by ~1e-13 from the integers, hence the round())."""
     from transoar_b200.conv3d_tc import conv3d_k3
     g = torch.Generator().manual_seed(1)
     x = torch.randint(-4, 5, (1, 24, 6, 20, 11), generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last_3d)
     w = torch.randint(-3, 4, (24, 24, 3, 3, 3), generator=g).float().to(DEV)
-    assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1))
+    assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1).round())

@@ -10,6 +10,7 @@ InstanceNorm3d -> ReLU pair runs as a fused sm_100a kernel (include/instnorm.h);
 import torch
 from torch import nn
 
+from .conv3d_tc import conv3d_k3, conv_tc_eligible
 from .instnorm import instance_norm_relu
 from .position_encoding import PositionEmbeddingSine3D
 from .refine import DecoderDefAttnBlock
@@ -41,7 +42,9 @@ class EncoderCnnBlock(nn.Module):
                 # a 1-channel input / weight is layout-ambiguous and cuDNN answers NCDHW: move to NDHWC once, here
                 x = x.contiguous(memory_format=torch.channels_last_3d)
         x = instance_norm_relu(x, norm1.weight, norm1.bias, norm1.eps)
-        return instance_norm_relu(conv2(x), norm2.weight, norm2.bias, norm2.eps)
+        # narrow full-resolution stage (24 -> 24): tcgen05 implicit-GEMM convolution, forward and input gradient (include/conv3d_tc.h)
+        x = conv3d_k3(x, conv2.weight) if conv_tc_eligible(conv2, x) else conv2(x)
+        return instance_norm_relu(x, norm2.weight, norm2.bias, norm2.eps)
 
 
 class Encoder(nn.Module):

@@ -28,7 +28,9 @@ EncodeTiled encode_fn()
   return fn;
 }
 
-bool ci_ok(int ci) { return ci == 8 || ci == 16 || ci == 24 || ci == 32 || ci == 48; }
+// two halo-tile stages + the weights of all 27 taps must fit the 227 KB of shared memory: 8, 16 or 24 input channels
+bool ci_ok(int ci) { return ci == 8 || ci == 16 || ci == 24; }
+static_assert(convtc::ConvCfg<24>::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
 
 template <int CI>
 int launch(cudaStream_t st, const CUtensorMap &mx, const float *w, float *y, int N, int D, int H, int W, int CO)
@@ -52,8 +54,7 @@ int launch(cudaStream_t st, const CUtensorMap &mx, const float *w, float *y, int
 
 extern "C" int conv3d_tc_supported(int in_channels, int out_channels)
 {
-  return ci_ok(in_channels) && out_channels > 0 && out_channels % 4 == 0 && out_channels <= convtc::NPAD &&
-         convtc::ConvCfg<48>::SMEM_BYTES * (in_channels == 48) <= 227 * 1024;
+  return ci_ok(in_channels) && out_channels > 0 && out_channels % 4 == 0 && out_channels <= convtc::NPAD;
 }
 
 extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w_taps, int batch, int depth, int height, int width,
@@ -78,8 +79,6 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
   switch (in_channels) {
     case 8: return launch<8>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
     case 16: return launch<16>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
-    case 24: return launch<24>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
-    case 32: return launch<32>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
-    default: return launch<48>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
+    default: return launch<24>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
   }
 }

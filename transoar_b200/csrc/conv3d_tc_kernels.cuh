@@ -23,7 +23,8 @@ using namespace tcgemm;
 
 constexpr int TH = 16, TW = 8;                 // tile: 1 x TH x TW voxels = 128 MMA rows
 constexpr int HH = TH + 2, HW = TW + 2;        // halo tile: 3 x HH x HW voxels
-constexpr int kPlaneBytes = 3 * HH * HW * 16;  // one 4-channel chunk of the halo tile
+constexpr int kPlaneData = 3 * HH * HW * 16;   // one 4-channel chunk of the halo tile: 8640 bytes
+constexpr int kPlaneBytes = (kPlaneData + 127) / 128 * 128;   // plane pitch: TMA destinations are 128-byte aligned
 constexpr int kThreadsConv = 192;
 constexpr int NPAD = 32;                       // MMA N (output channels padded to a multiple of 16)
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ float to_tf32(float x)
 
 template <int CI> struct ConvCfg {
   static constexpr int CHUNKS = CI / 4;
-  static constexpr int STAGE_BYTES = CHUNKS * kPlaneBytes;                   // 51840 for CI = 24
+  static constexpr int STAGE_BYTES = CHUNKS * kPlaneBytes;                   // 52224 for CI = 24
   static constexpr int W_TAP_BYTES = CHUNKS * NPAD * 16;                     // one tap of B: [k-chunk][n (32)][4 floats]
   static constexpr int W_BYTES = 27 * W_TAP_BYTES;                           // 82944 for CI = 24
   static constexpr int STAGES = 2;
@@ -108,7 +109,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
         mbar_wait(empty(stage), phase ^ 1u);
-        mbar_expect_tx(full(stage), C::STAGE_BYTES);
+        mbar_expect_tx(full(stage), C::CHUNKS * kPlaneData);
 #pragma unroll
         for (int c = 0; c < C::CHUNKS; ++c)
           tma_load_5d(base + stage * C::STAGE_BYTES + c * kPlaneBytes, &tmX, full(stage), 4 * c, iw * TW - 1, ih * TH - 1, d - 1, n);
