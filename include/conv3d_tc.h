@@ -24,6 +24,10 @@ int conv3d_tc_supported(int in_channels, int out_channels);
 int conv3d_tc_k3_forward(void *stream, const float *x, const float *w_taps, int batch, int depth, int height, int width, int in_channels,
                          int out_channels, float *y);
 
+/* Test hook: one 128 x 32 x 8 TF32 MMA whose operands are MN-major in the no-swizzle canonical layout (what a tensor-core weight
+ * gradient over channels-last volumes needs): D[m][n] = sum_k At[k][m] * Bt[k][n], At [8][128], Bt [8][32], D [128][32], device pointers. */
+int conv3d_tc_debug_mn_probe(void *stream, const float *At, const float *Bt, float *D);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,18 @@ def test_exact_on_tf32_representable_inputs():
     x = torch.randint(-4, 5, (1, 24, 6, 20, 11), generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last_3d)
     w = torch.randint(-3, 4, (24, 24, 3, 3, 3), generator=g).float().to(DEV)
     assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1).round())
+
+
+def test_mn_major_noswizzle_tf32_probe():
+    """The layout a tensor-core weight gradient over channels-last volumes needs: both operands MN-major, no swizzle."""
+    import ctypes
+    from transoar_b200 import _lib
+    g = torch.Generator().manual_seed(2)
+    At = torch.randint(-4, 5, (8, 128), generator=g).float().to(DEV)
+    Bt = torch.randint(-4, 5, (8, 32), generator=g).float().to(DEV)
+    D = torch.zeros(128, 32, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = _lib.lib().conv3d_tc_debug_mn_probe(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(At), p(Bt), p(D))
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert torch.equal(D, At.t() @ Bt)

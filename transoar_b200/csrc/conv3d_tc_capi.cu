@@ -82,3 +82,12 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
     default: return launch<24>(st, mx, w_taps, y, batch, depth, height, width, out_channels);
   }
 }
+
+// tests only: one 128 x 32 x 8 MMA with MN-major no-swizzle TF32 operands (At [8][128], Bt [8][32] -> D [128][32])
+extern "C" int conv3d_tc_debug_mn_probe(void *stream, const float *At, const float *Bt, float *D)
+{
+  if (!At || !Bt || !D) return MSDA3D_EINVAL;
+  convtc::mn_noswizzle_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(At, Bt, D);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}

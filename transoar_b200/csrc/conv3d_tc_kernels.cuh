@@ -127,21 +127,20 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
         mbar_wait(full(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * C::STAGE_BYTES, acc = tmem_base + (uint32_t)(as * NPAD);
-        uint32_t first = 0;
-#pragma unroll 1
-        for (int tap = 0; tap < 27; ++tap) {
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          const uint32_t a_tap = sa + (uint32_t)(((kd * HH + kh) * HW + kw) * 16);
-          const uint32_t b_tap = wbase + (uint32_t)tap * C::W_TAP_BYTES;
+        // One thread issues 27 x CI/8 MMAs per tile, so the issue loop must be cheap: the two descriptors are built once per tile
+        // and every tap / k-step only adds a compile-time constant to their 14-bit start-address fields (all shared-memory
+        // addresses are < 256 KB, so the field never carries into the LBO field).
+        //   A: rows (w) 16 B apart, 8-row groups (tile rows h) one halo row pitch apart, second 4-channel chunk one plane further
+        //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NPAD * 16 B further
+        const uint64_t da0 = desc_noswizzle(sa, kPlaneBytes, HW * 16), db0 = desc_noswizzle(wbase, NPAD * 16, 128);
 #pragma unroll
-          for (int s = 0; s < CI / 8; ++s) {
-            // A: rows (w) 16 B apart, 8-row groups (tile rows h) one halo row pitch apart, second 4-channel chunk one plane further
-            const uint64_t da = desc_noswizzle(a_tap + (uint32_t)(2 * s) * kPlaneBytes, kPlaneBytes, HW * 16);
-            // B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NPAD * 16 B further
-            const uint64_t db = desc_noswizzle(b_tap + (uint32_t)(2 * s) * (NPAD * 16), NPAD * 16, 128);
-            umma_tf32(acc, da, db, idesc, first);
-            first = 1u;
-          }
+        for (int tap = 0; tap < 27; ++tap) {
+          constexpr int kA16 = 2 * kPlaneBytes / 16, kB16 = 2 * NPAD;                        // k-step strides in 16-byte units
+          const uint32_t a16 = (uint32_t)(((tap / 9) * HH + (tap / 3) % 3) * HW + tap % 3);  // tap offset in the halo tile, 16-byte units
+          const uint32_t b16 = (uint32_t)(tap * (C::W_TAP_BYTES / 16));
+#pragma unroll
+          for (int s = 0; s < CI / 8; ++s)
+            umma_tf32(acc, da0 + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (tap | s) != 0 ? 1u : 0u);
         }
         umma_commit(empty(stage));
         umma_commit(tfull(as));
@@ -178,6 +177,46 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NPAD) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Probe (tests only): does the tensor core take MN-major TF32 operands in the NO-SWIZZLE canonical layout
+// [mn-chunk of 4][k row][4 floats] (k rows 16 bytes apart, chunks `plane` bytes apart)?  One MMA 128 x 32 x 8:
+// D[m][n] = sum_k At[k][m] * Bt[k][n].  The weight-gradient convolution needs exactly this form (voxels = k, channels = mn).
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) mn_noswizzle_probe_kernel(const float *__restrict__ At, const float *__restrict__ Bt, float *__restrict__ Dout)
+{
+  __shared__ __align__(128) float sA[32][8][4];     // [m chunk][k][4]
+  __shared__ __align__(128) float sB[8][8][4];      // [n chunk][k][4]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < 128 * 8; i += 128) { const int m = i % 128, k = i / 128; sA[m / 4][k][m % 4] = to_tf32(At[k * 128 + m]); }
+  for (int i = t; i < 32 * 8; i += 128) { const int n = i % 32, k = i / 32; sB[n / 4][k][n % 4] = to_tf32(Bt[k * 32 + n]); }
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (t == 0) {
+    // both operands MN-major (bits 15, 16), M = 128, N = 32; chunk pitch = 8 k rows * 16 B = 128 B (SBO), k groups of 8: 128 B (LBO, unused at K = 8)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    umma_tf32(tm, desc_noswizzle(smem_u32(&sA[0][0][0]), 128, 128), desc_noswizzle(smem_u32(&sB[0][0][0]), 128, 128), idesc, 0u);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16), v);
+  for (int n = 0; n < 32; ++n) Dout[(size_t)t * 32 + n] = v[n];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(32) : "memory");
 }
 
 }  // namespace convtc
