@@ -24,9 +24,18 @@ int conv3d_tc_supported(int in_channels, int out_channels);
 int conv3d_tc_k3_forward(void *stream, const float *x, const float *w_taps, int batch, int depth, int height, int width, int in_channels,
                          int out_channels, float *y);
 
-/* Test hook: one 128 x 32 x 8 TF32 MMA whose operands are MN-major in the no-swizzle canonical layout (what a tensor-core weight
- * gradient over channels-last volumes needs): D[m][n] = sum_k At[k][m] * Bt[k][n], At [8][128], Bt [8][32], D [128][32], device pointers. */
-int conv3d_tc_debug_mn_probe(void *stream, const float *At, const float *Bt, float *D);
+/* Weight gradient of the same convolution (autograd's cudnn_convolution_backward_weight): dweight [CO, CI, 3, 3, 3] (contiguous) =
+ * sum over voxels of dy[v][co] * x[v + tap][ci]; x [N, D, H, W, CI], dy [N, D, H, W, CO] channels-last fp32, CI, CO <= 32 and % 4 == 0.
+ * Both operands are MN-major for the tensor core (128-byte rows of 32 channels, padded by the copy engine); the three kw taps are the
+ * overlapping slabs of one MMA operand.  workspace: conv3d_tc_wgrad_workspace_floats() floats (per-CTA partial sums). */
+long long conv3d_tc_wgrad_workspace_floats(void);
+int conv3d_tc_k3_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
+                       int out_channels, float *dweight, float *workspace);
+
+/* Test hook for the weight-gradient formulation: one 128 x 32 x 8 TF32 MMA with MN-major operands in the 128-byte swizzle /
+ * 32-byte atom layout, the A operand being four OVERLAPPING 32-channel slabs (leading offset = one 128-byte row) starting at row `row0`:
+ * D[j * 32 + c][n] = sum_{k < 8} X[row0 + j + k][c] * Y[k][n], X [24][32], Y [8][32], D [128][32], device pointers. */
+int conv3d_tc_debug_mn_probe(void *stream, const float *X, const float *Y, float *D, int row0);
 
 #ifdef __cplusplus
 }

@@ -45,16 +45,19 @@ def test_exact_on_tf32_representable_inputs():
     assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1).round())
 
 
-def test_mn_major_noswizzle_tf32_probe():
-    """The layout a tensor-core weight gradient over channels-last volumes needs: both operands MN-major, no swizzle."""
+@pytest.mark.parametrize("row0", [0, 1, 2, 3, 5, 12])
+def test_mn_major_overlapping_slab_probe(row0):
+    """The operand form a tensor-core weight gradient over channels-last volumes needs (see conv3d_tc_kernels.cuh): MN-major, 128-byte
+    swizzle with 32-byte atoms, four slabs one row apart (= the kw taps), start address at any row."""
     import ctypes
     from transoar_b200 import _lib
-    g = torch.Generator().manual_seed(2)
-    At = torch.randint(-4, 5, (8, 128), generator=g).float().to(DEV)
-    Bt = torch.randint(-4, 5, (8, 32), generator=g).float().to(DEV)
+    g = torch.Generator().manual_seed(2 + row0)
+    X = torch.randint(-4, 5, (24, 32), generator=g).float().to(DEV)
+    Y = torch.randint(-4, 5, (8, 32), generator=g).float().to(DEV)
     D = torch.zeros(128, 32, device=DEV)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = _lib.lib().conv3d_tc_debug_mn_probe(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(At), p(Bt), p(D))
+    rc = _lib.lib().conv3d_tc_debug_mn_probe(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(X), p(Y), p(D), row0)
     torch.cuda.synchronize()
     assert rc == 0
-    assert torch.equal(D, At.t() @ Bt)
+    want = torch.cat([X[row0 + j:row0 + j + 8].t() @ Y for j in range(4)], 0)          # [4 * 32, 32]
+    assert torch.equal(D, want)

@@ -2,7 +2,7 @@
 
 ``conv3d_k3(x, weight)`` equals ``F.conv3d(x, weight, None, 1, 1)`` (TF32 multiply, fp32 accumulate) for channels-last ``x``
 [N, CI, D, H, W] and returns a channels-last tensor.  The gradient with respect to the input runs on the same kernel (flipped taps,
-transposed channels); the weight gradient is the library's (cuDNN) ``conv3d_weight``.  Used for the second convolution of the encoder's
+transposed channels); the weight gradient on its MN-major sibling (``conv3d_tc_k3_wgrad``: the three kw taps as overlapping slabs of one MMA operand).  Used for the second convolution of the encoder's
 first stage (24 -> 24 channels at full resolution), where cuDNN's input-gradient kernel is the slow one."""
 import ctypes
 
@@ -58,7 +58,13 @@ class Conv3dK3Function(Function):
             w_back = weight.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(27, ci, co).contiguous()    # [tap'][ci][co], taps mirrored
             dx = _run(dy, w_back, ci)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv3d_weight(x, weight.shape, dy, stride=1, padding=1)                # library (cuDNN) weight gradient
+            N, _, D, H, W = x.shape
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)                      # contiguous [CO, CI, 3, 3, 3]
+            ws = torch.empty(_lib.lib().conv3d_tc_wgrad_workspace_floats(), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                rc = _lib.lib().conv3d_tc_k3_wgrad(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(x), _p(dy), N, D, H, W, ci, co,
+                                                   _p(dw), _p(ws))
+            _lib.check(rc, "conv3d_tc_k3_wgrad")
             dw = dw.contiguous(memory_format=torch.channels_last_3d) if weight.is_contiguous(memory_format=torch.channels_last_3d) else dw
         return dx, dw
 

@@ -83,11 +83,57 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
   }
 }
 
-// tests only: one 128 x 32 x 8 MMA with MN-major no-swizzle TF32 operands (At [8][128], Bt [8][32] -> D [128][32])
-extern "C" int conv3d_tc_debug_mn_probe(void *stream, const float *At, const float *Bt, float *D)
+namespace {
+// channels-last fp32 volume [N, D, H, W, C] as rows of 32 channels (C <= 32: the copy engine zero-fills the rest), box = a tile of
+// bw x bh x bd voxels, 128-byte swizzle with 32-byte atoms (the MN-major TF32 operand layout)
+int make_row_map(CUtensorMap *map, const float *ptr, int N, int D, int H, int W, int C, int bw, int bh, int bd)
 {
-  if (!At || !Bt || !D) return MSDA3D_EINVAL;
-  convtc::mn_noswizzle_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(At, Bt, D);
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t c = (cuuint64_t)C, w = (cuuint64_t)W, h = (cuuint64_t)H, d = (cuuint64_t)D;
+  const cuuint64_t gdim[5] = {c, w, h, d, (cuuint64_t)N};
+  const cuuint64_t gstride[4] = {c * 4, w * c * 4, h * w * c * 4, d * h * w * c * 4};
+  const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float *>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0 : MSDA3D_EINVAL;
+}
+constexpr int kWgCtas = 148;
+}  // namespace
+
+extern "C" long long conv3d_tc_wgrad_workspace_floats(void) { return (long long)kWgCtas * 9 * 128 * 32; }
+
+extern "C" int conv3d_tc_k3_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
+                                  int out_channels, float *dweight, float *workspace)
+{
+  if (!x || !dy || !dweight || !workspace || batch <= 0 || depth <= 0 || height <= 0 || width <= 0) return MSDA3D_EINVAL;
+  if (in_channels <= 0 || in_channels > 32 || in_channels % 4 || out_channels <= 0 || out_channels > 32 || out_channels % 4) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(workspace)) & 15) return MSDA3D_EALIGN;
+  CUtensorMap mx, my;
+  int rc = make_row_map(&mx, x, batch, depth, height, width, in_channels, convtc::HW, convtc::HH, 3);
+  if (rc != 0) return rc;
+  rc = make_row_map(&my, dy, batch, depth, height, width, out_channels, convtc::TW, convtc::TH, 1);
+  if (rc != 0) return rc;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(convtc::conv3d_k3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, convtc::kWgSmemBytes); });
+  if (err != cudaSuccess) return (int)err;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long tiles = (long long)batch * depth * ((height + convtc::TH - 1) / convtc::TH) * ((width + convtc::TW - 1) / convtc::TW);
+  const int grid = (int)(tiles < kWgCtas ? tiles : kWgCtas);
+  convtc::conv3d_k3_wgrad_kernel<<<grid, convtc::kThreadsConv, convtc::kWgSmemBytes, st>>>(mx, my, workspace, batch, depth, height, width);
+  const int total = out_channels * in_channels * 27;
+  convtc::conv3d_k3_wgrad_finalize_kernel<<<(total + 31) / 32, 256, 0, st>>>(workspace, grid, in_channels, out_channels, dweight);
+  g_msda3d_launches += 2;
+  return (int)cudaGetLastError();
+}
+
+// tests only: one 128 x 32 x 8 MMA whose A operand is four overlapping 32-channel slabs of a [24][32] row matrix (see the kernel)
+extern "C" int conv3d_tc_debug_mn_probe(void *stream, const float *X, const float *Y, float *D, int row0)
+{
+  if (!X || !Y || !D || row0 < 0 || row0 + 3 + 8 > 24) return MSDA3D_EINVAL;
+  convtc::mn_sw32_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, Y, D, row0);
   ++g_msda3d_launches;
   return (int)cudaGetLastError();
 }

@@ -180,19 +180,25 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Probe (tests only): does the tensor core take MN-major TF32 operands in the NO-SWIZZLE canonical layout
-// [mn-chunk of 4][k row][4 floats] (k rows 16 bytes apart, chunks `plane` bytes apart)?  One MMA 128 x 32 x 8:
-// D[m][n] = sum_k At[k][m] * Bt[k][n].  The weight-gradient convolution needs exactly this form (voxels = k, channels = mn).
+// Probe (tests only) for the weight-gradient formulation.  MN-major TF32 operands are only accepted in the "128-byte swizzle with
+// 32-byte atoms" layout (rows of 32 mn-elements = 128 bytes, 32-byte chunks XORed with row % 4; the no-swizzle MN-major form gives
+// wrong results -- tried).  Stored as [voxel row][32 channels], a slab of 32 channels needs a leading-dimension offset to reach
+// the next 32 mn-elements: with LBO = 128 bytes = ONE ROW the four slabs of an M = 128 operand are the same rows shifted by 0..3
+// voxels -- exactly the kw taps of a convolution -- and a (kd, kh) tap is a start-address offset of whole rows.  The probe checks
+// that the hardware accepts overlapping slabs and start addresses that are not aligned to the 512-byte swizzle pattern:
+//   D[j * 32 + c][n] = sum_{k < 8} X[r0 + j + k][c] * Y[k][n]      X [24 rows][32], Y [8][32], D [128][32]
 // ---------------------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(128) mn_noswizzle_probe_kernel(const float *__restrict__ At, const float *__restrict__ Bt, float *__restrict__ Dout)
+__device__ __forceinline__ uint32_t swz32(uint32_t byte_off) { return byte_off ^ (((byte_off >> 7) & 3u) << 5); }
+
+static __global__ void __launch_bounds__(128) mn_sw32_probe_kernel(const float *__restrict__ X, const float *__restrict__ Y, float *__restrict__ Dout, int r0)
 {
-  __shared__ __align__(128) float sA[32][8][4];     // [m chunk][k][4]
-  __shared__ __align__(128) float sB[8][8][4];      // [n chunk][k][4]
+  __shared__ __align__(1024) uint8_t sX[24 * 128];
+  __shared__ __align__(1024) uint8_t sY[8 * 128];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
   const int t = threadIdx.x, warp = t >> 5;
-  for (int i = t; i < 128 * 8; i += 128) { const int m = i % 128, k = i / 128; sA[m / 4][k][m % 4] = to_tf32(At[k * 128 + m]); }
-  for (int i = t; i < 32 * 8; i += 128) { const int n = i % 32, k = i / 32; sB[n / 4][k][n % 4] = to_tf32(Bt[k * 32 + n]); }
+  for (int i = t; i < 24 * 32; i += 128) *reinterpret_cast<float *>(sX + swz32((uint32_t)i * 4u)) = to_tf32(X[i]);
+  for (int i = t; i < 8 * 32; i += 128) *reinterpret_cast<float *>(sY + swz32((uint32_t)i * 4u)) = to_tf32(Y[i]);
   if (t == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(32) : "memory");
@@ -204,9 +210,11 @@ static __global__ void __launch_bounds__(128) mn_noswizzle_probe_kernel(const fl
   tc_fence_after();
   const uint32_t tm = slot;
   if (t == 0) {
-    // both operands MN-major (bits 15, 16), M = 128, N = 32; chunk pitch = 8 k rows * 16 B = 128 B (SBO), k groups of 8: 128 B (LBO, unused at K = 8)
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    umma_tf32(tm, desc_noswizzle(smem_u32(&sA[0][0][0]), 128, 128), desc_noswizzle(smem_u32(&sB[0][0][0]), 128, 128), idesc, 0u);
+    auto desc = [](uint32_t addr, uint32_t lbo) {   // layout type 1 = SWIZZLE_128B_BASE32B, 4-row groups 512 bytes apart
+      return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+    };
+    umma_tf32(tm, desc(smem_u32(sX) + (uint32_t)r0 * 128u, 128), desc(smem_u32(sY), 128), idesc, 0u);
     umma_commit(smem_u32(&bar));
   }
   mbar_wait(smem_u32(&bar), 0);
@@ -217,6 +225,147 @@ static __global__ void __launch_bounds__(128) mn_noswizzle_probe_kernel(const fl
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(32) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co][ci][kd][kh][kw] = sum over voxels of dy[v][co] * x[v + (kd-1, kh-1, kw-1)][ci].
+//
+// The reduction index is the voxel, so both operands are MN-major (channels contiguous) -- for TF32 the tensor core takes that only in
+// the 128-byte swizzle / 32-byte atom layout, i.e. rows of 32 channels.  TMA pads for free: a box of 32 channels over a tensor with
+// 24 zero-fills channels 24..31 while it writes 128-byte rows.  One tile = 1 x 16 x 8 voxels; ONE TMA box brings its 3 x 18 x 10 halo of
+// x as 540 rows [voxel][32 ch], another the 128 rows of dy.  Per (kd, kh) and tile row h, ONE MMA (128 x 32 x 8) accumulates
+//     D_{kd,kh}[kw * 32 + ci][co] += sum_{w < 8} x[halo(kd, h + kh, w + kw)][ci] * dy[(h, w)][co]
+// because the "next 32 mn-elements" of the A operand are reached through a leading-dimension offset of ONE ROW (128 bytes): the four
+// slabs of the M = 128 operand are the same eight voxel rows shifted by kw = 0, 1, 2 (, 3: unused) -- the three kw taps cost nothing.
+// 9 accumulators of 32 columns stay in TMEM for the CTA's whole (persistent) run; at the end every CTA writes its partial
+// [9][128][32] to a workspace and a second kernel sums the CTAs.  cuDNN's kernel for the 24 -> 24 full-resolution layer takes 9.8 ms.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgXBytes = 3 * HH * HW * 128;                     // 69120: halo tile rows of 128 bytes
+constexpr int kWgDyBytes = TH * TW * 128;                        // 16384
+constexpr int kWgStageBytes = (kWgXBytes + kWgDyBytes + 1023) / 1024 * 1024;   // 86016
+constexpr int kWgSmemBytes = 2 * kWgStageBytes + 1024 + 128;
+static_assert(kWgXBytes % 1024 == 512 || kWgXBytes % 512 == 0, "dy tile must start on a 512-byte swizzle pattern boundary");
+
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr)   // MN-major, 128B swizzle / 32B atoms, LBO = one row, SBO = 4 rows
+{
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+// part [gridDim.x][9][128][32]
+static __global__ void __launch_bounds__(kThreadsConv, 1)
+conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, float *__restrict__ part, int N, int D,
+                       int H, int W)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + 2 * kWgStageBytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (2 + s); };
+  const uint32_t done = bars + 32, tmem_slot = bars + 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int th = (H + TH - 1) / TH, tw = (W + TW - 1) / TW;
+  const long long tiles = (long long)N * D * th * tw;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
+        mbar_wait(empty(stage), phase ^ 1u);
+        mbar_expect_tx(full(stage), kWgXBytes + kWgDyBytes);
+        const uint32_t sx = base + stage * kWgStageBytes;
+        tma_load_5d(sx, &tmX, full(stage), 0, iw * TW - 1, ih * TH - 1, d - 1, n);
+        tma_load_5d(sx + kWgXBytes, &tmDy, full(stage), 0, iw * TW, ih * TH, d, n);
+        if (++stage == 2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128, N = 32, both operands MN-major (bits 15 / 16), TF32 in, fp32 out
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, later = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sx = base + stage * kWgStageBytes;
+        const uint64_t dx0 = desc_mn_sw32(sx), dy0 = desc_mn_sw32(sx + kWgXBytes);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {                                        // a = kd * 3 + kh
+#pragma unroll
+          for (int hh = 0; hh < TH; ++hh) {
+            const uint32_t xrow16 = (uint32_t)((((a / 3) * HH + hh + a % 3) * HW) * (128 / 16));    // first voxel row of the A slab, 16-byte units
+            umma_tf32(tmem_base + (uint32_t)(a * 32), dx0 + xrow16, dy0 + (uint32_t)(hh * TW * (128 / 16)), idesc, (hh | later) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty(stage));
+        later = 1u;
+        if (++stage == 2) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // after the last MMA: this CTA's partial sums, accumulator a rows m = kw * 32 + ci, columns co
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float *dst = part + ((long long)blockIdx.x * 9 * 128 + q * 32 + lane) * 32;
+    const bool any = (long long)blockIdx.x < tiles;
+#pragma unroll 1
+    for (int a = 0; a < 9; ++a) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t)(a * 32) + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4 *>(dst + (long long)a * 128 * 32 + c) = any ? make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// dw [CO][CI][3][3][3] = sum over CTAs of part[cta][kd * 3 + kh][kw * 32 + ci][co]; 256 threads per 32 outputs (8 warps split the CTAs)
+static __global__ void __launch_bounds__(256) conv3d_k3_wgrad_finalize_kernel(const float *__restrict__ part, int ctas, int CI, int CO, float *__restrict__ dw)
+{
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane, total = CO * CI * 27;
+  double s = 0.0;
+  if (o < total) {
+    const int tap = o % 27, ci = (o / 27) % CI, co = o / (27 * CI);
+    const int a = tap / 3, kw = tap % 3;
+    const long long idx = ((long long)a * 128 + kw * 32 + ci) * 32 + co;
+    for (int b = w; b < ctas; b += 8) s += part[(long long)b * 9 * 128 * 32 + idx];
+  }
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && o < total) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][lane];
+    dw[o] = (float)s;
+  }
 }
 
 }  // namespace convtc
