@@ -45,6 +45,37 @@ def test_exact_on_tf32_representable_inputs():
     assert torch.equal(conv3d_k3(x, w).double(), F.conv3d(x.double(), w.double(), None, 1, 1).round())
 
 
+@pytest.mark.parametrize("shape,ci,co", [((2, 6, 20, 11), 24, 24), ((1, 3, 16, 8), 8, 16), ((1, 5, 33, 17), 16, 8), ((3, 2, 7, 5), 24, 24),
+                                         ((1, 40, 48, 40), 24, 24)])
+def test_weight_gradient_exact_on_integers(shape, ci, co):
+    """The weight gradient on its own entry point: small integers -> every product and partial sum is exact, so dweight must equal the
+    fp64 conv3d_weight result exactly -- a wrong tap, a wrong halo row or a dropped tile shows as an integer difference.  The last
+    shape has more tiles than CTAs (the persistent loop) and rows that cross the 16 x 8 tile raggedly."""
+    import ctypes
+    from transoar_b200 import _lib
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(D * H + W)
+    x = torch.randint(-2, 3, (N, ci, D, H, W), generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    dy = torch.randint(-2, 3, (N, co, D, H, W), generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    dw = torch.full((co, ci, 3, 3, 3), float("nan"), device=DEV)
+    ws = torch.empty(_lib.lib().conv3d_tc_wgrad_workspace_floats(), device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = _lib.lib().conv3d_tc_k3_wgrad(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(x), p(dy), N, D, H, W, ci, co, p(dw), p(ws))
+    assert rc == 0
+    ref = torch.nn.grad.conv3d_weight(x.double(), (co, ci, 3, 3, 3), dy.double(), stride=1, padding=1).round()
+    assert torch.equal(dw.double(), ref)
+
+
+def test_weight_gradient_rejects_unsupported_channels():
+    from transoar_b200 import _lib
+    assert _lib.lib().conv3d_tc_k3_wgrad(None, None, None, 1, 4, 4, 4, 24, 24, None, None) < 0
+    x = torch.zeros(64 * 40 * 4 * 4 * 4, device=DEV)
+    import ctypes
+    p = ctypes.c_void_p(x.data_ptr())
+    assert _lib.lib().conv3d_tc_k3_wgrad(None, p, p, 1, 4, 4, 4, 40, 24, p, p) < 0
+    assert _lib.lib().conv3d_tc_k3_wgrad(None, p, p, 1, 4, 4, 4, 24, 6, p, p) < 0
+
+
 @pytest.mark.parametrize("row0", [0, 1, 2, 3, 5, 12])
 def test_mn_major_overlapping_slab_probe(row0):
     """The operand form a tensor-core weight gradient over channels-last volumes needs (see conv3d_tc_kernels.cuh): MN-major, 128-byte
