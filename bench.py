@@ -149,7 +149,8 @@ def workload_config():
                        "channels_per_head": g.channels, "points": g.points},
             "decoder": {"queries": 540, "organs": 20, "layers": 3, "kv_tokens": 102400},
             "l2": "the step touches > 20 GB per batch (activations of 629 MB each at full resolution): every tensor is far larger than the 126 MB L2; no explicit flush",
-            "parallelism": "volume-sharded DDP, NCCL gradient all-reduce only"}
+            "execution": "whole step captured once as a CUDA graph and replayed (transoar_b200.engine.TrainStep(graph=True)); --no-graph runs it eagerly",
+            "parallelism": "volumes sharded over ranks; one NCCL gradient all-reduce per step (flat bucket inside the graph; DDP buckets when eager)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -386,6 +387,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (operator alone, GEMM, RoI attention, InstanceNorm)")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu --profile-from-start off: warm up, bracket ONE training step with cudaProfilerStart/Stop, exit")
     ap.add_argument("--dist", default=DIST, choices=["A", "B"], help="sampling-location distribution of the operator-alone extra")
@@ -427,14 +429,28 @@ def main():
     # ---- the headline: whole training step, inputs resident on the device
     cfg = visceral_train_config()
     torch.manual_seed(0)                                   # identical initial weights on every rank (DDP also broadcasts rank 0's)
-    ts = TrainStep(cfg, dev, world=world)
+    use_graph = not (args.no_graph or args.profile_one_step)
+    eager_warm = 4 if use_graph else 0                     # eager steps before the capture; the msda3d kernels are timed in them
+    ts = TrainStep(cfg, dev, world=world, graph=use_graph, graph_warmup=eager_warm)
     gen = torch.Generator().manual_seed(100 + volume_ids(0, rank, world)[0])
     n_sets = 2                                             # alternate between two resident batches
     vols_host = [torch.rand(BATCH, 1, *VOLUME, generator=gen).pin_memory() for _ in range(n_sets)]
     vols_dev = [v.to(dev) for v in vols_host]
     targets = [synthetic_targets(cfg, BATCH, 1000 * rank + i, dev) for i in range(n_sets)]
     warm = max(3, args.warmup)
-    for i in range(warm):
+    ev_log = []
+    launches_per_step = None
+    for i in range(eager_warm):                            # eager steps (not counted in `warmup`): autotuning, lazy init, then events
+        if i == 1:
+            torch.cuda.synchronize()
+            MSDA.set_event_log(ev_log)
+            launches0 = lib.msda3d_launch_count()
+        ts.step(vols_dev[i % n_sets], targets[i % n_sets])
+    if use_graph:
+        torch.cuda.synchronize()
+        MSDA.set_event_log(None)
+        launches_per_step = (lib.msda3d_launch_count() - launches0) / (eager_warm - 1)
+    for i in range(warm):                                  # the first of these captures the graph, the rest replay it
         ts.step(vols_dev[i % n_sets], targets[i % n_sets])
     fence()
     if args.profile_one_step:
@@ -443,9 +459,9 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0
-    ev_log = []
-    MSDA.set_event_log(ev_log)
-    launches0 = lib.msda3d_launch_count()
+    if not use_graph:
+        MSDA.set_event_log(ev_log)
+        launches0 = lib.msda3d_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         fence()
@@ -454,8 +470,11 @@ def main():
             loss = ts.step(vols_dev[i % n_sets], targets[i % n_sets])
         stop.record()
         fence()
-    launches = lib.msda3d_launch_count() - launches0
-    MSDA.set_event_log(None)
+    if use_graph:                                          # a replay re-issues, from the graph, exactly the launches of one eager step
+        launches = int(round(launches_per_step * args.steps))
+    else:
+        launches = lib.msda3d_launch_count() - launches0
+        MSDA.set_event_log(None)
     value, ms_total = aggregate_throughput(start.elapsed_time(stop), args.steps, world, all_reduce_max=reduce_max)
     ms_step = ms_total / args.steps
     final_loss = float(loss.item())
@@ -474,6 +493,9 @@ def main():
                 "achieved": bb / bwd_avg / 1e6, "peak": peak, "unit": "GB/s", "frac": bb / bwd_avg / 1e6 / peak,
                 "traffic": load_ncu_traffic("backward"), "peak_source": peaks["source"], "algorithmic_bytes": bb,
                 "launches_timed": len(bwd_ms), "share_of_step": LAYERS * bwd_avg / ms_step,
+                "timed_in": ("CUDA events on the launching stream around every launch of the eager steps that precede the graph capture in this "
+                             "run (same process, same inputs; events cannot be read inside a replayed graph)") if use_graph else
+                            "CUDA events on the launching stream around every launch inside the timed region",
                 "forward": {"ms": fwd_avg, "bytes": bf, "gbs": bf / fwd_avg / 1e6, "frac": bf / fwd_avg / 1e6 / peak,
                             "traffic": load_ncu_traffic("forward"), "share_of_step": LAYERS * fwd_avg / ms_step},
                 "backward": {"ms": bwd_avg, "bytes": bb, "gbs": bb / bwd_avg / 1e6, "frac": bb / bwd_avg / 1e6 / peak},
@@ -553,7 +575,7 @@ def main():
             "kernels": {"msda3d_fwd_ms": fwd_avg, "msda3d_bwd_ms": bwd_avg, "msda3d_fwd_ms_min": min(fwd_ms), "msda3d_bwd_ms_min": min(bwd_ms),
                         "launches_of_this_library_per_step": launches / args.steps},
             "model": {"params": params, "peak_mem_gib": peak_mem, "final_loss": final_loss},
-            "clocks": clocks.summary(), **extras,
+            "cuda_graph": use_graph, "clocks": clocks.summary(), **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

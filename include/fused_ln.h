@@ -33,6 +33,13 @@ int fused_ln_backward(void *stream, const float *dy, const float *z, const float
                       long long rows, int channels, float p_drop, unsigned long long seed, float *da, float *db, float *dgamma,
                       float *dbeta, float *workspace);
 
+/* Dropout masks under CUDA-graph replay.  The seeds above are passed by value, so a captured launch would repeat its mask on every
+ * replay.  While a device counter is installed here, every kernel of this library that draws a mask (fused_ln_forward/backward,
+ * tc_gemm_tf32_ex with p_drop > 0) folds *device_counter into its seed at run time: advance the counter once per step (inside the
+ * graph) and each replay draws fresh masks, forward and backward of one step still agreeing.  NULL (the default) removes it.
+ * Process-global; the pointer must stay valid while installed. */
+void hash_rng_set_epoch(const unsigned long long *device_counter);
+
 #ifdef __cplusplus
 }
 #endif

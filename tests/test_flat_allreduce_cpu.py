@@ -1,0 +1,51 @@
+"""engine.all_reduce_gradients (the gradient exchange of the graph-captured step at world > 1) on gloo, world_size 2: every rank ends
+with the mean gradient, in each parameter's own memory layout, and parameters without a gradient are skipped on every rank alike."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transoar_b200.engine import all_reduce_gradients
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(4, 3, 3, 3, 3).contiguous(memory_format=torch.channels_last_3d)),
+              torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(5, 2)), torch.nn.Parameter(torch.zeros(3))]
+    g = torch.Generator().manual_seed(10 + rank)
+    for p in params[:3]:
+        p.grad = torch.randn(p.shape, generator=g).contiguous(memory_format=torch.channels_last_3d) if p.dim() == 5 else torch.randn(p.shape, generator=g)
+    all_reduce_gradients(params, world)
+    assert params[3].grad is None
+    assert params[0].grad.is_contiguous(memory_format=torch.channels_last_3d)
+    if rank == 0:
+        torch.save([p.grad for p in params[:3]], out)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_all_reduce_averages_gradients(tmp_path):
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    shapes = [(4, 3, 3, 3, 3), (7,), (5, 2)]
+    want = []
+    for shp_i, shp in enumerate(shapes):
+        acc = torch.zeros(shp)
+        for rank in range(2):
+            g = torch.Generator().manual_seed(10 + rank)
+            for j, s in enumerate(shapes):
+                t = torch.randn(s, generator=g)
+                if j == shp_i:
+                    acc += t
+        want.append(acc / 2)
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b, atol=1e-6)

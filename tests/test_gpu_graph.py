@@ -1,0 +1,109 @@
+"""The CUDA-graph route of the training step (engine.TrainStep(graph=True)) and what makes it sound: the device epoch counter that is
+folded into the hash dropout seeds (include/fused_ln.h: hash_rng_set_epoch), so that a replayed graph draws new masks."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _fused(a, b, norm, seed):
+    from transoar_b200.fused_ln import add_dropout_layer_norm
+    return add_dropout_layer_norm(a, b, norm, 0.5, True, seed=seed)
+
+
+def test_epoch_counter_is_folded_into_the_seed():
+    from transoar_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    a, b = (torch.randn(300, 384, generator=g).to(DEV) for _ in range(2))
+    norm = torch.nn.LayerNorm(384).to(DEV)
+    plain = _fused(a, b, norm, 1234)
+    epoch = torch.zeros(1, dtype=torch.int64, device=DEV)
+    try:
+        _lib.lib().hash_rng_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
+        assert torch.equal(_fused(a, b, norm, 1234), plain)                   # epoch 0 leaves the seed alone
+        epoch.fill_(1)
+        other = _fused(a, b, norm, 1234)
+        assert not torch.equal(other, plain)
+        frac = float(((other - plain).abs() > 0).float().mean())
+        assert frac > 0.9                                                      # another mask moves the statistics of every row
+        # forward and backward of one epoch agree on the mask: the gradient w.r.t. b is zero exactly where b was dropped
+        bb = b.clone().requires_grad_(True)
+        w = torch.randn(a.shape, generator=g).to(DEV)
+        out = _fused(torch.zeros_like(a), bb, norm, 77)                        # = LN(dropout(b)): a dropped element of b is exactly 0 in z
+        (out * w).sum().backward()
+        epoch.fill_(0)
+        dropped_now = _fused(torch.zeros_like(a), b, norm, 77)                 # the mask of another epoch, for contrast
+        assert not torch.equal(dropped_now, out.detach())
+        dropped = bb.grad == 0
+        assert 0.4 < float(dropped.float().mean()) < 0.6
+        epoch.fill_(1)
+        again = torch.autograd.grad((_fused(torch.zeros_like(a), bb, norm, 77) * w).sum(), bb)[0]
+        assert torch.equal(again == 0, dropped)
+    finally:
+        _lib.lib().hash_rng_set_epoch(None)
+    assert torch.equal(_fused(a, b, norm, 1234), plain)
+
+
+def test_replayed_graph_draws_new_dropout_masks():
+    from transoar_b200 import _lib
+    from transoar_b200.linear import TCLinear, ffn
+    g = torch.Generator().manual_seed(1)
+    a, b = (torch.randn(256, 384, generator=g).to(DEV) for _ in range(2))
+    norm = torch.nn.LayerNorm(384).to(DEV)
+    l1, l2 = TCLinear(384, 1024).to(DEV), TCLinear(1024, 384).to(DEV)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    epoch = torch.zeros(1, dtype=torch.int64, device=DEV)
+    try:
+        with torch.no_grad():
+            _fused(a, b, norm, 5), ffn(a, l1, l2, 0.5, True)                   # lazy initialisation outside the capture
+        torch.cuda.synchronize()
+        _lib.lib().hash_rng_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            epoch.add_(1)
+            y_ln = _fused(a, b, norm, 5)
+            y_ffn = ffn(a, l1, l2, 0.5, True)
+        outs = []
+        for _ in range(3):
+            graph.replay()
+            outs.append((y_ln.clone(), y_ffn.clone()))
+        assert int(epoch.item()) == 3
+        for i in range(3):
+            for j in range(i + 1, 3):
+                assert not torch.equal(outs[i][0], outs[j][0]) and not torch.equal(outs[i][1], outs[j][1])
+    finally:
+        _lib.lib().hash_rng_set_epoch(None)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_graph_step_follows_the_eager_step():
+    """Same weights, same inputs, dropout off (eval-mode modules but gradients and AdamW on): the replayed graph must reproduce the
+    eager losses step for step -- the fp32 atomics of the msda3d backward are the only source of differences."""
+    from transoar_b200.engine import TrainStep, synthetic_targets, visceral_train_config
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        shape = (64, 64, 128)
+        cfg = visceral_train_config()
+        cfg["neck_input_shape"] = tuple(s // 4 for s in shape)
+        torch.manual_seed(0)
+        eager = TrainStep(cfg, DEV, cudnn_autotune=False)
+        graph = TrainStep(cfg, DEV, cudnn_autotune=False, graph=True, graph_warmup=2)
+        graph.net.load_state_dict(eager.net.state_dict())
+        eager.net.eval(); graph.net.eval()
+        gen = torch.Generator().manual_seed(2)
+        xs = [torch.rand(1, 1, *shape, generator=gen).to(DEV) for _ in range(3)]
+        tgs = [synthetic_targets(cfg, 1, i, DEV) for i in range(3)]
+        le = [float(eager.step(xs[i % 3], tgs[i % 3])) for i in range(6)]
+        lg = [float(graph.step(xs[i % 3], tgs[i % 3])) for i in range(6)]
+        assert graph._cuda_graph is not None
+        for a, b in zip(le, lg):
+            assert abs(a - b) < 2e-3 * abs(a), (le, lg)
+        assert le[-1] < le[0]
+        graph.close()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
+        torch.cuda.empty_cache()

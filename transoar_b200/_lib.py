@@ -45,6 +45,7 @@ _SIGNATURES = {
     "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
     # include/conv3d_tc.h
     "conv3d_tc_supported": (_ci, [_ci, _ci]),
+    "hash_rng_set_epoch": (None, [_vp]),
     "conv3d_tc_wgrad_workspace_floats": (ctypes.c_longlong, []),
     "conv3d_tc_k3_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 6 + [_vp, _vp]),
     "conv3d_tc_debug_mn_probe": (_ci, [_vp] * 4 + [_ci]),

@@ -8,6 +8,7 @@
 #include "../../include/msda3d.h"
 
 extern std::atomic<unsigned long long> g_msda3d_launches;
+std::atomic<const unsigned long long *> g_hashrng_epoch{nullptr};   // shared with tc_gemm_capi.cu
 
 namespace {
 
@@ -23,7 +24,7 @@ int fwd(cudaStream_t st, const float *a, const float *b, const float *gamma, con
         unsigned long long seed, float *z, float *y, float *mean, float *rstd)
 {
   fusedln::fwd_kernel<NV><<<grid_of(rows), fusedln::kThreads, 0, st>>>(a, b, gamma, beta, rows, C, eps, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f,
-                                                                        seed, z, y, mean, rstd);
+                                                                        seed, g_hashrng_epoch.load(), z, y, mean, rstd);
   ++g_msda3d_launches;
   return (int)cudaGetLastError();
 }
@@ -39,13 +40,15 @@ int bwd(cudaStream_t st, const float *dy, const float *z, const float *gamma, co
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fusedln::kWarps * 2 * 4 * 32 * fusedln::kMaxNV * (int)sizeof(float)); });
   if (err != cudaSuccess) return (int)err;
-  kern<<<grid, fusedln::kThreads, smem, st>>>(dy, z, gamma, mean, rstd, rows, C, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed, da, db, ws);
+  kern<<<grid, fusedln::kThreads, smem, st>>>(dy, z, gamma, mean, rstd, rows, C, thresh_of(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed, g_hashrng_epoch.load(), da, db, ws);
   fusedln::bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(ws, grid, C, dgamma, dbeta);
   g_msda3d_launches += 2;
   return (int)cudaGetLastError();
 }
 
 }  // namespace
+
+extern "C" void hash_rng_set_epoch(const unsigned long long *device_counter) { g_hashrng_epoch.store(device_counter); }
 
 extern "C" {
 

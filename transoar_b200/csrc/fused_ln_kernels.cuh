@@ -36,9 +36,10 @@ __device__ __forceinline__ float warp_sum(float v)
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ gamma, const float *__restrict__ beta,
-           long long rows, int C, float eps, uint32_t thresh, float scale, uint64_t seed, float *__restrict__ z, float *__restrict__ y,
-           float *__restrict__ mean, float *__restrict__ rstd)
+           long long rows, int C, float eps, uint32_t thresh, float scale, uint64_t seed, const unsigned long long *__restrict__ epoch,
+           float *__restrict__ z, float *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd)
 {
+  seed = hashrng::with_epoch(seed, epoch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c4 = C >> 2;
   float g[NV][4], be[NV][4];
 #pragma unroll
@@ -102,9 +103,10 @@ fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const float *__restrict__ gamma, const float *__restrict__ mean,
-           const float *__restrict__ rstd, long long rows, int C, uint32_t thresh, float scale, uint64_t seed, float *__restrict__ da,
-           float *__restrict__ db, float *__restrict__ part)
+           const float *__restrict__ rstd, long long rows, int C, uint32_t thresh, float scale, uint64_t seed,
+           const unsigned long long *__restrict__ epoch, float *__restrict__ da, float *__restrict__ db, float *__restrict__ part)
 {
+  seed = hashrng::with_epoch(seed, epoch);
   extern __shared__ float red[];                                   // [kWarps][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c4 = C >> 2;
   float g[NV][4], dg[NV][4], dbt[NV][4];

@@ -16,6 +16,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx)
   x ^= x >> 31;
   return x;
 }
+// Under CUDA-graph replay a seed passed by value is frozen into the graph.  `epoch` (NULL = none) points to a device counter the
+// caller advances between replays (hash_rng_set_epoch, include/fused_ln.h); it is folded into the seed at run time, so every replay
+// draws new masks while a forward / backward pair inside one replay still sees the same ones.
+__device__ __forceinline__ uint64_t with_epoch(uint64_t seed, const unsigned long long *epoch)
+{
+  return epoch == nullptr ? seed : seed + (uint64_t)(*epoch) * 0xD1342543DE82EF95ull;
+}
 // keep element j (0..3) of float4 number `idx` iff its 16-bit uniform >= thresh (thresh = round(p * 65536))
 __device__ __forceinline__ void keep4(uint64_t seed, uint64_t idx, uint32_t thresh, float scale, float (&m)[4])
 {

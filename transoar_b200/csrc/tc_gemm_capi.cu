@@ -9,6 +9,7 @@
 #include "../../include/tc_gemm.h"
 
 extern std::atomic<unsigned long long> g_msda3d_launches;
+extern std::atomic<const unsigned long long *> g_hashrng_epoch;   // fused_ln_capi.cu (hash_rng_set_epoch)
 
 namespace {
 
@@ -193,7 +194,7 @@ extern "C" int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, lon
   if (splits > r_blocks) splits = r_blocks;
   tcgemm::Problem p;
   p.M = M; p.N = N; p.R = R; p.ldd = ldd; p.relu = relu; p.atomic = accumulate ? 1 : 0;
-  p.gate = gate; p.gate_scale = gate_scale; p.seed = seed;
+  p.gate = gate; p.gate_scale = gate_scale; p.seed = seed; p.epoch = g_hashrng_epoch.load();
   p.drop_thresh = p_drop > 0.f ? (unsigned int)(p_drop * 65536.f + 0.5f) : 0u;
   p.drop_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.prof = g_prof.load();

@@ -185,6 +185,7 @@ struct Problem {
   unsigned int drop_thresh;    // dropout after bias / ReLU: keep iff 16-bit hash(seed, element) >= drop_thresh, kept values * drop_scale
   float drop_scale;
   unsigned long long seed;
+  const unsigned long long *epoch;   // hashrng::with_epoch: device counter folded into seed (graph replay), or NULL
   unsigned long long *prof;    // diagnostics (tc_gemm_debug_profile): per CTA 8 cycle counters of the three roles' waits, or NULL
 };
 
@@ -374,7 +375,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
           float *dst = D + (long long)m * p.ldd + n;
           if (p.drop_thresh != 0u) {                              // host guarantees the vector path: N % 4 == 0
             float keep[4];
-            hashrng::keep4(p.seed, ((unsigned long long)m * p.N + n) >> 2, p.drop_thresh, p.drop_scale, keep);
+            hashrng::keep4(hashrng::with_epoch(p.seed, p.epoch), ((unsigned long long)m * p.N + n) >> 2, p.drop_thresh, p.drop_scale, keep);
             o.x *= keep[0]; o.y *= keep[1]; o.z *= keep[2]; o.w *= keep[3];
           }
           if (p.gate != nullptr) {
