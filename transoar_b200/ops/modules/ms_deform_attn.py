@@ -6,6 +6,7 @@ sm_100a kernels behind ``MSDeformAttnFunction``.  ``use_cuda=False`` selected th
 reference (ms_deform_attn.py:137-138); this package has no such route and raises instead of silently falling back.
 """
 import warnings
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -31,6 +32,24 @@ def _direction_table(n_heads):
     if n_heads == 6:
         return cube[l1 == 1]
     raise ValueError("Only nheads of value 26 or 6 are supported.")           # ms_deform_attn.py:72-73
+
+
+_COVER_CHECKED = {}
+
+
+def _assert_levels_cover(spatial_shapes, S):
+    """The reference's ``assert (shapes.prod(1)).sum() == S`` (ms_deform_attn.py:107) reads a device tensor on the host in every forward
+    of every layer.  Here the answer is remembered per shapes tensor (identity + version counter), so a model that reuses its shapes
+    tensor -- as ``DecoderDefAttnBlock`` does -- synchronises once, and the forward can be captured into a CUDA graph afterwards."""
+    hit = _COVER_CHECKED.get(id(spatial_shapes))
+    if hit is not None and hit[0]() is spatial_shapes and hit[1] == spatial_shapes._version and hit[2] == S:
+        return
+    if spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("MSDeformAttn: run one eager forward with this spatial_shapes tensor before capturing a CUDA graph")
+    assert int(spatial_shapes.prod(1).sum()) == S
+    if len(_COVER_CHECKED) > 256:
+        _COVER_CHECKED.clear()
+    _COVER_CHECKED[id(spatial_shapes)] = (weakref.ref(spatial_shapes), spatial_shapes._version, S)
 
 
 class MSDeformAttn(nn.Module):
@@ -71,7 +90,7 @@ class MSDeformAttn(nn.Module):
         """query [N,Lq,C]; reference_points [N|1,Lq,L,3] in (x,y,z); input_flatten [N,S,C]; shapes [L,3]=(D,H,W) -> [N,Lq,C]."""
         N, Lq, _ = query.shape
         _, S, _ = input_flatten.shape
-        assert int(input_spatial_shapes.prod(1).sum()) == S                    # ms_deform_attn.py:107
+        _assert_levels_cover(input_spatial_shapes, S)                          # ms_deform_attn.py:107
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
         value = self.value_proj(input_flatten)
