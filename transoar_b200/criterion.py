@@ -30,9 +30,12 @@ def box_cxcyczwhd_to_xyzxyz(b):
 def paired_giou_3d(a, b):
     """Generalised IoU of box pairs (xyzxyz, broadcastable leading dims) -- utils/bboxes.py:6-29,99-136 for matched pairs."""
     vol = lambda x: (x[..., 3] - x[..., 0]) * (x[..., 4] - x[..., 1]) * (x[..., 5] - x[..., 2])
-    inter = (torch.minimum(a[..., 3:], b[..., 3:]) - torch.maximum(a[..., :3], b[..., :3])).clamp(min=0).prod(-1)
+    # the product of the three extents written out: autograd's prod() backward looks for zeros with nonzero(), a host synchronisation
+    # (and not capturable into a CUDA graph)
+    prod3 = lambda e: e[..., 0] * e[..., 1] * e[..., 2]
+    inter = prod3((torch.minimum(a[..., 3:], b[..., 3:]) - torch.maximum(a[..., :3], b[..., :3])).clamp(min=0))
     union = vol(a) + vol(b) - inter
-    hull = (torch.maximum(a[..., 3:], b[..., 3:]) - torch.minimum(a[..., :3], b[..., :3])).clamp(min=0).prod(-1)
+    hull = prod3((torch.maximum(a[..., 3:], b[..., 3:]) - torch.minimum(a[..., :3], b[..., :3])).clamp(min=0))
     return inter / union - (hull - union) / hull
 
 
