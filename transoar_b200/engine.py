@@ -105,6 +105,7 @@ class TrainStep:
                                        capturable=self.graph, fused=True)
         self._staging = None
         self._cuda_graph, self._seen, self._static = None, 0, None
+        self._stream = torch.cuda.Stream(self.device) if self.graph else None
 
     def to_device(self, volumes):
         """Host volumes (ideally pinned) -> a reused device buffer, asynchronously on the current stream."""
@@ -148,17 +149,23 @@ class TrainStep:
         epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._static = {"boxes": boxes.clone(), "valid": valid.clone(), "epoch": epoch}
         _lib.lib().hash_rng_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
-        side = torch.cuda.Stream(self.device)                          # one more eager step on a side stream: autograd's accumulation
-        side.wait_stream(torch.cuda.current_stream(self.device))       # streams and the allocator see what the capture will see
-        with torch.cuda.stream(side):
-            self._run(x, (self._static["boxes"], self._static["valid"]), None)
-        torch.cuda.current_stream(self.device).wait_stream(side)
         self.optim.zero_grad(set_to_none=True)
+        torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self._stream):                 # recorded, not executed: the first replay is this step
             epoch.add_(1)
             self._static["loss"] = self._run(x, (self._static["boxes"], self._static["valid"]), None)
         self._cuda_graph = g
+
+    def _eager_on_side_stream(self, x, targets):
+        """The eager steps before the capture run on the stream the capture will use, so that autograd's gradient-accumulation nodes
+        and the allocator are bound to it from the start (a node bound to the default stream cannot join a capture)."""
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            loss = self._run(x, targets, None)
+        cur.wait_stream(self._stream)
+        return loss
 
     def step(self, volumes, targets, seg_targets=None):
         """targets: the reference's list of {'boxes','labels'} dicts or the dense (boxes [B,O,6], valid [B,O]) pair.  Returns the total loss (device scalar)."""
@@ -169,7 +176,7 @@ class TrainStep:
         if self._cuda_graph is None:
             self._seen += 1
             if self._seen <= self.graph_warmup:                         # eager: cuDNN autotuning, lazy initialisation, NCCL communicator
-                return self._run(x, (boxes, valid), None)
+                return self._eager_on_side_stream(x, (boxes, valid))
             self._capture(x, boxes, valid)
         self._static["boxes"].copy_(boxes, non_blocking=True)
         self._static["valid"].copy_(valid, non_blocking=True)
