@@ -193,6 +193,25 @@ def cpu_sample_text(shape, sec, steps):
             f"= {frac:.4f} of a 160x160x256 volume's voxels: {sec:.2f} s per step (mean of {steps}); time scaled linearly by voxels")
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to file descriptor 1 (NCCL's version banner, cuDNN notes) goes to stderr from here on; the JSON line
+    is written to the real stdout by ``emit``, so stdout carries that one line and nothing else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +233,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -392,6 +411,7 @@ def main():
                     help="for ncu --profile-from-start off: warm up, bracket ONE training step with cudaProfilerStart/Stop, exit")
     ap.add_argument("--dist", default=DIST, choices=["A", "B"], help="sampling-location distribution of the operator-alone extra")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -577,7 +597,7 @@ def main():
             "model": {"params": params, "peak_mem_gib": peak_mem, "final_loss": final_loss},
             "cuda_graph": use_graph, "clocks": clocks.summary(), **extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
