@@ -246,9 +246,12 @@ constexpr int kWgStageBytes = (kWgXBytes + kWgDyBytes + 1023) / 1024 * 1024;   /
 constexpr int kWgSmemBytes = 2 * kWgStageBytes + 1024 + 128;
 static_assert(kWgXBytes % 1024 == 512 || kWgXBytes % 512 == 0, "dy tile must start on a 512-byte swizzle pattern boundary");
 
-__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr)   // MN-major, 128B swizzle / 32B atoms, LBO = one row, SBO = 4 rows
+// MN-major, 128B swizzle / 32B atoms: K rows of 128 bytes (32 channels), SBO = 4 rows; LBO = distance between the 32-wide slabs of the
+// M / N extent: one row (128 B) for the x operand -- slab kw starts one voxel further, the slabs overlap -- and one tile row of dy
+// (TW rows = 1024 B) for the dy operand, whose slabs are consecutive tile rows.
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr, uint32_t lbo_bytes = 128)
 {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
 // part [gridDim.x][9][128][32]
@@ -298,21 +301,27 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // M = 128, N = 32, both operands MN-major (bits 15 / 16), TF32 in, fp32 out
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // M = 128 (kw * 32 + ci), N = 32 * (number of dy rows paired with this x row), both operands MN-major (bits 15 / 16), TF32 in, fp32 out
+      constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, later = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(full(stage), phase);
         tc_fence_after();
         const uint32_t sx = base + stage * kWgStageBytes;
-        const uint64_t dx0 = desc_mn_sw32(sx), dy0 = desc_mn_sw32(sx + kWgXBytes);
+        const uint64_t dx0 = desc_mn_sw32(sx), dy0 = desc_mn_sw32(sx + kWgXBytes, TW * 128);
+        // x row r of plane kd meets dy rows hh = r - kh (kh = 0..2, 0 <= hh < TH) in ONE MMA: the dy rows are consecutive N slabs, their
+        // products land in accumulator kd at column block 2 - kh.  Row 2 goes first: it is the first to touch all three blocks at once,
+        // so on the first tile it alone carries accumulate = 0.
 #pragma unroll
-        for (int a = 0; a < 9; ++a) {                                        // a = kd * 3 + kh
+        for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-          for (int hh = 0; hh < TH; ++hh) {
-            const uint32_t xrow16 = (uint32_t)((((a / 3) * HH + hh + a % 3) * HW) * (128 / 16));    // first voxel row of the A slab, 16-byte units
-            umma_tf32(tmem_base + (uint32_t)(a * 32), dx0 + xrow16, dy0 + (uint32_t)(hh * TW * (128 / 16)), idesc, (hh | later) != 0 ? 1u : 0u);
+          for (int i = 0; i < HH; ++i) {
+            const int r = i == 0 ? 2 : (i <= 2 ? i - 1 : i);
+            const int hh_lo = r - 2 > 0 ? r - 2 : 0, hh_hi = r < TH - 1 ? r : TH - 1, cnt = hh_hi - hh_lo + 1, kh_max = r - hh_lo;
+            const uint32_t xrow16 = (uint32_t)(((kd * HH + r) * HW) * (128 / 16));
+            umma_tf32(tmem_base + (uint32_t)(kd * 96 + (2 - kh_max) * 32), dx0 + xrow16, dy0 + (uint32_t)(hh_lo * TW * (128 / 16)),
+                      idesc0 | ((uint32_t)((32 * cnt) >> 3) << 17), (i | later) != 0 ? 1u : 0u);
           }
         }
         umma_commit(empty(stage));
@@ -331,7 +340,7 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll 1
     for (int a = 0; a < 9; ++a) {
       float v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t)(a * 32) + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_32x32(tmem_base + (uint32_t)((a / 3) * 96 + (2 - a % 3) * 32) + ((uint32_t)(q * 32) << 16), v);
 #pragma unroll
       for (int c = 0; c < 32; c += 4)
         *reinterpret_cast<float4 *>(dst + (long long)a * 128 * 32 + c) = any ? make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
