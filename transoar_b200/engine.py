@@ -118,6 +118,11 @@ class TrainStep:
             self._staging.copy_(volumes, non_blocking=True)
         return self._staging
 
+    def invalidate_graph(self):
+        """Drop the captured graph (the next ``step`` captures again): needed when something baked into it changes -- the learning
+        rate after a scheduler step, a frozen / unfrozen parameter."""
+        self._cuda_graph = None
+
     def close(self):
         """Uninstall this object's dropout epoch counter from the library (see ``_capture``)."""
         if self._static is not None:
