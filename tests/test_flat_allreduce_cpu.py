@@ -49,3 +49,51 @@ def test_flat_bucket_all_reduce_averages_gradients(tmp_path):
         want.append(acc / 2)
     for a, b in zip(got, want):
         assert torch.allclose(a, b, atol=1e-6)
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transoar_b200.engine import OverlappedGradientAverage
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"stem": torch.nn.Linear(6, 6), "body": torch.nn.Linear(6, 6), "head": torch.nn.Linear(6, 2),
+                               "unused": torch.nn.Linear(3, 3)})
+    avg = OverlappedGradientAverage(net, world, late_prefixes=("stem.",))
+    assert len(avg.late) == 2 and len(avg.early) == 6
+    log = []
+    for step in range(3):
+        x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+        for p in net.parameters():
+            p.grad = None
+        avg.before_backward()
+        net["head"](net["body"](net["stem"](x))).square().sum().backward()
+        fired_in_backward = avg.fired
+        avg.after_backward()
+        log.append((fired_in_backward, [None if p.grad is None else p.grad.clone() for p in net.parameters()]))
+    assert avg.expected == 4                                             # body + head; the unused layer never gets a gradient
+    assert [f for f, _ in log] == [False, True, True]                    # calibration step, then the early bucket fires inside backward
+    if rank == 0:
+        torch.save([g for _, g in log], out)
+    dist.destroy_process_group()
+
+
+def test_two_bucket_average_fires_inside_backward_and_matches_the_mean(tmp_path):
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_overlap_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"stem": torch.nn.Linear(6, 6), "body": torch.nn.Linear(6, 6), "head": torch.nn.Linear(6, 2),
+                               "unused": torch.nn.Linear(3, 3)})
+    for step in range(3):
+        want = None
+        for rank in range(2):
+            x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+            for p in net.parameters():
+                p.grad = None
+            net["head"](net["body"](net["stem"](x))).square().sum().backward()
+            grads = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+            want = grads if want is None else [None if a is None else a + b for a, b in zip(want, grads)]
+        for a, b in zip(got[step], want):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.allclose(a, b / 2, atol=1e-6)
