@@ -14,6 +14,7 @@ Multi-GPU: one process per GPU, ``world > 1`` wraps the model in DistributedData
 with the backward); volumes are sharded by rank, nothing else crosses GPUs."""
 import copy
 import ctypes
+import os
 
 import torch
 
@@ -57,8 +58,12 @@ def all_reduce_gradients(parameters, world):
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads:
         return
+    diag = os.environ.get("TRANSOAR_B200_DIAG_ALLREDUCE", "")          # diagnostics only: "skip" = no exchange at all, "local" = copies without NCCL
+    if diag == "skip":
+        return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
+    if diag != "local":
+        dist.all_reduce(flat)
     flat.div_(world)
     torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
