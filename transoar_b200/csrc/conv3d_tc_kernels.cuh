@@ -4,15 +4,19 @@
 // 34-40 via attn_fpn.py:170-182), forward and -- called with the flipped / transposed weights -- the gradient with respect to the input.
 // cuDNN's choice for that input gradient on B200 is a "strided dgrad" kernel that takes 4.1 ms per step; the forward takes 1.5 ms.
 //
-// Implicit GEMM without an im2col copy.  One CTA tile = 1 x 16 x 8 output voxels (d, h, w) = the 128 rows of the MMA.  The input
-// halo tile (3 x 18 x 10 voxels) is loaded ONCE per tile by TMA as CI/4 "channel-chunk planes" [chunk][d][h][w][4 floats] (5-D tensor
+// Implicit GEMM without an im2col copy.  One CTA tile = 1 x 8 x 16 INPUT columns (d, h, w) = the 128 rows of the MMA.  The input
+// halo tile (3 x 10 x 16 voxels) is loaded ONCE per tile by TMA as CI/4 "channel-chunk planes" [chunk][d][h][w][4 floats] (5-D tensor
 // map over N, D, H, W, C with a 4-channel box; out-of-bounds parts are zero-filled, which is the convolution's padding).  In that form
-// the A operand of every filter tap (kd, kh, kw) is the no-swizzle K-major canonical layout of the tensor core -- rows (voxels) 16
-// bytes apart inside a plane, the tile's h rows one halo row pitch (160 bytes) apart, the next four channels one plane further -- so a
-// tap is nothing but a START-ADDRESS OFFSET of ((kd * 18 + kh) * 10 + kw) * 16 bytes in the shared-memory descriptor: 27 taps x CI/8
-// k-steps = 81 MMAs (128 x 32 x 8) read the same tile.  The weights of all 27 taps live in shared memory for the whole (persistent)
-// kernel, rounded to TF32 when they are staged.  Pipeline as in tc_gemm_kernels.cuh: TMA producer warp, single-thread MMA issuer,
-// four epilogue warps (TMEM -> registers -> one contiguous CO * 4-byte row per voxel), two tile stages, two TMEM accumulators.
+// the A operand of a filter tap pair (kd, kh) is the no-swizzle K-major canonical layout of the tensor core -- rows (voxels) 16 bytes
+// apart, the next four channels one plane further -- so a tap is nothing but a START-ADDRESS OFFSET of (kd * 10 + kh) * 16 * 16 bytes
+// in the shared-memory descriptor.  The three kw taps are NOT three more offsets: they are folded into N.  Row r = (h, wi) of the
+// accumulator holds, in column block kw, the partial sum P_kw[wi] = sum_{kd, kh, ci} x[d + kd - 1, h + kh - 1, w0 - 1 + wi, ci] *
+// w[kd, kh, kw, ci, co]; the output is y[w0 + j] = P_0[j] + P_1[j + 1] + P_2[j + 2], which the epilogue forms with two warp shuffles
+// per channel (a warp owns two complete tile rows).  So a tile costs 9 x CI/8 = 27 MMAs of 128 x 96 x 8 instead of 81 of 128 x 32 x 8:
+// the tensor pipe is bound by the shared-memory bytes an MMA reads (A 4 KB + B), and this reads 2.1x fewer per output (14 of the
+// 16 columns of a tile row are outputs).  The weights of all 27 taps live in shared memory for the whole (persistent) kernel,
+// rounded to TF32 when they are staged.  Pipeline as in tc_gemm_kernels.cuh: TMA producer warp, single-thread MMA issuer, four
+// epilogue warps (TMEM -> registers -> shuffles -> one contiguous CO * 4-byte row per voxel), two tile stages, two TMEM accumulators.
 #pragma once
 
 #include "tc_gemm_kernels.cuh"
@@ -21,10 +25,8 @@ namespace convtc {
 
 using namespace tcgemm;
 
-constexpr int TH = 16, TW = 8;                 // tile: 1 x TH x TW voxels = 128 MMA rows
-constexpr int HH = TH + 2, HW = TW + 2;        // halo tile: 3 x HH x HW voxels
-constexpr int kPlaneData = 3 * HH * HW * 16;   // one 4-channel chunk of the halo tile: 8640 bytes
-constexpr int kPlaneBytes = (kPlaneData + 127) / 128 * 128;   // plane pitch: TMA destinations are 128-byte aligned
+constexpr int TH = 16, TW = 8;                 // weight-gradient tile: 1 x TH x TW voxels of dy
+constexpr int HH = TH + 2, HW = TW + 2;        // and its halo tile of x: 3 x HH x HW voxels
 constexpr int kThreadsConv = 192;
 constexpr int NPAD = 32;                       // MMA N (output channels padded to a multiple of 16)
 
@@ -47,11 +49,20 @@ __device__ __forceinline__ float to_tf32(float x)
   return __uint_as_float(r);
 }
 
+// forward / input-gradient tile geometry
+constexpr int FTH = 8;                          // tile rows (h)
+constexpr int FWI = 16;                         // input columns per tile row = MMA rows per tile row (two 8-row groups)
+constexpr int FWO = FWI - 2;                    // output columns per tile row
+constexpr int FHH = FTH + 2;                    // halo rows
+constexpr int kFPlaneBytes = 3 * FHH * FWI * 16;   // one 4-channel chunk of the halo tile: 7680 bytes (a multiple of 128: TMA destination)
+constexpr int NF = 3 * NPAD;                    // MMA N: (kw, co)
+static_assert(kFPlaneBytes % 128 == 0 && FTH * FWI == 128, "tile geometry");
+
 template <int CI> struct ConvCfg {
   static constexpr int CHUNKS = CI / 4;
-  static constexpr int STAGE_BYTES = CHUNKS * kPlaneBytes;                   // 52224 for CI = 24
-  static constexpr int W_TAP_BYTES = CHUNKS * NPAD * 16;                     // one tap of B: [k-chunk][n (32)][4 floats]
-  static constexpr int W_BYTES = 27 * W_TAP_BYTES;                           // 82944 for CI = 24
+  static constexpr int STAGE_BYTES = CHUNKS * kFPlaneBytes;                  // 46080 for CI = 24
+  static constexpr int W_PAIR_BYTES = CHUNKS * NF * 16;                      // B of one (kd, kh): [k-chunk][n = kw * 32 + co (96)][4 floats]
+  static constexpr int W_BYTES = 9 * W_PAIR_BYTES;                           // 82944 for CI = 24
   static constexpr int STAGES = 2;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 128 + 128;
 };
@@ -74,12 +85,14 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   const uint32_t tmem_slot = bars + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // weights -> shared memory, B operand of tap t: [k-chunk kc][n][4 floats] = wg[t][n][4 kc .. 4 kc + 3], rows n >= CO zero
-  for (int i = threadIdx.x; i < 27 * C::CHUNKS * NPAD; i += kThreadsConv) {
-    const int n = i % NPAD, kc = (i / NPAD) % C::CHUNKS, t = i / (NPAD * C::CHUNKS);
+  // weights -> shared memory, B operand of the tap pair a = kd * 3 + kh: [k-chunk kc][n = kw * 32 + co][4 floats]
+  //   = wg[a * 3 + kw][co][4 kc .. 4 kc + 3], rows co >= CO zero
+  for (int i = threadIdx.x; i < 9 * C::CHUNKS * NF; i += kThreadsConv) {
+    const int n = i % NF, kc = (i / NF) % C::CHUNKS, a = i / (NF * C::CHUNKS);
+    const int kw = n / NPAD, co = n % NPAD;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < CO) {
-      const float4 g = __ldg(reinterpret_cast<const float4 *>(wg + ((long long)t * CO + n) * CI + 4 * kc));
+    if (co < CO) {
+      const float4 g = __ldg(reinterpret_cast<const float4 *>(wg + ((long long)(a * 3 + kw) * CO + co) * CI + 4 * kc));
       v = make_float4(to_tf32(g.x), to_tf32(g.y), to_tf32(g.z), to_tf32(g.w));
     }
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -89,7 +102,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * NPAD) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy weight stores must be visible to the tensor core
@@ -99,7 +112,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int th = (H + TH - 1) / TH, tw = (W + TW - 1) / TW;
+  const int th = (H + FTH - 1) / FTH, tw = (W + FWO - 1) / FWO;
   const long long tiles = (long long)N * D * th * tw;
 
   if (warp == 0) {
@@ -109,38 +122,38 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
         mbar_wait(empty(stage), phase ^ 1u);
-        mbar_expect_tx(full(stage), C::CHUNKS * kPlaneData);
+        mbar_expect_tx(full(stage), C::CHUNKS * kFPlaneBytes);
 #pragma unroll
         for (int c = 0; c < C::CHUNKS; ++c)
-          tma_load_5d(base + stage * C::STAGE_BYTES + c * kPlaneBytes, &tmX, full(stage), 4 * c, iw * TW - 1, ih * TH - 1, d - 1, n);
+          tma_load_5d(base + stage * C::STAGE_BYTES + c * kFPlaneBytes, &tmX, full(stage), 4 * c, iw * FWO - 1, ih * FTH - 1, d - 1, n);
         if (++stage == 2) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // M = 128, N = 32, both operands K-major, TF32 in, fp32 out
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // M = 128, N = 96, both operands K-major, TF32 in, fp32 out
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(tempty(as), aphase ^ 1u);
         mbar_wait(full(stage), phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * C::STAGE_BYTES, acc = tmem_base + (uint32_t)(as * NPAD);
-        // One thread issues 27 x CI/8 MMAs per tile, so the issue loop must be cheap: the two descriptors are built once per tile
-        // and every tap / k-step only adds a compile-time constant to their 14-bit start-address fields (all shared-memory
+        const uint32_t sa = base + stage * C::STAGE_BYTES, acc = tmem_base + (uint32_t)(as * NF);
+        // One thread issues every MMA of a tile, so the issue loop must be cheap: the two descriptors are built once per tile and
+        // every tap pair / k-step only adds a compile-time constant to their 14-bit start-address fields (all shared-memory
         // addresses are < 256 KB, so the field never carries into the LBO field).
-        //   A: rows (w) 16 B apart, 8-row groups (tile rows h) one halo row pitch apart, second 4-channel chunk one plane further
-        //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NPAD * 16 B further
-        const uint64_t da0 = desc_noswizzle(sa, kPlaneBytes, HW * 16), db0 = desc_noswizzle(wbase, NPAD * 16, 128);
+        //   A: rows (h, wi) 16 B apart (a tile row is two 8-row groups, 128 B apart), second 4-channel chunk one plane further
+        //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NF * 16 B further
+        const uint64_t da0 = desc_noswizzle(sa, kFPlaneBytes, 128), db0 = desc_noswizzle(wbase, NF * 16, 128);
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-          constexpr int kA16 = 2 * kPlaneBytes / 16, kB16 = 2 * NPAD;                        // k-step strides in 16-byte units
-          const uint32_t a16 = (uint32_t)(((tap / 9) * HH + (tap / 3) % 3) * HW + tap % 3);  // tap offset in the halo tile, 16-byte units
-          const uint32_t b16 = (uint32_t)(tap * (C::W_TAP_BYTES / 16));
+        for (int a = 0; a < 9; ++a) {
+          constexpr int kA16 = 2 * kFPlaneBytes / 16, kB16 = 2 * NF;                          // k-step strides in 16-byte units
+          const uint32_t a16 = (uint32_t)(((a / 3) * FHH + a % 3) * FWI);                     // (kd, kh) offset in the halo tile, 16-byte units
+          const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
 #pragma unroll
           for (int s = 0; s < CI / 8; ++s)
-            umma_tf32(acc, da0 + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (tap | s) != 0 ? 1u : 0u);
+            umma_tf32(acc, da0 + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (a | s) != 0 ? 1u : 0u);
         }
         umma_commit(empty(stage));
         umma_commit(tfull(as));
@@ -149,19 +162,26 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       }
     }
   } else {
-    const int q = warp & 3, row = q * 32 + lane, hh = row / TW, ww = row % TW;
+    // warp q owns accumulator rows q * 32 .. + 31 = tile rows 2 q and 2 q + 1, lane = (row parity, wi)
+    const int q = warp & 3, hh = q * 2 + (lane >> 4), wi = lane & 15;
     int as = 0;
     uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
       mbar_wait(tfull(as), aphase);
       tc_fence_after();
-      float v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t)(as * NPAD) + ((uint32_t)(q * 32) << 16), v);
+      float v[32], v1[32], v2[32];
+      const uint32_t tacc = tmem_base + (uint32_t)(as * NF) + ((uint32_t)(q * 32) << 16);
+      tmem_ld_32x32(tacc, v);
+      tmem_ld_32x32(tacc + NPAD, v1);
+      tmem_ld_32x32(tacc + 2 * NPAD, v2);
       tc_fence_before();
       mbar_arrive(tempty(as));                                   // the accumulator is in registers: the next tile may overwrite it
-      const int h = ih * TH + hh, w = iw * TW + ww;
-      if (h < H && w < W) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)                               // y[j] = P_0[j] + P_1[j + 1] + P_2[j + 2] (lanes j + 1, j + 2 of the same tile row)
+        v[c] += __shfl_down_sync(0xffffffffu, v1[c], 1) + __shfl_down_sync(0xffffffffu, v2[c], 2);
+      const int h = ih * FTH + hh, w = iw * FWO + wi;
+      if (wi < FWO && h < H && w < W) {
         float *dst = y + ((((long long)n * D + d) * H + h) * W + w) * CO;
 #pragma unroll
         for (int c = 0; c < 32; c += 4)
@@ -175,7 +195,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NPAD) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 

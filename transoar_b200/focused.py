@@ -205,12 +205,13 @@ class FocusedDecoderLayer(nn.Module):
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = nn.LayerNorm(d_model)
 
-    def forward(self, tgt, query_pos, src_pos, src):
+    def forward(self, tgt, query_pos, src_pos, src, src_k=None):
+        """``src_k``: ``src + src_pos`` computed by the caller (it is the same tensor for every layer of the decoder)."""
         qk = tgt if query_pos is None else tgt + query_pos
         sa = self.self_attn(qk.transpose(0, 1), qk.transpose(0, 1), tgt.transpose(0, 1))[0].transpose(0, 1)
         tgt = add_dropout_layer_norm(tgt, sa, self.norm2, self.dropout2.p, self.training)
         q = tgt if query_pos is None else tgt + query_pos
-        k = src if src_pos is None else src + src_pos
+        k = src_k if src_k is not None else (src if src_pos is None else src + src_pos)
         ca, weights = self.cross_attn(q, k, src)
         tgt = add_dropout_layer_norm(tgt, ca, self.norm1, self.dropout1.p, self.training)
         if self._fuse_relu:
@@ -230,8 +231,9 @@ class FocusedDecoderModel(nn.Module):
 
     def forward(self, tgt, src, src_pos, query_pos=None):
         output, inter = tgt, []
+        src_k = src if src_pos is None else src + src_pos               # focused_decoder.py:173 forms this sum in every layer
         for layer in self.layers:
-            output, _ = layer(output, query_pos, src_pos, src)
+            output, _ = layer(output, query_pos, src_pos, src, src_k=src_k)
             if self.return_intermediate:
                 inter.append(output)
         return torch.stack(inter) if self.return_intermediate else output
