@@ -41,7 +41,7 @@ int launch(cudaStream_t st, const CUtensorMap &mx, const float *w, float *y, int
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
   if (err != cudaSuccess) return (int)err;
-  const long long tiles = (long long)N * D * ((H + convtc::FTH - 1) / convtc::FTH) * ((W + convtc::FWO - 1) / convtc::FWO);
+  const long long tiles = (long long)N * ((D + convtc::DSEG - 1) / convtc::DSEG) * ((H + convtc::FTH - 1) / convtc::FTH) * ((W + convtc::FWO - 1) / convtc::FWO);
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(tiles < sms ? tiles : sms);
@@ -68,7 +68,7 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
   const cuuint64_t C = (cuuint64_t)in_channels, W = (cuuint64_t)width, H = (cuuint64_t)height, D = (cuuint64_t)depth;
   const cuuint64_t gdim[5] = {C, W, H, D, (cuuint64_t)batch};
   const cuuint64_t gstride[4] = {C * 4, W * C * 4, H * W * C * 4, D * H * W * C * 4};
-  const cuuint32_t box[5] = {4, (cuuint32_t)convtc::FWI, (cuuint32_t)convtc::FHH, 3, 1};
+  const cuuint32_t box[5] = {4, (cuuint32_t)convtc::FWI, (cuuint32_t)convtc::FHH, 1, 1};      // one depth plane of the halo per copy
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMap mx;
   // TFLOAT32: the copy engine rounds the activations to TF32; out-of-bounds voxels of the halo box are zero-filled (= padding 1)

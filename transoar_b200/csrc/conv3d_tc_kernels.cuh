@@ -54,17 +54,18 @@ constexpr int FTH = 8;                          // tile rows (h)
 constexpr int FWI = 16;                         // input columns per tile row = MMA rows per tile row (two 8-row groups)
 constexpr int FWO = FWI - 2;                    // output columns per tile row
 constexpr int FHH = FTH + 2;                    // halo rows
-constexpr int kFPlaneBytes = 3 * FHH * FWI * 16;   // one 4-channel chunk of the halo tile: 7680 bytes (a multiple of 128: TMA destination)
+constexpr int kFPlaneBytes = FHH * FWI * 16;    // one 4-channel chunk of one depth plane of the halo: 2560 bytes (a multiple of 128: TMA destination)
 constexpr int NF = 3 * NPAD;                    // MMA N: (kw, co)
+constexpr int DSEG = 40;                        // output planes a CTA marches through per work item (2 extra halo planes per item)
 static_assert(kFPlaneBytes % 128 == 0 && FTH * FWI == 128, "tile geometry");
 
 template <int CI> struct ConvCfg {
   static constexpr int CHUNKS = CI / 4;
-  static constexpr int STAGE_BYTES = CHUNKS * kFPlaneBytes;                  // 46080 for CI = 24
+  static constexpr int STAGE_BYTES = CHUNKS * kFPlaneBytes;                  // one depth plane of the halo, all channels: 15360 for CI = 24
   static constexpr int W_PAIR_BYTES = CHUNKS * NF * 16;                      // B of one (kd, kh): [k-chunk][n = kw * 32 + co (96)][4 floats]
   static constexpr int W_BYTES = 9 * W_PAIR_BYTES;                           // 82944 for CI = 24
-  static constexpr int STAGES = 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 128 + 128;
+  static constexpr int STAGES = 8;                                           // ring of depth planes: 3 in use, 5 in flight
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 256 + 128;
 };
 
 // x [N, D, H, W, CI] through the tensor map; wg [27][CO][CI] (tap-major; for the input gradient: flipped taps, transposed channels);
@@ -78,11 +79,12 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t wbase = base + C::STAGES * C::STAGE_BYTES;
   const uint32_t bars = wbase + C::W_BYTES;
+  constexpr int R = C::STAGES;
   auto full = [&](int s) { return bars + 8u * s; };
-  auto empty = [&](int s) { return bars + 8u * (2 + s); };
-  auto tfull = [&](int a) { return bars + 8u * (4 + a); };
-  auto tempty = [&](int a) { return bars + 8u * (6 + a); };
-  const uint32_t tmem_slot = bars + 64;
+  auto empty = [&](int s) { return bars + 8u * (R + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * R + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * R + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * R + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // weights -> shared memory, B operand of the tap pair a = kd * 3 + kh: [k-chunk kc][n = kw * 32 + co][4 floats]
@@ -98,7 +100,8 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
+    for (int s = 0; s < R; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -112,53 +115,79 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int th = (H + FTH - 1) / FTH, tw = (W + FWO - 1) / FWO;
-  const long long tiles = (long long)N * D * th * tw;
+  // work item = (n, depth segment, h tile, w tile): the CTA marches through the segment's output planes; input plane d + 1 is the only
+  // new data per output plane (planes d - 1 and d are still in the ring), so the halo is read from L2 1.05 x 1.43 times instead of 4.3
+  const int th = (H + FTH - 1) / FTH, tw = (W + FWO - 1) / FWO, segs = (D + DSEG - 1) / DSEG;
+  const long long items = (long long)N * segs * th * tw;
+  auto item_coords = [&](long long t, int &iw, int &ih, int &d0, int &seg, int &n) {
+    iw = (int)(t % tw); ih = (int)((t / tw) % th);
+    const int sg = (int)((t / ((long long)tw * th)) % segs);
+    n = (int)(t / ((long long)tw * th * segs));
+    d0 = sg * DSEG; seg = min(DSEG, D - d0);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
-        mbar_wait(empty(stage), phase ^ 1u);
-        mbar_expect_tx(full(stage), C::CHUNKS * kFPlaneBytes);
+      uint32_t g = 0;                                             // running plane index: slot g % R, parity (g / R) & 1
+      for (long long t = blockIdx.x; t < items; t += gridDim.x) {
+        int iw, ih, d0, seg, n;
+        item_coords(t, iw, ih, d0, seg, n);
+        for (int p = 0; p < seg + 2; ++p, ++g) {
+          const uint32_t slot = g % R, par = (g / R) & 1u;
+          mbar_wait(empty(slot), par ^ 1u);
+          mbar_expect_tx(full(slot), C::CHUNKS * kFPlaneBytes);
 #pragma unroll
-        for (int c = 0; c < C::CHUNKS; ++c)
-          tma_load_5d(base + stage * C::STAGE_BYTES + c * kFPlaneBytes, &tmX, full(stage), 4 * c, iw * FWO - 1, ih * FTH - 1, d - 1, n);
-        if (++stage == 2) { stage = 0; phase ^= 1u; }
+          for (int c = 0; c < C::CHUNKS; ++c)
+            tma_load_5d(base + slot * C::STAGE_BYTES + c * kFPlaneBytes, &tmX, full(slot), 4 * c, iw * FWO - 1, ih * FTH - 1, d0 - 1 + p, n);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // M = 128, N = 96, both operands K-major, TF32 in, fp32 out
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        mbar_wait(tempty(as), aphase ^ 1u);
-        mbar_wait(full(stage), phase);
-        tc_fence_after();
-        const uint32_t sa = base + stage * C::STAGE_BYTES, acc = tmem_base + (uint32_t)(as * NF);
-        // One thread issues every MMA of a tile, so the issue loop must be cheap: the two descriptors are built once per tile and
-        // every tap pair / k-step only adds a compile-time constant to their 14-bit start-address fields (all shared-memory
-        // addresses are < 256 KB, so the field never carries into the LBO field).
-        //   A: rows (h, wi) 16 B apart (a tile row is two 8-row groups, 128 B apart), second 4-channel chunk one plane further
-        //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NF * 16 B further
-        const uint64_t da0 = desc_noswizzle(sa, kFPlaneBytes, 128), db0 = desc_noswizzle(wbase, NF * 16, 128);
+      int as = 0;
+      uint32_t aphase = 0, g0 = 0;
+      const uint64_t db0 = desc_noswizzle(wbase, NF * 16, 128);
+      for (long long t = blockIdx.x; t < items; t += gridDim.x) {
+        int iw, ih, d0, seg, n;
+        item_coords(t, iw, ih, d0, seg, n);
+        for (int j = 0; j < seg; ++j) {
+          mbar_wait(tempty(as), aphase ^ 1u);
+          if (j == 0) {
+            mbar_wait(full(g0 % R), (g0 / R) & 1u);
+            mbar_wait(full((g0 + 1) % R), ((g0 + 1) / R) & 1u);
+          }
+          const uint32_t gn = g0 + j + 2;
+          mbar_wait(full(gn % R), (gn / R) & 1u);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)(as * NF);
+          // One thread issues every MMA of a tile, so the issue loop must be cheap: one descriptor per depth plane of the ring and
+          // per tile, then every (kh, k-step) only adds a compile-time constant to the 14-bit start-address field (all shared-memory
+          // addresses are < 256 KB, so the field never carries into the LBO field).
+          //   A: rows (h, wi) 16 B apart (a tile row is two 8-row groups, 128 B apart), second 4-channel chunk one chunk plane further
+          //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NF * 16 B further
+          uint64_t da[3];
 #pragma unroll
-        for (int a = 0; a < 9; ++a) {
-          constexpr int kA16 = 2 * kFPlaneBytes / 16, kB16 = 2 * NF;                          // k-step strides in 16-byte units
-          const uint32_t a16 = (uint32_t)(((a / 3) * FHH + a % 3) * FWI);                     // (kd, kh) offset in the halo tile, 16-byte units
-          const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
+          for (int kd = 0; kd < 3; ++kd) da[kd] = desc_noswizzle(base + ((g0 + j + kd) % R) * C::STAGE_BYTES, kFPlaneBytes, 128);
 #pragma unroll
-          for (int s = 0; s < CI / 8; ++s)
-            umma_tf32(acc, da0 + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (a | s) != 0 ? 1u : 0u);
+          for (int a = 0; a < 9; ++a) {
+            constexpr int kA16 = 2 * kFPlaneBytes / 16, kB16 = 2 * NF;                        // k-step strides in 16-byte units
+            const uint32_t a16 = (uint32_t)((a % 3) * FWI);                                   // kh offset inside the plane, 16-byte units
+            const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
+#pragma unroll
+            for (int s = 0; s < CI / 8; ++s)
+              umma_tf32(acc, da[a / 3] + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (a | s) != 0 ? 1u : 0u);
+          }
+          umma_commit(tfull(as));
+          umma_commit(empty((g0 + j) % R));                        // plane d - 1 is not needed again
+          if (j == seg - 1) {                                      // end of the segment: its last two planes as well
+            umma_commit(empty((g0 + j + 1) % R));
+            umma_commit(empty((g0 + j + 2) % R));
+          }
+          if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-        umma_commit(empty(stage));
-        umma_commit(tfull(as));
-        if (++stage == 2) { stage = 0; phase ^= 1u; }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        g0 += (uint32_t)(seg + 2);
       }
     }
   } else {
@@ -166,28 +195,32 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
     const int q = warp & 3, hh = q * 2 + (lane >> 4), wi = lane & 15;
     int as = 0;
     uint32_t aphase = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int iw = (int)(t % tw), ih = (int)((t / tw) % th), d = (int)((t / ((long long)tw * th)) % D), n = (int)(t / ((long long)tw * th * D));
-      mbar_wait(tfull(as), aphase);
-      tc_fence_after();
-      float v[32], v1[32], v2[32];
-      const uint32_t tacc = tmem_base + (uint32_t)(as * NF) + ((uint32_t)(q * 32) << 16);
-      tmem_ld_32x32(tacc, v);
-      tmem_ld_32x32(tacc + NPAD, v1);
-      tmem_ld_32x32(tacc + 2 * NPAD, v2);
-      tc_fence_before();
-      mbar_arrive(tempty(as));                                   // the accumulator is in registers: the next tile may overwrite it
-#pragma unroll
-      for (int c = 0; c < 32; ++c)                               // y[j] = P_0[j] + P_1[j + 1] + P_2[j + 2] (lanes j + 1, j + 2 of the same tile row)
-        v[c] += __shfl_down_sync(0xffffffffu, v1[c], 1) + __shfl_down_sync(0xffffffffu, v2[c], 2);
+    for (long long t = blockIdx.x; t < items; t += gridDim.x) {
+      int iw, ih, d0, seg, n;
+      item_coords(t, iw, ih, d0, seg, n);
       const int h = ih * FTH + hh, w = iw * FWO + wi;
-      if (wi < FWO && h < H && w < W) {
-        float *dst = y + ((((long long)n * D + d) * H + h) * W + w) * CO;
+      const bool store = wi < FWO && h < H && w < W;
+      for (int j = 0; j < seg; ++j) {
+        mbar_wait(tfull(as), aphase);
+        tc_fence_after();
+        float v[32], v1[32], v2[32];
+        const uint32_t tacc = tmem_base + (uint32_t)(as * NF) + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(tacc, v);
+        tmem_ld_32x32(tacc + NPAD, v1);
+        tmem_ld_32x32(tacc + 2 * NPAD, v2);
+        tc_fence_before();
+        mbar_arrive(tempty(as));                                   // the accumulator is in registers: the next tile may overwrite it
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          if (c < CO) __stcs(reinterpret_cast<float4 *>(dst + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+        for (int c = 0; c < 32; ++c)                               // y[j] = P_0[j] + P_1[j + 1] + P_2[j + 2] (lanes j + 1, j + 2 of the same tile row)
+          v[c] += __shfl_down_sync(0xffffffffu, v1[c], 1) + __shfl_down_sync(0xffffffffu, v2[c], 2);
+        if (store) {
+          float *dst = y + ((((long long)n * D + d0 + j) * H + h) * W + w) * CO;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            if (c < CO) __stcs(reinterpret_cast<float4 *>(dst + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
 
