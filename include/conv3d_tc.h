@@ -32,6 +32,10 @@ long long conv3d_tc_wgrad_workspace_floats(void);
 int conv3d_tc_k3_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
                        int out_channels, float *dweight, float *workspace);
 
+/* Timing experiments only (tools/exp_conv.py): bit 0 = the forward kernel's epilogue neither reads the accumulators nor stores, bit 1 = no
+ * MMAs are issued, bit 2 = no stores.  Results are wrong while a mode is set; 0 (the default) is the product. */
+void conv3d_tc_debug_mode(int mode);
+
 /* Test hook for the weight-gradient formulation: one 128 x 32 x 8 TF32 MMA with MN-major operands in the 128-byte swizzle /
  * 32-byte atom layout, the A operand being four OVERLAPPING 32-channel slabs (leading offset = one 128-byte row) starting at row `row0`:
  * D[j * 32 + c][n] = sum_{k < 8} X[row0 + j + k][c] * Y[k][n], X [24][32], Y [8][32], D [128][32], device pointers. */

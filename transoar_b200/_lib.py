@@ -48,6 +48,7 @@ _SIGNATURES = {
     "hash_rng_set_epoch": (None, [_vp]),
     "conv3d_tc_wgrad_workspace_floats": (ctypes.c_longlong, []),
     "conv3d_tc_k3_wgrad": (_ci, [_vp, _vp, _vp] + [_ci] * 6 + [_vp, _vp]),
+    "conv3d_tc_debug_mode": (None, [_ci]),
     "conv3d_tc_debug_mn_probe": (_ci, [_vp] * 4 + [_ci]),
     "conv3d_tc_k3_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 6 + [_vp]),
     # include/fused_ln.h

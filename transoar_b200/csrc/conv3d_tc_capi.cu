@@ -11,6 +11,8 @@ extern std::atomic<unsigned long long> g_msda3d_launches;
 
 namespace {
 
+std::atomic<int> g_conv_diag{0};
+
 using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -28,7 +30,7 @@ EncodeTiled encode_fn()
   return fn;
 }
 
-// two halo-tile stages + the weights of all 27 taps must fit the 227 KB of shared memory: 8, 16 or 24 input channels
+// the ring of halo planes + the weights of all 27 taps (rows padded to 32 channels) fill the 227 KB of shared memory; 8, 16 or 24 input channels
 bool ci_ok(int ci) { return ci == 8 || ci == 16 || ci == 24; }
 static_assert(convtc::ConvCfg<24>::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
 
@@ -45,12 +47,14 @@ int launch(cudaStream_t st, const CUtensorMap &mx, const float *w, float *y, int
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, convtc::kThreadsConv, C::SMEM_BYTES, st>>>(mx, w, y, N, D, H, W, CO);
+  kern<<<grid, convtc::kThreadsConv, C::SMEM_BYTES, st>>>(mx, w, y, N, D, H, W, CO, g_conv_diag.load());
   ++g_msda3d_launches;
   return (int)cudaGetLastError();
 }
 
 }  // namespace
+
+extern "C" void conv3d_tc_debug_mode(int mode) { g_conv_diag.store(mode); }
 
 extern "C" int conv3d_tc_supported(int in_channels, int out_channels)
 {
@@ -68,12 +72,13 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
   const cuuint64_t C = (cuuint64_t)in_channels, W = (cuuint64_t)width, H = (cuuint64_t)height, D = (cuuint64_t)depth;
   const cuuint64_t gdim[5] = {C, W, H, D, (cuuint64_t)batch};
   const cuuint64_t gstride[4] = {C * 4, W * C * 4, H * W * C * 4, D * H * W * C * 4};
-  const cuuint32_t box[5] = {4, (cuuint32_t)convtc::FWI, (cuuint32_t)convtc::FHH, 1, 1};      // one depth plane of the halo per copy
+  // one depth plane of the halo per copy, rows of 32 channels (the copy engine zero-fills channels >= CI), 128-byte swizzle
+  const cuuint32_t box[5] = {32, (cuuint32_t)convtc::FWI, (cuuint32_t)convtc::FHH, 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMap mx;
   // TFLOAT32: the copy engine rounds the activations to TF32; out-of-bounds voxels of the halo box are zero-filled (= padding 1)
   if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, const_cast<float *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return MSDA3D_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (in_channels) {

@@ -4,19 +4,19 @@
 // 34-40 via attn_fpn.py:170-182), forward and -- called with the flipped / transposed weights -- the gradient with respect to the input.
 // cuDNN's choice for that input gradient on B200 is a "strided dgrad" kernel that takes 4.1 ms per step; the forward takes 1.5 ms.
 //
-// Implicit GEMM without an im2col copy.  One CTA tile = 1 x 8 x 16 INPUT columns (d, h, w) = the 128 rows of the MMA.  The input
-// halo tile (3 x 10 x 16 voxels) is loaded ONCE per tile by TMA as CI/4 "channel-chunk planes" [chunk][d][h][w][4 floats] (5-D tensor
-// map over N, D, H, W, C with a 4-channel box; out-of-bounds parts are zero-filled, which is the convolution's padding).  In that form
-// the A operand of a filter tap pair (kd, kh) is the no-swizzle K-major canonical layout of the tensor core -- rows (voxels) 16 bytes
-// apart, the next four channels one plane further -- so a tap is nothing but a START-ADDRESS OFFSET of (kd * 10 + kh) * 16 * 16 bytes
-// in the shared-memory descriptor.  The three kw taps are NOT three more offsets: they are folded into N.  Row r = (h, wi) of the
-// accumulator holds, in column block kw, the partial sum P_kw[wi] = sum_{kd, kh, ci} x[d + kd - 1, h + kh - 1, w0 - 1 + wi, ci] *
-// w[kd, kh, kw, ci, co]; the output is y[w0 + j] = P_0[j] + P_1[j + 1] + P_2[j + 2], which the epilogue forms with two warp shuffles
-// per channel (a warp owns two complete tile rows).  So a tile costs 9 x CI/8 = 27 MMAs of 128 x 96 x 8 instead of 81 of 128 x 32 x 8:
-// the tensor pipe is bound by the shared-memory bytes an MMA reads (A 4 KB + B), and this reads 2.1x fewer per output (14 of the
-// 16 columns of a tile row are outputs).  The weights of all 27 taps live in shared memory for the whole (persistent) kernel,
-// rounded to TF32 when they are staged.  Pipeline as in tc_gemm_kernels.cuh: TMA producer warp, single-thread MMA issuer, four
-// epilogue warps (TMEM -> registers -> shuffles -> one contiguous CO * 4-byte row per voxel), two tile stages, two TMEM accumulators.
+// Implicit GEMM without an im2col copy.  One CTA tile = 1 x 8 x 16 INPUT columns (d, h, w) = the 128 rows of the MMA.  A CTA takes a
+// work item (n, 40 output planes, h tile, w tile) and marches through its depth planes: the 10 x 16 halo of ONE input plane arrives per
+// output plane by one 5-D TMA box (rows of 32 channels: the copy engine zero-fills channels >= CI and the out-of-bounds voxels, which
+// is the convolution's padding; 128-byte swizzle) into a ring of 5 planes -- planes d - 1 and d are still there from the previous
+// output planes, so the input is read from L2 1.5 x instead of 4.3 x.  In that form the A operand of a tap pair (kd, kh) is the ring
+// slot of plane d + kd - 1 plus a START-ADDRESS OFFSET of kh tile rows (16 rows = two swizzle atoms) in the shared-memory descriptor.
+// The three kw taps are NOT three more offsets: they are folded into N.  Row r = (h, wi) of the accumulator holds, in column block kw,
+// the partial sum P_kw[wi] = sum_{kd, kh, ci} x[d + kd - 1, h + kh - 1, w0 - 1 + wi, ci] * w[kd, kh, kw, ci, co]; the output is
+// y[w0 + j] = P_0[j] + P_1[j + 1] + P_2[j + 2], which the epilogue forms with two warp shuffles per channel (a warp owns two complete
+// tile rows; 14 of the 16 columns of a tile row are outputs).  So a tile costs 9 x CI/8 = 27 MMAs of 128 x 96 x 8 instead of 81 of
+// 128 x 32 x 8.  The weights of all 27 taps live in shared memory for the whole (persistent) kernel, rounded to TF32 when they are
+// staged.  Roles as in tc_gemm_kernels.cuh: TMA producer warp, single-thread MMA issuer, four epilogue warps (TMEM -> registers ->
+// shuffles -> one contiguous CO * 4-byte row per voxel), four TMEM accumulators.
 #pragma once
 
 #include "tc_gemm_kernels.cuh"
@@ -54,58 +54,69 @@ constexpr int FTH = 8;                          // tile rows (h)
 constexpr int FWI = 16;                         // input columns per tile row = MMA rows per tile row (two 8-row groups)
 constexpr int FWO = FWI - 2;                    // output columns per tile row
 constexpr int FHH = FTH + 2;                    // halo rows
-constexpr int kFPlaneBytes = FHH * FWI * 16;    // one 4-channel chunk of one depth plane of the halo: 2560 bytes (a multiple of 128: TMA destination)
+constexpr int kFPlaneBytes = FHH * FWI * 128;   // one depth plane of the halo, rows of 32 channels (CI real + zero fill) = 128 B: 20480 bytes
 constexpr int NF = 3 * NPAD;                    // MMA N: (kw, co)
+constexpr int NACC = 4;                         // TMEM accumulators (4 x 96 columns): tiles in flight between the MMA issuer and the epilogue
 constexpr int DSEG = 40;                        // output planes a CTA marches through per work item (2 extra halo planes per item)
-static_assert(kFPlaneBytes % 128 == 0 && FTH * FWI == 128, "tile geometry");
+static_assert(kFPlaneBytes % 1024 == 0 && FTH * FWI == 128 && (FWI * 128) % 1024 == 0, "tile geometry / swizzle atom alignment");
 
 template <int CI> struct ConvCfg {
-  static constexpr int CHUNKS = CI / 4;
-  static constexpr int STAGE_BYTES = CHUNKS * kFPlaneBytes;                  // one depth plane of the halo, all channels: 15360 for CI = 24
-  static constexpr int W_PAIR_BYTES = CHUNKS * NF * 16;                      // B of one (kd, kh): [k-chunk][n = kw * 32 + co (96)][4 floats]
-  static constexpr int W_BYTES = 9 * W_PAIR_BYTES;                           // 82944 for CI = 24
-  static constexpr int STAGES = 8;                                           // ring of depth planes: 3 in use, 5 in flight
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 256 + 128;
+  static constexpr int STAGE_BYTES = kFPlaneBytes;                           // one depth plane of the halo
+  static constexpr int W_PAIR_BYTES = NF * 128;                              // B of one (kd, kh): [n = kw * 32 + co (96)][32 ci] rows of 128 B
+  static constexpr int W_BYTES = 9 * W_PAIR_BYTES;                           // 110592
+  static constexpr int STAGES = 5;                                           // ring of depth planes: 3 in use, 2 in flight
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 256 + 1024;
 };
+
+// K-major operand in the 128-byte swizzle: rows of 128 B (32 floats of K), 8-row atoms of 1024 B, 16-byte chunk c of row r at chunk
+// c ^ (r % 8); a k-step of 8 floats is +32 B on the start address.  (The no-swizzle canonical layout -- chunk planes
+// [ci / 4][voxel][4 floats], six 4-channel TMA boxes per plane -- was the first version of this kernel and runs the MMAs at exactly
+// the same rate, ~100 clocks per 128 x 96 x 8; the swizzled form needs one TMA per plane instead of six.)
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t addr)
+{
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 
 // x [N, D, H, W, CI] through the tensor map; wg [27][CO][CI] (tap-major; for the input gradient: flipped taps, transposed channels);
 // y [N, D, H, W, CO].  CI % 8 == 0, CO % 4 == 0, CO <= 32.
 template <int CI>
 __global__ void __launch_bounds__(kThreadsConv, 1)
-conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restrict__ wg, float *__restrict__ y, int N, int D, int H, int W, int CO)
+conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restrict__ wg, float *__restrict__ y, int N, int D, int H, int W, int CO,
+                 int diag)   // diag (conv3d_tc_debug_mode, timing experiments only): 1 = epilogue does not read / store, 2 = no MMAs, 4 = no stores
 {
   using C = ConvCfg<CI>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wbase = base + C::STAGES * C::STAGE_BYTES;
   const uint32_t bars = wbase + C::W_BYTES;
   constexpr int R = C::STAGES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (R + s); };
   auto tfull = [&](int a) { return bars + 8u * (2 * R + a); };
-  auto tempty = [&](int a) { return bars + 8u * (2 * R + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * R + 4);
+  auto tempty = [&](int a) { return bars + 8u * (2 * R + NACC + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * R + 2 * NACC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // weights -> shared memory, B operand of the tap pair a = kd * 3 + kh: [k-chunk kc][n = kw * 32 + co][4 floats]
-  //   = wg[a * 3 + kw][co][4 kc .. 4 kc + 3], rows co >= CO zero
-  for (int i = threadIdx.x; i < 9 * C::CHUNKS * NF; i += kThreadsConv) {
-    const int n = i % NF, kc = (i / NF) % C::CHUNKS, a = i / (NF * C::CHUNKS);
+  // weights -> shared memory, B operand of the tap pair a = kd * 3 + kh: row n = kw * 32 + co holds wg[a * 3 + kw][co][0 .. CI) and
+  // zeros up to 32 channels, 16-byte chunks swizzled; rows co >= CO zero
+  for (int i = threadIdx.x; i < 9 * NF * 8; i += kThreadsConv) {
+    const int c = i % 8, n = (i / 8) % NF, a = i / (8 * NF);
     const int kw = n / NPAD, co = n % NPAD;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (co < CO) {
-      const float4 g = __ldg(reinterpret_cast<const float4 *>(wg + ((long long)(a * 3 + kw) * CO + co) * CI + 4 * kc));
+    if (co < CO && 4 * c < CI) {
+      const float4 g = __ldg(reinterpret_cast<const float4 *>(wg + ((long long)(a * 3 + kw) * CO + co) * CI + 4 * c));
       v = make_float4(to_tf32(g.x), to_tf32(g.y), to_tf32(g.z), to_tf32(g.w));
     }
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    const uint32_t dst = wbase + (uint32_t)(a * C::W_PAIR_BYTES + n * 128 + ((c ^ (n & 7)) << 4));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < R; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy weight stores must be visible to the tensor core
@@ -135,10 +146,8 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
         for (int p = 0; p < seg + 2; ++p, ++g) {
           const uint32_t slot = g % R, par = (g / R) & 1u;
           mbar_wait(empty(slot), par ^ 1u);
-          mbar_expect_tx(full(slot), C::CHUNKS * kFPlaneBytes);
-#pragma unroll
-          for (int c = 0; c < C::CHUNKS; ++c)
-            tma_load_5d(base + slot * C::STAGE_BYTES + c * kFPlaneBytes, &tmX, full(slot), 4 * c, iw * FWO - 1, ih * FTH - 1, d0 - 1 + p, n);
+          mbar_expect_tx(full(slot), kFPlaneBytes);
+          tma_load_5d(base + slot * C::STAGE_BYTES, &tmX, full(slot), 0, iw * FWO - 1, ih * FTH - 1, d0 - 1 + p, n);
         }
       }
     }
@@ -148,7 +157,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int as = 0;
       uint32_t aphase = 0, g0 = 0;
-      const uint64_t db0 = desc_noswizzle(wbase, NF * 16, 128);
+      const uint64_t db0 = desc_k_sw128(wbase);
       for (long long t = blockIdx.x; t < items; t += gridDim.x) {
         int iw, ih, d0, seg, n;
         item_coords(t, iw, ih, d0, seg, n);
@@ -164,20 +173,17 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
           const uint32_t acc = tmem_base + (uint32_t)(as * NF);
           // One thread issues every MMA of a tile, so the issue loop must be cheap: one descriptor per depth plane of the ring and
           // per tile, then every (kh, k-step) only adds a compile-time constant to the 14-bit start-address field (all shared-memory
-          // addresses are < 256 KB, so the field never carries into the LBO field).
-          //   A: rows (h, wi) 16 B apart (a tile row is two 8-row groups, 128 B apart), second 4-channel chunk one chunk plane further
-          //   B: rows (n) 16 B apart, 8-row groups 128 B apart, second k-chunk NF * 16 B further
+          // addresses are < 256 KB, so the field never carries into the LBO field): kh = 16 rows = two swizzle atoms, k-step = 32 B.
           uint64_t da[3];
 #pragma unroll
-          for (int kd = 0; kd < 3; ++kd) da[kd] = desc_noswizzle(base + ((g0 + j + kd) % R) * C::STAGE_BYTES, kFPlaneBytes, 128);
+          for (int kd = 0; kd < 3; ++kd) da[kd] = desc_k_sw128(base + ((g0 + j + kd) % R) * C::STAGE_BYTES);
 #pragma unroll
           for (int a = 0; a < 9; ++a) {
-            constexpr int kA16 = 2 * kFPlaneBytes / 16, kB16 = 2 * NF;                        // k-step strides in 16-byte units
-            const uint32_t a16 = (uint32_t)((a % 3) * FWI);                                   // kh offset inside the plane, 16-byte units
+            const uint32_t a16 = (uint32_t)((a % 3) * FWI * 128 / 16);
             const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
 #pragma unroll
             for (int s = 0; s < CI / 8; ++s)
-              umma_tf32(acc, da[a / 3] + (a16 + (uint32_t)s * kA16), db0 + (b16 + (uint32_t)s * kB16), idesc, (a | s) != 0 ? 1u : 0u);
+              if (!(diag & 2)) umma_tf32(acc, da[a / 3] + (a16 + (uint32_t)(2 * s)), db0 + (b16 + (uint32_t)(2 * s)), idesc, (a | s) != 0 ? 1u : 0u);
           }
           umma_commit(tfull(as));
           umma_commit(empty((g0 + j) % R));                        // plane d - 1 is not needed again
@@ -185,7 +191,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
             umma_commit(empty((g0 + j + 1) % R));
             umma_commit(empty((g0 + j + 2) % R));
           }
-          if (++as == 2) { as = 0; aphase ^= 1u; }
+          if (++as == NACC) { as = 0; aphase ^= 1u; }
         }
         g0 += (uint32_t)(seg + 2);
       }
@@ -203,6 +209,12 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       for (int j = 0; j < seg; ++j) {
         mbar_wait(tfull(as), aphase);
         tc_fence_after();
+        if (diag & 1) {
+          tc_fence_before();
+          mbar_arrive(tempty(as));
+          if (++as == NACC) { as = 0; aphase ^= 1u; }
+          continue;
+        }
         float v[32], v1[32], v2[32];
         const uint32_t tacc = tmem_base + (uint32_t)(as * NF) + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(tacc, v);
@@ -213,13 +225,13 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
 #pragma unroll
         for (int c = 0; c < 32; ++c)                               // y[j] = P_0[j] + P_1[j + 1] + P_2[j + 2] (lanes j + 1, j + 2 of the same tile row)
           v[c] += __shfl_down_sync(0xffffffffu, v1[c], 1) + __shfl_down_sync(0xffffffffu, v2[c], 2);
-        if (store) {
+        if (store && !(diag & 4)) {
           float *dst = y + ((((long long)n * D + d0 + j) * H + h) * W + w) * CO;
 #pragma unroll
           for (int c = 0; c < 32; c += 4)
-            if (c < CO) __stcs(reinterpret_cast<float4 *>(dst + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+            if (c < CO) *reinterpret_cast<float4 *>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == NACC) { as = 0; aphase ^= 1u; }
       }
     }
   }
@@ -228,7 +240,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
