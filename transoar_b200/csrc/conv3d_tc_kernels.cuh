@@ -60,6 +60,17 @@ constexpr int NACC = 4;                         // TMEM accumulators (4 x 96 col
 constexpr int DSEG = 40;                        // output planes a CTA marches through per work item (2 extra halo planes per item)
 static_assert(kFPlaneBytes % 1024 == 0 && FTH * FWI == 128 && (FWI * 128) % 1024 == 0, "tile geometry / swizzle atom alignment");
 
+// One lane of a converged warp.  The MMA issuer runs its loop with the WHOLE warp converged and only the tcgen05 instructions under
+// this predicate: every operand (descriptors, TMEM addresses, barrier addresses) is then warp-uniform for the compiler and lives in
+// uniform registers.  Under `if (lane == 0)` the same values count as divergent and every MMA pays a vector-to-uniform "waterfall"
+// (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~12 instructions) -- which, not the tensor pipe, set the pace of this kernel's MMA chain.
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <int CI> struct ConvCfg {
   static constexpr int STAGE_BYTES = kFPlaneBytes;                           // one depth plane of the halo
   static constexpr int W_PAIR_BYTES = NF * 128;                              // B of one (kd, kh): [n = kw * 32 + co (96)][32 ci] rows of 128 B
@@ -95,7 +106,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
   auto tfull = [&](int a) { return bars + 8u * (2 * R + a); };
   auto tempty = [&](int a) { return bars + 8u * (2 * R + NACC + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * R + 2 * NACC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for the compiler
 
   // weights -> shared memory, B operand of the tap pair a = kd * 3 + kh: row n = kw * 32 + co holds wg[a * 3 + kw][co][0 .. CI) and
   // zeros up to 32 channels, 16-byte chunks swizzled; rows co >= CO zero
@@ -152,9 +163,10 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // M = 128, N = 96, both operands K-major, TF32 in, fp32 out
+    {
+      // M = 128, N = 96, both operands K-major, TF32 in, fp32 out.  The whole warp walks the loop (see elect_one).
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int as = 0;
       uint32_t aphase = 0, g0 = 0;
       const uint64_t db0 = desc_k_sw128(wbase);
@@ -170,27 +182,30 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restric
           const uint32_t gn = g0 + j + 2;
           mbar_wait(full(gn % R), (gn / R) & 1u);
           tc_fence_after();
-          const uint32_t acc = tmem_base + (uint32_t)(as * NF);
-          // One thread issues every MMA of a tile, so the issue loop must be cheap: one descriptor per depth plane of the ring and
-          // per tile, then every (kh, k-step) only adds a compile-time constant to the 14-bit start-address field (all shared-memory
-          // addresses are < 256 KB, so the field never carries into the LBO field): kh = 16 rows = two swizzle atoms, k-step = 32 B.
+          const uint32_t acc = tmem_u + (uint32_t)(as * NF);
+          // One descriptor per depth plane of the ring and per tile, then every (kh, k-step) only adds a compile-time constant to the
+          // 14-bit start-address field (all shared-memory addresses are < 256 KB, so the field never carries into the LBO field):
+          // kh = 16 rows = two swizzle atoms, k-step = 32 B.
           uint64_t da[3];
 #pragma unroll
           for (int kd = 0; kd < 3; ++kd) da[kd] = desc_k_sw128(base + ((g0 + j + kd) % R) * C::STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int a = 0; a < 9; ++a) {
-            const uint32_t a16 = (uint32_t)((a % 3) * FWI * 128 / 16);
-            const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
+            for (int a = 0; a < 9; ++a) {
+              const uint32_t a16 = (uint32_t)((a % 3) * FWI * 128 / 16);
+              const uint32_t b16 = (uint32_t)(a * (C::W_PAIR_BYTES / 16));
 #pragma unroll
-            for (int s = 0; s < CI / 8; ++s)
-              if (!(diag & 2)) umma_tf32(acc, da[a / 3] + (a16 + (uint32_t)(2 * s)), db0 + (b16 + (uint32_t)(2 * s)), idesc, (a | s) != 0 ? 1u : 0u);
+              for (int s = 0; s < CI / 8; ++s)
+                if (!(diag & 2)) umma_tf32(acc, da[a / 3] + (a16 + (uint32_t)(2 * s)), db0 + (b16 + (uint32_t)(2 * s)), idesc, (a | s) != 0 ? 1u : 0u);
+            }
+            umma_commit(tfull(as));
+            umma_commit(empty((g0 + j) % R));                        // plane d - 1 is not needed again
+            if (j == seg - 1) {                                      // end of the segment: its last two planes as well
+              umma_commit(empty((g0 + j + 1) % R));
+              umma_commit(empty((g0 + j + 2) % R));
+            }
           }
-          umma_commit(tfull(as));
-          umma_commit(empty((g0 + j) % R));                        // plane d - 1 is not needed again
-          if (j == seg - 1) {                                      // end of the segment: its last two planes as well
-            umma_commit(empty((g0 + j + 1) % R));
-            umma_commit(empty((g0 + j + 2) % R));
-          }
+          __syncwarp();
           if (++as == NACC) { as = 0; aphase ^= 1u; }
         }
         g0 += (uint32_t)(seg + 2);
