@@ -64,13 +64,7 @@ static_assert(kFPlaneBytes % 1024 == 0 && FTH * FWI == 128 && (FWI * 128) % 1024
 // this predicate: every operand (descriptors, TMEM addresses, barrier addresses) is then warp-uniform for the compiler and lives in
 // uniform registers.  Under `if (lane == 0)` the same values count as divergent and every MMA pays a vector-to-uniform "waterfall"
 // (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~12 instructions) -- which, not the tensor pipe, set the pace of this kernel's MMA chain.
-__device__ __forceinline__ bool elect_one()
-{
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
+// (tcgemm::elect_one, tc_gemm_kernels.cuh)
 template <int CI> struct ConvCfg {
   static constexpr int STAGE_BYTES = kFPlaneBytes;                           // one depth plane of the halo
   static constexpr int W_PAIR_BYTES = NF * 128;                              // B of one (kd, kh): [n = kw * 32 + co (96)][32 ci] rows of 128 B

@@ -114,6 +114,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -212,7 +219,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
   auto tfull = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
   auto tempty = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for the compiler
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;          // rank 0 = leader: owns the "full" / "tmem empty" barriers, issues the MMAs
 
   if (warp == 0 && lane == 0) {
@@ -277,8 +284,11 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
       if (p.prof != nullptr) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop and one elected lane issues: descriptors, TMEM and barrier addresses are then warp-uniform for
+    // the compiler (uniform registers); under `if (lane == 0)` every tcgen05.mma paid a vector-to-uniform waterfall of ~12 instructions.
+    if (rank == 0) {
       constexpr uint32_t idesc = instr_desc<BN, A_MN, B_MN, CTAS>();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       unsigned long long t_full = 0, t_tempty = 0;
@@ -288,24 +298,28 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
         const int kb0 = sp * p.rb_per_split, kb1 = min(r_blocks, kb0 + p.rb_per_split);
         mbar_wait_timed(tempty(as), aphase ^ 1u, p.prof, t_tempty);   // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(as * BN);
+        const uint32_t acc = tmem_u + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_timed(full(stage), phase, p.prof, t_full);
           tc_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = smem_desc<A_MN>(sa + k * kstep_bytes<A_MN>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
-            if (CTAS == 2) umma_tf32_pair(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = smem_desc<A_MN>(sa + k * kstep_bytes<A_MN>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
+              if (CTAS == 2) umma_tf32_pair(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CTAS == 2) umma_commit_pair(empty(stage)); else umma_commit(empty(stage));   // smem slot(s) free once these MMAs have read them
           }
-          if (CTAS == 2) umma_commit_pair(empty(stage)); else umma_commit(empty(stage));   // smem slot(s) free once these MMAs have read them
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (CTAS == 2) umma_commit_pair(tfull(as)); else umma_commit(tfull(as));           // accumulator complete (in both CTAs)
+        if (elect_one()) { if (CTAS == 2) umma_commit_pair(tfull(as)); else umma_commit(tfull(as)); }   // accumulator complete (in both CTAs)
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      if (p.prof != nullptr) {
+      if (p.prof != nullptr && lane == 0) {
         p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty;
         p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
       }
