@@ -339,7 +339,7 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (2 + s); };
   const uint32_t done = bars + 32, tmem_slot = bars + 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(done, 1);
@@ -374,9 +374,11 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // The whole warp walks the loop, one elected lane issues (tcgemm::elect_one: operands stay in uniform registers).
       // M = 128 (kw * 32 + ci), N = 32 * (number of dy rows paired with this x row), both operands MN-major (bits 15 / 16), TF32 in, fp32 out
       constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0, later = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -384,6 +386,7 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tc_fence_after();
         const uint32_t sx = base + stage * kWgStageBytes;
         const uint64_t dx0 = desc_mn_sw32(sx), dy0 = desc_mn_sw32(sx + kWgXBytes, TW * 128);
+        if (elect_one()) {
         // x row r of plane kd meets dy rows hh = r - kh (kh = 0..2, 0 <= hh < TH) in ONE MMA: the dy rows are consecutive N slabs, their
         // products land in accumulator kd at column block 2 - kh.  Row 2 goes first: it is the first to touch all three blocks at once,
         // so on the first tile it alone carries accumulate = 0.
@@ -394,15 +397,18 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const int r = i == 0 ? 2 : (i <= 2 ? i - 1 : i);
             const int hh_lo = r - 2 > 0 ? r - 2 : 0, hh_hi = r < TH - 1 ? r : TH - 1, cnt = hh_hi - hh_lo + 1, kh_max = r - hh_lo;
             const uint32_t xrow16 = (uint32_t)(((kd * HH + r) * HW) * (128 / 16));
-            umma_tf32(tmem_base + (uint32_t)(kd * 96 + (2 - kh_max) * 32), dx0 + xrow16, dy0 + (uint32_t)(hh_lo * TW * (128 / 16)),
+            umma_tf32(tmem_u + (uint32_t)(kd * 96 + (2 - kh_max) * 32), dx0 + xrow16, dy0 + (uint32_t)(hh_lo * TW * (128 / 16)),
                       idesc0 | ((uint32_t)((32 * cnt) >> 3) << 17), (i | later) != 0 ? 1u : 0u);
           }
         }
         umma_commit(empty(stage));
+        }
+        __syncwarp();
         later = 1u;
         if (++stage == 2) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done);
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
     }
   } else {
     // after the last MMA: this CTA's partial sums, accumulator a rows m = kw * 32 + ci, columns co
