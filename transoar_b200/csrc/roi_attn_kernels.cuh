@@ -233,46 +233,6 @@ combine_kernel(const float *__restrict__ part, int rows, int Nq, int H, int S, f
   if (lane == 0) lse[row] = M + __logf(L);
 }
 
-__device__ __forceinline__ void red_add_v4(float *p, const float4 &a)
-{
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-}
-
-// dst[tok][c] += sum_r W[r][tok] * A[r][c] for the TK tokens of the chunk (dV: W = P, A = dO; dK: W = dS, A = Q).  Thread t owns tokens
-// 2 (t / 4), + 1 and the float4 columns t % 4 + 4 j: per row one 8-byte and HD/16 16-byte shared-memory loads feed 8 * HD/16 FMAs, and
-// the results leave as 128-bit reductions (the boxes of different organs overlap, hence atomics).
-template <int HD>
-__device__ __forceinline__ void scatter_chunk(const float (*sW)[TK + 4], const float (*sA)[HD + 4], const int *sTok, float *dst, long long row_stride, int t)
-{
-  constexpr int CPT = HD / 16;
-  const int tg = t / 4, cl = t % 4;
-  float4 acc[2][CPT];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[i][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int r = 0; r < TQ; ++r) {
-    const float2 w = *reinterpret_cast<const float2 *>(&sW[r][tg * 2]);
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const float4 a = *reinterpret_cast<const float4 *>(&sA[r][4 * (cl + 4 * c)]);
-      acc[0][c].x = fmaf(w.x, a.x, acc[0][c].x); acc[0][c].y = fmaf(w.x, a.y, acc[0][c].y);
-      acc[0][c].z = fmaf(w.x, a.z, acc[0][c].z); acc[0][c].w = fmaf(w.x, a.w, acc[0][c].w);
-      acc[1][c].x = fmaf(w.y, a.x, acc[1][c].x); acc[1][c].y = fmaf(w.y, a.y, acc[1][c].y);
-      acc[1][c].z = fmaf(w.y, a.z, acc[1][c].z); acc[1][c].w = fmaf(w.y, a.w, acc[1][c].w);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int tok = sTok[tg * 2 + i];
-    if (tok >= 0) {
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) red_add_v4(dst + (long long)tok * row_stride + 4 * (cl + 4 * c), acc[i][c]);
-    }
-  }
-}
-
 // Backward.  grid = (Gn * S, H, B).  P = exp(S - lse), dV += P^T dO, dP = dO V^T, dS = P * (dP - D), D = rowsum(dO * O),
 // dQ += dS K, dK += dS^T Q.  dk / dv are accumulated with atomics (boxes of different organs overlap); dq is exclusive.
 template <int HD>
@@ -392,34 +352,83 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
     }
     __syncthreads();
     // dV[tok][c] += sum_r P[r][tok] * dO[r][c]
-    scatter_chunk<HD>(sP, sdO, sTok, dv + (long long)b * Nkv * HHD + h * HD, HHD, t);
+    {
+      // 64 tokens x HD channels; thread handles tokens tg*4..+3 (tg = t/8 in 0..15) and channels (t%8) + 8*i (i < HD/8)
+      const int tg = t / 8, cl = t % 8;
+      float acc[4][HD / 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) acc[i][c] = 0.f;
+      for (int r = 0; r < TQ; ++r) {
+        float dv_[HD / 8];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) dv_[c] = sdO[r][cl + 8 * c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p = sP[r][tg * 4 + i];
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) acc[i][c] = fmaf(p, dv_[c], acc[i][c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = sTok[tg * 4 + i];
+        if (tok >= 0) {
+          float *dst = dv + ((long long)b * Nkv + tok) * HHD + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) atomicAdd(dst + cl + 8 * c, acc[i][c]);
+        }
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) sP[rg * 4 + i][cg + 16 * j] = ds[i][j];
     __syncthreads();
-    // dQ += dS K (four tokens per step: dS rows come as float4)
-#pragma unroll 2
-    for (int kk = 0; kk < TK; kk += 4) {
-      float4 d4[4];
+    // dQ += dS K
+#pragma unroll 4
+    for (int kk = 0; kk < TK; ++kk) {
+      float kv[OC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d4[i] = *reinterpret_cast<const float4 *>(&sP[rg * 4 + i][kk]);
+      for (int c = 0; c < OC; ++c) kv[c] = sK[kk][cg + 16 * c];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float kv[OC];
+      for (int i = 0; i < 4; ++i) {
+        const float d_ = sP[rg * 4 + i][kk];
 #pragma unroll
-        for (int c = 0; c < OC; ++c) kv[c] = sK[kk + u][cg + 16 * c];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float d_ = u == 0 ? d4[i].x : (u == 1 ? d4[i].y : (u == 2 ? d4[i].z : d4[i].w));
-#pragma unroll
-          for (int c = 0; c < OC; ++c) dqa[i][c] = fmaf(d_, kv[c], dqa[i][c]);
-        }
+        for (int c = 0; c < OC; ++c) dqa[i][c] = fmaf(d_, kv[c], dqa[i][c]);
       }
     }
     // dK[tok][c] += sum_r dS[r][tok] * Q[r][c]
-    scatter_chunk<HD>(sP, sQ, sTok, dk + (long long)b * Nkv * HHD + h * HD, HHD, t);
+    {
+      const int tg = t / 8, cl = t % 8;
+      float acc[4][HD / 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) acc[i][c] = 0.f;
+      for (int r = 0; r < TQ; ++r) {
+        float qv[HD / 8];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) qv[c] = sQ[r][cl + 8 * c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d_ = sP[r][tg * 4 + i];
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) acc[i][c] = fmaf(d_, qv[c], acc[i][c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = sTok[tg * 4 + i];
+        if (tok >= 0) {
+          float *dst = dk + ((long long)b * Nkv + tok) * HHD + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) atomicAdd(dst + cl + 8 * c, acc[i][c]);
+        }
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
