@@ -16,8 +16,10 @@ Multi-GPU   : one process per GPU, volumes sharded by rank (weak scaling); the o
               the timed region, against the measured HBM peak.
 `msda3d_op` : the operator alone (forward + gradient of both refinement layers) incl. the reference's own CUDA op on the same
               inputs; `tc_gemm`, `roi_attention`, `instnorm_relu`: the other hand-written kernels of the path.
-`cpu_baseline` / `--impl reference`: the reference's CPU route of the same training step (oracle/model_oracle.py) on the
-              host cores, on a bounded sample (a smaller volume, time scaled by the voxel ratio).
+`ref_gpu_model`: the UNMODIFIED reference model (baseline/_ref) with its OWN compiled CUDA op (oracle/_ref) running the same
+              training step on the same GPU in the same run -- the comparator BASELINE.json's north_star names.
+`cpu_baseline` / `--impl reference`: the unmodified reference's use_cuda=False route of the same training step on the host
+              cores (oracle/reference_model.py drives baseline/_ref), one real 160x160x256 volume per step, nothing extrapolated.
 """
 from __future__ import annotations
 
@@ -39,7 +41,6 @@ BATCH = 2             # config/attn_fpn_foc_dec_visceral.yaml:25  `batch_size: 2
 VOLUME = (160, 160, 256)
 GEOM = "visceral_refine"
 DIST = "B"
-CPU_SAMPLE_SHAPES = [(32, 32, 64), (64, 64, 128), (96, 96, 160), (128, 128, 192), (160, 160, 256)]   # all divisible by 32 (five stride-2 stages)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -154,43 +155,54 @@ def workload_config():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's CPU route of the training step (oracle/model_oracle.py), bounded sample
+# CPU arm: the UNMODIFIED reference (baseline/_ref, installed by tools/install_reference.py) through its use_cuda=False route on the
+# host cores -- transoar.models.transoarnet.TransoarNet + build_criterion + the AdamW step of scripts/train.py, at the REAL volume size
+# (one 160x160x256 volume per step; no crop, no scaling).  If the reference is not installed, the port in oracle/model_oracle.py runs.
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_step_times(shape, steps, warmup, threads):
-    import torch
-    from oracle.model_oracle import CpuTrainStep
-    from transoar_b200.engine import synthetic_targets, visceral_train_config
-    cfg = visceral_train_config()
-    ts = CpuTrainStep(cfg, shape, threads=threads)
-    x = torch.rand(1, 1, *shape, generator=torch.Generator().manual_seed(1))
-    tg = synthetic_targets(cfg, 1, 0, "cpu")
-    times = [ts.step(x, tg)[0] for _ in range(warmup + steps)]
-    return times[warmup:]
+CPU_STEP_VOLUMES = 1          # volumes per CPU step: the reference's host step at batch 2 needs > 50 GB and a minute per step
 
 
-def cpu_sample_shape(budget_s, threads):
-    """Largest sample volume whose step is expected to fit `budget_s` (probe the smallest, scale by voxels)."""
-    vox = lambda s: s[0] * s[1] * s[2]
-    t = cpu_step_times(CPU_SAMPLE_SHAPES[1], 1, 1, threads)[0]
-    per_voxel = t / vox(CPU_SAMPLE_SHAPES[1])
-    best = CPU_SAMPLE_SHAPES[0]
-    for s in CPU_SAMPLE_SHAPES:
-        if per_voxel * vox(s) <= budget_s:
-            best = s
-    return best
+class CpuArm:
+    def __init__(self, threads):
+        import torch
+        torch.set_num_threads(threads)
+        from oracle import reference_model as R
+        self.threads = torch.get_num_threads()
+        if R.available():
+            self.kind = "reference"
+            self.ts = R.ReferenceTrainStep("cpu", op=None, seed=0)
+            self.targets = R.list_targets(self.ts.config, CPU_STEP_VOLUMES, 0, "cpu")
+            self.what = ("UNMODIFIED reference (baseline/_ref: transoar.models.transoarnet.TransoarNet, build_criterion, AdamW of scripts/train.py:52-64, "
+                         "step of trainer.py:50-87 without autocast) through its use_cuda=False route (ms_deform_attn_core_pytorch)")
+        else:
+            from oracle.model_oracle import CpuTrainStep
+            from transoar_b200.engine import synthetic_targets, visceral_train_config
+            cfg = visceral_train_config()
+            self.kind = "port"
+            self._port = CpuTrainStep(cfg, VOLUME, threads=threads)
+            self.targets = synthetic_targets(cfg, CPU_STEP_VOLUMES, 0, "cpu")
+            self.ts = None
+            self.what = "port of the reference's use_cuda=False route (oracle/model_oracle.py; baseline/_ref not installed)"
+        self.x = torch.rand(CPU_STEP_VOLUMES, 1, *VOLUME, generator=torch.Generator().manual_seed(1))
 
+    def step(self):
+        t0 = time.perf_counter()
+        if self.ts is not None:
+            self.ts.step(self.x, self.targets)
+        else:
+            self._port.step(self.x, self.targets)
+        return time.perf_counter() - t0
 
-def cpu_value(shape, sec):
-    """volumes/s at full size: one sample step covers vox(shape)/vox(VOLUME) of a volume."""
-    frac = shape[0] * shape[1] * shape[2] / (VOLUME[0] * VOLUME[1] * VOLUME[2])
-    return frac / sec
+    def close(self):
+        if self.ts is not None:
+            from oracle import reference_model as R
+            R.leave_cpu_mode()
+        self.ts = self._port = None
 
-
-def cpu_sample_text(shape, sec, steps):
-    frac = shape[0] * shape[1] * shape[2] / (VOLUME[0] * VOLUME[1] * VOLUME[2])
-    return (f"whole training step (fwd + criterion + bwd + AdamW) of the same model through the reference's use_cuda=False route "
-            f"(F.grid_sample, nn.InstanceNorm3d, dense masked attention; oracle/model_oracle.py) on one {shape[0]}x{shape[1]}x{shape[2]} volume "
-            f"= {frac:.4f} of a 160x160x256 volume's voxels: {sec:.2f} s per step (mean of {steps}); time scaled linearly by voxels")
+    def sample_text(self, times, warm):
+        return (f"{self.what}; whole training step (fwd + matcher + losses + bwd + AdamW) on {CPU_STEP_VOLUMES} synthetic "
+                f"{VOLUME[0]}x{VOLUME[1]}x{VOLUME[2]} volume per step at the real size (no crop, no extrapolation), {self.threads} threads: "
+                f"{sum(times) / len(times):.2f} s per step (mean of {len(times)} timed step(s) after {warm} warm-up)")
 
 
 _REAL_STDOUT = None
@@ -213,25 +225,37 @@ def emit(line):
 
 
 def run_reference_arm(args):
-    import torch
+    """`--impl reference`: rank 0 alone; K timed steps after W warm-up steps of the reference's CPU step at the real volume size.  A step
+    takes 20-60 s of host time, so the run is bounded by a wall budget (TRANSOAR_REF_BUDGET_S, default 780 s): when K + W steps would not
+    fit, warm-up is cut to one step first and then the timed steps; `steps` / `warmup` in the line are what was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    per_step = 150.0 / max(1, args.steps + args.warmup)
-    shape = cpu_sample_shape(per_step, cores)
-    times = cpu_step_times(shape, args.steps, args.warmup, cores)
+    budget = float(os.environ.get("TRANSOAR_REF_BUDGET_S", "780"))
+    t_start = time.perf_counter()
+    arm = CpuArm(os.cpu_count() or 1)
+    first = arm.step()                                       # always a warm-up step (allocator, thread pool)
+    warm_done, times = 1, []
+    left = lambda: budget - (time.perf_counter() - t_start)
+    want_warm = max(args.warmup, 1)
+    if first * (want_warm - 1 + args.steps) > left():        # cannot afford the requested warm-up: keep the one already done
+        want_warm = 1
+    while warm_done < want_warm:
+        arm.step()
+        warm_done += 1
+    while len(times) < args.steps and (len(times) < 2 or left() > 1.1 * max(times)):
+        times.append(arm.step())
     sec = sum(times) / len(times)
-    value = cpu_value(shape, sec)
+    value = CPU_STEP_VOLUMES / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": 1e3 * sec,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": cpu_sample_text(shape, sec, len(times))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_text(times, warm_done)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "volumes_per_step": CPU_STEP_VOLUMES, "wall_budget_s": budget,
+        "note": "host-only arm: one process, all host cores, independent of --gpus (at N > 1 only rank 0 runs it)",
     }
     emit(line)
     return 0
@@ -394,6 +418,57 @@ def measure_kernels(dev, rank):
     return out
 
 
+def measure_reference_gpu_model(dev, rank, steps=6, warm=3):
+    """The comparator BASELINE.json's north_star names: the UNMODIFIED reference model (baseline/_ref) with its OWN compiled CUDA op
+    (oracle/_ref, bound as `MSDA` -- oracle/reference_model.py) running the same training step on this GPU: visceral yaml with
+    use_decoder_attn / use_cuda on, batch 2, same synthetic volumes and targets, fp32 + TF32 (torch 1.10's default, the reference's pin;
+    no autocast: the reference op cannot run under it).  Three variants: cuDNN as scripts/train.py:113-114 sets it
+    (benchmark off, deterministic on), cuDNN autotuned (the favourable setting; our arm autotunes too), and the same unmodified model
+    on THIS repository's op through install_into_reference().  Every step ends with the reference's own `.item()` host read."""
+    import torch
+    from oracle import msda3d_oracle as O
+    from oracle import reference_model as R
+    if not R.available():
+        return {"unavailable": "baseline/_ref not installed (python tools/install_reference.py in the build container)"}
+    if not O.refcuda_available():
+        return {"unavailable": "oracle/_ref/libmsda3d_refcuda.so not built"}
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    gen = torch.Generator().manual_seed(100 + volume_ids(0, rank, 1)[0])
+    vols = [torch.rand(BATCH, 1, *VOLUME, generator=gen).to(dev) for _ in range(2)]
+    out = {"what": "unmodified reference TransoarNet + TransoarCriterion + AdamW (baseline/_ref) on cuda, visceral yaml with use_decoder_attn / use_cuda = True, "
+                   f"batch {BATCH} x {VOLUME[0]}x{VOLUME[1]}x{VOLUME[2]}, fp32 + TF32, whole training step, CUDA events, {warm} warm-up + {steps} timed steps",
+           "variants": {}}
+    try:
+        for label, op, bench_flag, det in (("reference_op_cudnn_as_shipped", "reference", False, True),
+                                           ("reference_op_cudnn_autotuned", "reference", True, False),
+                                           ("this_repo_op_in_reference_model", "ours", True, False)):
+            torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = bench_flag, det
+            ts = R.ReferenceTrainStep(dev, op=op, seed=0)
+            tgs = [R.list_targets(ts.config, BATCH, 1000 * rank + i, dev) for i in range(2)]
+            for i in range(warm):
+                ts.step(vols[i % 2], tgs[i % 2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                loss = ts.step(vols[i % 2], tgs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["variants"][label] = {"ms_per_step": ms, "volumes_per_s": BATCH / (ms / 1e3), "final_loss": loss,
+                                      "cudnn_benchmark": bench_flag, "cudnn_deterministic": det, "op": op}
+            del ts
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = saved
+    best = max((v["volumes_per_s"] for k, v in out["variants"].items() if k.startswith("reference_op")), default=None)
+    out["volumes_per_s"] = best
+    out["volumes_per_s_is"] = "the faster of the two reference_op variants"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -406,6 +481,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (operator alone, GEMM, RoI attention, InstanceNorm)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-model-on-GPU comparator (ref_gpu_model)")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu --profile-from-start off: warm up, bracket ONE training step with cudaProfilerStart/Stop, exit")
@@ -452,6 +528,7 @@ def main():
     use_graph = not (args.no_graph or args.profile_one_step)
     eager_warm = 4 if use_graph else 0                     # eager steps before the capture; the msda3d kernels are timed in them
     ts = TrainStep(cfg, dev, world=world, graph=use_graph, graph_warmup=eager_warm)
+    torch.manual_seed(1 + 7919 * rank)                     # per-rank dropout streams (weights are already identical / broadcast)
     gen = torch.Generator().manual_seed(100 + volume_ids(0, rank, world)[0])
     n_sets = 2                                             # alternate between two resident batches
     vols_host = [torch.rand(BATCH, 1, *VOLUME, generator=gen).pin_memory() for _ in range(n_sets)]
@@ -575,16 +652,27 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- the reference's own model + its own compiled op on this GPU (rank 0, single-GPU runs only): the north-star comparator
+    if rank == 0 and world == 1 and not args.no_extras and not args.no_ref_gpu:
+        try:
+            extras["ref_gpu_model"] = measure_reference_gpu_model(dev, rank)
+            best = extras["ref_gpu_model"].get("volumes_per_s")
+            if best:
+                extras["vs_reference_gpu_model"] = {"value_over_reference": value / best, "e2e_over_reference": (e2e["value"] / best) if e2e else None,
+                                                    "reference_volumes_per_s": best,
+                                                    "what": "this arm's volumes/s divided by the unmodified reference model running its own compiled CUDA op on the same GPU, same run"}
+        except Exception as exc:
+            extras["ref_gpu_model"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU route of the same step, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        shape = cpu_sample_shape(12.0, cores)
-        times = cpu_step_times(shape, 2, 1, cores)
-        sec = sum(times) / len(times)
-        cpu_baseline = {"value": cpu_value(shape, sec), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": cpu_sample_text(shape, sec, len(times))}
+        arm = CpuArm(os.cpu_count() or 1)
+        times = [arm.step()]                                # ONE full-size step, no warm-up: 20-60 s of host time (bounded sample)
+        cpu_baseline = {"value": CPU_STEP_VOLUMES / times[0], "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
+                        "sample": arm.sample_text(times, 0)}
+        arm.close()
 
     if rank == 0:
         line = {

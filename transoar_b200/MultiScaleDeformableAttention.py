@@ -133,6 +133,10 @@ def fused_supported(value, reference_points, n_levels, n_points):
     if not (value.is_cuda and value.dtype == torch.float32 and reference_points.dtype == torch.float32 and reference_points.shape[-1] == 3
             and not torch.is_autocast_enabled()):
         return False
+    if reference_points.requires_grad and torch.is_grad_enabled():
+        # learnable reference points (Deformable-DETR decoders): the fused functions return no gradient for them, the unfused route
+        # propagates it through sampling_locations as the reference does
+        return False
     return bool(_lib.lib().msda3d_fused_supported(value.shape[3], n_levels, n_points)) and reference_points.shape[0] in (1, value.shape[0])
 
 

@@ -31,6 +31,19 @@ struct Group {
   int q0, nq, x1, y1, z1, x2, y2, z2;
 };
 
+// A group's box clamped to the key/value grid (X = Nkv / (Y*Z)): a box built for another feature-map shape can then never address a
+// token outside [0, Nkv) -- neither the forward's reads nor the backward's dk / dv reductions.  (The python module raises on such a
+// mismatch like the reference's `attn += mask` does; this is the memory-safety net underneath the C ABI.)
+__device__ __forceinline__ Group load_group(const int *__restrict__ groups, int gi, int X, int Y, int Z)
+{
+  const int *gp = groups + gi * 8;
+  Group g;
+  g.q0 = gp[0]; g.nq = gp[1];
+  g.x1 = max(gp[2], 0); g.y1 = max(gp[3], 0); g.z1 = max(gp[4], 0);
+  g.x2 = min(gp[5], X); g.y2 = min(gp[6], Y); g.z2 = min(gp[7], Z);
+  return g;
+}
+
 // token id of the j-th voxel of the box (z fastest, then y, then x), or -1 past the end
 __device__ __forceinline__ int box_token(const Group &g, int j, int Y, int Z)
 {
@@ -59,11 +72,7 @@ fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   __shared__ int sTok[TK];
 
   const int gi = blockIdx.x / S, split = blockIdx.x % S, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
-  Group g;
-  {
-    const int *gp = groups + gi * 8;
-    g.q0 = gp[0]; g.nq = gp[1]; g.x1 = gp[2]; g.y1 = gp[3]; g.z1 = gp[4]; g.x2 = gp[5]; g.y2 = gp[6]; g.z2 = gp[7];
-  }
+  const Group g = load_group(groups, gi, Nkv / (Y * Z), Y, Z);
   const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
   const long long HHD = (long long)H * HD;
   // this CTA's share of the box: chunks [c_beg, c_end) of TK tokens (S > 1: partial softmax state goes to `part`)
@@ -252,11 +261,7 @@ bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float
   __shared__ int sTok[TK];
 
   const int gi = blockIdx.x / S, split = blockIdx.x % S, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
-  Group g;
-  {
-    const int *gp = groups + gi * 8;
-    g.q0 = gp[0]; g.nq = gp[1]; g.x1 = gp[2]; g.y1 = gp[3]; g.z1 = gp[4]; g.x2 = gp[5]; g.y2 = gp[6]; g.z2 = gp[7];
-  }
+  const Group g = load_group(groups, gi, Nkv / (Y * Z), Y, Z);
   const int ntok = max(0, g.x2 - g.x1) * max(0, g.y2 - g.y1) * max(0, g.z2 - g.z1);
   const long long HHD = (long long)H * HD;
   const int nchunk = (ntok + TK - 1) / TK, cps = (nchunk + S - 1) / S;

@@ -51,6 +51,17 @@ def synthetic_targets(config, batch, seed, device):
     return dense_targets(targets, med.shape[0], device)
 
 
+def optimizer_param_groups(net, config):
+    """The reference's two AdamW groups in the reference's order (scripts/train.py:52-60): parameters whose name contains ``_backbone``
+    at ``lr_backbone``, everything else at ``lr``.  The three dead ``q_proj`` tensors of every FocusedAttn stay IN their
+    group although ``TrainStep`` freezes them for DDP: in the reference they have ``requires_grad=True`` and simply never receive a
+    gradient (AdamW skips a parameter whose ``.grad`` is None), so group sizes and parameter indices -- and therefore
+    ``optimizer.state_dict()`` / ``load_state_dict`` of a checkpoint -- are interchangeable with the reference in both directions."""
+    named = [(n, p) for n, p in net.named_parameters() if p.requires_grad or ".q_proj." in n]
+    return [{"params": [p for n, p in named if "_backbone" in n]},
+            {"params": [p for n, p in named if "_backbone" not in n], "lr": float(config["lr"])}]
+
+
 def all_reduce_gradients(parameters, world):
     """Average the gradients over the ranks through one flat bucket: one collective per step instead of DDP's per-bucket hooks, which
     is what lets the whole step sit in one CUDA graph (at 41 M parameters the bucket is 164 MB -- well under a millisecond over NVLink)."""
@@ -153,9 +164,7 @@ class TrainStep:
                     dist.broadcast(t, 0)
             self._averager = OverlappedGradientAverage(self.net, world)
         self.criterion = build_criterion(config).to(self.device)
-        named = [(n, p) for n, p in self.net.named_parameters() if p.requires_grad]
-        groups = [{"params": [p for n, p in named if "_backbone" in n]},
-                  {"params": [p for n, p in named if "_backbone" not in n], "lr": float(config["lr"])}]
+        groups = optimizer_param_groups(self.net, config)
         self.optim = torch.optim.AdamW(groups, lr=float(config["lr_backbone"]), weight_decay=float(config["weight_decay"]),
                                        capturable=self.graph, fused=True)
         self._staging = None

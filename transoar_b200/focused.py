@@ -156,6 +156,11 @@ class FocusedAttn(nn.Module):
         B, Nkv, C = k.shape
         Nq = q.shape[1]
         H = self.num_heads
+        if Nkv != self.grid_shape[0] * self.grid_shape[1] * self.grid_shape[2]:
+            # the reference fails here too: its [Nq, X*Y*Z] mask does not broadcast against [B, H, Nq, Nkv] (focused_decoder.py:243-245)
+            raise RuntimeError(f"FocusedAttn: {Nkv} key/value tokens, but the RoI boxes were built for a {self.grid_shape} feature map "
+                               f"({self.grid_shape[0] * self.grid_shape[1] * self.grid_shape[2]} tokens); pass the feature-map shape "
+                               "(config['neck_input_shape'] / FocusedDecoderLayer(input_shape=...))")
         kp = self.k_proj(k).reshape(B, Nkv, H, C // H)
         vp = self.v_proj(v).reshape(B, Nkv, H, C // H)
         qp = self.k_proj(q).reshape(B, Nq, H, C // H) * self.scale              # :235-236 (k_proj on the query: reference quirk)

@@ -102,6 +102,10 @@ def train(config, args):
     # to get reproducible results (train.py:108-115); identical initial weights on every rank
     torch.manual_seed(config["seed"]); np.random.seed(config["seed"]); random.seed(config["seed"])
     ts = TrainStep(config, device, world=world, graph=args.graph, cudnn_autotune=not args.deterministic)
+    if world > 1:
+        # weights are identical on every rank now (broadcast from rank 0); the dropout streams must not be: the hash seeds of the fused
+        # LayerNorm / FFN kernels are drawn from torch's CPU generator and ATen's dropout from the CUDA generator
+        torch.manual_seed(config["seed"] + 7919 * rank)
     scheduler = torch.optim.lr_scheduler.StepLR(ts.optim, config["lr_drop"])
     epoch, metric_max_val = 0, 0
     if args.resume is not None:
