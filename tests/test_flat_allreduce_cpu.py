@@ -63,14 +63,18 @@ def _overlap_worker(rank, world, port, out):
     log = []
     for step in range(3):
         x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * step + rank))
-        for p in net.parameters():
-            p.grad = None
+        avg.zero()
         avg.before_backward()
         net["head"](net["body"](net["stem"](x))).square().sum().backward()
         fired_in_backward = avg.fired
         avg.after_backward()
         log.append((fired_in_backward, [None if p.grad is None else p.grad.clone() for p in net.parameters()]))
+        # after the calibration step every gradient is a view into the one persistent flat buffer: no cat, no copy back
+        lo, hi = avg.flat.data_ptr(), avg.flat.data_ptr() + avg.flat.numel() * 4
+        assert all(lo <= p.grad.data_ptr() < hi for p in net.parameters() if p.grad is not None)
+        assert avg.flat.numel() == sum(p.numel() for n, p in net.named_parameters() if not n.startswith("unused"))
     assert avg.expected == 4                                             # body + head; the unused layer never gets a gradient
+    assert all(p.grad is None for p in net["unused"].parameters())       # ... and keeps grad None (AdamW skips it, as in the reference)
     assert [f for f, _ in log] == [False, True, True]                    # calibration step, then the early bucket fires inside backward
     if rank == 0:
         torch.save([g for _, g in log], out)
@@ -97,3 +101,19 @@ def test_two_bucket_average_fires_inside_backward_and_matches_the_mean(tmp_path)
             assert (a is None) == (b is None)
             if a is not None:
                 assert torch.allclose(a, b / 2, atol=1e-6)
+
+
+def test_dense_view_keeps_channels_last_strides():
+    from transoar_b200.engine import _dense_view
+    flat = torch.zeros(1000)
+    p = torch.nn.Parameter(torch.randn(4, 3, 2, 3, 3).contiguous(memory_format=torch.channels_last_3d))
+    v = _dense_view(flat, 10, p)
+    assert v.shape == p.shape and v.stride() == p.stride() and v.data_ptr() == flat.data_ptr() + 40
+    v.copy_(p.detach())
+    assert torch.equal(v, p.detach()) and flat[:10].abs().sum() == 0 and flat[10 + p.numel():].abs().sum() == 0
+    q = torch.nn.Parameter(torch.randn(6, 5))
+    w = _dense_view(flat, 300, q)
+    assert w.is_contiguous() and w.shape == q.shape
+    import pytest
+    with pytest.raises(ValueError):
+        _dense_view(flat, 0, torch.nn.Parameter(torch.randn(4, 8)[:, ::2]))

@@ -30,6 +30,11 @@ for name, g in geoms.items():
         tbn = timeit(b)
         _lib.lib().msda3d_set_tuning(b"diag_bwd_skip_red", 2)
         tbq = timeit(b)
+        _lib.lib().msda3d_set_tuning(b"diag_bwd_skip_red", 3)
+        tb3 = timeit(b)
+        _lib.lib().msda3d_set_tuning(b"diag_bwd_skip_red", 4)
+        tb4 = timeit(b)
         _lib.lib().msda3d_set_tuning(b"diag_bwd_skip_red", 0)
-        print(f"{name:28s} dist {dist}: fwd {tf:7.3f} ms  bwd {tb:7.3f} ms  bwd(no RED) {tbn:7.3f} ms  bwd(1/4 RED) {tbq:7.3f} ms", flush=True)
+        print(f"{name:28s} dist {dist}: fwd {tf:7.3f} ms  bwd {tb:7.3f} ms  bwd(no RED) {tbn:7.3f} ms  bwd(1/4 RED) {tbq:7.3f} ms  "
+              f"bwd(no RED coarsest level) {tb3:7.3f} ms  bwd(no RED two coarsest) {tb4:7.3f} ms", flush=True)
         del x

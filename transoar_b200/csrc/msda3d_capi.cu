@@ -164,10 +164,15 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
   int g_ = 0, nv_ = 0;
   if (vec_ok<VT>(d, value, gout, g_, nv_) && aligned(gv, 16)) {
     const int grid = vec_grid(units, g_);
-    if (g_diag_skip_red.load() == 2 && g_ == 16 && nv_ == 1) {
-      bwd_vec_kernel<VT, 16, 1, MinBlocks<VT, 1>::bwd, 2><<<grid, kThreads, 0, st>>>(
-          (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P,
-          (float *)gv, (float *)gl, (float *)ga, use_brick(d));
+    const int skip = g_diag_skip_red.load();
+    if (skip >= 2 && skip <= 4 && g_ == 16 && nv_ == 1 && std::is_same<VT, float>::value) {
+      // diagnostics: 2 = every fourth sample reduces, 3 = all but the coarsest level, 4 = all but the two coarsest levels
+#define MSDA3D_DIAG(SK)                                                                                                             \
+  bwd_vec_kernel<float, 16, 1, 3, SK><<<grid, kThreads, 0, st>>>((const float *)gout, (const float *)value, shapes, starts,       \
+                                                                 (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq,  \
+                                                                 d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d))
+      if (skip == 2) MSDA3D_DIAG(2); else if (skip == 3) MSDA3D_DIAG(3); else MSDA3D_DIAG(4);
+#undef MSDA3D_DIAG
     } else if (g_diag_skip_red.load()) {
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd, 1><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,

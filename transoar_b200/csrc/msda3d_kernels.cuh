@@ -671,7 +671,7 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
           float w[8];
           unsigned o[8];
           q = sample_backward<VT, G, NV>(value, top, pa, pb, pc, lane_off, w, o);
-          if (SKIP_RED == 0 || (SKIP_RED == 2 && (j & 3) == 0)) {
+          if (SKIP_RED == 0 || (SKIP_RED == 2 && (j & 3) == 0) || (SKIP_RED == 3 && (s0 + j) / P < L - 1) || (SKIP_RED == 4 && (s0 + j) / P < L - 2)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               if (w[k] != 0.f) {

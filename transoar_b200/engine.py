@@ -62,30 +62,63 @@ def optimizer_param_groups(net, config):
             {"params": [p for n, p in named if "_backbone" not in n], "lr": float(config["lr"])}]
 
 
-def all_reduce_gradients(parameters, world):
-    """Average the gradients over the ranks through one flat bucket: one collective per step instead of DDP's per-bucket hooks, which
-    is what lets the whole step sit in one CUDA graph (at 41 M parameters the bucket is 164 MB -- well under a millisecond over NVLink)."""
+def _all_reduce_mean(flat, world):
+    """Mean over the ranks, in place, one collective: NCCL averages inside the reduction (ReduceOp.AVG); gloo sums and we divide."""
     import torch.distributed as dist
+    diag = os.environ.get("TRANSOAR_B200_DIAG_ALLREDUCE", "")          # diagnostics only: "skip" = no exchange at all, "local" = no NCCL call
+    if diag == "skip" or flat.numel() == 0:
+        return
+    if diag == "local":
+        flat.div_(world)
+        return
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world)
+
+
+def all_reduce_gradients(parameters, world):
+    """Average the gradients of ``parameters`` over the ranks through one temporary flat bucket (``cat`` -> all-reduce -> copy back).
+    Used for the calibration step of ``OverlappedGradientAverage`` and by callers whose gradients do not live in a persistent flat
+    buffer; the steady state of the graph-captured step does not copy (see ``OverlappedGradientAverage``)."""
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads:
         return
-    diag = os.environ.get("TRANSOAR_B200_DIAG_ALLREDUCE", "")          # diagnostics only: "skip" = no exchange at all, "local" = copies without NCCL
-    if diag == "skip":
+    if os.environ.get("TRANSOAR_B200_DIAG_ALLREDUCE", "") == "skip":
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    if diag != "local":
-        dist.all_reduce(flat)
-    flat.div_(world)
+    _all_reduce_mean(flat, world)
     torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
+def _dense_view(flat, offset, p):
+    """A view of ``flat[offset : offset + p.numel()]`` with the parameter's own size and strides (contiguous or channels-last: any dense
+    permutation), so that autograd accumulates into it in place and the fused AdamW sees gradient and parameter in one layout."""
+    if p.is_contiguous():
+        return flat[offset:offset + p.numel()].view(p.shape)
+    strides = sorted(((st, sz) for st, sz in zip(p.stride(), p.shape) if sz > 1), reverse=True)
+    dense, expect = True, 1
+    for st, sz in reversed(strides):
+        dense &= st == expect
+        expect *= sz
+    if not dense:
+        raise ValueError("parameter is neither contiguous nor a dense permutation; cannot alias its gradient into the flat buffer")
+    return flat.as_strided(p.shape, p.stride(), offset)
+
+
 class OverlappedGradientAverage:
-    """Gradient averaging for the graph-captured step at ``world > 1`` in two flat buckets.  The backward reaches the encoder's
-    full-resolution stages last: they hold under 1 % of the parameters but a quarter of the backward's time.  So the moment every
-    *other* parameter has its gradient (counted by post-accumulate hooks) the first bucket -- 99 % of the bytes -- is all-reduced on a
-    side stream, under the rest of the backward; the small second bucket follows on the main stream.  Everything is stream-ordered
-    (fork and join by events), so the sequence is capturable.  The set of parameters that receive gradients is learnt from one
-    un-overlapped step (``calibrate``)."""
+    """Gradient averaging for the graph-captured step at ``world > 1``: the gradients LIVE in one persistent flat fp32 buffer
+    (``p.grad`` of every parameter is a view into it, laid out [early parameters | late parameters]), so the exchange is two bare
+    all-reduces on slices of that buffer -- no ``cat``, no copy back (those copies were ~1 ms of the 2.1 ms per step lost
+    at 8 GPUs).  The backward reaches the encoder's full-resolution stages last: they hold under 1 % of the parameters but a quarter
+    of the backward's time.  So the moment every *other* parameter has its gradient (counted by post-accumulate hooks) the early
+    slice -- 99 % of the bytes -- is all-reduced on a side stream, under the rest of the backward; the small late slice follows on
+    the main stream.  Everything is stream-ordered (fork and join by events), so the sequence is capturable.
+
+    Which parameters receive gradients is learnt from one un-overlapped step (``calibrate``: ordinary ``.grad`` tensors, one temporary
+    bucket); parameters that never get a gradient keep ``grad = None`` (AdamW skips them, as in the reference) and are not in the
+    buffer.  From then on ``zero()`` replaces ``optimizer.zero_grad()``: one memset of the buffer, the views stay."""
 
     def __init__(self, net, world, late_prefixes=("_backbone._encoder._stages.0.", "_backbone._encoder._stages.1.", "_backbone._encoder._stages.2.")):
         named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
@@ -93,6 +126,7 @@ class OverlappedGradientAverage:
         self.late = [p for n, p in named if n.startswith(tuple(late_prefixes))]
         self.early = [p for n, p in named if not n.startswith(tuple(late_prefixes))]
         self.expected, self.pending, self.fired = None, 0, False
+        self.flat, self.n_early = None, 0
         cuda = bool(named) and named[0][1].is_cuda
         self.side = torch.cuda.Stream(named[0][1].device) if cuda else None
         for p in self.early:
@@ -105,25 +139,50 @@ class OverlappedGradientAverage:
         if self.pending == 0 and not self.fired:
             self.fired = True
             if self.side is None:
-                all_reduce_gradients(self.early, self.world)
+                _all_reduce_mean(self.flat[:self.n_early], self.world)
                 return
-            self.side.wait_stream(torch.cuda.current_stream())          # fork: the gradients of the first bucket are complete
+            self.side.wait_stream(torch.cuda.current_stream())          # fork: the gradients of the early slice are complete
             with torch.cuda.stream(self.side):
-                all_reduce_gradients(self.early, self.world)
+                _all_reduce_mean(self.flat[:self.n_early], self.world)
+
+    def zero(self):
+        """Start of a step: gradients to zero (or to None before the calibration step)."""
+        if self.flat is None:
+            for p in self.early + self.late:
+                p.grad = None
+        else:
+            self.flat.zero_()
 
     def before_backward(self):
         self.pending, self.fired = (self.expected or 0), False
 
+    def _adopt(self):
+        """After the calibration backward: move the gradients into the persistent buffer and alias ``p.grad`` to it."""
+        early = [p for p in self.early if p.grad is not None]
+        late = [p for p in self.late if p.grad is not None]
+        self.expected = len(early)
+        self.n_early = sum(p.numel() for p in early)
+        total = self.n_early + sum(p.numel() for p in late)
+        ref = (early + late)[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        with torch.no_grad():
+            for p in early + late:
+                view = _dense_view(self.flat, off, p)
+                view.copy_(p.grad)
+                p.grad = view
+                off += p.numel()
+
     def after_backward(self):
-        if self.expected is None:                                       # calibration step: count, then reduce everything at once
-            self.expected = sum(p.grad is not None for p in self.early)
-            all_reduce_gradients(self.early + self.late, self.world)
+        if self.expected is None:                                       # calibration step: adopt, then reduce everything at once
+            self._adopt()
+            _all_reduce_mean(self.flat, self.world)
             return
         if not self.fired:                                              # fewer gradients than calibrated: still correct, not overlapped
-            all_reduce_gradients(self.early, self.world)
+            _all_reduce_mean(self.flat[:self.n_early], self.world)
         elif self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)          # join
-        all_reduce_gradients(self.late, self.world)
+        _all_reduce_mean(self.flat[self.n_early:], self.world)
 
 
 class TrainStep:
@@ -201,7 +260,10 @@ class TrainStep:
             pass
 
     def _run(self, x, targets, seg_targets):
-        self.optim.zero_grad(set_to_none=True)
+        if self.world > 1 and self.graph:
+            self._averager.zero()                                       # gradients live in the averager's flat buffer
+        else:
+            self.optim.zero_grad(set_to_none=True)
         out = self.model(x)
         losses = self.criterion(out, targets, seg_targets, self.net._anchors)
         loss = total_loss(losses, self.config["loss_coefs"])
@@ -220,7 +282,8 @@ class TrainStep:
         epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._static = {"boxes": boxes.clone(), "valid": valid.clone(), "epoch": epoch}
         _lib.lib().hash_rng_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
-        self.optim.zero_grad(set_to_none=True)
+        if not (self.world > 1 and self.graph):
+            self.optim.zero_grad(set_to_none=True)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._stream):                 # recorded, not executed: the first replay is this step
