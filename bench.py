@@ -470,6 +470,129 @@ def measure_reference_gpu_model(dev, rank, steps=6, warm=3):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations as bench workloads (`--workload`): configs[2] and configs[3], bf16.  Same contract line; the
+# headline (`python bench.py` with no flags) stays configs[1].
+# ---------------------------------------------------------------------------------------------------------------
+def other_workloads():
+    import torch
+    from transoar_b200.engine import defdetr_train_config, swin_focused_train_config
+    return {
+        "defdetr_300_amos_bf16": dict(
+            cfg=defdetr_train_config, volume=(256, 256, 128), amp=torch.bfloat16, dtype="bf16",
+            what="BASELINE configs[2]: 3D Deformable-DETR style detector (transoar_b200/def_detr.py: AttnFPN + 2 multi-level deformable encoder layers over "
+                 "P2..P5 + 3 deformable decoder layers, 300 queries), synthetic AMOS-shape 256x256x128 volumes, bf16 autocast; neck restated (not in the "
+                 "reference tree, SURVEY D5: parity unpinned at neck level, operator pinned)"),
+        "swin_focused_192_bf16": dict(
+            cfg=swin_focused_train_config, volume=(192, 192, 384), amp=torch.bfloat16, dtype="bf16",
+            what="BASELINE configs[3]: SwinFPN backbone (use_encoder_attn=True, stages 2-5 Swin3D) + deformable FPN refinement + Focused Decoder on synthetic "
+                 "192x192x384 volumes, bf16 autocast; RoI grid derived from the P2 map (48x48x96; no row in the reference's shape table, SURVEY D4)"),
+    }
+
+
+def run_other_workload(args):
+    import torch
+    import torch.distributed as dist
+    from transoar_b200 import MultiScaleDeformableAttention as MSDA
+    from transoar_b200 import _lib
+    from transoar_b200.engine import TrainStep, synthetic_targets
+    wl = other_workloads()[args.workload]
+    lib = _lib.lib()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = wl["cfg"](volume=wl["volume"])
+    torch.manual_seed(0)
+    use_graph = bool(args.graph)
+    ts = TrainStep(cfg, dev, world=world, graph=use_graph, graph_warmup=3, amp_dtype=wl["amp"])
+    torch.manual_seed(1 + 7919 * rank)
+    gen = torch.Generator().manual_seed(100 + volume_ids(0, rank, world)[0])
+    vols_host = [torch.rand(BATCH, 1, *wl["volume"], generator=gen).pin_memory() for _ in range(2)]
+    vols_dev = [v.to(dev) for v in vols_host]
+    targets = [synthetic_targets(cfg, BATCH, 1000 * rank + i, dev) for i in range(2)]
+    warm = max(3, args.warmup) + (4 if use_graph else 0)
+    for i in range(warm):
+        ts.step(vols_dev[i % 2], targets[i % 2])
+    fence()
+    ev_log = []
+    if not use_graph:
+        MSDA.set_event_log(ev_log)
+    launches0 = lib.msda3d_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        fence()
+        start.record()
+        for i in range(args.steps):
+            loss = ts.step(vols_dev[i % 2], targets[i % 2])
+        stop.record()
+        fence()
+    MSDA.set_event_log(None)
+    launches = lib.msda3d_launch_count() - launches0
+    value, ms_total = aggregate_throughput(start.elapsed_time(stop), args.steps, world, all_reduce_max=reduce_max)
+    final_loss = float(loss.item())
+    peaks = load_peaks()
+    roofline = None
+    if ev_log:                                                    # the op's launches inside the timed region, by kind; algorithmic bytes from each launch's own dims
+        tot = {"fwd": [0.0, 0.0, 0], "bwd": [0.0, 0.0, 0]}
+        for kind, a, b, d in ev_log:
+            N, S, M, C, L, Lq, P, ev = d
+            bf, bb = algorithmic_bytes(N, S, M, C, L, Lq, P, ev=ev)
+            tot[kind][0] += bf if kind == "fwd" else bb
+            tot[kind][1] += a.elapsed_time(b)
+            tot[kind][2] += 1
+        dom = max(tot, key=lambda k: tot[k][1])
+        gbs = {k: (v[0] / v[1] / 1e6 if v[1] else None) for k, v in tot.items()}
+        roofline = {"bound": "hbm", "kernel": f"msda3d {dom} launches of the step (encoder Lq = S and decoder Lq = {cfg['neck']['num_queries']} calls together)",
+                    "achieved": gbs[dom], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs[dom] / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source"], "launches_timed": tot[dom][2], "share_of_step": tot[dom][1] / ms_total,
+                    "forward_gbs": gbs["fwd"], "backward_gbs": gbs["bwd"],
+                    "timed_in": "CUDA events on the launching stream around every launch inside the timed region (eager steps)"}
+    e2e_steps = max(3, min(args.steps, 6))
+    for i in range(2):
+        float(ts.step(vols_host[i % 2], targets[i % 2]).item())
+    fence()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        float(ts.step(vols_host[i % 2], targets[i % 2]).item())
+    fence()
+    dt = reduce_max(time.perf_counter() - t0)
+    e2e = {"value": world * BATCH * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": vols_host[0].numel() * 4, "d2h_bytes_per_step": 4,
+           "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+           "api": "transoar_b200.engine.TrainStep.step(volumes_in_pinned_host_memory, targets) -> loss; float(loss) on the host every step"}
+    if rank == 0:
+        emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+              "config": {"workload": args.workload, "volume": "x".join(map(str, wl["volume"])), "batch_per_gpu": BATCH, "what": wl["what"],
+                         "step": "forward + matcher + losses + backward + AdamW; nothing skipped",
+                         "precision": "torch.autocast(bfloat16): bf16 tcgen05 GEMMs (kind::f16) for every Linear, bf16 `value` into the msda3d kernels with fp32 "
+                                      "locations / weights, bf16 NDHWC InstanceNorm kernels, cuDNN bf16 convolutions; fp32 master weights and optimiser",
+                         "l2": "activations of hundreds of MB per tensor: far larger than the 126 MB L2; no explicit flush",
+                         "execution": "CUDA graph replay" if use_graph else "eager launches",
+                         "parallelism": "volumes sharded over ranks; one NCCL gradient all-reduce per step"},
+              "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "cuda_graph": use_graph,
+              "model": {"params": sum(p.numel() for p in ts.net.parameters()), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30, "final_loss": final_loss},
+              "clocks": clocks.summary()})
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 def main():
@@ -481,6 +604,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (operator alone, GEMM, RoI attention, InstanceNorm)")
+    ap.add_argument("--workload", default="visceral_train_step", choices=["visceral_train_step", "defdetr_300_amos_bf16", "swin_focused_192_bf16"],
+                    help="visceral_train_step = BASELINE configs[1] (the headline); the other two are configs[2] / configs[3]")
+    ap.add_argument("--graph", action="store_true", help="other workloads only: capture the step into a CUDA graph (default eager)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-model-on-GPU comparator (ref_gpu_model)")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--profile-one-step", action="store_true",
@@ -490,6 +616,8 @@ def main():
     quiet_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload != "visceral_train_step":
+        return run_other_workload(args)
 
     import torch
     import torch.distributed as dist
@@ -577,8 +705,8 @@ def main():
     final_loss = float(loss.item())
 
     # per-launch times of the msda3d kernels inside the timed region (events on the launching stream)
-    fwd_ms = [a.elapsed_time(b) for k, a, b in ev_log if k == "fwd"]
-    bwd_ms = [a.elapsed_time(b) for k, a, b in ev_log if k == "bwd"]
+    fwd_ms = [a.elapsed_time(b) for k, a, b, _ in ev_log if k == "fwd"]
+    bwd_ms = [a.elapsed_time(b) for k, a, b, _ in ev_log if k == "bwd"]
     g = synth.GEOMETRIES[GEOM]
     N, S, M, C, L, Lq, P = BATCH, g.spatial_size, g.heads, g.channels, g.levels, g.num_query, g.points
     bf, bb = algorithmic_bytes(N, S, M, C, L, Lq, P)

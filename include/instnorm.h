@@ -40,6 +40,15 @@ int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, 
                                  const float *rstd, int batch, int channels, long long voxels, float *dx, float *dgamma, float *dbeta,
                                  float *workspace);
 
+/* The NDHWC kernels with bf16 storage for x / y / dy / dx (8-byte aligned); gamma / beta / statistics / workspace stay fp32 and all
+ * arithmetic is fp32.  Used when the encoder runs under the bf16 autocast region of the trainer (transoar/trainer.py:67-69). */
+int instnorm_relu_forward_ndhwc_bf16(void *stream, const void *x, const float *gamma, const float *beta, int batch, int channels,
+                                     long long voxels, float eps, void *y, float *mean, float *rstd, float *workspace);
+
+int instnorm_relu_backward_ndhwc_bf16(void *stream, const void *dy, const void *x, const float *gamma, const float *beta, const float *mean,
+                                      const float *rstd, int batch, int channels, long long voxels, void *dx, float *dgamma, float *dbeta,
+                                      float *workspace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,15 @@ int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, long long lda,
                     float *D, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k,
                     const float *gate, float gate_scale, float p_drop, unsigned long long seed);
 
+/* The same GEMM with bf16 operands (tcgen05.mma kind::f16, fp32 accumulation in TMEM) -- the Linear layers under the reference
+ * trainer's autocast region (transoar/trainer.py:67-69; bf16 here, BASELINE configs[2] / [3]).  A / B are bf16 in either layout
+ * (lda % 8 == 0, ldb % 8 == 0: TMA strides are multiples of 16 bytes); D is bf16 (out_fp32 == 0) or fp32 (out_fp32 != 0, required when
+ * accumulate != 0: weight gradients go straight into fp32).  bias is fp32; gate has D's element type.  Same epilogue options, error
+ * codes and stream semantics as tc_gemm_tf32_ex. */
+int tc_gemm_bf16(void *stream, const void *A, int a_mn_major, long long lda, const void *B, int b_mn_major, long long ldb,
+                 void *D, int out_fp32, long long ldd, const float *bias, int M, int N, int R, int relu, int accumulate, int split_k,
+                 const void *gate, float gate_scale, float p_drop, unsigned long long seed);
+
 /* Column sums out[c] = sum_rows x[row * ld + c] of a row-major fp32 matrix: the bias gradient of a Linear layer (autograd's
  * grad_output.sum(0), an ATen reduce kernel in the reference).  channels % 4 == 0, channels <= 1024, ld % 4 == 0, x and workspace
  * 16-byte aligned; workspace holds tc_colsum_workspace_floats(channels) floats.  One HBM pass + a tiny finalize kernel. */

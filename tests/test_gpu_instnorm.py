@@ -82,3 +82,28 @@ def test_channels_last_first_stage_statistics_at_full_size():
     y = instance_norm_relu(x, w, b)
     ref = F.relu(F.instance_norm(x, weight=w, bias=b, eps=1e-5))
     assert _rel(y, ref) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 16, 16, 32), (1, 48, 9, 7, 13), (2, 96, 5, 6, 7), (1, 768, 5, 5, 8), (1, 24, 40, 41, 67)])
+def test_channels_last_bf16_storage(shape):
+    """NDHWC kernels with bf16 storage (the encoder under the bf16 autocast route): fp32 arithmetic on bf16-rounded inputs, bf16 outputs."""
+    g = torch.Generator().manual_seed(sum(shape) + 2)
+    x = (torch.randn(*shape, generator=g) * 2 + 3).to(DEV).to(torch.bfloat16)
+    w = (torch.rand(shape[1], generator=g) + 0.5).to(DEV)
+    b = (torch.randn(shape[1], generator=g) * 0.3).to(DEV)
+    dy = torch.randn(*shape, generator=g).to(DEV).to(torch.bfloat16)
+    xs = x.contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    ws, bs = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    from transoar_b200 import _lib
+    n0 = _lib.lib().msda3d_launch_count()
+    y = instance_norm_relu(xs, ws, bs, 1e-5)
+    y.backward(dy.contiguous(memory_format=torch.channels_last_3d))
+    assert _lib.lib().msda3d_launch_count() - n0 == 7
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last_3d)
+    assert xs.grad.dtype == torch.bfloat16 and xs.grad.is_contiguous(memory_format=torch.channels_last_3d)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.relu(F.instance_norm(xr, weight=wr, bias=br, eps=1e-5))
+    yr.backward(dy.double())
+    assert _rel(y, yr) < 1e-2 and _rel(xs.grad, xr.grad) < 2e-2
+    assert _rel(ws.grad, wr.grad) < 1e-2 and _rel(bs.grad, br.grad) < 1e-2

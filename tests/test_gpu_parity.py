@@ -481,3 +481,22 @@ def test_merged_layout_of_the_fused_op_equals_the_dense_one(ref_batch):
     assert _relerr(_np(got[1]), _np(value.grad)) < 1e-5                          # atomics: order differs run to run
     assert torch.equal(got[2][..., :3 * M * L * P].reshape(off.shape), off.grad)
     assert torch.equal(got[2][..., 3 * M * L * P:].reshape(logit.shape), logit.grad)
+
+
+@pytest.mark.parametrize("ctas", [2, 3, 4])
+@pytest.mark.parametrize("widen", [False, True])
+def test_tma_staged_forward_experiment_is_bit_identical(ctas, widen):
+    """msda3d_set_tuning("stage", n): the coarsest level gathered from a shared-memory slab filled by TMA bulk copies
+    (fwd_stage_kernel) must give exactly what the shipped LDG kernel gives -- it is an A/B experiment on the data path only."""
+    g = synth.Geometry("stage", ((8, 8, 16), (4, 4, 8), (2, 2, 4), (1, 1, 2)), 6, 64, 4)       # brick order (queries = voxels), C = 64
+    x = synth.make_inputs(g, 2, "B", seed=11, device=DEV)
+    if widen:
+        x["loc"] = (x["loc"] * 1.5 - 0.25).contiguous()
+    want = _run_fwd(x)
+    lib = _lib.lib()
+    assert lib.msda3d_set_tuning(b"stage", ctas) == 0
+    try:
+        got = _run_fwd(x)
+    finally:
+        lib.msda3d_set_tuning(b"stage", 0)
+    assert torch.equal(got, want)

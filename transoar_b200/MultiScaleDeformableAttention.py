@@ -26,14 +26,15 @@ _EVENT_LOG = None
 
 
 def set_event_log(log):
-    """Install (or with None remove) the list that receives ("fwd"|"bwd", start, stop) CUDA-event triples per launch."""
+    """Install (or with None remove) the list that receives ("fwd"|"bwd", start_event, stop_event, dims) per launch;
+    dims = (N, S, M, C, L, Lq, P, bytes per value element)."""
     global _EVENT_LOG
     _EVENT_LOG = log
 
 
 class _timed:
-    def __init__(self, kind):
-        self.kind = kind
+    def __init__(self, kind, dims=None):
+        self.kind, self.dims = kind, dims
 
     def __enter__(self):
         if _EVENT_LOG is not None:
@@ -44,7 +45,7 @@ class _timed:
         if _EVENT_LOG is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _EVENT_LOG.append((self.kind, self.e0, e1))
+            _EVENT_LOG.append((self.kind, self.e0, e1, self.dims))
 
 
 def _p(t: torch.Tensor) -> ctypes.c_void_p:
@@ -94,7 +95,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         sampling_loc, attn_weight = sampling_loc.to(aux), attn_weight.to(aux)
     N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_loc)
     out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device), _timed("fwd"):
+    with torch.cuda.device(value.device), _timed("fwd", (N, S, M, C, L, Lq, P, value.element_size())):
         rc = _lib.lib().msda3d_forward(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(value), _p(spatial_shapes),
             _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P, _p(out))
@@ -116,7 +117,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty(value.shape, dtype=aux, device=value.device)       # zero-filled by the library
     grad_loc = torch.empty_like(sampling_loc)
     grad_aw = torch.empty_like(attn_weight)
-    with torch.cuda.device(value.device), _timed("bwd"):
+    with torch.cuda.device(value.device), _timed("bwd", (N, S, M, C, L, Lq, P, value.element_size())):
         rc = _lib.lib().msda3d_backward(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), dt, _p(grad_output), _p(value), _p(spatial_shapes),
             _p(level_start_index), _p(sampling_loc), _p(attn_weight), N, S, M, C, L, Lq, P,
@@ -146,7 +147,7 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
             ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits)], 1)
     N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_offsets)
     out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device), _timed("fwd"):
+    with torch.cuda.device(value.device), _timed("fwd", (N, S, M, C, L, Lq, P, 4)):
         rc = _lib.lib().msda3d_forward_fused(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(value), _p(spatial_shapes), _p(level_start_index),
             _p(reference_points), reference_points.shape[0], _p(sampling_offsets), _p(attn_logits), N, S, M, C, L, Lq, P, _p(out))
@@ -161,7 +162,7 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, refe
     N, S, M, C, L, Lq, P = _dims(value, spatial_shapes, sampling_offsets)
     grad_value = torch.empty_like(value)                                         # zero-filled by the library
     grad_off, grad_logit = torch.empty_like(sampling_offsets), torch.empty_like(attn_logits)
-    with torch.cuda.device(value.device), _timed("bwd"):
+    with torch.cuda.device(value.device), _timed("bwd", (N, S, M, C, L, Lq, P, 4)):
         rc = _lib.lib().msda3d_backward_fused(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(grad_output), _p(value), _p(spatial_shapes), _p(level_start_index),
             _p(reference_points), reference_points.shape[0], _p(sampling_offsets), _p(attn_logits), N, S, M, C, L, Lq, P,
@@ -177,7 +178,7 @@ def ms_deform_attn_forward_merged(value, spatial_shapes, level_start_index, refe
     N, S, M, C = value.shape
     Lq, ld = merged.shape[1], merged.shape[2]
     out = torch.empty((N, Lq, M * C), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device), _timed("fwd"):
+    with torch.cuda.device(value.device), _timed("fwd", (N, S, M, C, n_levels, Lq, n_points, 4)):
         rc = _lib.lib().msda3d_forward_fused_ld(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(value), _p(spatial_shapes), _p(level_start_index),
             _p(reference_points), reference_points.shape[0], _p(merged), None, ld, N, S, M, C, n_levels, Lq, n_points, _p(out))
@@ -192,7 +193,7 @@ def ms_deform_attn_backward_merged(value, spatial_shapes, level_start_index, ref
     Lq, ld = merged.shape[1], merged.shape[2]
     grad_value = torch.empty_like(value)
     grad_merged = torch.empty_like(merged) if ld == 4 * M * n_levels * n_points else torch.zeros_like(merged)
-    with torch.cuda.device(value.device), _timed("bwd"):
+    with torch.cuda.device(value.device), _timed("bwd", (N, S, M, C, n_levels, Lq, n_points, 4)):
         rc = _lib.lib().msda3d_backward_fused_ld(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(grad_output), _p(value), _p(spatial_shapes), _p(level_start_index),
             _p(reference_points), reference_points.shape[0], _p(merged), None, ld, N, S, M, C, n_levels, Lq, n_points,

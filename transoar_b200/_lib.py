@@ -39,6 +39,8 @@ _SIGNATURES = {
     "instnorm_ndhwc_workspace_floats": (ctypes.c_longlong, [_ci, _ci, ctypes.c_longlong]),
     "instnorm_relu_forward_ndhwc": (_ci, [_vp] * 4 + [_ci, _ci, ctypes.c_longlong, ctypes.c_float] + [_vp] * 4),
     "instnorm_relu_backward_ndhwc": (_ci, [_vp] * 7 + [_ci, _ci, ctypes.c_longlong] + [_vp] * 4),
+    "instnorm_relu_forward_ndhwc_bf16": (_ci, [_vp] * 4 + [_ci, _ci, ctypes.c_longlong, ctypes.c_float] + [_vp] * 4),
+    "instnorm_relu_backward_ndhwc_bf16": (_ci, [_vp] * 7 + [_ci, _ci, ctypes.c_longlong] + [_vp] * 4),
     # include/roi_attn.h
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
@@ -66,6 +68,8 @@ _SIGNATURES = {
     "tc_gemm_tf32_ex": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6
                         + [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong]),
     "tc_gemm_tf32": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp] + [_ci] * 6),
+    "tc_gemm_bf16": (_ci, [_vp, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp, _ci, ctypes.c_longlong, _vp] + [_ci] * 6
+                     + [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong]),
 }
 
 

@@ -49,3 +49,25 @@ def amos_config(seed=0, volume=(256, 256, 128)):
     neck = copy.deepcopy(VISCERAL_NECK)
     neck.update(input_levels="P3", num_queries=405, num_organs=15)
     return {"backbone": bb, "neck": neck, "bbox_properties": synthetic_atlas(15, seed), "neck_input_shape": tuple(v // 8 for v in volume)}
+
+
+def defdetr_amos_config(seed=0, volume=(256, 256, 128), queries=300, dec_layers=3):
+    """BASELINE.json configs[2]: "3D Deformable DETR (attn-fpn-def-detr), 4-level FPN, 300 queries, synthetic AMOS shapes".  The neck is
+    not in the reference tree -- ``transoar_b200.def_detr`` restates it (parity unpinned at neck level, op pinned).  Backbone
+    keys are the amos yaml's with all four FPN levels refined and returned; 300 queries = 20 per organ for the 15 AMOS organs."""
+    bb = copy.deepcopy(VISCERAL_BACKBONE)
+    bb.update(out_fmaps=["P2", "P3", "P4", "P5"], feature_levels=["P2", "P3", "P4", "P5"])
+    neck = dict(name="def_detr", hidden_dim=384, dropout=0.1, nheads=8, dim_feedforward=1024, dec_layers=dec_layers, n_points=4,
+                num_queries=queries, num_organs=15, aux_loss=True)
+    return {"model_family": "def_detr", "backbone": bb, "neck": neck, "bbox_properties": synthetic_atlas(15, seed), "volume": tuple(volume)}
+
+
+def swin_focused_config(seed=0, volume=(192, 192, 384)):
+    """BASELINE.json configs[3]: "SwinFPN backbone (use_encoder_attn=True) + Focused Decoder, VISCERAL-shape 192x192x384".  The visceral yaml
+    with the Swin encoder switched on (encoder_blocks.py:56-334); 192x192x384 has no row in the reference's RoI shape table
+    (focused_decoder.py:99-117), so the mask grid is derived from the P2 feature map (48x48x96)."""
+    cfg = visceral_config(seed)
+    cfg["backbone"]["use_encoder_attn"] = True
+    cfg["neck_input_shape"] = tuple(v // 4 for v in volume)
+    cfg["volume"] = tuple(volume)
+    return cfg

@@ -17,6 +17,19 @@ using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a driver-API call and needs a context current on the CALLING thread.  A fresh host thread (autograd's
+// backward thread on device 0: torch skips cudaSetDevice when the device index already matches) has none until its first runtime
+// call binds the primary context -- bind it explicitly, once per thread (cudaSetDevice is legal during stream capture).
+void ensure_context_on_this_thread()
+{
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    bound = true;
+  }
+}
+
 EncodeTiled encode_fn()
 {
   static EncodeTiled fn = nullptr;
@@ -67,6 +80,7 @@ extern "C" int conv3d_tc_k3_forward(void *stream, const float *x, const float *w
   if (!x || !w_taps || !y || batch <= 0 || depth <= 0 || height <= 0 || width <= 0) return MSDA3D_EINVAL;
   if (!conv3d_tc_supported(in_channels, out_channels)) return MSDA3D_EINVAL;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w_taps)) & 15) return MSDA3D_EALIGN;
+  ensure_context_on_this_thread();
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) return MSDA3D_ENODEV;
   const cuuint64_t C = (cuuint64_t)in_channels, W = (cuuint64_t)width, H = (cuuint64_t)height, D = (cuuint64_t)depth;
@@ -93,6 +107,7 @@ namespace {
 // bw x bh x bd voxels, 128-byte swizzle with 32-byte atoms (the MN-major TF32 operand layout)
 int make_row_map(CUtensorMap *map, const float *ptr, int N, int D, int H, int W, int C, int bw, int bh, int bd)
 {
+  ensure_context_on_this_thread();
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) return MSDA3D_ENODEV;
   const cuuint64_t c = (cuuint64_t)C, w = (cuuint64_t)W, h = (cuuint64_t)H, d = (cuuint64_t)D;

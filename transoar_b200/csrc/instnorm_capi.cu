@@ -71,6 +71,44 @@ bool bad(int dtype, int B, int C, long long V) { return (dtype != MSDA3D_F32 && 
 
 }  // namespace
 
+template <typename T>
+static int cl_forward(void *stream, const T *x, const float *gamma, const float *beta, int batch, int channels, long long voxels,
+                      float eps, T *y, float *mean, float *rstd, float *workspace)
+{
+  if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace || cl_bad(batch, channels, voxels)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & (4 * sizeof(T) - 1)) return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ClPlan p = cl_plan(batch, channels, voxels);
+  const int I = batch * channels;
+  const dim3 grid(p.chunks, batch);
+  instnorm::cl_stats_partial_kernel<T><<<grid, instnorm::kClThreads, 0, st>>>(x, voxels, channels, p.chunks, p.chunk_vox, workspace);
+  instnorm::stats_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, eps, mean, rstd);
+  instnorm::cl_apply_kernel<T><<<grid, instnorm::kClThreads, 0, st>>>(x, gamma, beta, mean, rstd, voxels, channels, p.chunk_vox, y);
+  g_msda3d_launches += 3;
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int cl_backward(void *stream, const T *dy, const T *x, const float *gamma, const float *beta, const float *mean, const float *rstd,
+                       int batch, int channels, long long voxels, T *dx, float *dgamma, float *dbeta, float *workspace)
+{
+  if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !workspace || cl_bad(batch, channels, voxels))
+    return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & (4 * sizeof(T) - 1))
+    return MSDA3D_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ClPlan p = cl_plan(batch, channels, voxels);
+  const int I = batch * channels;
+  const dim3 grid(p.chunks, batch);
+  float *sums = workspace + (long long)I * p.chunks * 2;
+  instnorm::cl_bwd_partial_kernel<T><<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, voxels, channels, p.chunks, p.chunk_vox, workspace);
+  instnorm::bwd_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, sums);
+  instnorm::bwd_param_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, batch, channels, dgamma, dbeta);
+  instnorm::cl_bwd_apply_kernel<T><<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, sums, voxels, channels, p.chunk_vox, dx);
+  g_msda3d_launches += 4;
+  return (int)cudaGetLastError();
+}
+
 extern "C" {
 
 long long instnorm_workspace_floats(int dtype, int batch, int channels, long long voxels)
@@ -110,38 +148,29 @@ long long instnorm_ndhwc_workspace_floats(int batch, int channels, long long vox
 int instnorm_relu_forward_ndhwc(void *stream, const float *x, const float *gamma, const float *beta, int batch, int channels, long long voxels,
                                 float eps, float *y, float *mean, float *rstd, float *workspace)
 {
-  if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace || cl_bad(batch, channels, voxels)) return MSDA3D_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return MSDA3D_EALIGN;
-  cudaStream_t st = (cudaStream_t)stream;
-  const ClPlan p = cl_plan(batch, channels, voxels);
-  const int I = batch * channels;
-  const dim3 grid(p.chunks, batch);
-  instnorm::cl_stats_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(x, voxels, channels, p.chunks, p.chunk_vox, workspace);
-  instnorm::stats_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, eps, mean, rstd);
-  instnorm::cl_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(x, gamma, beta, mean, rstd, voxels, channels, p.chunk_vox, y);
-  g_msda3d_launches += 3;
-  return (int)cudaGetLastError();
+  return cl_forward<float>(stream, x, gamma, beta, batch, channels, voxels, eps, y, mean, rstd, workspace);
 }
 
 int instnorm_relu_backward_ndhwc(void *stream, const float *dy, const float *x, const float *gamma, const float *beta, const float *mean,
                                  const float *rstd, int batch, int channels, long long voxels, float *dx, float *dgamma, float *dbeta,
                                  float *workspace)
 {
-  if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !workspace || cl_bad(batch, channels, voxels))
-    return MSDA3D_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
-    return MSDA3D_EALIGN;
-  cudaStream_t st = (cudaStream_t)stream;
-  const ClPlan p = cl_plan(batch, channels, voxels);
-  const int I = batch * channels;
-  const dim3 grid(p.chunks, batch);
-  float *sums = workspace + (long long)I * p.chunks * 2;
-  instnorm::cl_bwd_partial_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, voxels, channels, p.chunks, p.chunk_vox, workspace);
-  instnorm::bwd_finalize_kernel<<<(I + 3) / 4, 128, 0, st>>>(workspace, p.chunks, I, sums);
-  instnorm::bwd_param_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, batch, channels, dgamma, dbeta);
-  instnorm::cl_bwd_apply_kernel<<<grid, instnorm::kClThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, sums, voxels, channels, p.chunk_vox, dx);
-  g_msda3d_launches += 4;
-  return (int)cudaGetLastError();
+  return cl_backward<float>(stream, dy, x, gamma, beta, mean, rstd, batch, channels, voxels, dx, dgamma, dbeta, workspace);
+}
+
+/* bf16 storage (x, y, dy, dx), fp32 parameters / statistics / arithmetic: the activations of the encoder under the bf16 autocast route */
+int instnorm_relu_forward_ndhwc_bf16(void *stream, const void *x, const float *gamma, const float *beta, int batch, int channels, long long voxels,
+                                     float eps, void *y, float *mean, float *rstd, float *workspace)
+{
+  return cl_forward<__nv_bfloat16>(stream, (const __nv_bfloat16 *)x, gamma, beta, batch, channels, voxels, eps, (__nv_bfloat16 *)y, mean, rstd, workspace);
+}
+
+int instnorm_relu_backward_ndhwc_bf16(void *stream, const void *dy, const void *x, const float *gamma, const float *beta, const float *mean,
+                                      const float *rstd, int batch, int channels, long long voxels, void *dx, float *dgamma, float *dbeta,
+                                      float *workspace)
+{
+  return cl_backward<__nv_bfloat16>(stream, (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, gamma, beta, mean, rstd, batch, channels, voxels,
+                                    (__nv_bfloat16 *)dx, dgamma, dbeta, workspace);
 }
 
 }  // extern "C"

@@ -294,6 +294,23 @@ constexpr int kClUnroll = 8;
 
 __host__ __device__ inline bool cl_supported(int C) { return C > 0 && C % 4 == 0 && kClThreads % (C / 4) == 0; }
 
+// four channels of storage type T (fp32: 16 bytes, bf16: 8 bytes) <-> fp32 registers; the arithmetic is fp32 for both
+__device__ __forceinline__ float4 cl_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 cl_ld4(const __nv_bfloat16 *p)
+{
+  const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&t.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&t.y);
+  return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x), __bfloat162float(b.y));
+}
+__device__ __forceinline__ void cl_st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void cl_st4(__nv_bfloat16 *p, float4 v)
+{
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162 *>(&t.x) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162 *>(&t.y) = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2 *>(p) = t;
+}
+
 // sum NV float4-wide values over the voxel rows of the CTA; result valid in the threads of row 0 (t < cg)
 template <int NV>
 __device__ __forceinline__ void cl_reduce_rows(float (&v)[NV][4], int cg, int rows, float *red /* [kClThreads][NV * 4] */)
@@ -319,22 +336,23 @@ __device__ __forceinline__ void cl_reduce_rows(float (&v)[NV][4], int cg, int ro
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kClThreads)
-cl_stats_partial_kernel(const float *__restrict__ x, long long V, int C, int chunks, long long chunk_vox, float *__restrict__ part)
+cl_stats_partial_kernel(const T *__restrict__ x, long long V, int C, int chunks, long long chunk_vox, float *__restrict__ part)
 {
   __shared__ float red[kClThreads * 8];
   const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int b = blockIdx.y, ch = blockIdx.x;
   const long long v0 = (long long)ch * chunk_vox, v1 = min(V, v0 + chunk_vox);
-  const float *base = x + (long long)b * V * C + g * 4;
-  const float4 K = __ldg(reinterpret_cast<const float4 *>(base + v0 * C));
+  const T *base = x + (long long)b * V * C + g * 4;
+  const float4 K = cl_ld4(base + v0 * C);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (long long v = v0 + r; v < v1; v += (long long)rows * kClUnroll) {
     float4 q[kClUnroll];
 #pragma unroll
     for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
-      q[u] = vv < v1 ? __ldg(reinterpret_cast<const float4 *>(base + vv * C)) : K;
+      q[u] = vv < v1 ? cl_ld4(base + vv * C) : K;
     }
 #pragma unroll
     for (int u = 0; u < kClUnroll; ++u) {
@@ -356,9 +374,10 @@ cl_stats_partial_kernel(const float *__restrict__ x, long long V, int C, int chu
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kClThreads)
-cl_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ mean,
-                const float *__restrict__ rstd, long long V, int C, long long chunk_vox, float *__restrict__ y)
+cl_apply_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ mean,
+                const float *__restrict__ rstd, long long V, int C, long long chunk_vox, T *__restrict__ y)
 {
   const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int b = blockIdx.y;
@@ -376,22 +395,23 @@ cl_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, co
 #pragma unroll
     for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
-      if (vv < v1) q[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+      if (vv < v1) q[u] = cl_ld4(x + off + vv * C);
     }
 #pragma unroll
     for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
       if (vv < v1)
-        *reinterpret_cast<float4 *>(y + off + vv * C) = make_float4(fmaxf(fmaf(q[u].x, a[0], o[0]), 0.f), fmaxf(fmaf(q[u].y, a[1], o[1]), 0.f),
-                                                                     fmaxf(fmaf(q[u].z, a[2], o[2]), 0.f), fmaxf(fmaf(q[u].w, a[3], o[3]), 0.f));
+        cl_st4(y + off + vv * C, make_float4(fmaxf(fmaf(q[u].x, a[0], o[0]), 0.f), fmaxf(fmaf(q[u].y, a[1], o[1]), 0.f),
+                                             fmaxf(fmaf(q[u].z, a[2], o[2]), 0.f), fmaxf(fmaf(q[u].w, a[3], o[3]), 0.f)));
     }
   }
 }
 
 // The ReLU mask is recomputed from x with the forward's own arithmetic (fmaf(x, rstd * gamma, beta - mean * rstd * gamma) > 0), so the
 // backward reads two tensors per pass (dy, x) instead of three (dy, x, y): 5 instead of 7 passes over the activation in total.
+template <typename T>
 __global__ void __launch_bounds__(kClThreads)
-cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+cl_bwd_partial_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                       const float *__restrict__ mean, const float *__restrict__ rstd, long long V, int C, int chunks, long long chunk_vox,
                       float *__restrict__ part)
 {
@@ -414,8 +434,8 @@ cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
       if (vv < v1) {
-        gq[u] = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
-        xq[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+        gq[u] = cl_ld4(dy + off + vv * C);
+        xq[u] = cl_ld4(x + off + vv * C);
       }
     }
 #pragma unroll
@@ -442,10 +462,11 @@ cl_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x,
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kClThreads)
-cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+cl_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ sums, long long V, int C,
-                    long long chunk_vox, float *__restrict__ dx)
+                    long long chunk_vox, T *__restrict__ dx)
 {
   const int cg = C >> 2, rows = kClThreads / cg, g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int b = blockIdx.y;
@@ -464,8 +485,8 @@ cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, c
     for (int u = 0; u < kClUnroll; ++u) {
       const long long vv = v + (long long)u * rows;
       if (vv < v1) {
-        gq[u] = __ldg(reinterpret_cast<const float4 *>(dy + off + vv * C));
-        xq[u] = __ldg(reinterpret_cast<const float4 *>(x + off + vv * C));
+        gq[u] = cl_ld4(dy + off + vv * C);
+        xq[u] = cl_ld4(x + off + vv * C);
       }
     }
 #pragma unroll
@@ -479,7 +500,7 @@ cl_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, c
           const float dz = fmaf(xx[j], a[j], fo[j]) > 0.f ? gg[j] : 0.f;
           o[j] = a[j] * (dz - m1[j] - (xx[j] - mu[j]) * rs[j] * m2[j]);
         }
-        *reinterpret_cast<float4 *>(dx + off + vv * C) = make_float4(o[0], o[1], o[2], o[3]);
+        cl_st4(dx + off + vv * C, make_float4(o[0], o[1], o[2], o[3]));
       }
     }
   }

@@ -57,6 +57,7 @@ int grid_for(long long units, int units_per_block)
 std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d_set_tuning "nv")
 std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
 std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
+std::atomic<int> g_tune_stage{0};       // experiment: forward with the coarsest level staged in shared memory by TMA bulk copies (2 / 3 / 4 = CTAs per SM)
 std::atomic<int> g_tune_pair{0};        // 1 = pair-combining backward (kernels.cuh, PAIR) in brick order for 16-lane fp32 units; measured slower, off by default
 
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
@@ -143,6 +144,24 @@ int forward_half_or_float(cudaStream_t st, const Dims &d, const void *value, con
   int g_ = 0, nv_ = 0;
   if (vec_ok<VT>(d, value, out, g_, nv_)) {
     const int grid = vec_grid(units, g_);
+    const int stage = g_tune_stage.load();
+    if (stage && std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && d.L >= 1) {
+      // experiment: coarsest level staged in shared memory by TMA bulk copies (kernels.cuh, fwd_stage_kernel); needs the level's shape on the host
+      int64_t shp[3];                                                  // experiment only: the level's extent is read back per call (a host sync)
+      if (cudaMemcpyAsync(shp, shapes + 3 * (d.L - 1), sizeof(shp), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return (int)cudaGetLastError();
+      const size_t smem = (size_t)shp[0] * shp[1] * shp[2] * d.C * sizeof(float);
+      if (smem <= 100 * 1024) {
+        auto launch = [&](auto kern) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          kern<<<grid, kThreads, smem, st>>>((const float *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L,
+                                             d.Lq, d.P, (float *)out);
+        };
+        if (stage == 2) launch(fwd_stage_kernel<2>); else if (stage == 4) launch(fwd_stage_kernel<4>); else launch(fwd_stage_kernel<3>);
+        ++g_launches;
+        return (int)cudaGetLastError();
+      }
+    }
     VEC_DISPATCH(g_, nv_, fwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::fwd><<<grid, kThreads, 0, st>>>(
                               (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq,
                               d.P, (VT *)out, use_brick(d)));
@@ -211,6 +230,7 @@ int msda3d_set_tuning(const char *key, int value)
   if (k == "diag_bwd_skip_red") { g_diag_skip_red = value; return MSDA3D_OK; }
   if (k == "nv" && value >= 0 && value <= 2) { g_tune_nv = value; return MSDA3D_OK; }
   if (k == "grid_mult" && value >= 0) { g_tune_grid_mult = value; return MSDA3D_OK; }
+  if (k == "stage" && value >= 0 && value <= 4) { g_tune_stage = value; return MSDA3D_OK; }
   if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
   if (k == "pair" && value >= 0 && value <= 1) { g_tune_pair = value; return MSDA3D_OK; }
   return MSDA3D_EINVAL;

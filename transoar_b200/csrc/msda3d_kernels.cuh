@@ -477,6 +477,123 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (msda3d_set_tuning("stage", 1); profiles/r02_experiments.md): the forward with the COARSEST level's slab of the current
+// (batch, head) staged in shared memory by the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP) and gathered from there with
+// LDS.128; the other levels keep the LDG path.  This is the part of BASELINE.json's "stage per-level 3D feature tiles into shared
+// memory via TMA" design that fits on chip at all: sampling offsets are measured in voxels of the SAMPLED level, so a query brick's
+// footprint on any level is brick + a halo of +-(n_points + jitter) voxels -- at 256 B per (voxel, head) the halo alone is
+// 15^3 x 256 B = 864 KB for every level, against 227 KB of shared memory.  Only a whole small level fits: 5x5x8 x 256 B = 51 KB.
+// Brick order only (all units of a CTA share one (batch, head)), fp32, 16 lanes x one float4 per unit.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+fwd_stage_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
+                 const float *__restrict__ loc, const float *__restrict__ aw, int N, int S, int M, int L, int Lq, int P,
+                 float *__restrict__ out)
+{
+  constexpr int G = 16, VEC = 4, C = 64, UPW = 2, WARPS = kThreads / 32, UPB = WARPS * UPW;
+  extern __shared__ __align__(128) float slab[];                  // [V][C]: coarsest level of the staged (batch, head)
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int4 lv[kMaxLevels];
+  __shared__ BrickPlan bp;
+  __shared__ float4 sA[WARPS][32];
+  __shared__ float4 sB[WARPS][32];
+  __shared__ int4 sC[WARPS][32];
+  if (threadIdx.x < L)
+    lv[threadIdx.x] = make_int4((int)shapes[3 * threadIdx.x], (int)shapes[3 * threadIdx.x + 1],
+                                (int)shapes[3 * threadIdx.x + 2], (int)starts[threadIdx.x]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, g0 = lane - gl;
+  const int MC = M * C, LP = L * P;
+  const long long total = (long long)N * Lq * M;
+  if (threadIdx.x == 0) {
+    make_brick_plan<UPB>(bp, lv, L);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int lc = L - 1;
+  const int4 lic = lv[lc];
+  const int V = lic.x * lic.y * lic.z;
+  const long long slots = (long long)N * M * bp.nb;
+  const long long per = (slots + gridDim.x - 1) / gridDim.x;
+  const long long t_end = min(slots, (blockIdx.x + 1) * per);
+  const unsigned lane_off = gl * VEC;
+  long long staged = -1;
+  unsigned phase = 0;
+  for (long long t = blockIdx.x * per; t < t_end; ++t) {
+    const long long bm = t / bp.nb;                                // b * M + m of this slot (brick order)
+    if (bm != staged) {
+      __syncthreads();                                             // nobody still gathers from the old slab
+      const long long b = bm / M;
+      const int m = (int)(bm - b * M);
+      if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"((unsigned)(V * C * 4)) : "memory");
+      __syncthreads();
+      for (int v = threadIdx.x; v < V; v += kThreads) {
+        const float *src = value + ((b * S + lic.w + v) * (long long)M + m) * C;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(slab + v * C)), "l"(src), "r"(C * 4), "r"(smem_u32(&mbar)) : "memory");
+      }
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+      phase ^= 1u;
+      staged = bm;
+    }
+    const UnitCoords uc = slot_unit<UPB>(true, t, warp * UPW + lane / G, total, bp, lv, L, M, Lq);
+    float acc[VEC] = {0.f, 0.f, 0.f, 0.f};
+    for (int s0 = 0; s0 < LP; s0 += G) {
+      const int s = s0 + gl;
+      PreparedSample mine;
+      if (uc.active && s < LP && s / P == lc) {                    // coarsest level: offsets relative to the compact slab [V][C]
+        UnitCoords cu = uc;
+        cu.b = 0; cu.m = 0;
+        const long long si = uc.u * LP + s;
+        mine = prepare_located(make_int4(lic.x, lic.y, lic.z, 0), ldg_stream(loc + 3 * si), ldg_stream(loc + 3 * si + 1),
+                               ldg_stream(loc + 3 * si + 2), ldg_stream(aw + si), cu, 0, C, C);
+      } else {
+        mine = prepare_sample(lv, loc, aw, uc, s, LP, P, S, MC, C);
+      }
+      __syncwarp();
+      sA[warp][lane] = mine.a; sB[warp][lane] = mine.b; sC[warp][lane] = mine.c;
+      __syncwarp();
+      const int cnt = min(G, LP - s0);
+      for (int j = 0; j < cnt; ++j) {
+        const int4 pc = sC[warp][g0 + j];
+        if (pc.w == 0) continue;
+        const float4 pa = sA[warp][g0 + j], pb = sB[warp][g0 + j];
+        float w[8];
+        corner_weights_axes(pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, w);
+        unsigned o[8];
+        o[0] = __float_as_uint(pa.x) + lane_off; o[1] = o[0] + pc.z; o[2] = o[0] + pc.y; o[3] = o[2] + pc.z;
+        o[4] = o[0] + pc.x; o[5] = o[4] + pc.z; o[6] = o[4] + pc.y; o[7] = o[6] + pc.z;
+        float v[8][VEC];
+        if ((s0 + j) / P == lc) {                                   // warp-uniform: both units of the warp are at sample j
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 q = *reinterpret_cast<const float4 *>(slab + o[k]);
+            v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) Vec16<float>::load(value + o[k], v[k]);
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          const float val = blend<float>(w, v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
+          acc[c] = __fmaf_rn(pa.y, val, acc[c]);
+        }
+      }
+    }
+    if (uc.active) Vec16<float>::store(out + uc.u * C + lane_off, acc);
+  }
+}
+
 template <int G> __device__ __forceinline__ float group_sum(float v)
 {
 #pragma unroll

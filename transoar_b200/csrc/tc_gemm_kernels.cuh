@@ -22,6 +22,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,12 +31,28 @@
 namespace tcgemm {
 
 constexpr int BM = 128;               // rows of D per tile = TMEM lanes
-constexpr int BK = 32;                // reduction elements per stage = 128 bytes = one swizzle row
+constexpr int BK = 32;                // fp32 / TF32: reduction elements per stage = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;             // tf32
 constexpr int kEpiWarps = 8;           // two epilogue warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kSlabBytes = BK * 128;  // MN-major operands: one 32(mn) x BK(r) slab per TMA box
+constexpr int kSlabBytes = BK * 128;  // TF32 MN-major operands: one 32(mn) x BK(r) slab per TMA box
 constexpr unsigned kSpinLimit = 1u << 28;
+
+// Operand element types.  A stage row is always 128 bytes (one swizzle row) and an MMA always consumes 32 bytes of reduction
+// per row, so the pipeline geometry in BYTES is the same for both; what changes is how many elements that is, the MN-major
+// shared-memory form the tensor core accepts, and the instruction kind.
+//   float (kind::tf32)          : 32 elements per stage row, UMMA_K = 8;  MN-major = 128B swizzle with 32-byte atoms (layout type 1),
+//                                 slabs of 32 mn-elements, 4-row groups 512 bytes apart
+//   __nv_bfloat16 (kind::f16)   : 64 elements per stage row, UMMA_K = 16; MN-major = the plain 128-byte swizzle (layout type 2),
+//                                 slabs of 64 mn-elements, 8-row groups 1024 bytes apart
+template <typename ET> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int BKE = 32, MMA_K = 8, SLAB_MN = 32, MN_SBO = 512, MN_TYPE = 1, FMT = 2, IS_BF16 = 0;
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int BKE = 64, MMA_K = 16, SLAB_MN = 64, MN_SBO = 1024, MN_TYPE = 2, FMT = 1, IS_BF16 = 1;
+};
+template <typename ET> __host__ __device__ constexpr int slab_bytes() { return Elem<ET>::BKE * 128; }     // one MN-major TMA box: SLAB_MN mn-elements (128 B) x BKE rows
 
 // CTAS = 1: one CTA computes a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so the operand bytes an SM pulls
@@ -131,6 +148,16 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
@@ -165,20 +192,22 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
 //             32-byte chunks of a 128-byte row XORed with row % 4).  Slabs of 32 mn-elements (128 bytes) x BK reduction rows;
 //             4-row groups 512 bytes apart (SBO), the next 32 mn-elements one slab (kSlabBytes) further (LBO).
 //             TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-template <bool MN> __device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
+template <bool MN, typename ET = float> __device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
 {
-  const uint64_t lbo = MN ? (uint64_t)(kSlabBytes >> 4) : 1ull;
-  const uint64_t sbo = MN ? (uint64_t)(512 >> 4) : (uint64_t)(1024 >> 4);
-  const uint64_t type = MN ? 1ull : 2ull;
+  const uint64_t lbo = MN ? (uint64_t)(slab_bytes<ET>() >> 4) : 1ull;
+  const uint64_t sbo = MN ? (uint64_t)(Elem<ET>::MN_SBO >> 4) : (uint64_t)(1024 >> 4);
+  const uint64_t type = MN ? (uint64_t)Elem<ET>::MN_TYPE : 2ull;
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
-template <bool MN> __device__ __forceinline__ uint32_t kstep_bytes() { return MN ? 1024u : (uint32_t)(UMMA_K * 4); }
+// bytes between the operand windows of consecutive MMAs of a stage: MN-major = MMA_K reduction rows of 128 bytes, K-major = 32 bytes
+template <bool MN, typename ET = float> __device__ __forceinline__ uint32_t kstep_bytes() { return MN ? (uint32_t)(Elem<ET>::MMA_K * 128) : 32u; }
 
-template <int BN, bool A_MN, bool B_MN, int CTAS> __host__ __device__ constexpr uint32_t instr_desc()
+template <int BN, bool A_MN, bool B_MN, int CTAS, typename ET = float> __host__ __device__ constexpr uint32_t instr_desc()
 {
-  // c_format F32 (bits 4-5 = 1), a/b format TF32 (bits 7-9 / 10-12 = 2), a/b major (bits 15 / 16), N >> 3 (bits 17-22), M >> 4 (24-28)
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-         ((uint32_t)((BM * CTAS) >> 4) << 24);
+  // c_format F32 (bits 4-5 = 1), a/b format (bits 7-9 / 10-12: kind::tf32 TF32 = 2; kind::f16 BF16 = 1), a/b major (bits 15 / 16),
+  // N >> 3 (bits 17-22), M >> 4 (24-28)
+  return (1u << 4) | ((uint32_t)Elem<ET>::FMT << 7) | ((uint32_t)Elem<ET>::FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
 }
 
 struct Problem {
@@ -187,7 +216,7 @@ struct Problem {
   int splits, rb_per_split;    // split-K: split s reduces r-blocks [s * rb_per_split, ...)
   int relu, atomic;            // atomic: D += (split-K or accumulate into an existing gradient)
   // fused epilogue extras (NULL / 0 = off); both need the vector path (ldd % 4 == 0, N % 4 == 0, 16-byte aligned D / gate)
-  const float *gate;           // D = result * (gate[m, n] > 0 ? gate_scale : 0): gradient of ReLU (+ dropout) taken from the saved activation
+  const void *gate;            // D = result * (gate[m, n] > 0 ? gate_scale : 0): gradient of ReLU (+ dropout) taken from the saved activation (element type of D)
   float gate_scale;
   unsigned int drop_thresh;    // dropout after bias / ReLU: keep iff 16-bit hash(seed, element) >= drop_thresh, kept values * drop_scale
   float drop_scale;
@@ -205,11 +234,35 @@ __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, c
   acc += (unsigned long long)(clock64() - t0);
 }
 
-template <int BN, bool A_MN, bool B_MN, int CTAS>
-__device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUtensorMap &tmB, float *__restrict__ D,
+// four values of the output / gate element type as fp32, and back
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16 *p)
+{
+  const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&t.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&t.y);
+  return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x), __bfloat162float(b.y));
+}
+__device__ __forceinline__ void st4(float *p, float4 o) { *reinterpret_cast<float4 *>(p) = o; }
+__device__ __forceinline__ void st4(__nv_bfloat16 *p, float4 o)
+{
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162 *>(&t.x) = __floats2bfloat162_rn(o.x, o.y);
+  *reinterpret_cast<__nv_bfloat162 *>(&t.y) = __floats2bfloat162_rn(o.z, o.w);
+  *reinterpret_cast<uint2 *>(p) = t;
+}
+__device__ __forceinline__ void st1(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ET: operand element type (float = TF32 multiply, __nv_bfloat16 = kind::f16); OT: element type of D (float, or bf16 for the
+// forward / grad-input GEMMs of the bf16 route; accumulating launches always write fp32).
+template <int BN, bool A_MN, bool B_MN, int CTAS, typename ET = float, typename OT = float>
+__device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUtensorMap &tmB, OT *__restrict__ D,
                  const float *__restrict__ bias, const Problem p)
 {
   using C = Cfg<BN, CTAS>;
+  using E = Elem<ET>;
+  static_assert(!B_MN || (BN / CTAS) % E::SLAB_MN == 0, "MN-major B: the CTA's share of the tile must be whole slabs");
+  constexpr int BKE = E::BKE;                                                   // reduction ELEMENTS per stage (128 bytes)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // 128-byte swizzle atoms are 1024-byte aligned
   const uint32_t epi_base = base + C::STAGES * C::STAGE_BYTES;
@@ -244,7 +297,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (p.N + BN - 1) / BN;      // a tile is 128 * CTAS rows
-  const int r_blocks = (p.R + BK - 1) / BK;
+  const int r_blocks = (p.R + BKE - 1) / BKE;
   const long long work = (long long)m_tiles * n_tiles * p.splits;
   const long long w_first = blockIdx.x / CTAS, w_step = gridDim.x / CTAS;                     // both CTAs of a pair walk the same tiles
 
@@ -267,16 +320,16 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
             else tma_load_2d(dst, map, full(stage), c0, c1);
           };
           if (!A_MN) {
-            load(sa, &tmA, kb * BK, m0);
+            load(sa, &tmA, kb * BKE, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 32; ++i) load(sa + i * kSlabBytes, &tmA, m0 + 32 * i, kb * BK);
+            for (int i = 0; i < BM / E::SLAB_MN; ++i) load(sa + i * slab_bytes<ET>(), &tmA, m0 + E::SLAB_MN * i, kb * BKE);
           }
           if (!B_MN) {
-            load(sb, &tmB, kb * BK, n0);
+            load(sb, &tmB, kb * BKE, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / CTAS / 32; ++i) load(sb + i * kSlabBytes, &tmB, n0 + 32 * i, kb * BK);
+            for (int i = 0; i < BN / CTAS / E::SLAB_MN; ++i) load(sb + i * slab_bytes<ET>(), &tmB, n0 + E::SLAB_MN * i, kb * BKE);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -287,7 +340,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
     // The whole warp walks the loop and one elected lane issues: descriptors, TMEM and barrier addresses are then warp-uniform for
     // the compiler (uniform registers); under `if (lane == 0)` every tcgen05.mma paid a vector-to-uniform waterfall of ~12 instructions.
     if (rank == 0) {
-      constexpr uint32_t idesc = instr_desc<BN, A_MN, B_MN, CTAS>();
+      constexpr uint32_t idesc = instr_desc<BN, A_MN, B_MN, CTAS, ET>();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
@@ -305,10 +358,11 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = smem_desc<A_MN>(sa + k * kstep_bytes<A_MN>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
-              if (CTAS == 2) umma_tf32_pair(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BKE / E::MMA_K; ++k) {
+              const uint64_t da = smem_desc<A_MN, ET>(sa + k * kstep_bytes<A_MN, ET>()), db = smem_desc<B_MN, ET>(sb + k * kstep_bytes<B_MN, ET>());
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (E::IS_BF16) { if (CTAS == 2) umma_f16_pair(acc, da, db, idesc, accum); else umma_f16(acc, da, db, idesc, accum); }
+              else { if (CTAS == 2) umma_tf32_pair(acc, da, db, idesc, accum); else umma_tf32(acc, da, db, idesc, accum); }
             }
             if (CTAS == 2) umma_commit_pair(empty(stage)); else umma_commit(empty(stage));   // smem slot(s) free once these MMAs have read them
           }
@@ -339,7 +393,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
       // 16-byte accesses of both phases are conflict-free) and stores 4 full 128-byte row segments per instruction.
       const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * (32 * 36 * 4);
       const int sub_row = lane >> 3, quad = lane & 7;
-      const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+      const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & (4 * sizeof(OT) - 1)) == 0);
       const bool timed = p.prof != nullptr && warp == 2 && lane == 0;
 #pragma unroll 1
       for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {   // the quarter's warps take alternating chunks
@@ -351,7 +405,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int mg = (mt * CTAS + (int)rank) * BM + q * 32 + 4 * i + sub_row;
-            g4[i] = (mg < p.M && ng + 3 < p.N) ? __ldg(reinterpret_cast<const float4 *>(p.gate + (long long)mg * p.ldd + ng)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[i] = (mg < p.M && ng + 3 < p.N) ? ld4(reinterpret_cast<const OT *>(p.gate) + (long long)mg * p.ldd + ng) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float v[32];
@@ -386,7 +440,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
           if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           const int m = (mt * CTAS + (int)rank) * BM + q * 32 + r;
           if (m >= p.M || n >= p.N) continue;
-          float *dst = D + (long long)m * p.ldd + n;
+          OT *dst = D + (long long)m * p.ldd + n;
           if (p.drop_thresh != 0u) {                              // host guarantees the vector path: N % 4 == 0
             float keep[4];
             hashrng::keep4(hashrng::with_epoch(p.seed, p.epoch), ((unsigned long long)m * p.N + n) >> 2, p.drop_thresh, p.drop_scale, keep);
@@ -398,17 +452,18 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
             o.z = gq.z > 0.f ? o.z * p.gate_scale : 0.f; o.w = gq.w > 0.f ? o.w * p.gate_scale : 0.f;
           }
           if (vec_ok && n + 3 < p.N) {
-            if (p.atomic)
+            if (p.atomic) {                                           // host guarantees OT == float for accumulating launches
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-            else
-              *reinterpret_cast<float4 *>(dst) = o;                   // (evict-first .cs stores measured 20 % slower here)
+            } else {
+              st4(dst, o);                                            // (evict-first .cs stores measured 20 % slower here)
+            }
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (n + j < p.N) {
-                if (p.atomic) atomicAdd(dst + j, ov[j]);
-                else dst[j] = ov[j];
+                if (p.atomic) atomicAdd(reinterpret_cast<float *>(dst) + j, ov[j]);
+                else st1(dst + j, ov[j]);
               }
             }
           }
@@ -443,6 +498,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const float *__restrict__ bias, const Problem p)
 {
   gemm_tf32_body<BN, A_MN, B_MN, 1>(tmA, tmB, D, bias, p);
+}
+
+// bf16 operands (tcgen05.mma kind::f16, fp32 accumulation in TMEM), D in bf16 (forward / grad-input) or fp32 (weight gradients, split-K)
+template <int BN, bool A_MN, bool B_MN, typename OT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OT *__restrict__ D,
+                 const float *__restrict__ bias, const Problem p)
+{
+  gemm_tf32_body<BN, A_MN, B_MN, 1, __nv_bfloat16, OT>(tmA, tmB, D, bias, p);
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OT *__restrict__ D,
+                      const float *__restrict__ bias, const Problem p)
+{
+  gemm_tf32_body<BN, A_MN, B_MN, 2, __nv_bfloat16, OT>(tmA, tmB, D, bias, p);
 }
 
 // CTA-pair variant: cluster of two CTAs on one TPC, 256 x BN tiles, tcgen05.mma.cta_group::2.

@@ -40,6 +40,31 @@ def amos_train_config(seed=0, volume=(256, 256, 128)):
     return cfg
 
 
+def defdetr_train_config(seed=0, volume=(256, 256, 128)):
+    """configs.defdetr_amos_config + the reference's training keys; matching runs on the predicted boxes (there are no atlas anchors)."""
+    from .configs import defdetr_amos_config
+    cfg = defdetr_amos_config(seed, volume)
+    cfg.update(lr=2e-4, lr_backbone=2e-5, weight_decay=1e-4, clip_max_norm=-1, batch_size=2, anchor_matching=False,
+               set_cost_class=1, set_cost_bbox=5, set_cost_giou=2, loss_coefs=copy.deepcopy(VISCERAL_LOSS_COEFS), num_classes=15)
+    return cfg
+
+
+def swin_focused_train_config(seed=0, volume=(192, 192, 384)):
+    from .configs import swin_focused_config
+    cfg = swin_focused_config(seed, volume)
+    cfg.update(lr=2e-4, lr_backbone=2e-5, weight_decay=1e-4, clip_max_norm=-1, batch_size=2, anchor_matching=True,
+               set_cost_class=1, set_cost_bbox=0, set_cost_giou=0, loss_coefs=copy.deepcopy(VISCERAL_LOSS_COEFS), num_classes=20)
+    return cfg
+
+
+def build_model(config):
+    """``TransoarNet`` (Focused Decoder, the reference's shipped model) or the restated 3D Deformable-DETR (config['model_family'] == 'def_detr')."""
+    if config.get("model_family") == "def_detr":
+        from .def_detr import DefDetrNet
+        return DefDetrNet(config)
+    return TransoarNet(config)
+
+
 def synthetic_targets(config, batch, seed, device):
     """One box per organ = the atlas median jittered by a few percent, labels 1..num_organs; dense form."""
     g = torch.Generator().manual_seed(seed)
@@ -194,8 +219,11 @@ class TrainStep:
     path averages the gradients through two flat buckets (``OverlappedGradientAverage``: NCCL all-reduce inside the graph, the large
     one under the tail of the backward) instead of DDP's hooks; parameters are broadcast from rank 0 at construction as DDP would."""
 
-    def __init__(self, config, device, world=1, tf32=True, channels_last=True, cudnn_autotune=True, graph=False, graph_warmup=3):
+    def __init__(self, config, device, world=1, tf32=True, channels_last=True, cudnn_autotune=True, graph=False, graph_warmup=3, amp_dtype=None):
         self.config, self.device = config, torch.device(device)
+        # amp_dtype=torch.bfloat16: forward + criterion inside torch.autocast, as the reference's trainer runs them (fp16 + GradScaler there,
+        # trainer.py:67-69; bf16 needs no loss scaling).  Linear layers then take the bf16 tcgen05 GEMM route, the op gets bf16 `value`.
+        self.amp_dtype = amp_dtype
         if tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
@@ -203,7 +231,7 @@ class TrainStep:
             # the reference pins cudnn.benchmark = False for reproducibility (scripts/train.py:113-114); with fixed shapes the
             # autotuner picks the weight-stationary tensor-core kernels for the 24- and 48-channel stages (105 -> 93 ms per step)
             torch.backends.cudnn.benchmark = True
-        self.net = TransoarNet(config).to(self.device).train()
+        self.net = build_model(config).to(self.device).train()
         if channels_last:
             # conv weights NDHWC: the backbone's activations then stay in the layout the tensor-core convolutions use, the fused
             # InstanceNorm kernels follow it, and flatten(2).transpose(1, 2) of a feature map is a view
@@ -264,9 +292,10 @@ class TrainStep:
             self._averager.zero()                                       # gradients live in the averager's flat buffer
         else:
             self.optim.zero_grad(set_to_none=True)
-        out = self.model(x)
-        losses = self.criterion(out, targets, seg_targets, self.net._anchors)
-        loss = total_loss(losses, self.config["loss_coefs"])
+        with torch.autocast("cuda", dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            out = self.model(x)
+            losses = self.criterion(out, targets, seg_targets, self.net._anchors)
+            loss = total_loss(losses, self.config["loss_coefs"])
         if self.world > 1 and self.graph:
             self._averager.before_backward()
         loss.backward()

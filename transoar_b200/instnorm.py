@@ -21,9 +21,9 @@ def _p(t):
 
 
 def _channels_last(x):
-    """True when x is a 5-D fp32 tensor stored NDHWC (and not also NCDHW-contiguous) with a channel count the NDHWC kernels take."""
+    """True when x is a 5-D fp32 / bf16 tensor stored NDHWC (and not also NCDHW-contiguous) with a channel count the NDHWC kernels take."""
     C = x.shape[1] if x.dim() == 5 else 0
-    return (x.dim() == 5 and x.dtype == torch.float32 and C % 4 == 0 and C > 0 and 192 % (C // 4) == 0
+    return (x.dim() == 5 and x.dtype in (torch.float32, torch.bfloat16) and C % 4 == 0 and C > 0 and 192 % (C // 4) == 0
             and x.is_contiguous(memory_format=torch.channels_last_3d) and not x.is_contiguous())
 
 
@@ -46,9 +46,10 @@ class InstanceNormReLUFunction(Function):
         ctx.channels_last = cl
         if cl:
             ws = torch.empty(_lib.lib().instnorm_ndhwc_workspace_floats(B, C, V), dtype=torch.float32, device=x.device)
+            fwd = _lib.lib().instnorm_relu_forward_ndhwc_bf16 if x.dtype == torch.bfloat16 else _lib.lib().instnorm_relu_forward_ndhwc
             with torch.cuda.device(x.device):
-                rc = _lib.lib().instnorm_relu_forward_ndhwc(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(x), _p(w), _p(b),
-                                                            B, C, V, float(eps), _p(y), _p(mean), _p(rstd), _p(ws))
+                rc = fwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(x), _p(w), _p(b),
+                         B, C, V, float(eps), _p(y), _p(mean), _p(rstd), _p(ws))
             _lib.check(rc, "instnorm_relu_forward_ndhwc")
             ctx.save_for_backward(x, b, w, mean, rstd)            # the NDHWC backward recomputes the ReLU mask from x: y is not kept
             ctx.param_dtypes = (weight.dtype, bias.dtype)
@@ -75,9 +76,10 @@ class InstanceNormReLUFunction(Function):
         db = torch.empty_like(dw)
         if ctx.channels_last:
             ws = torch.empty(_lib.lib().instnorm_ndhwc_workspace_floats(B, C, V), dtype=torch.float32, device=x.device)
+            bwd = _lib.lib().instnorm_relu_backward_ndhwc_bf16 if x.dtype == torch.bfloat16 else _lib.lib().instnorm_relu_backward_ndhwc
             with torch.cuda.device(x.device):
-                rc = _lib.lib().instnorm_relu_backward_ndhwc(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy), _p(x), _p(w),
-                                                             _p(y), _p(mean), _p(rstd), B, C, V, _p(dx), _p(dw), _p(db), _p(ws))
+                rc = bwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy), _p(x), _p(w),
+                         _p(y), _p(mean), _p(rstd), B, C, V, _p(dx), _p(dw), _p(db), _p(ws))
             _lib.check(rc, "instnorm_relu_backward_ndhwc")
             return dx, dw.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
         ws = torch.empty(_lib.lib().instnorm_workspace_floats(_DT[x.dtype], B, C, V), dtype=torch.float32, device=x.device)

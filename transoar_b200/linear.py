@@ -36,6 +36,22 @@ def gemm(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=None, relu=False, accumula
     return D
 
 
+def gemm_bf16(A, a_mn, lda, B, b_mn, ldb, D, M, N, R, bias=None, relu=False, accumulate=False, split_k=1, gate=None, gate_scale=1.0,
+              p_drop=0.0, seed=0):
+    """The same GEMM with bf16 operands (tcgen05.mma kind::f16, fp32 accumulation): D is bf16, or fp32 when it accumulates (weight
+    gradients).  ``bias`` stays fp32.  include/tc_gemm.h: tc_gemm_bf16."""
+    if not (A.is_cuda and B.is_cuda and D.is_cuda):
+        raise RuntimeError("tc_gemm: Not implemented on the CPU")
+    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16 or D.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("tc_gemm_bf16: bf16 operands, bf16 or fp32 result")
+    with torch.cuda.device(D.device):
+        rc = _lib.lib().tc_gemm_bf16(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(A), int(a_mn), lda, _p(B), int(b_mn), ldb,
+                                     _p(D), int(D.dtype == torch.float32), D.stride(0), _p(bias), M, N, R, int(relu), int(accumulate), split_k,
+                                     _p(gate), float(gate_scale), float(p_drop), int(seed))
+    _lib.check(rc, "tc_gemm_bf16")
+    return D
+
+
 def colsum(x2):
     """Column sums of a contiguous fp32 CUDA matrix [rows, C] (bias gradient); ATen's reduction where the kernel's shape limits do not hold."""
     rows, C = x2.shape
@@ -83,6 +99,46 @@ class LinearFunction(Function):
             gemm(dy2, 1, N, x2, 1, K, dw, N, K, M, accumulate=True, split_k=0)           # dW = dY^T X      (both MN-major, split-K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
+        return dx, dw, db, None
+
+
+class LinearBf16Function(Function):
+    """``LinearFunction`` for the bf16 route (autocast / bf16 activations): x and a bf16 copy of the fp32 master weight go through the
+    kind::f16 tcgen05 GEMM, y and grad_input are bf16, grad_weight / grad_bias are accumulated in fp32 straight into master-weight
+    precision (autocast's own route produces a bf16 weight gradient and casts it)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        if not x.is_cuda:
+            raise RuntimeError("tc linear: Not implemented on the CPU")
+        K, N = x.shape[-1], weight.shape[0]
+        x2 = x.reshape(-1, K).to(torch.bfloat16).contiguous()
+        w = weight.to(torch.bfloat16).contiguous()
+        M = x2.shape[0]
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+        gemm_bf16(x2, 0, K, w, 0, K, y, M, N, K, bias=None if bias is None else bias.float().contiguous(), relu=relu)
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.has_bias, ctx.in_shape, ctx.in_dtype = bias is not None, x.shape, x.dtype
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N).to(torch.bfloat16)
+        dy2 = dy2 * (y > 0) if y is not None else dy2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy.device)
+            gemm_bf16(dy2, 0, N, w, 1, K, dx, M, K, N)
+            dx = dx.reshape(ctx.in_shape).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
+            gemm_bf16(dy2, 1, N, x2, 1, K, dw, N, K, M, accumulate=True, split_k=0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0, dtype=torch.float32)
         return dx, dw, db, None
 
 
@@ -138,7 +194,20 @@ def ffn(x, linear1, linear2, p, training):
 
 
 def linear(x, weight, bias=None, relu=False):
+    if bf16_eligible(x, weight):
+        return LinearBf16Function.apply(x, weight, bias, relu)
     return LinearFunction.apply(x, weight, bias, relu)
+
+
+def bf16_eligible(x, weight):
+    """The bf16 route: CUDA, fp32 master weights, and either bf16 activations or an active bf16 autocast region (what the reference's
+    trainer runs the model under -- fp16 there, trainer.py:67-69; bf16 is BASELINE configs[2] / [3]).  Feature counts must be multiples
+    of 8 (TMA strides are multiples of 16 bytes)."""
+    if not (x.is_cuda and weight.is_cuda and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0):
+        return False
+    if torch.is_autocast_enabled():
+        return torch.get_autocast_dtype("cuda") == torch.bfloat16 and x.dtype in (torch.float32, torch.bfloat16)
+    return x.dtype == torch.bfloat16
 
 
 def tc_eligible(x, weight):
@@ -155,7 +224,7 @@ class TCLinear(nn.Linear):
     it is the plain library GEMM, exactly as in the reference.  ``relu=True`` fuses the activation into the GEMM epilogue."""
 
     def forward(self, x, relu=False):
-        if tc_eligible(x, self.weight):
+        if tc_eligible(x, self.weight) or bf16_eligible(x, self.weight):
             return linear(x, self.weight, self.bias, relu)
         y = F.linear(x, self.weight, self.bias)
         return F.relu(y) if relu else y
