@@ -38,6 +38,19 @@ int roi_attn_backward(void *stream, const float *q, const float *k, const float 
                       int batch, int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z,
                       const float *out, const float *dout, const float *lse, float *dq, float *dk, float *dv);
 
+/* The same two entry points with the five contractions (Q K^T, P V; dO V^T, P^T dO, dS^T Q, dS K) on the tensor cores: mma.sync m16n8k8
+ * with TF32 operands and fp32 accumulation (transoar_b200/csrc/roi_attn_tc_kernels.cuh).  TF32 is what the reference's torch.matmul calls
+ * in FocusedAttn.forward (focused_decoder.py:238,254) run at when torch.backends.cuda.matmul.allow_tf32 is on (torch 1.10's default);
+ * the python module selects these when that flag is set and the fp32 CUDA-core kernels above otherwise.  Arguments, workspace, partial
+ * state and error codes are identical. */
+int roi_attn_forward_tf32(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                          int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse,
+                          float *workspace, long long workspace_floats);
+
+int roi_attn_backward_tf32(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups,
+                           int batch, int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z,
+                           const float *out, const float *dout, const float *lse, float *dq, float *dk, float *dv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,3 +169,37 @@ def test_transoarnet_against_reference_fixture():
             errs["grad " + k] = (_rel(p.grad, t("pg." + k)), 1e-1 if k.startswith("_backbone._encoder") else 5e-3)
     bad = {k: v for k, v in errs.items() if not v[0] < v[1]}
     assert not bad, f"{len(bad)} of {len(errs)} quantities off: {bad}"
+
+
+@pytest.mark.parametrize("hd,H,per,grid", [(48, 8, 27, (6, 7, 9)), (16, 2, 1, (3, 3, 3)), (32, 3, 7, (5, 4, 8)), (64, 2, 54, (4, 6, 5)),
+                                           (96, 1, 27, (3, 5, 7)), (128, 1, 5, (2, 3, 9)), (48, 8, 27, (12, 14, 20))])
+def test_roi_attention_tensor_core_kernels_match_dense_oracle_at_tf32_tolerance(hd, H, per, grid):
+    """The mma.sync TF32 kernels (include/roi_attn.h, *_tf32): same results as the dense fp64-free oracle up to TF32 rounding of the
+    operands (10 mantissa bits: relative 1e-3 on products; scores here are O(sqrt(hd)) so 3e-3 of each tensor's maximum), and the
+    yardstick -- torch's own TF32 matmul on the dense formulation -- is not closer."""
+    gen = torch.Generator().manual_seed(hd + per + 1)
+    boxes = _random_boxes(3, per, grid, gen)
+    boxes[0:per] = torch.tensor([0, 0, 0, *grid], dtype=torch.int32)
+    boxes[per:2 * per] = torch.tensor([1, 1, 1, 2, 2, 2], dtype=torch.int32)
+    Nq, Nkv, B = boxes.shape[0], grid[0] * grid[1] * grid[2], 2
+    mk = lambda *s: (torch.randn(*s, generator=gen) * 0.5).to(DEV).requires_grad_(True)
+    q, k, v = mk(B, Nq, H, hd), mk(B, Nkv, H, hd), mk(B, Nkv, H, hd)
+    g = torch.randn(B, Nq, H * hd, generator=gen).to(DEV)
+    groups = focused.groups_from_boxes(boxes).to(DEV)
+    from transoar_b200 import _lib
+    n0 = _lib.lib().msda3d_launch_count()
+    out = focused.RoIAttentionFunction.apply(q, k, v, groups, grid[1:], True)
+    out.backward(g)
+    assert _lib.lib().msda3d_launch_count() - n0 in (2, 3)
+    got = [out.detach(), q.grad.clone(), k.grad.clone(), v.grad.clone()]
+    q.grad = k.grad = v.grad = None
+    want = dense_masked_attention(q, k, v, boxes, grid)
+    want.backward(g)
+    for a, b in zip(got, [want.detach(), q.grad, k.grad, v.grad]):
+        assert _rel(a, b) < 4e-3, _rel(a, b)
+    # against the strict-fp32 CUDA-core kernels of the same library: the two must differ only at TF32 level too
+    q.grad = k.grad = v.grad = None
+    out32 = focused.RoIAttentionFunction.apply(q, k, v, groups, grid[1:], False)
+    out32.backward(g)
+    for a, b in zip(got, [out32.detach(), q.grad, k.grad, v.grad]):
+        assert _rel(a, b) < 4e-3

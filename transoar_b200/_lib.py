@@ -45,6 +45,12 @@ _SIGNATURES = {
     "roi_attn_workspace_floats": (ctypes.c_longlong, [_ci] * 5),
     "roi_attn_forward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
     "roi_attn_backward": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
+    "roi_attn_forward_tf32": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp, _vp, _vp, ctypes.c_longlong]),
+    "roi_attn_backward_tf32": (_ci, [_vp] * 5 + [_ci] * 8 + [_vp] * 6),
+    # include/win_attn.h
+    "win_attn_supported": (_ci, [_ci, _ci]),
+    "win_attn_forward": (_ci, [_vp] * 4 + [_ci] * 5 + [ctypes.c_float, _vp, _vp]),
+    "win_attn_backward": (_ci, [_vp] * 8 + [_ci] * 5 + [ctypes.c_float, _vp, _vp]),
     # include/conv3d_tc.h
     "conv3d_tc_supported": (_ci, [_ci, _ci]),
     "hash_rng_set_epoch": (None, [_vp]),

@@ -1,5 +1,5 @@
 // roi_attn_capi.cu -- C ABI of the fused RoI attention (include/roi_attn.h).
-#include "roi_attn_kernels.cuh"
+#include "roi_attn_tc_kernels.cuh"
 
 #include <atomic>
 
@@ -10,12 +10,12 @@ extern std::atomic<unsigned long long> g_msda3d_launches;
 
 namespace {
 
-template <int HD>
+template <int HD, bool TC>
 int launch_fwd(cudaStream_t st, int G, int B, const float *q, const float *k, const float *v, const int *groups, int Nq, int Nkv, int H,
                int Y, int Z, float *out, float *lse, int S, float *part)
 {
-  auto kern = roiattn::fwd_kernel<HD>;
-  constexpr size_t smem = roiattn::fwd_smem_bytes<HD>();
+  auto kern = TC ? roiattn::fwd_tc_kernel<HD> : roiattn::fwd_kernel<HD>;
+  constexpr size_t smem = TC ? roiattn::fwd_tc_smem_bytes<HD>() : roiattn::fwd_smem_bytes<HD>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<dim3(G * S, H, B), roiattn::kThreads, smem, st>>>(q, k, v, groups, Nq, Nkv, H, Y, Z, out, lse, S, part);
@@ -26,12 +26,12 @@ int launch_fwd(cudaStream_t st, int G, int B, const float *q, const float *k, co
   return (int)cudaGetLastError();
 }
 
-template <int HD>
+template <int HD, bool TC>
 int launch_bwd(cudaStream_t st, int G, int B, const float *q, const float *k, const float *v, const int *groups, const float *out,
                const float *dout, const float *lse, int Nq, int Nkv, int H, int Y, int Z, float *dq, float *dk, float *dv, int S)
 {
-  auto kern = roiattn::bwd_kernel<HD>;
-  constexpr size_t smem = roiattn::bwd_smem_bytes<HD>();
+  auto kern = TC ? roiattn::bwd_tc_kernel<HD> : roiattn::bwd_kernel<HD>;
+  constexpr size_t smem = TC ? roiattn::bwd_tc_smem_bytes<HD>() : roiattn::bwd_smem_bytes<HD>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<dim3(G * S, H, B), roiattn::kThreads, smem, st>>>(q, k, v, groups, out, dout, lse, Nq, Nkv, H, Y, Z, dq, dk, dv, S);
@@ -65,9 +65,8 @@ bool bad_dims(int G, int B, int Nq, int Nkv, int H, int Y, int Z)
     default: return MSDA3D_EINVAL;                            \
   }
 
-extern "C" {
-
-int roi_attn_forward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+template <bool TC>
+static int roi_forward_impl(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
                      int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse,
                      float *workspace, long long workspace_floats)
 {
@@ -77,20 +76,15 @@ int roi_attn_forward(void *stream, const float *q, const float *k, const float *
   const long long need = (long long)batch * num_heads * num_query * (head_dim + 2);
   while (S > 1 && (!workspace || need * S > workspace_floats)) --S;       // no / small workspace: fewer splits, still correct
   int rc = 0;
-  HD_DISPATCH(head_dim, rc = launch_fwd<HD>((cudaStream_t)stream, num_groups, batch, q, k, v, groups, num_query, num_kv, num_heads,
+  HD_DISPATCH(head_dim, rc = launch_fwd<HD, TC>((cudaStream_t)stream, num_groups, batch, q, k, v, groups, num_query, num_kv, num_heads,
                                             grid_y, grid_z, out, lse, S, workspace));
   g_msda3d_launches += (S > 1) ? 2 : 1;
   return rc;
 }
 
-long long roi_attn_workspace_floats(int num_groups, int batch, int num_query, int num_heads, int head_dim)
-{
-  if (num_groups <= 0 || batch <= 0 || num_query <= 0 || num_heads <= 0 || head_dim <= 0) return 0;
-  const int S = pick_splits(num_groups, num_heads, batch);
-  return S > 1 ? (long long)batch * num_heads * num_query * (head_dim + 2) * S : 0;
-}
 
-int roi_attn_backward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+template <bool TC>
+static int roi_backward_impl(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
                       int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, const float *out,
                       const float *dout, const float *lse, float *dq, float *dk, float *dv)
 {
@@ -104,10 +98,52 @@ int roi_attn_backward(void *stream, const float *q, const float *k, const float 
   if (e == cudaSuccess && S > 1) e = cudaMemsetAsync(dq, 0, (size_t)batch * num_query * num_heads * head_dim * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   int rc = 0;
-  HD_DISPATCH(head_dim, rc = launch_bwd<HD>(st, num_groups, batch, q, k, v, groups, out, dout, lse, num_query, num_kv, num_heads,
+  HD_DISPATCH(head_dim, rc = launch_bwd<HD, TC>(st, num_groups, batch, q, k, v, groups, out, dout, lse, num_query, num_kv, num_heads,
                                             grid_y, grid_z, dq, dk, dv, S));
   ++g_msda3d_launches;
   return rc;
+}
+
+
+extern "C" {
+
+int roi_attn_forward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                     int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse,
+                     float *workspace, long long workspace_floats)
+{
+  return roi_forward_impl<false>(stream, q, k, v, groups, num_groups, batch, num_query, num_kv, num_heads, head_dim, grid_y, grid_z, out, lse,
+                                 workspace, workspace_floats);
+}
+
+int roi_attn_forward_tf32(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                          int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, float *out, float *lse,
+                          float *workspace, long long workspace_floats)
+{
+  return roi_forward_impl<true>(stream, q, k, v, groups, num_groups, batch, num_query, num_kv, num_heads, head_dim, grid_y, grid_z, out, lse,
+                                workspace, workspace_floats);
+}
+
+long long roi_attn_workspace_floats(int num_groups, int batch, int num_query, int num_heads, int head_dim)
+{
+  if (num_groups <= 0 || batch <= 0 || num_query <= 0 || num_heads <= 0 || head_dim <= 0) return 0;
+  const int S = pick_splits(num_groups, num_heads, batch);
+  return S > 1 ? (long long)batch * num_heads * num_query * (head_dim + 2) * S : 0;
+}
+
+int roi_attn_backward(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                      int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, const float *out,
+                      const float *dout, const float *lse, float *dq, float *dk, float *dv)
+{
+  return roi_backward_impl<false>(stream, q, k, v, groups, num_groups, batch, num_query, num_kv, num_heads, head_dim, grid_y, grid_z, out, dout,
+                                  lse, dq, dk, dv);
+}
+
+int roi_attn_backward_tf32(void *stream, const float *q, const float *k, const float *v, const int32_t *groups, int num_groups, int batch,
+                           int num_query, int num_kv, int num_heads, int head_dim, int grid_y, int grid_z, const float *out,
+                           const float *dout, const float *lse, float *dq, float *dk, float *dv)
+{
+  return roi_backward_impl<true>(stream, q, k, v, groups, num_groups, batch, num_query, num_kv, num_heads, head_dim, grid_y, grid_z, out, dout,
+                                 lse, dq, dk, dv);
 }
 
 }  // extern "C"

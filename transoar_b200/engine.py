@@ -330,6 +330,15 @@ class TrainStep:
         cur.wait_stream(self._stream)
         return loss
 
+    def eager_step(self, volumes, targets):
+        """One step launched eagerly (kernel by kernel) even when this object replays a CUDA graph: same model, optimiser state and
+        stream.  bench.py uses it to time individual kernels with CUDA events, which cannot be read inside a replayed graph."""
+        x = self.to_device(volumes)
+        boxes, valid = targets if isinstance(targets, tuple) else dense_targets(targets, self.criterion.num_classes, self.device)
+        if self._stream is None:
+            return self._run(x, (boxes, valid), None)
+        return self._eager_on_side_stream(x, (boxes, valid))
+
     def step(self, volumes, targets, seg_targets=None):
         """targets: the reference's list of {'boxes','labels'} dicts or the dense (boxes [B,O,6], valid [B,O]) pair.  Returns the total loss (device scalar)."""
         x = self.to_device(volumes)

@@ -82,9 +82,12 @@ class RoIAttentionFunction(Function):
     """out[B,Nq,H*HD] = softmax_{tokens in box(q)}(q k^T) v  -- the core of focused_decoder.py:238-254."""
 
     @staticmethod
-    def forward(ctx, q, k, v, groups, grid_yz):
+    def forward(ctx, q, k, v, groups, grid_yz, tf32=None):
         if not (q.is_cuda and k.is_cuda and v.is_cuda and groups.is_cuda):
             raise RuntimeError("RoI attention: Not implemented on the CPU")
+        # TF32 tensor-core kernels exactly where torch itself would use TF32 for the reference's q @ k^T / attn @ v (focused_decoder.py:238,254)
+        ctx.tf32 = torch.backends.cuda.matmul.allow_tf32 if tf32 is None else bool(tf32)
+        fwd = _lib.lib().roi_attn_forward_tf32 if ctx.tf32 else _lib.lib().roi_attn_forward
         q, k, v = q.float().contiguous(), k.float().contiguous(), v.float().contiguous()
         B, Nq, H, HD = q.shape
         Nkv = k.shape[1]
@@ -93,7 +96,7 @@ class RoIAttentionFunction(Function):
         ws_n = _lib.lib().roi_attn_workspace_floats(groups.shape[0], B, Nq, H, HD)
         ws = torch.empty(max(ws_n, 1), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            rc = _lib.lib().roi_attn_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(q), _p(k), _p(v), _p(groups),
+            rc = fwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(q), _p(k), _p(v), _p(groups),
                                              groups.shape[0], B, Nq, Nkv, H, HD, grid_yz[0], grid_yz[1], _p(out), _p(lse),
                                              _p(ws), ws_n)
         _lib.check(rc, "roi_attn_forward")
@@ -110,11 +113,12 @@ class RoIAttentionFunction(Function):
         dout = dout.float().contiguous()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         with torch.cuda.device(q.device):
-            rc = _lib.lib().roi_attn_backward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(q), _p(k), _p(v), _p(groups),
+            bwd = _lib.lib().roi_attn_backward_tf32 if ctx.tf32 else _lib.lib().roi_attn_backward
+            rc = bwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(q), _p(k), _p(v), _p(groups),
                                               groups.shape[0], B, Nq, Nkv, H, HD, ctx.grid_yz[0], ctx.grid_yz[1], _p(out), _p(dout),
                                               _p(lse), _p(dq), _p(dk), _p(dv))
         _lib.check(rc, "roi_attn_backward")
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
 
 
 class FocusedAttn(nn.Module):

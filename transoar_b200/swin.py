@@ -9,11 +9,16 @@ The four Linear layers of every block are ``TCLinear`` (TF32 tcgen05 GEMMs when 
 window attention itself (head dim 16) is ``scaled_dot_product_attention`` with the relative-position bias and the shift mask
 as one additive term -- a library call: at 5x5x5 windows it is tiny next to the projections.  Device-agnostic torch code, so the
 fixtures generated from the reference modules are checked on the CPU (tests/test_swin_cpu.py)."""
+import ctypes
 import math
 
 import torch
 import torch.nn.functional as F
 from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
 
 from .linear import TCLinear
 
@@ -76,6 +81,48 @@ class DropPath(nn.Module):
         return x * gate / keep
 
 
+class WindowAttentionFunction(Function):
+    """softmax((q * scale) k^T + bias[head] (+ mask[window])) v on the fused sm_100a kernel (include/win_attn.h).
+    ``qkv`` [Bw, n, 3, H, 16] (the qkv Linear's output, viewed), ``bias`` [H, n, n], ``mask`` [nW, n, n] or None -> [Bw, n, H * 16]."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias, mask, scale):
+        if not qkv.is_cuda:
+            raise RuntimeError("window attention: Not implemented on the CPU")
+        qkv = qkv.float().contiguous()
+        bias = bias.float().contiguous()
+        bias_t = bias.transpose(1, 2).contiguous()
+        mask = None if mask is None else mask.float().contiguous()
+        Bw, n, _, H, hd = qkv.shape
+        out = torch.empty(Bw, n, H * hd, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(Bw, H, n, dtype=torch.float32, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.lib().win_attn_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _ptr(qkv), _ptr(bias_t), _ptr(mask), Bw, n, H, hd,
+                                             0 if mask is None else mask.shape[0], float(scale), _ptr(out), _ptr(lse))
+        _lib.check(rc, "win_attn_forward")
+        ctx.save_for_backward(qkv, bias, bias_t, mask, out, lse)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        qkv, bias, bias_t, mask, out, lse = ctx.saved_tensors
+        Bw, n, _, H, hd = qkv.shape
+        dout = dout.float().contiguous()
+        dqkv, dbias = torch.empty_like(qkv), torch.empty_like(bias)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.lib().win_attn_backward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _ptr(qkv), _ptr(bias), _ptr(bias_t), _ptr(mask),
+                                              _ptr(out), _ptr(dout), _ptr(lse), Bw, n, H, hd, 0 if mask is None else mask.shape[0], ctx.scale,
+                                              _ptr(dqkv), _ptr(dbias))
+        _lib.check(rc, "win_attn_backward")
+        return dqkv, dbias, None, None
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
 class WindowAttention3D(nn.Module):
     def __init__(self, dim, window_size, num_heads, qkv_bias, qk_scale, attn_drop, proj_drop):
         super().__init__()
@@ -97,8 +144,14 @@ class WindowAttention3D(nn.Module):
         """x [B * nW, n, C]; mask [nW, n, n] or None."""
         Bw, n, C = x.shape
         H = self.num_heads
-        q, k, v = self.qkv(x).reshape(Bw, n, 3, H, C // H).permute(2, 0, 3, 1, 4)                  # each [Bw, H, n, hd]
+        qkv = self.qkv(x)
         bias = self.relative_position_bias_table[self.relative_position_index[:n, :n].reshape(-1)].reshape(n, n, H).permute(2, 0, 1)
+        if (x.is_cuda and not (self.training and self.attn_drop.p > 0) and (mask is None or Bw % mask.shape[0] == 0)
+                and _lib.lib().win_attn_supported(n, C // H)):
+            # fused kernel: reads q, k, v in place out of the Linear's output, keeps K / V in shared memory, never builds [Bw, H, n, n]
+            out = WindowAttentionFunction.apply(qkv.reshape(Bw, n, 3, H, C // H), bias, mask, self.scale)
+            return self.proj_drop(self.proj(out.to(qkv.dtype)))
+        q, k, v = qkv.reshape(Bw, n, 3, H, C // H).permute(2, 0, 3, 1, 4)                          # each [Bw, H, n, hd]
         if mask is None:
             add = bias[None]                                                                        # [1, H, n, n]
         else:
