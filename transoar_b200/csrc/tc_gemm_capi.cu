@@ -68,6 +68,22 @@ int make_map(CUtensorMap *map, const float *ptr, long long inner, long long oute
   return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
 }
 
+// D [M][N] fp32 for the TMA-store epilogue: box = 32 columns (128 bytes) x 32 rows, 128-byte swizzle (kernels.cuh); parts of a box past
+// M / N are clipped on the way out.
+int make_map_out(CUtensorMap *map, float *ptr, long long N, long long M, long long ldd)
+{
+  ensure_context_on_this_thread();
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ldd * sizeof(float)};
+  const cuuint32_t box[2] = {32u, 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
+}
+
 // 2-D bf16 tensor: box = 64 inner elements (128 bytes) x box_outer rows, plain 128-byte swizzle for both operand layouts (kernels.cuh, Elem<bf16>).
 int make_map_bf16(CUtensorMap *map, const void *ptr, long long inner, long long outer, long long ld, int box_outer)
 {
@@ -298,6 +314,14 @@ extern "C" int tc_gemm_tf32_ex(void *stream, const float *A, int a_mn_major, lon
   p.prof = g_prof.load();
   p.rb_per_split = (r_blocks + splits - 1) / splits;
   p.splits = (r_blocks + p.rb_per_split - 1) / p.rb_per_split;   // no empty split
+  // TMA-store epilogue for plain (non-accumulating, un-gated) results: forward and grad-input GEMMs; TC_GEMM_TMA_STORE=0 keeps the
+  // register-store epilogue (diagnostics / A-B timing)
+  static const bool tma_store_enabled = [] { const char *e = getenv("TC_GEMM_TMA_STORE"); return e == nullptr || e[0] != '0'; }();
+  p.tma_store = 0;
+  if (tma_store_enabled && !accumulate && gate == nullptr && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0) {
+    if (int rc = make_map_out(&p.tmD, D, N, M, ldd)) return rc;
+    p.tma_store = 1;
+  }
 
   // CTA pairs (256-row tiles, B tile split over the pair) when there are enough row tiles to fill the machine with pairs;
   // TC_GEMM_PAIR=0 forces the single-CTA kernel (diagnostics).
@@ -352,6 +376,7 @@ extern "C" int tc_gemm_bf16(void *stream, const void *A, int a_mn_major, long lo
   p.drop_thresh = p_drop > 0.f ? (unsigned int)(p_drop * 65536.f + 0.5f) : 0u;
   p.drop_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.prof = nullptr;
+  p.tma_store = 0;
   p.rb_per_split = (r_blocks + splits - 1) / splits;
   p.splits = (r_blocks + p.rb_per_split - 1) / p.rb_per_split;
   static const bool pair_enabled = [] { const char *e = getenv("TC_GEMM_PAIR"); return e == nullptr || e[0] != '0'; }();

@@ -61,10 +61,11 @@ template <int BN, int CTAS> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (184 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;      // 1 CTA: 5 / 4 / 3 (BN = 128 / 192 / 256); pair: 7 / 6 / 5
+  static constexpr int STAGES_RAW = (160 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;      // 1 CTA: 5 / 4 / 3 (BN = 128 / 192 / 256); pair: 6 / 5 / 5
   static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;              // two accumulators of BN columns, rounded to a power of two
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * 36 * 4;            // per epilogue warp: a 32 x 32 fp32 chunk, rows padded to 36 floats
+  static constexpr int EPI_WARP_BYTES = 2 * 4096;                      // per epilogue warp: two 32 x 32 fp32 chunks (TMA-store staging, double-buffered);
+  static constexpr int EPI_BYTES = kEpiWarps * EPI_WARP_BYTES;         // the register-store path uses the first 32 x 36 floats of it
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -223,6 +224,8 @@ struct Problem {
   unsigned long long seed;
   const unsigned long long *epoch;   // hashrng::with_epoch: device counter folded into seed (graph replay), or NULL
   unsigned long long *prof;    // diagnostics (tc_gemm_debug_profile): per CTA 8 cycle counters of the three roles' waits, or NULL
+  int tma_store;               // 1: the epilogue writes D with cp.async.bulk.tensor stores through tmD (fp32 D, no gate, no accumulation)
+  alignas(64) CUtensorMap tmD; // D as a 2-D tensor [M][N], box 32 columns (128 bytes) x 32 rows, 128-byte swizzle
 };
 
 // wait + (diagnostics only) the cycles it took
@@ -257,7 +260,7 @@ __device__ __forceinline__ void st1(__nv_bfloat16 *p, float v) { *p = __float2bf
 // forward / grad-input GEMMs of the bf16 route; accumulating launches always write fp32).
 template <int BN, bool A_MN, bool B_MN, int CTAS, typename ET = float, typename OT = float>
 __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUtensorMap &tmB, OT *__restrict__ D,
-                 const float *__restrict__ bias, const Problem p)
+                 const float *__restrict__ bias, const Problem &p)
 {
   using C = Cfg<BN, CTAS>;
   using E = Elem<ET>;
@@ -380,7 +383,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
     }
   } else {
     const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-    int as = 0;
+    int as = 0, tma_buf = 0;
     uint32_t aphase = 0;
     unsigned long long t_tfull = 0, t_ph[3] = {0, 0, 0};
     const long long t_begin = clock64();
@@ -391,7 +394,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
       // The accumulator comes out of TMEM one row per thread; a row-per-thread store would touch 32 different lines per
       // instruction.  Each warp therefore turns its 32 x 32 chunk around in shared memory (rows padded to 36 floats: the
       // 16-byte accesses of both phases are conflict-free) and stores 4 full 128-byte row segments per instruction.
-      const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * (32 * 36 * 4);
+      const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * C::EPI_WARP_BYTES;
       const int sub_row = lane >> 3, quad = lane & 7;
       const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & (4 * sizeof(OT) - 1)) == 0);
       const bool timed = p.prof != nullptr && warp == 2 && lane == 0;
@@ -413,6 +416,58 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
         const int n0 = nt * BN + c0;
         if (n0 >= p.N) continue;                                  // warp-uniform
         const long long tp1 = timed ? clock64() : 0;
+        if constexpr (sizeof(OT) == 4) {
+          if (p.tma_store) {
+            // TMA-store epilogue: lane r holds row r of the 32 x 32 chunk; bias / ReLU / dropout in registers, the row goes to shared memory
+            // in the 128-byte-swizzled layout of the D tensor map (16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4): conflict-free
+            // for row-per-lane writes), and ONE bulk tensor store per chunk moves 4 KB to global memory asynchronously (SASS UTMASTG).
+            // Rows / columns past M / N are clipped by the copy engine.  Two staging buffers per warp: the store of chunk i overlaps the
+            // TMEM read and the arithmetic of chunk i + 1.
+            const int m_row = (mt * CTAS + (int)rank) * BM + q * 32 + lane;
+            if (bias != nullptr) {
+              if (n0 + 31 < p.N && (reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + n0) + j);
+                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.drop_thresh != 0u) {
+              const unsigned long long sd = hashrng::with_epoch(p.seed, p.epoch);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float keep[4];
+                hashrng::keep4(sd, ((unsigned long long)m_row * p.N + n0 + j) >> 2, p.drop_thresh, p.drop_scale, keep);
+                v[j] *= keep[0]; v[j + 1] *= keep[1]; v[j + 2] *= keep[2]; v[j + 3] *= keep[3];
+              }
+            }
+            const uint32_t buf = epi_base + (uint32_t)(warp - 2) * C::EPI_WARP_BYTES + (uint32_t)(tma_buf * 4096);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store issued from this buffer two chunks ago has read it
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)(lane * 128 + ((i ^ (lane & 7)) << 4))), "f"(v[4 * i]),
+                           "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&p.tmD), "r"(buf), "r"(n0), "r"((mt * CTAS + (int)rank) * BM + q * 32) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            tma_buf ^= 1;
+            if (timed) { const long long tp3 = clock64(); t_ph[0] += (unsigned long long)(tp1 - tp0); t_ph[2] += (unsigned long long)(tp3 - tp1); }
+            continue;
+          }
+        }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -477,6 +532,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
       if (CTAS == 2) mbar_arrive_cluster(tempty(as), 0u); else mbar_arrive(tempty(as));     // the leader's MMA warp waits for both CTAs' epilogues
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // all bulk stores of this warp have completed
     if (p.prof != nullptr && warp == 2 && lane == 0) {
       p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin);
       p.prof[296 * 8 + blockIdx.x * 4 + 0] = t_ph[0]; p.prof[296 * 8 + blockIdx.x * 4 + 1] = t_ph[1]; p.prof[296 * 8 + blockIdx.x * 4 + 2] = t_ph[2];
@@ -495,7 +551,7 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap &tmA, const CUt
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ D,
-                 const float *__restrict__ bias, const Problem p)
+                 const float *__restrict__ bias, const __grid_constant__ Problem p)
 {
   gemm_tf32_body<BN, A_MN, B_MN, 1>(tmA, tmB, D, bias, p);
 }
@@ -504,7 +560,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, bool A_MN, bool B_MN, typename OT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OT *__restrict__ D,
-                 const float *__restrict__ bias, const Problem p)
+                 const float *__restrict__ bias, const __grid_constant__ Problem p)
 {
   gemm_tf32_body<BN, A_MN, B_MN, 1, __nv_bfloat16, OT>(tmA, tmB, D, bias, p);
 }
@@ -512,7 +568,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, bool A_MN, bool B_MN, typename OT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OT *__restrict__ D,
-                      const float *__restrict__ bias, const Problem p)
+                      const float *__restrict__ bias, const __grid_constant__ Problem p)
 {
   gemm_tf32_body<BN, A_MN, B_MN, 2, __nv_bfloat16, OT>(tmA, tmB, D, bias, p);
 }
@@ -521,7 +577,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ D,
-                      const float *__restrict__ bias, const Problem p)
+                      const float *__restrict__ bias, const __grid_constant__ Problem p)
 {
   gemm_tf32_body<BN, A_MN, B_MN, 2>(tmA, tmB, D, bias, p);
 }
