@@ -1,4 +1,4 @@
-"""BASELINE.json config 5: MSDeformAttn3D fwd / bwd microbenchmark sweep -> markdown table (gpurun_out/r01_sweep.md).
+"""BASELINE.json config 5: MSDeformAttn3D fwd / bwd microbenchmark sweep -> markdown table (gpurun_out/r02_sweep.md).
 
 CUDA-event timing, 3 warm-up + 10 timed launches, median; algorithmic bytes per DESIGN.md section 6; fraction of the
 measured HBM peak.  Levels are prefixes of the VISCERAL pyramid (40,40,64),(20,20,32),(10,10,16),(5,5,8); M=6, C=64."""
@@ -10,7 +10,7 @@ import bench
 from transoar_b200 import MultiScaleDeformableAttention as MSDA, synth
 
 PYR = ((40, 40, 64), (20, 20, 32), (10, 10, 16), (5, 5, 8))
-peak, _ = bench.load_peaks()
+peak = bench.load_peaks()["hbm_gbs"]
 
 
 def median_ms(fn, warm=3, reps=10):
@@ -27,32 +27,44 @@ def median_ms(fn, warm=3, reps=10):
 
 def run(N, L, P, queries, dtype, dist):
     g = synth.Geometry("sweep", PYR[:L], 6, 64, P, queries=queries)
-    x = synth.make_inputs(g, N, dist, seed=1234, device="cuda:0", dtype=dtype)
+    # one batch element is generated (host RNG) and repeated on the device: the sweep's largest case has 1.4 G samples (17 GB of
+    # locations); every batch element still has its own value slab and its own location / weight / gradient memory
+    x1 = synth.make_inputs(g, 1, dist, seed=1234, device="cuda:0", dtype=dtype)
+    x = {k: (v if k in ("shapes", "starts") else v.repeat(N, *([1] * (v.dim() - 1))).contiguous()) for k, v in x1.items()}
+    del x1
     f = lambda: MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], 64)
     b = lambda: MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["starts"], x["loc"], x["aw"], x["grad_out"], 64)
     tf, tb = median_ms(f), median_ms(b)
+    del f, b
     ev = 4 if dtype == torch.float32 else 2
     bf, bb = bench.algorithmic_bytes(N, g.spatial_size, 6, 64, L, g.num_query, P, ev=ev)
+    del x
+    torch.cuda.empty_cache()
     return tf, tb, bf / tf / 1e6, bb / tb / 1e6
 
 
-rows = []
 cases = []
+# the full batch x levels x points cross of BASELINE.json configs[4] (Lq = S, fp32, model-like sampling pattern)
 for N in (1, 2, 4, 8, 16):
-    for dt in (torch.float32, torch.bfloat16):
-        cases.append((N, 4, 4, 0, dt, "B"))
-for L in (1, 2, 3):
-    cases.append((2, L, 4, 0, torch.float32, "B"))
-for P in (8, 16, 32):
-    cases.append((1, 4, P, 0, torch.float32, "B"))
-for N in (1, 16):
-    for dt in (torch.float32, torch.bfloat16):
-        cases.append((N, 4, 4, 300, dt, "B"))
+    for L in (1, 2, 3, 4):
+        for P in (4, 8, 16, 32):
+            cases.append((N, L, P, 0, torch.float32, "B"))
+# bf16 value storage, decoder-like calls (Lq = 300), and the reference test's uniform locations (dist A) / no jitter (B0)
+for N in (1, 2, 4, 8, 16):
+    cases.append((N, 4, 4, 0, torch.bfloat16, "B"))
+for N in (1, 2, 16):
+    for L in (1, 4):
+        for P in (4, 32):
+            for dt in (torch.float32, torch.bfloat16):
+                cases.append((N, L, P, 300, dt, "B"))
+for N in (1, 2, 16):
+    for P in (4, 32):
+        cases.append((N, 4, P, 0, torch.float32, "A"))
 for dt in (torch.float32, torch.bfloat16):
     cases.append((2, 4, 4, 0, dt, "A"))
     cases.append((2, 4, 4, 0, dt, "B0"))
 
-out = ["# MSDeformAttn3D microbenchmark sweep on B200 (round 1)", "",
+out = ["# MSDeformAttn3D microbenchmark sweep on B200 (round 2: full batch x levels x points cross)", "",
        f"M=6, C=64, levels = first L of {PYR}; Lq = S unless stated; median of 10 launches, CUDA events; HBM peak {peak} GB/s (measured).",
        "GB/s = algorithmic (compulsory) bytes / time, DESIGN.md section 6; bwd includes the grad_value zero-fill.", "",
        "| N | L | P | Lq | value dtype | dist | fwd ms | bwd ms | fwd GB/s (frac) | bwd GB/s (frac) |", "|---|---|---|---|---|---|---|---|---|---|"]
@@ -63,4 +75,4 @@ for (N, L, P, q, dt, dist) in cases:
     print(line, flush=True)
     out.append(line)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-open(os.path.join(ROOT, "gpurun_out", "r01_sweep.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "gpurun_out", "r02_sweep.md"), "w").write("\n".join(out) + "\n")
