@@ -40,6 +40,16 @@ int fused_ln_backward(void *stream, const float *dy, const float *z, const float
  * Process-global; the pointer must stay valid while installed. */
 void hash_rng_set_epoch(const unsigned long long *device_counter);
 
+/* The bf16 route: the branch b (and its gradient db) is the bf16 output of a bf16 GEMM, the residual stream a / z / y / dy / da stays fp32 --
+ * the dtypes torch.autocast(bfloat16) produces around `norm(x + dropout(branch))` (its layer_norm runs and returns fp32).  b / db are
+ * 8-byte aligned; db is always written (it cannot alias the fp32 da), with p_drop == 0 it is the bf16 rounding of da. */
+int fused_ln_forward_bf16b(void *stream, const float *a, const void *b, const float *gamma, const float *beta, long long rows, int channels,
+                           float eps, float p_drop, unsigned long long seed, float *z, float *y, float *mean, float *rstd);
+
+int fused_ln_backward_bf16b(void *stream, const float *dy, const float *z, const float *gamma, const float *mean, const float *rstd, long long rows,
+                            int channels, float p_drop, unsigned long long seed, float *da, void *db, float *dgamma, float *dbeta,
+                            float *workspace);
+
 #ifdef __cplusplus
 }
 #endif

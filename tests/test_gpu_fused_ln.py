@@ -76,3 +76,32 @@ def test_training_mode_is_reproducible_under_manual_seed_and_falls_back_off_devi
     ncpu = nn.LayerNorm(64)
     out = add_dropout_layer_norm(a.cpu(), b.cpu(), ncpu, 0.3, False)                      # CPU tensors: the plain composition
     assert torch.allclose(out, ncpu(a.cpu() + b.cpu()))
+
+
+@pytest.mark.parametrize("shape", [(2, 1000, 384), (3, 7, 48), (2, 33, 1024)])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_bf16_branch_with_fp32_residual_stream(shape, autocast):
+    """The bf16 route: a (residual stream) fp32, b (branch, output of a bf16 GEMM) bf16 -- the dtypes around norm(x + dropout(y)) under
+    torch.autocast(bfloat16).  Output and da stay fp32, db is bf16; same kernel count as the fp32 case."""
+    import contextlib
+    from transoar_b200 import _lib
+    from transoar_b200.fused_ln import add_dropout_layer_norm
+    g = torch.Generator().manual_seed(sum(shape) + 5)
+    C = shape[-1]
+    norm = nn.LayerNorm(C).to(DEV)
+    a = (torch.randn(*shape, generator=g) * 2 + 1).to(DEV).requires_grad_(True)
+    b = torch.randn(*shape, generator=g).to(DEV).to(torch.bfloat16).requires_grad_(True)
+    dy = torch.randn(*shape, generator=g).to(DEV)
+    n0 = _lib.lib().msda3d_launch_count()
+    with (torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()):
+        y = add_dropout_layer_norm(a, b, norm, 0.1, training=False)
+    y.backward(dy)
+    assert _lib.lib().msda3d_launch_count() - n0 == 3
+    assert y.dtype == torch.float32 and a.grad.dtype == torch.float32 and b.grad.dtype == torch.bfloat16
+    ad, bd = a.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    wd, bid = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    yd = F.layer_norm(ad + bd, (C,), wd, bid, norm.eps)
+    yd.backward(dy.double())
+    assert _rel(y, yd) < 1e-5 and _rel(a.grad, ad.grad) < 1e-4
+    assert _rel(b.grad, bd.grad) < 1e-2                                              # one bf16 rounding
+    assert _rel(norm.weight.grad, wd.grad) < 1e-4 and _rel(norm.bias.grad, bid.grad) < 1e-4

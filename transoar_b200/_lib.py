@@ -63,6 +63,8 @@ _SIGNATURES = {
     "fused_ln_workspace_floats": (ctypes.c_longlong, [_ci]),
     "fused_ln_forward": (_ci, [_vp] * 5 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 4),
     "fused_ln_backward": (_ci, [_vp] * 6 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 5),
+    "fused_ln_forward_bf16b": (_ci, [_vp] * 5 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 4),
+    "fused_ln_backward_bf16b": (_ci, [_vp] * 6 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 5),
     # include/stem_conv.h
     "stem_conv3d_workspace_floats": (ctypes.c_longlong, [_ci]),
     "stem_conv3d_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 5 + [_vp]),

@@ -13,6 +13,7 @@
 // registers over all rows of a warp, reduced across the CTA in shared memory, one partial per CTA, summed by a second kernel.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,9 +34,27 @@ __device__ __forceinline__ float warp_sum(float v)
   return v;
 }
 
-template <int NV>
+// four consecutive elements of the branch tensor b / its gradient db, stored as fp32 or bf16 (the bf16 route: the branch is the output
+// of a bf16 GEMM, the residual stream a / z / y stays fp32 -- what torch.autocast does, whose layer_norm runs and returns fp32)
+__device__ __forceinline__ float4 ldb4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ldb4(const __nv_bfloat16 *p)
+{
+  const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&t.x), hi = *reinterpret_cast<const __nv_bfloat162 *>(&t.y);
+  return make_float4(__bfloat162float(lo.x), __bfloat162float(lo.y), __bfloat162float(hi.x), __bfloat162float(hi.y));
+}
+__device__ __forceinline__ void stb4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void stb4(__nv_bfloat16 *p, float4 v)
+{
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162 *>(&t.x) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162 *>(&t.y) = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2 *>(p) = t;
+}
+
+template <int NV, typename TB = float>
 __global__ void __launch_bounds__(kThreads)
-fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ gamma, const float *__restrict__ beta,
+fwd_kernel(const float *__restrict__ a, const TB *__restrict__ b, const float *__restrict__ gamma, const float *__restrict__ beta,
            long long rows, int C, float eps, uint32_t thresh, float scale, uint64_t seed, const unsigned long long *__restrict__ epoch,
            float *__restrict__ z, float *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd)
 {
@@ -53,7 +72,7 @@ fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float
   const float inv_c = 1.f / (float)C;
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < rows; row += (long long)gridDim.x * kWarps) {
     const float4 *ar = reinterpret_cast<const float4 *>(a + row * C);
-    const float4 *br = b != nullptr ? reinterpret_cast<const float4 *>(b + row * C) : nullptr;
+    const TB *br = b != nullptr ? b + row * C : nullptr;
     float v[NV][4];
     float s = 0.f;
 #pragma unroll
@@ -63,7 +82,7 @@ fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float
         const float4 av = __ldg(ar + i);
         v[k][0] = av.x; v[k][1] = av.y; v[k][2] = av.z; v[k][3] = av.w;
         if (br != nullptr) {
-          const float4 bv = __ldg(br + i);
+          const float4 bv = ldb4(br + 4 * i);
           float m[4] = {1.f, 1.f, 1.f, 1.f};
           if (thresh != 0u) keep4(seed, (uint64_t)row * c4 + i, thresh, scale, m);
           v[k][0] = fmaf(bv.x, m[0], v[k][0]); v[k][1] = fmaf(bv.y, m[1], v[k][1]);
@@ -100,11 +119,11 @@ fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, const float
 }
 
 // part [gridDim.x][2][C]: per-CTA sums of dy * xhat (dgamma) and dy (dbeta)
-template <int NV>
+template <int NV, typename TB = float>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const float *__restrict__ gamma, const float *__restrict__ mean,
            const float *__restrict__ rstd, long long rows, int C, uint32_t thresh, float scale, uint64_t seed,
-           const unsigned long long *__restrict__ epoch, float *__restrict__ da, float *__restrict__ db, float *__restrict__ part)
+           const unsigned long long *__restrict__ epoch, float *__restrict__ da, TB *__restrict__ db, float *__restrict__ part)
 {
   seed = hashrng::with_epoch(seed, epoch);
   extern __shared__ float red[];                                   // [kWarps][2][C]
@@ -147,7 +166,7 @@ bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const floa
     }
     const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
     float4 *ar = reinterpret_cast<float4 *>(da + row * C);
-    float4 *br = db != nullptr ? reinterpret_cast<float4 *>(db + row * C) : nullptr;
+    TB *br = db != nullptr ? db + row * C : nullptr;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int i = k * 32 + lane;
@@ -157,9 +176,9 @@ bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const floa
         for (int j = 0; j < 4; ++j) o[j] = rs * (gy[k][j] - m1 - xh[k][j] * m2);
         ar[i] = make_float4(o[0], o[1], o[2], o[3]);
         if (br != nullptr) {
-          float m[4];
-          keep4(seed, (uint64_t)row * c4 + i, thresh, scale, m);
-          br[i] = make_float4(o[0] * m[0], o[1] * m[1], o[2] * m[2], o[3] * m[3]);
+          float m[4] = {1.f, 1.f, 1.f, 1.f};
+          if (thresh != 0u) keep4(seed, (uint64_t)row * c4 + i, thresh, scale, m);
+          stb4(br + 4 * i, make_float4(o[0] * m[0], o[1] * m[1], o[2] * m[2], o[3] * m[3]));
         }
       }
     }

@@ -21,9 +21,10 @@ def _p(t):
 
 def fused_eligible(a, b, norm):
     C = a.shape[-1]
-    return (a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape and C % 4 == 0 and C <= 1024
+    # fp32 everywhere, or -- the bf16 route (autocast) -- an fp32 residual stream with a bf16 branch
+    return (a.is_cuda and a.dtype == torch.float32 and b.dtype in (torch.float32, torch.bfloat16) and a.shape == b.shape and C % 4 == 0 and C <= 1024
             and norm.elementwise_affine and norm.bias is not None and norm.weight.dtype == torch.float32
-            and tuple(norm.normalized_shape) == (C,) and not torch.is_autocast_enabled())
+            and tuple(norm.normalized_shape) == (C,) and (not torch.is_autocast_enabled() or torch.get_autocast_dtype("cuda") == torch.bfloat16))
 
 
 class AddDropoutLayerNormFunction(Function):
@@ -38,9 +39,11 @@ class AddDropoutLayerNormFunction(Function):
         z, y = torch.empty_like(a2), torch.empty_like(a2)
         mean = torch.empty(rows, dtype=torch.float32, device=a.device)
         rstd = torch.empty_like(mean)
+        ctx.bf16_branch = b2.dtype == torch.bfloat16
+        fwd = _lib.lib().fused_ln_forward_bf16b if ctx.bf16_branch else _lib.lib().fused_ln_forward
         with torch.cuda.device(a.device):
-            rc = _lib.lib().fused_ln_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(a2), _p(b2), _p(w), _p(bi), rows, C,
-                                             float(eps), float(p), seed, _p(z), _p(y), _p(mean), _p(rstd))
+            rc = fwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(a2), _p(b2), _p(w), _p(bi), rows, C,
+                     float(eps), float(p), seed, _p(z), _p(y), _p(mean), _p(rstd))
         _lib.check(rc, "fused_ln_forward")
         ctx.save_for_backward(z, w, mean, rstd)
         ctx.p, ctx.seed, ctx.shape = float(p), seed, a.shape
@@ -53,12 +56,16 @@ class AddDropoutLayerNormFunction(Function):
         rows, C = z.shape
         dy2 = dy.reshape(rows, C).contiguous()
         da = torch.empty_like(z)
-        db = torch.empty_like(z) if ctx.p > 0 else None
+        if ctx.bf16_branch:
+            db = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device)
+        else:
+            db = torch.empty_like(z) if ctx.p > 0 else None
         dw, dbias = torch.empty(C, dtype=torch.float32, device=z.device), torch.empty(C, dtype=torch.float32, device=z.device)
         ws = torch.empty(_lib.lib().fused_ln_workspace_floats(C), dtype=torch.float32, device=z.device)
         with torch.cuda.device(z.device):
-            rc = _lib.lib().fused_ln_backward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy2), _p(z), _p(w), _p(mean), _p(rstd),
-                                              rows, C, ctx.p, ctx.seed, _p(da), _p(db), _p(dw), _p(dbias), _p(ws))
+            bwd = _lib.lib().fused_ln_backward_bf16b if ctx.bf16_branch else _lib.lib().fused_ln_backward
+            rc = bwd(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(dy2), _p(z), _p(w), _p(mean), _p(rstd),
+                     rows, C, ctx.p, ctx.seed, _p(da), _p(db), _p(dw), _p(dbias), _p(ws))
         _lib.check(rc, "fused_ln_backward")
         da = da.reshape(ctx.shape)
         return da, (db.reshape(ctx.shape) if db is not None else da), dw, dbias, None, None, None
