@@ -105,3 +105,28 @@ def test_bf16_branch_with_fp32_residual_stream(shape, autocast):
     assert _rel(y, yd) < 1e-5 and _rel(a.grad, ad.grad) < 1e-4
     assert _rel(b.grad, bd.grad) < 1e-2                                              # one bf16 rounding
     assert _rel(norm.weight.grad, wd.grad) < 1e-4 and _rel(norm.bias.grad, bid.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 6, 7, 9, 48), torch.float32), ((3, 1000, 384), torch.float32), ((2, 5, 5, 8, 768), torch.bfloat16),
+                                         ((4, 100, 96), torch.bfloat16)])
+def test_plain_layer_norm_on_the_warp_per_row_kernel(shape, dtype):
+    from transoar_b200 import _lib
+    from transoar_b200.fused_ln import layer_norm
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[-1]
+    norm = nn.LayerNorm(C).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        norm.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    x = (torch.randn(*shape, generator=g) * 2 + 1).to(DEV).to(dtype).requires_grad_(True)
+    dy = torch.randn(*shape, generator=g).to(DEV)
+    n0 = _lib.lib().msda3d_launch_count()
+    y = layer_norm(x, norm)
+    y.backward(dy)
+    assert _lib.lib().msda3d_launch_count() - n0 == 3 and y.dtype == torch.float32 and x.grad.dtype == dtype
+    xd = x.detach().double().requires_grad_(True)
+    wd, bd = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    yd = F.layer_norm(xd, (C,), wd, bd, norm.eps)
+    yd.backward(dy.double())
+    assert _rel(y, yd) < 1e-5 and _rel(x.grad, xd.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+    assert _rel(norm.weight.grad, wd.grad) < 1e-4 and _rel(norm.bias.grad, bd.grad) < 1e-4

@@ -47,9 +47,11 @@ def test_stages_against_reference_fixture(tf32, tol):
         launched = _lib.lib().msda3d_launch_count() - n0
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    # 3 stages x (2 blocks x 4 Linear + 1 merging Linear) x (forward + 2 gradient GEMMs) on the tcgen05 kernel, none with strict fp32
-    # (+ two column-sum kernels per bias gradient over >= 1024 tokens)
-    assert (launched >= 3 * 9 * 3) if tf32 else (launched == 0), launched
+    # 3 stages x (2 blocks x 4 Linear + 1 merging Linear) x (forward + 2 gradient GEMMs) on the tcgen05 kernel with TF32 (+ two column-sum
+    # kernels per bias gradient over >= 1024 tokens); with strict fp32 the GEMMs are library calls and only the LayerNorm kernels
+    # (3 launches per norm: forward, backward, finalize; 3 stages x 5 norms) and, where the window shape qualifies, the window attention run
+    ln = 3 * 5 * 3
+    assert (launched >= 3 * 9 * 3 + ln) if tf32 else (ln <= launched <= ln + 3 * 2 * 2), launched
     for i, f in enumerate(feats):
         assert _rel(f, z[f"out{i}"]) < tol, i
     assert _rel(x.grad, z["grad_x"]) < 5 * tol

@@ -54,7 +54,7 @@ int win_attn_backward(void *stream, const float *qkv, const float *bias, const f
   long long chunks = (2LL * sm_count_() + heads - 1) / heads;
   if (chunks > windows) chunks = windows;
   if (chunks < 1) chunks = 1;
-  winattn::bwd_kernel<<<dim3((unsigned)chunks, heads), winattn::kThreads, smem, st>>>(qkv, bias, bias_t, mask, out, dout, lse, windows, tokens, heads,
+  winattn::bwd_kernel<<<dim3((unsigned)chunks, heads), winattn::kBwdThreads, smem, st>>>(qkv, bias, bias_t, mask, out, dout, lse, windows, tokens, heads,
                                                                                       mask ? mask_windows : 1, scale, dqkv, dbias);
   ++g_msda3d_launches;
   return (int)cudaGetLastError();

@@ -87,21 +87,37 @@ fwd_kernel(const float *__restrict__ qkv, const float *__restrict__ biasT, const
   if (i >= n) return;
   const float *bT = biasT + (long long)h * n * n + i;                 // + j * n
   const float *mk = mask != nullptr ? mask + ((long long)(bw % nW) * n) * n + i : nullptr;   // symmetric: mask[w][j][i] == mask[w][i][j]
+  // both passes fetch the bias / mask values of four keys before using them: the loops are bound by the latency of those loads otherwise
   float m = -CUDART_INF_F;
-  for (int j = 0; j < n; ++j) {
-    float s = dot16(q, sK[j]) + __ldg(bT + (long long)j * n);
-    if (mk != nullptr) s += __ldg(mk + (long long)j * n);
-    m = fmaxf(m, s);
+  for (int j0 = 0; j0 < n; j0 += 4) {
+    float add[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(j0 + u, n - 1);
+      add[u] = __ldg(bT + (long long)j * n) + (mk != nullptr ? __ldg(mk + (long long)j * n) : 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u < n) m = fmaxf(m, dot16(q, sK[j0 + u]) + add[u]);
   }
   float l = 0.f, o[HD];
 #pragma unroll
   for (int c = 0; c < HD; ++c) o[c] = 0.f;
-  for (int j = 0; j < n; ++j) {
-    float s = dot16(q, sK[j]) + __ldg(bT + (long long)j * n);
-    if (mk != nullptr) s += __ldg(mk + (long long)j * n);
-    const float p = __expf(s - m);
-    l += p;
-    axpy16(p, sV[j], o);
+  for (int j0 = 0; j0 < n; j0 += 4) {
+    float add[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(j0 + u, n - 1);
+      add[u] = __ldg(bT + (long long)j * n) + (mk != nullptr ? __ldg(mk + (long long)j * n) : 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u < n) {
+        const float p = __expf(dot16(q, sK[j0 + u]) + add[u] - m);
+        l += p;
+        axpy16(p, sV[j0 + u], o);
+      }
+    }
   }
   const float inv = 1.f / l;
   float *dst = out + ((long long)bw * n + i) * H * HD + h * HD;
@@ -111,9 +127,14 @@ fwd_kernel(const float *__restrict__ qkv, const float *__restrict__ biasT, const
   lse[((long long)bw * H + h) * n + i] = m + __logf(l);
 }
 
-// Backward.  grid = (chunks, H): CTA (c, h) walks windows c, c + chunks, ... of head h.  dynamic smem: dbias tile [n][ld] (ld odd).
+// Backward.  grid = (chunks, H): CTA (c, h) walks windows c, c + chunks, ... of head h.  256 threads: threads 0..127 run the row phase
+// (thread = query row) while threads 128..255 run the column phase (thread = key row) of the same window at the same time -- both only
+// read the window's tiles -- so an SM holds twice the warps for the same shared memory.  The bias / mask values of four keys are loaded
+// before they are used (the loops are latency-bound on those loads otherwise).  dynamic smem: tiles + dbias tile [n][ld] (ld odd).
 // dqkv [Bw][n][3][H][HD]; dbias [H][n][n] (natural layout, accumulated with atomicAdd: zero it first).
-__global__ void __launch_bounds__(kThreads)
+constexpr int kBwdThreads = 2 * kThreads;
+
+__global__ void __launch_bounds__(kBwdThreads, 2)
 bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ bias, const float *__restrict__ biasT, const float *__restrict__ mask,
            const float *__restrict__ out, const float *__restrict__ dout, const float *__restrict__ lse, int Bw, int n, int H, int nW, float scale,
            float *__restrict__ dqkv, float *__restrict__ dbias)
@@ -127,66 +148,92 @@ bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ bias, const 
   float *sD = sL + kThreads;                                                         // D_i = dO_i . O_i
   float *sB = sD + kThreads;                                                         // dbias tile [n][ld]
   const int ld = n | 1;
-  const int h = blockIdx.y, t = threadIdx.x;
+  const int h = blockIdx.y, role = threadIdx.x / kThreads, t = threadIdx.x % kThreads;
   const long long tok = 3LL * H * HD;
-  for (int e = t; e < n * ld; e += kThreads) sB[e] = 0.f;
+  for (int e = threadIdx.x; e < n * ld; e += kBwdThreads) sB[e] = 0.f;
 
   for (int bw = blockIdx.x; bw < Bw; bw += gridDim.x) {
     __syncthreads();                                                                 // previous window's phases are done with the tiles
     const float *base = qkv + (long long)bw * n * tok + h * HD;
-    float dO[HD], qs[HD];
-    float Di = 0.f, li = 0.f;
     if (t < n) {
       float v[HD];
-      load16(base + t * tok, qs);
+      if (role == 0) {
+        load16(base + t * tok, v);
 #pragma unroll
-      for (int c = 0; c < HD; ++c) { qs[c] *= scale; sQ[t][c] = qs[c]; }
-      load16(base + t * tok + (long long)H * HD, v);
+        for (int c = 0; c < HD; ++c) sQ[t][c] = v[c] * scale;
+        load16(base + t * tok + (long long)H * HD, v);
 #pragma unroll
-      for (int c = 0; c < HD; ++c) sK[t][c] = v[c];
-      load16(base + t * tok + 2LL * H * HD, v);
+        for (int c = 0; c < HD; ++c) sK[t][c] = v[c];
+      } else {
+        float dO[HD];
+        load16(base + t * tok + 2LL * H * HD, v);
 #pragma unroll
-      for (int c = 0; c < HD; ++c) sV[t][c] = v[c];
-      const long long orow = ((long long)bw * n + t) * H * HD + h * HD;
-      load16(dout + orow, dO);
-      load16(out + orow, v);
+        for (int c = 0; c < HD; ++c) sV[t][c] = v[c];
+        const long long orow = ((long long)bw * n + t) * H * HD + h * HD;
+        load16(dout + orow, dO);
+        load16(out + orow, v);
+        float Di = 0.f;
 #pragma unroll
-      for (int c = 0; c < HD; ++c) { sdO[t][c] = dO[c]; Di = fmaf(dO[c], v[c], Di); }
-      li = lse[((long long)bw * H + h) * n + t];
-      sL[t] = li; sD[t] = Di;
+        for (int c = 0; c < HD; ++c) { sdO[t][c] = dO[c]; Di = fmaf(dO[c], v[c], Di); }
+        sL[t] = lse[((long long)bw * H + h) * n + t];
+        sD[t] = Di;
+      }
     }
     __syncthreads();
-    const float *mk = mask != nullptr ? mask + ((long long)(bw % nW) * n) * n : nullptr;
-    if (t < n) {
+    if (t >= n) continue;                                                            // (no barrier below this point inside the iteration)
+    const float *mk = mask != nullptr ? mask + ((long long)(bw % nW) * n) * n + t : nullptr;   // mask[w][x][t], x = the loop index
+    if (role == 0) {
       // ---- row phase: thread t = query row i
-      const float *bT = biasT + (long long)h * n * n + t;
-      float dq[HD];
+      float qs[HD], dO[HD], dq[HD];
 #pragma unroll
-      for (int c = 0; c < HD; ++c) dq[c] = 0.f;
-      for (int j = 0; j < n; ++j) {
-        float s = dot16(qs, sK[j]) + __ldg(bT + (long long)j * n);
-        if (mk != nullptr) s += __ldg(mk + (long long)j * n + t);
-        const float p = __expf(s - li);
-        const float ds = p * (dot16(dO, sV[j]) - Di);
-        axpy16(ds, sK[j], dq);
-        sB[t * ld + j] += ds;
+      for (int c = 0; c < HD; ++c) { qs[c] = sQ[t][c]; dO[c] = sdO[t][c]; dq[c] = 0.f; }
+      const float li = sL[t], Di = sD[t];
+      const float *bT = biasT + (long long)h * n * n + t;
+      for (int j0 = 0; j0 < n; j0 += 4) {
+        float add[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, n - 1);
+          add[u] = __ldg(bT + (long long)j * n) + (mk != nullptr ? __ldg(mk + (long long)j * n) : 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j < n) {
+            const float p = __expf(dot16(qs, sK[j]) + add[u] - li);
+            const float ds = p * (dot16(dO, sV[j]) - Di);
+            axpy16(ds, sK[j], dq);
+            sB[t * ld + j] += ds;
+          }
+        }
       }
       float *dst = dqkv + ((long long)bw * n + t) * tok + h * HD;
 #pragma unroll
       for (int c = 0; c < HD; c += 4)
         *reinterpret_cast<float4 *>(dst + c) = make_float4(dq[c] * scale, dq[c + 1] * scale, dq[c + 2] * scale, dq[c + 3] * scale);
+    } else {
       // ---- column phase: thread t = key row j
       float kj[HD], vj[HD], dk[HD], dv[HD];
 #pragma unroll
       for (int c = 0; c < HD; ++c) { kj[c] = sK[t][c]; vj[c] = sV[t][c]; dk[c] = 0.f; dv[c] = 0.f; }
       const float *bN = bias + (long long)h * n * n + t;                                // bias[h][i][j = t]
-      for (int i = 0; i < n; ++i) {
-        float s = dot16(kj, sQ[i]) + __ldg(bN + (long long)i * n);
-        if (mk != nullptr) s += __ldg(mk + (long long)i * n + t);
-        const float p = __expf(s - sL[i]);
-        const float ds = p * (dot16(vj, sdO[i]) - sD[i]);
-        axpy16(ds, sQ[i], dk);
-        axpy16(p, sdO[i], dv);
+      for (int i0 = 0; i0 < n; i0 += 4) {
+        float add[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = min(i0 + u, n - 1);
+          add[u] = __ldg(bN + (long long)i * n) + (mk != nullptr ? __ldg(mk + (long long)i * n) : 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          if (i < n) {
+            const float p = __expf(dot16(kj, sQ[i]) + add[u] - sL[i]);
+            const float ds = p * (dot16(vj, sdO[i]) - sD[i]);
+            axpy16(ds, sQ[i], dk);
+            axpy16(p, sdO[i], dv);
+          }
+        }
       }
       float *dkp = dqkv + ((long long)bw * n + t) * tok + (long long)H * HD + h * HD;
       float *dvp = dkp + (long long)H * HD;
@@ -199,7 +246,7 @@ bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ bias, const 
   }
   __syncthreads();
   float *db = dbias + (long long)h * n * n;
-  for (int e = t; e < n * n; e += kThreads) atomicAdd(db + e, sB[(e / n) * ld + e % n]);
+  for (int e = threadIdx.x; e < n * n; e += kBwdThreads) atomicAdd(db + e, sB[(e / n) * ld + e % n]);
 }
 
 }  // namespace winattn

@@ -20,6 +20,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 
+from .fused_ln import layer_norm
 from .linear import TCLinear
 
 
@@ -192,7 +193,7 @@ class SwinBlock(nn.Module):
     def _attend(self, x, mask):
         B, D, H, W, C = x.shape
         win, shift = effective_window((D, H, W), self.window_size, self.shift_size)
-        x = self.norm1(x)
+        x = layer_norm(x, self.norm1)
         pad = [(w - s % w) % w for s, w in zip((D, H, W), win)]
         x = F.pad(x, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))                                      # pad the high side of W, H, D
         Dp, Hp, Wp = x.shape[1:4]
@@ -207,7 +208,7 @@ class SwinBlock(nn.Module):
 
     def forward(self, x, mask_matrix):
         x = x + self.drop_path(self._attend(x, mask_matrix))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        return x + self.drop_path(self.mlp(layer_norm(x, self.norm2)))
 
 
 class PatchMerging(nn.Module):
@@ -224,7 +225,7 @@ class PatchMerging(nn.Module):
         if H % 2 or W % 2:
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         parts = [x[:, d::2, h::2, w::2] for d in (0, 1) for w in (0, 1) for h in (0, 1)]            # x0..x7 of the reference
-        return self.reduction(self.norm(torch.cat(parts, -1)))
+        return self.reduction(layer_norm(torch.cat(parts, -1), self.norm))
 
 
 class ConvPatchMerging(nn.Module):
