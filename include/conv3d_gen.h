@@ -1,0 +1,43 @@
+/*
+ * conv3d_gen.h -- C ABI of the general tcgen05 implicit-GEMM 3x3x3 convolution in libmsda3d.so (sm_100a): zero padding 1, stride 1 or 2,
+ * any channel counts that are multiples of 4, channels-last fp32 tensors, TF32 multiply / fp32 accumulate, operands staged by TMA,
+ * accumulators in TMEM.  Replaces the cuDNN calls behind
+ *   nn.Conv3d(cin, cout, 3, stride, 1, bias=False)   EncoderCnnBlock._block[0] / [3] of stages 1-5
+ *                                                    (transoar/models/backbones/encoder_blocks.py:28-46 via attn_fpn.py:170-182)
+ *   nn.Conv3d(cin, fpn_channels, 3, padding=1)       Decoder._out (transoar/models/backbones/attn_fpn.py:65-74), with bias
+ * and autograd's cudnn_convolution_backward_input / _weight of both.  (The 24 -> 24 full-resolution layer keeps its specialised
+ * kernel, include/conv3d_tc.h; the 1-channel stem its stencil, include/stem_conv.h.)
+ *
+ *   x    fp32 [N, D, H, W, CI]      channels-last (torch.channels_last_3d memory of an [N, CI, D, H, W] tensor), 16-byte aligned
+ *   w    fp32 [CO, 27, CI]          the channels-last memory of torch's [CO, CI, 3, 3, 3] weight: w[co][(kd*3 + kh)*3 + kw][ci];
+ *                                   read in place by forward AND input gradient (no transposed copy)
+ *   y    fp32 [N, OD, OH, OW, CO]   OD = ceil(D / stride) etc. (= floor((D + 2 - 3) / stride) + 1)
+ *   bias fp32 [CO] or NULL
+ * Cross-correlation, as torch.  depth / height / width are always the INPUT volume's.  Device pointers, work enqueued on `stream`, no
+ * allocation, no synchronisation (capturable).  Returns 0 / MSDA3D_E* / cudaError_t.
+ */
+#ifndef CONV3D_GEN_H_
+#define CONV3D_GEN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int conv3d_gen_supported(int in_channels, int out_channels, int stride);
+
+int conv3d_gen_forward(void *stream, const float *x, const float *w, const float *bias, int batch, int depth, int height, int width,
+                       int in_channels, int out_channels, int stride, float *y);
+
+/* dx [N, D, H, W, CI] = gradient of the convolution with respect to its input, from dy [N, OD, OH, OW, CO].  Every element of dx is written. */
+int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, int batch, int depth, int height, int width, int in_channels,
+                     int out_channels, int stride, float *dx);
+
+/* dw [CO, 27, CI] (channels-last weight memory) = sum over output voxels of dy[v][co] * x[stride * v + tap - 1][ci].  dw is zero-filled by the
+ * call, then accumulated with fp32 reductions (split over voxel ranges: the summation order is not deterministic). */
+int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
+                     int out_channels, int stride, float *dw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONV3D_GEN_H_ */

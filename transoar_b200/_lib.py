@@ -59,6 +59,11 @@ _SIGNATURES = {
     "conv3d_tc_debug_mode": (None, [_ci]),
     "conv3d_tc_debug_mn_probe": (_ci, [_vp] * 4 + [_ci]),
     "conv3d_tc_k3_forward": (_ci, [_vp, _vp, _vp] + [_ci] * 6 + [_vp]),
+    # include/conv3d_gen.h
+    "conv3d_gen_supported": (_ci, [_ci, _ci, _ci]),
+    "conv3d_gen_forward": (_ci, [_vp] * 4 + [_ci] * 7 + [_vp]),
+    "conv3d_gen_dgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
+    "conv3d_gen_wgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
     # include/fused_ln.h
     "fused_ln_workspace_floats": (ctypes.c_longlong, [_ci]),
     "fused_ln_forward": (_ci, [_vp] * 5 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 4),

@@ -1,0 +1,312 @@
+// conv3d_gen_capi.cu -- C ABI of the general tcgen05 3x3x3 convolution (include/conv3d_gen.h): tile-box choice, tensor maps (incl. the
+// eight parity-class views that express stride 2), step tables, launch.
+#include "conv3d_gen_kernels.cuh"
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/conv3d_gen.h"
+#include "../../include/msda3d.h"
+
+extern std::atomic<unsigned long long> g_msda3d_launches;
+
+namespace {
+
+using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled needs a context current on the calling thread (autograd's backward thread may have none yet)
+void ensure_context_on_this_thread()
+{
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    bound = true;
+  }
+}
+
+EncodeTiled encode_fn()
+{
+  static EncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiled>(p);
+  });
+  return fn;
+}
+
+int sm_count()
+{
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms = n;
+  }
+  return sms;
+}
+
+struct Vol { int N, D, H, W, C; };
+
+// Channels-last volume [N, D, H, W, C], or -- step == 2 -- its parity class (pd, ph, pw): the voxels with index % 2 == p per axis, a plain
+// 5-D tensor with doubled strides.  Box = 32 channels x (bw, bh, bd) voxels.  `load`: TF32-rounding loads, else fp32 stores.
+int make_vol_map(CUtensorMap *map, const float *ptr, const Vol &v, int step, int pd, int ph, int pw, int bw, int bh, int bd, bool mn_major, bool load)
+{
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t C = (cuuint64_t)v.C, W = (cuuint64_t)v.W, H = (cuuint64_t)v.H, D = (cuuint64_t)v.D;
+  const cuuint64_t vw = (W - pw + step - 1) / step, vh = (H - ph + step - 1) / step, vd = (D - pd + step - 1) / step;
+  if (vw == 0 || vh == 0 || vd == 0) return MSDA3D_EINVAL;
+  const cuuint64_t gdim[5] = {C, vw, vh, vd, (cuuint64_t)v.N};
+  const cuuint64_t gstride[4] = {step * C * 4, step * W * C * 4, step * H * W * C * 4, D * H * W * C * 4};
+  const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const float *base = ptr + (((size_t)pd * H + ph) * W + pw) * C;
+  const CUresult r = enc(map, load ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         load ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
+}
+
+// weights in channels-last memory [CO][27][CI] as the 3-D tensor (ci, tap, co); box = 32 ci x 1 tap x rows co
+int make_weight_map(CUtensorMap *map, const float *w, int CI, int CO, int rows, bool mn_major)
+{
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) return MSDA3D_ENODEV;
+  const cuuint64_t gdim[3] = {(cuuint64_t)CI, 27, (cuuint64_t)CO};
+  const cuuint64_t gstride[2] = {(cuuint64_t)CI * 4, (cuuint64_t)CI * 27 * 4};
+  const cuuint32_t box[3] = {32, 1, (cuuint32_t)rows};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float *>(w), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
+}
+
+// box of `vox` (128 or 32) voxels over a W x H x D grid with the least padding; power-of-two edges, bw <= 32
+void choose_box(int vox, int W, int H, int D, int *bw, int *bh, int *bd)
+{
+  long long best = -1;
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (w > vox) continue;
+    for (int h = vox / w; h >= 1; h >>= 1) {
+      const int d = vox / (w * h);
+      if (d > 64) continue;
+      const long long pad = (long long)((W + w - 1) / w * w) * ((H + h - 1) / h * h) * ((D + d - 1) / d * d);
+      if (best < 0 || pad < best) { best = pad; *bw = w; *bh = h; *bd = d; }
+    }
+  }
+}
+
+int choose_bn(int N)
+{
+  for (int c : {32, 64, 96, 128, 192, 256}) if (N <= c) return c;
+  int bn = 128, best_tiles = 1 << 30, best_pad = 1 << 30;
+  for (int c : {128, 192, 256}) {
+    const int tiles = (N + c - 1) / c, pad = tiles * c - N;
+    if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best_tiles = tiles; best_pad = pad; bn = c; }
+  }
+  return bn;
+}
+
+template <int BN, bool B_MN> int launch_k(cudaStream_t st, const convgen::Problem &p, const float *bias)
+{
+  using C = tcgemm::Cfg<BN, 1>;
+  auto kern = convgen::conv_kmajor_kernel<BN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
+  if (err != cudaSuccess) return (int)err;
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * ((p.N + BN - 1) / BN);
+  const int grid = (int)(work < sm_count() ? work : sm_count());
+  kern<<<grid, tcgemm::kThreads, C::SMEM_BYTES, st>>>(p, bias);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+template <bool B_MN> int dispatch_k(cudaStream_t st, int bn, const convgen::Problem &p, const float *bias)
+{
+  switch (bn) {
+    case 32: return launch_k<32, B_MN>(st, p, bias);
+    case 64: return launch_k<64, B_MN>(st, p, bias);
+    case 96: return launch_k<96, B_MN>(st, p, bias);
+    case 128: return launch_k<128, B_MN>(st, p, bias);
+    case 192: return launch_k<192, B_MN>(st, p, bias);
+    default: return launch_k<256, B_MN>(st, p, bias);
+  }
+}
+
+template <int BN> int launch_w(cudaStream_t st, const convgen::WProblem &p)
+{
+  using C = convgen::WCfg<BN>;
+  auto kern = convgen::conv_wgrad_kernel<BN>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
+  if (err != cudaSuccess) return (int)err;
+  const long long work = (long long)((p.nslabs + 3) / 4) * ((p.CO + BN - 1) / BN) * p.splits;
+  const int grid = (int)(work < sm_count() ? work : sm_count());
+  kern<<<grid, convgen::kThreadsW, C::SMEM_BYTES, st>>>(p);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+bool shape_ok(int batch, int D, int H, int W, int ci, int co, int stride)
+{
+  if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || ci <= 0 || co <= 0 || ci % 4 || co % 4) return false;
+  if (stride != 1 && stride != 2) return false;
+  if (stride == 2 && (D < 2 || H < 2 || W < 2)) return false;
+  return true;
+}
+
+// per-axis tap geometry under stride 2, seen from the output grid: tap k reads parity class par(k) of the input at index o + off(k)
+inline int s2_par(int k) { return k == 1 ? 0 : 1; }
+inline int s2_off(int k) { return k == 0 ? -1 : 0; }
+
+}  // namespace
+
+extern "C" int conv3d_gen_supported(int in_channels, int out_channels, int stride)
+{
+  return in_channels > 0 && out_channels > 0 && in_channels % 4 == 0 && out_channels % 4 == 0 && (stride == 1 || stride == 2);
+}
+
+extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, const float *bias, int batch, int depth, int height, int width,
+                                  int in_channels, int out_channels, int stride, float *y)
+{
+  if (!x || !w || !y || !shape_ok(batch, depth, height, width, in_channels, out_channels, stride)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) return MSDA3D_EALIGN;
+  ensure_context_on_this_thread();
+  const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
+  convgen::Problem p = {};
+  choose_box(128, OW, OH, OD, &p.BW, &p.BH, &p.BD);
+  p.qh = p.BH < 32 / p.BW ? p.BH : 32 / p.BW;
+  p.qd = 32 / (p.BW * p.qh);
+  p.batch = batch; p.tw = (OW + p.BW - 1) / p.BW; p.th = (OH + p.BH - 1) / p.BH; p.td = (OD + p.BD - 1) / p.BD;
+  p.N = out_channels; p.chunks = (in_channels + 31) / 32; p.nclass = 1; p.nsteps[0] = 27;
+  const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
+  int rc;
+  if (stride == 1) {
+    if ((rc = make_vol_map(&p.tmA[0], x, vx, 1, 0, 0, 0, p.BW, p.BH, p.BD, false, true))) return rc;
+  } else {
+    for (int c = 0; c < 8; ++c)
+      if ((rc = make_vol_map(&p.tmA[c], x, vx, 2, c >> 2, (c >> 1) & 1, c & 1, p.BW, p.BH, p.BD, false, true))) return rc;
+  }
+  for (int kd = 0; kd < 3; ++kd)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        convgen::Step &s = p.steps[0][(kd * 3 + kh) * 3 + kw];
+        s.tap = (kd * 3 + kh) * 3 + kw;
+        if (stride == 1) { s.amap = 0; s.dw = (signed char)(kw - 1); s.dh = (signed char)(kh - 1); s.dd = (signed char)(kd - 1); }
+        else { s.amap = (signed char)(s2_par(kd) * 4 + s2_par(kh) * 2 + s2_par(kw)); s.dw = (signed char)s2_off(kw); s.dh = (signed char)s2_off(kh); s.dd = (signed char)s2_off(kd); }
+      }
+  if ((rc = make_vol_map(&p.tmD[0], y, vy, 1, 0, 0, 0, p.BW, p.qh, p.qd, false, false))) return rc;
+  const int bn = choose_bn(out_channels);
+  if ((rc = make_weight_map(&p.tmB, w, in_channels, out_channels, bn, false))) return rc;
+  return dispatch_k<false>(reinterpret_cast<cudaStream_t>(stream), bn, p, bias);
+}
+
+extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, int batch, int depth, int height, int width, int in_channels,
+                                int out_channels, int stride, float *dx)
+{
+  if (!dy || !w || !dx || !shape_ok(batch, depth, height, width, in_channels, out_channels, stride)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(w)) & 15) return MSDA3D_EALIGN;
+  ensure_context_on_this_thread();
+  const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
+  convgen::Problem p = {};
+  // stride 1: tiles over dx; stride 2: every parity class of dx is tiled over the dy grid (its own extent is that or one less)
+  choose_box(128, OW, OH, OD, &p.BW, &p.BH, &p.BD);
+  p.qh = p.BH < 32 / p.BW ? p.BH : 32 / p.BW;
+  p.qd = 32 / (p.BW * p.qh);
+  p.batch = batch; p.tw = (OW + p.BW - 1) / p.BW; p.th = (OH + p.BH - 1) / p.BH; p.td = (OD + p.BD - 1) / p.BD;
+  p.N = in_channels; p.chunks = (out_channels + 31) / 32;
+  const Vol vdy = {batch, OD, OH, OW, out_channels}, vdx = {batch, depth, height, width, in_channels};
+  int rc;
+  if ((rc = make_vol_map(&p.tmA[0], dy, vdy, 1, 0, 0, 0, p.BW, p.BH, p.BD, false, true))) return rc;
+  if (stride == 1) {
+    p.nclass = 1; p.nsteps[0] = 27;
+    for (int kd = 0; kd < 3; ++kd)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          convgen::Step &s = p.steps[0][(kd * 3 + kh) * 3 + kw];
+          s.tap = (kd * 3 + kh) * 3 + kw; s.amap = 0;
+          s.dw = (signed char)(1 - kw); s.dh = (signed char)(1 - kh); s.dd = (signed char)(1 - kd);      // dx[i] = sum_k dy[i + 1 - k] W[k]
+        }
+    if ((rc = make_vol_map(&p.tmD[0], dx, vdx, 1, 0, 0, 0, p.BW, p.qh, p.qd, false, false))) return rc;
+  } else {
+    p.nclass = 8;
+    for (int c = 0; c < 8; ++c) {
+      const int par[3] = {c >> 2, (c >> 1) & 1, c & 1};                  // (pd, ph, pw)
+      int n = 0;
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int k[3] = {kd, kh, kw};
+            bool ok = true;
+            for (int a = 0; a < 3; ++a) ok = ok && (par[a] == 0 ? k[a] == 1 : k[a] != 1);
+            if (!ok) continue;
+            convgen::Step &s = p.steps[c][n++];
+            s.tap = (kd * 3 + kh) * 3 + kw; s.amap = 0;
+            s.dd = (signed char)(kd == 0); s.dh = (signed char)(kh == 0); s.dw = (signed char)(kw == 0);   // dx[2 j + 1] takes dy[j + 1] W[0] + dy[j] W[2]
+          }
+      p.nsteps[c] = n;
+      if ((rc = make_vol_map(&p.tmD[c], dx, vdx, 2, par[0], par[1], par[2], p.BW, p.qh, p.qd, false, false))) return rc;
+    }
+  }
+  const int bn = choose_bn(in_channels);
+  if ((rc = make_weight_map(&p.tmB, w, in_channels, out_channels, 32, true))) return rc;
+  return dispatch_k<true>(reinterpret_cast<cudaStream_t>(stream), bn, p, nullptr);
+}
+
+extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
+                                int out_channels, int stride, float *dw)
+{
+  if (!x || !dy || !dw || !shape_ok(batch, depth, height, width, in_channels, out_channels, stride)) return MSDA3D_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return MSDA3D_EALIGN;
+  ensure_context_on_this_thread();
+  const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
+  convgen::WProblem p = {};
+  choose_box(32, OW, OH, OD, &p.bw, &p.bh, &p.bd);
+  p.batch = batch; p.tw = (OW + p.bw - 1) / p.bw; p.th = (OH + p.bh - 1) / p.bh; p.td = (OD + p.bd - 1) / p.bd;
+  p.CI = in_channels; p.CO = out_channels; p.chunks = (in_channels + 31) / 32; p.nslabs = 27 * p.chunks; p.dw = dw;
+  const Vol vx = {batch, depth, height, width, in_channels}, vdy = {batch, OD, OH, OW, out_channels};
+  int rc;
+  if (stride == 1) {
+    if ((rc = make_vol_map(&p.tmX[0], x, vx, 1, 0, 0, 0, p.bw, p.bh, p.bd, true, true))) return rc;
+  } else {
+    for (int c = 0; c < 8; ++c)
+      if ((rc = make_vol_map(&p.tmX[c], x, vx, 2, c >> 2, (c >> 1) & 1, c & 1, p.bw, p.bh, p.bd, true, true))) return rc;
+  }
+  if ((rc = make_vol_map(&p.tmDy, dy, vdy, 1, 0, 0, 0, p.bw, p.bh, p.bd, true, true))) return rc;
+  for (int kd = 0; kd < 3; ++kd)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        convgen::WTap &t = p.taps[(kd * 3 + kh) * 3 + kw];
+        if (stride == 1) { t.xmap = 0; t.dw = (signed char)(kw - 1); t.dh = (signed char)(kh - 1); t.dd = (signed char)(kd - 1); }
+        else { t.xmap = (signed char)(s2_par(kd) * 4 + s2_par(kh) * 2 + s2_par(kw)); t.dw = (signed char)s2_off(kw); t.dh = (signed char)s2_off(kh); t.dd = (signed char)s2_off(kd); }
+      }
+  int bn = choose_bn(out_channels);
+  if (bn == 32) bn = 64;
+  const long long kblocks = (long long)batch * p.td * p.th * p.tw;
+  const long long items = (long long)((p.nslabs + 3) / 4) * ((out_channels + bn - 1) / bn);
+  long long splits = (2LL * sm_count() + items - 1) / items;
+  const long long max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (kblocks + splits - 1) / splits;
+  p.splits = (int)((kblocks + p.kb_per_split - 1) / p.kb_per_split);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)out_channels * 27 * in_channels * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  switch (bn) {
+    case 64: return launch_w<64>(st, p);
+    case 96: return launch_w<96>(st, p);
+    case 128: return launch_w<128>(st, p);
+    case 192: return launch_w<192>(st, p);
+    default: return launch_w<256>(st, p);
+  }
+}

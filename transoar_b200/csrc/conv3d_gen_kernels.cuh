@@ -1,0 +1,391 @@
+// conv3d_gen_kernels.cuh -- 3x3x3 convolutions of channels-last (NDHWC) fp32 volumes with ANY channel counts, stride 1 or 2, on the
+// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands by TMA): forward, gradient with respect to the
+// input, gradient with respect to the weights.  These are the convolutions of the AttnFPN backbone that conv3d_tc_kernels.cuh (24 -> 24
+// only: all 27 taps' weights resident in shared memory) does not cover: EncoderCnnBlock stages 1-5 (24 -> 48 -> ... -> 768 channels, the
+// first convolution of each stage with stride 2; transoar/models/backbones/encoder_blocks.py:28-46 via attn_fpn.py:170-182) and the FPN's
+// 3x3x3 output convolutions with bias (attn_fpn.py:65-74: 96 / 192 / 384 / 384 -> 384).  The reference runs them through cuDNN.
+//
+// Implicit GEMM, no im2col copy anywhere:
+//
+//   forward / input gradient ("K-major" kernel, conv_kmajor_kernel)
+//     D[v, n] = sum over steps s, reduction channels r of  A_s[v + delta_s, r] * B[tap_s][n][r]      (+ bias[n])
+//     A tile of 128 output voxels is a BW x BH x BD box of the volume.  One K-step = one tap and one chunk of 32 reduction channels:
+//     ONE 5-D TMA box (32 channels, BW, BH, BD, 1) at the tile origin shifted by the tap brings the 128 x 32 A operand (rows of 128 bytes,
+//     128-byte swizzle: exactly the K-major operand form of tc_gemm_kernels.cuh); voxels outside the volume and channels past the tensor's
+//     count are zero-filled by the copy engine -- that is the convolution's zero padding and the channel padding.  The B operand comes
+//     straight from the channels-last weight tensor [CO][27][CI] through a 3-D tensor map: K-major rows for the forward (reduction = ci),
+//     MN-major 32 x 32 slabs for the input gradient (reduction = co, n = ci), so no transposed / re-laid-out weight copy exists.
+//     Stride 2 without element strides: the eight parity classes of a volume (even / odd index per axis) are eight plain 5-D tensors with
+//     doubled strides.  Forward: tap k reads class (k + 1) % 2 at index o + (k == 0 ? -1 : 0) per axis.  Input gradient: the inputs of
+//     parity class p receive dx[2 j + p] = sum over the taps with k = 1 (p = 0) or k in {0, 2} (p = 1) per axis of dy[j + (k == 0)] W[k]:
+//     eight stride-1 problems on the dy grid with 1 / 2 / 4 / 8 taps, each stored through the tensor map of ITS class of dx.
+//     The epilogue writes with 5-D bulk tensor stores (one per 32-voxel x 32-channel chunk), which also clip ragged volumes / channels.
+//
+//   weight gradient (conv_wgrad_kernel)
+//     dW[co][tap][ci] = sum over output voxels v of dy[v][co] * x[stride * v + tap - 1][ci]
+//     The reduction index is the voxel, so both operands are MN-major (channels contiguous): 32-voxel x 32-channel slabs in the 128-byte
+//     swizzle / 32-byte atom form, each ONE 5-D TMA box.  The M extent of a tile is four x slabs = four (tap, ci-chunk) pairs -- so narrow
+//     layers (24 / 48 channels) still fill the 128 rows of the MMA with different taps --, the N extent is BN output channels of dy.
+//     Split over voxel ranges; partial tiles are added into the zero-initialised gradient with red.global.add.f32, already in the
+//     channels-last weight layout [CO][27][CI].
+//
+// Roles, barriers, ring and TMEM double buffering are those of tc_gemm_kernels.cuh.
+#pragma once
+
+#include "tc_gemm_kernels.cuh"
+
+namespace convgen {
+
+using namespace tcgemm;
+
+constexpr int kMaxClasses = 8, kMaxSteps = 27;
+
+struct Step {
+  signed char amap, dw, dh, dd;   // which A tensor map (parity class), shift of the box origin in (that map's) voxels
+  int tap;                        // row block of the weight tensor: kd * 9 + kh * 3 + kw
+};
+
+struct Problem {
+  int batch, tw, th, td;          // tile grid (per class)
+  int BW, BH, BD;                 // tile box, BW * BH * BD == 128, BW <= 32
+  int qh, qd;                     // the 32 rows of one TMEM lane quarter as a box: BW x qh x qd
+  int N;                          // columns of D (output channels of this launch)
+  int chunks;                     // ceil(reduction channels / 32)
+  int nclass;
+  int nsteps[kMaxClasses];
+  Step steps[kMaxClasses][kMaxSteps];
+  CUtensorMap tmA[kMaxClasses];
+  CUtensorMap tmD[kMaxClasses];
+  CUtensorMap tmB;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
+{
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// work item w -> (class, sample, tile origin, column tile); column tiles fastest so that neighbouring CTAs share the A boxes in L2
+struct Item { int cls, n, w0, h0, d0, nt; };
+__device__ __forceinline__ Item decode(const Problem &p, long long w, int n_tiles)
+{
+  Item it;
+  it.nt = (int)(w % n_tiles); w /= n_tiles;
+  it.w0 = (int)(w % p.tw) * p.BW; w /= p.tw;
+  it.h0 = (int)(w % p.th) * p.BH; w /= p.th;
+  it.d0 = (int)(w % p.td) * p.BD; w /= p.td;
+  it.n = (int)(w % p.batch);
+  it.cls = (int)(w / p.batch);
+  return it;
+}
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ bias)
+{
+  using C = Cfg<BN, 1>;
+  static_assert(BN % 32 == 0 && BN <= 256, "column tile");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bars = epi_base + C::EPI_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+        const Item it = decode(p, w, n_tiles);
+        const int n0 = it.nt * BN, ns = p.nsteps[it.cls];
+        for (int s = 0; s < ns; ++s) {
+          const Step st = p.steps[it.cls][s];
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait(empty(stage), phase ^ 1u);
+            mbar_expect_tx(full(stage), C::STAGE_BYTES);
+            const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+            tma_load_5d(sa, &p.tmA[st.amap], full(stage), c * 32, it.w0 + st.dw, it.h0 + st.dh, it.d0 + st.dd, it.n);
+            if (!B_MN) {
+              tma_load_3d(sb, &p.tmB, full(stage), c * 32, st.tap, n0);                           // BN rows (n) x 32 reduction channels
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + i * kSlabBytes, &p.tmB, full(stage), n0 + 32 * i, st.tap, c * 32);   // 32 reduction rows x 32 n
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc<BN, false, B_MN, 1, float>();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      const Item it = decode(p, w, n_tiles);
+      const int ksteps = p.nsteps[it.cls] * p.chunks;
+      mbar_wait(tempty(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_u + (uint32_t)(as * BN);
+      for (int kb = 0; kb < ksteps; ++kb) {
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = smem_desc<false>(sa + k * kstep_bytes<false>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
+            umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty(stage));
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (elect_one()) umma_commit(tfull(as));
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    const int q = warp & 3;
+    int as = 0, tma_buf = 0;
+    uint32_t aphase = 0;
+    // rows 32 q .. 32 q + 31 of the tile (w fastest, then h, then d) are the box BW x qh x qd starting here
+    const int r0 = 32 * q;
+    const int qh0 = (r0 / p.BW) % p.BH, qd0 = r0 / (p.BW * p.BH);
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      const Item it = decode(p, w, n_tiles);
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(q * 32) << 16), v);
+        const int n0 = it.nt * BN + c0;
+        if (n0 >= p.N) continue;                                  // warp-uniform
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+        }
+        const uint32_t buf = epi_base + (uint32_t)(warp - 2) * C::EPI_WARP_BYTES + (uint32_t)(tma_buf * 4096);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)(lane * 128 + ((i ^ (lane & 7)) << 4))), "f"(v[4 * i]),
+                       "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        tma_buf ^= 1;
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------------------------
+struct WTap { signed char xmap, dw, dh, dd; };
+
+struct WProblem {
+  int batch, tw, th, td;          // grid of 32-voxel blocks over the OUTPUT volume (dy)
+  int bw, bh, bd;                 // block box, bw * bh * bd == 32
+  int CI, CO, chunks;             // chunks = ceil(CI / 32)
+  int nslabs;                     // 27 * chunks: M slab s = (tap s / chunks, ci chunk s % chunks)
+  int splits;
+  long long kb_per_split;         // voxel blocks per split
+  float *dw;                      // [CO][27][CI], zero-initialised
+  WTap taps[27];
+  CUtensorMap tmX[kMaxClasses];
+  CUtensorMap tmDy;
+};
+
+template <int BN> struct WCfg {
+  static constexpr int A_BYTES = 4 * kSlabBytes;                     // four x slabs: 32 voxels x 32 channels each
+  static constexpr int B_BYTES = (BN / 32) * kSlabBytes;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+constexpr int kThreadsW = 192;    // warp 0 producer, warp 1 MMA, warps 2-5 epilogue (one per TMEM lane quarter = one M slab)
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsW, 1)
+conv_wgrad_kernel(const __grid_constant__ WProblem p)
+{
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  const uint32_t tfull = bars + 8u * (2 * C::STAGES), tempty = bars + 8u * (2 * C::STAGES + 1);
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 2);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int m_tiles = (p.nslabs + 3) / 4, n_tiles = (p.CO + BN - 1) / BN;
+  const long long kblocks = (long long)p.batch * p.td * p.th * p.tw;
+  const long long work = (long long)m_tiles * n_tiles * p.splits;          // M tiles fastest: concurrent CTAs read the same voxel range
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+        const int mt = (int)(w % m_tiles), nt = (int)((w / m_tiles) % n_tiles), sp = (int)(w / ((long long)m_tiles * n_tiles));
+        const int nvalid = min(4, p.nslabs - 4 * mt);
+        const long long kb0 = sp * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+        for (long long kb = kb0; kb < kb1; ++kb) {
+          long long t = kb;
+          const int w0 = (int)(t % p.tw) * p.bw; t /= p.tw;
+          const int h0 = (int)(t % p.th) * p.bh; t /= p.th;
+          const int d0 = (int)(t % p.td) * p.bd; t /= p.td;
+          const int n = (int)t;
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), (uint32_t)(nvalid + BN / 32) * kSlabBytes);
+          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nvalid) {
+              const int s = 4 * mt + j, tap = s / p.chunks, ch = s % p.chunks;
+              const WTap tp = p.taps[tap];
+              tma_load_5d(sa + j * kSlabBytes, &p.tmX[tp.xmap], full(stage), ch * 32, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, n);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_5d(sb + i * kSlabBytes, &p.tmDy, full(stage), nt * BN + 32 * i, w0, h0, d0, n);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc<BN, true, true, 1, float>();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      const int sp = (int)(w / ((long long)m_tiles * n_tiles));
+      const long long kb0 = sp * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+      mbar_wait(tempty, aphase ^ 1u);
+      tc_fence_after();
+      for (long long kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = smem_desc<true>(sa + k * kstep_bytes<true>()), db = smem_desc<true>(sb + k * kstep_bytes<true>());
+            umma_tf32(tmem_u, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty(stage));
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
+      aphase ^= 1u;
+    }
+  } else {
+    const int q = warp & 3;                                        // TMEM lane quarter = M slab of the tile
+    uint32_t aphase = 0;
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      const int mt = (int)(w % m_tiles), nt = (int)((w / m_tiles) % n_tiles);
+      mbar_wait(tfull, aphase);
+      tc_fence_after();
+      const int s = 4 * mt + q;
+      const int tap = s / p.chunks, ci = (s % p.chunks) * 32 + lane;
+      const bool row_ok = s < p.nslabs && ci < p.CI;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t)c0 + ((uint32_t)(q * 32) << 16), v);
+        const int co0 = nt * BN + c0;
+        if (row_ok) {
+          float *dst = p.dw + ((long long)co0 * 27 + tap) * p.CI + ci;           // lanes = consecutive ci: coalesced reductions
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (co0 + j < p.CO) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * 27 * p.CI), "f"(v[j]) : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+      aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace convgen
