@@ -141,21 +141,6 @@ template <bool B_MN> int dispatch_k(cudaStream_t st, int bn, const convgen::Prob
   }
 }
 
-template <int BN> int launch_w(cudaStream_t st, const convgen::WProblem &p)
-{
-  using C = convgen::WCfg<BN>;
-  auto kern = convgen::conv_wgrad_kernel<BN>;
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
-  if (err != cudaSuccess) return (int)err;
-  const long long work = (long long)((p.nslabs + 3) / 4) * ((p.CO + BN - 1) / BN) * p.splits;
-  const int grid = (int)(work < sm_count() ? work : sm_count());
-  kern<<<grid, convgen::kThreadsW, C::SMEM_BYTES, st>>>(p);
-  ++g_msda3d_launches;
-  return (int)cudaGetLastError();
-}
-
 bool shape_ok(int batch, int D, int H, int W, int ci, int co, int stride)
 {
   if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || ci <= 0 || co <= 0 || ci % 4 || co % 4) return false;
@@ -270,43 +255,95 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
   ensure_context_on_this_thread();
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   convgen::WProblem p = {};
-  choose_box(32, OW, OH, OD, &p.bw, &p.bh, &p.bd);
-  p.batch = batch; p.tw = (OW + p.bw - 1) / p.bw; p.th = (OH + p.bh - 1) / p.bh; p.td = (OD + p.bd - 1) / p.bd;
-  p.CI = in_channels; p.CO = out_channels; p.chunks = (in_channels + 31) / 32; p.nslabs = 27 * p.chunks; p.dw = dw;
+  // K-block = 8 x BH x BD output voxels (16 lines): least padded volume, then the smallest halo
+  {
+    long long best = -1;
+    for (int bh : {16, 8, 4}) {
+      const int bd = 16 / bh;
+      const long long pad = (long long)((OH + bh - 1) / bh * bh) * ((OD + bd - 1) / bd * bd) * 1000 + (bh + 2) * bd;
+      if (best < 0 || pad < best) { best = pad; p.BH = bh; p.BD = bd; }
+    }
+  }
+  p.batch = batch; p.tw = (OW + 7) / 8; p.th = (OH + p.BH - 1) / p.BH; p.td = (OD + p.BD - 1) / p.BD;
+  p.CI = in_channels; p.CO = out_channels; p.chunks = (in_channels + 31) / 32; p.dw = dw;
   const Vol vx = {batch, depth, height, width, in_channels}, vdy = {batch, OD, OH, OW, out_channels};
   int rc;
+  auto add_box = [&](int b, int cls_hw, int ow, int oh, int lw, int lh) {
+    convgen::WBox &bx = p.boxes[b];
+    bx.cls_hw = cls_hw; bx.ow = ow; bx.oh = oh; bx.lw = lw; bx.lh = lh;
+    bx.off = b == 0 ? 0 : (p.boxes[b - 1].off + p.boxes[b - 1].lw * p.boxes[b - 1].lh * p.BD * 128 + 1023) / 1024 * 1024;
+    p.x_bytes += lw * lh * p.BD * 128;
+  };
+  auto add_group = [&](int g, int box, int oh, int t0, int t1, int t2) {
+    convgen::WGroup &gr = p.groups[g];
+    gr.box = box; gr.oh = oh; gr.tap[0] = t0; gr.tap[1] = t1; gr.tap[2] = t2; gr.tap[3] = -1;
+  };
+  int max_acc;
   if (stride == 1) {
-    if ((rc = make_vol_map(&p.tmX[0], x, vx, 1, 0, 0, 0, p.bw, p.bh, p.bd, true, true))) return rc;
+    p.nbox = 1; p.ngroups = 3; max_acc = 3;
+    add_box(0, 0, -1, -1, 10, p.BH + 2);
+    for (int kh = 0; kh < 3; ++kh) add_group(kh, 0, kh, kh * 3, kh * 3 + 1, kh * 3 + 2);
+    for (int kd = 0; kd < 3; ++kd) { p.kd_cls[kd] = 0; p.kd_off[kd] = kd - 1; }
+    if ((rc = make_vol_map(&p.tmX[0], x, vx, 1, 0, 0, 0, 10, p.BH + 2, p.BD, true, true))) return rc;
   } else {
-    for (int c = 0; c < 8; ++c)
-      if ((rc = make_vol_map(&p.tmX[c], x, vx, 2, c >> 2, (c >> 1) & 1, c & 1, p.bw, p.bh, p.bd, true, true))) return rc;
+    p.nbox = 4; p.ngroups = 6; max_acc = 6;
+    add_box(0, 3, -1, -1, 9, p.BH + 1);            // odd h, odd w: (kh, kw) in {0, 2} x {0, 2}
+    add_box(1, 2, 0, -1, 8, p.BH + 1);             // odd h, even w: kh in {0, 2}, kw = 1
+    add_box(2, 1, -1, 0, 9, p.BH);                 // even h, odd w: kh = 1, kw in {0, 2}
+    add_box(3, 0, 0, 0, 8, p.BH);                  // even h, even w: the centre tap of the plane
+    add_group(0, 0, 0, 0, 2, -1); add_group(1, 1, 0, 1, -1, -1);        // kh = 0
+    add_group(2, 0, 1, 6, 8, -1); add_group(3, 1, 1, 7, -1, -1);        // kh = 2: one line further in the odd-h boxes
+    add_group(4, 2, 0, 3, 5, -1); add_group(5, 3, 0, 4, -1, -1);        // kh = 1
+    for (int kd = 0; kd < 3; ++kd) { p.kd_cls[kd] = s2_par(kd); p.kd_off[kd] = s2_off(kd); }
+    for (int c = 0; c < 8; ++c) {
+      const int ph = (c >> 1) & 1, pw = c & 1;
+      if ((rc = make_vol_map(&p.tmX[c], x, vx, 2, c >> 2, ph, pw, 8 + pw, p.BH + ph, p.BD, true, true))) return rc;
+    }
   }
-  if ((rc = make_vol_map(&p.tmDy, dy, vdy, 1, 0, 0, 0, p.bw, p.bh, p.bd, true, true))) return rc;
-  for (int kd = 0; kd < 3; ++kd)
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw) {
-        convgen::WTap &t = p.taps[(kd * 3 + kh) * 3 + kw];
-        if (stride == 1) { t.xmap = 0; t.dw = (signed char)(kw - 1); t.dh = (signed char)(kh - 1); t.dd = (signed char)(kd - 1); }
-        else { t.xmap = (signed char)(s2_par(kd) * 4 + s2_par(kh) * 2 + s2_par(kw)); t.dw = (signed char)s2_off(kw); t.dh = (signed char)s2_off(kh); t.dd = (signed char)s2_off(kd); }
-      }
-  int bn = choose_bn(out_channels);
-  if (bn == 32) bn = 64;
+  if ((rc = make_vol_map(&p.tmDy, dy, vdy, 1, 0, 0, 0, 8, p.BH, p.BD, true, true))) return rc;
+  const int last = p.nbox - 1;
+  p.dy_off = (p.boxes[last].off + p.boxes[last].lw * p.boxes[last].lh * p.BD * 128 + 1023) / 1024 * 1024;
+  // co tile: as wide as the accumulators (512 TMEM columns / max_acc) and the shared memory allow, least padding first
+  {
+    const int cap = 512 / max_acc;
+    long long best = -1;
+    for (int bn : {128, 96, 64, 32}) {
+      if (bn > cap) continue;
+      if (2 * (p.dy_off + bn / 32 * convgen::kWDyChunkBytes) + 1024 + 256 > 227 * 1024) continue;
+      const int tiles = (out_channels + bn - 1) / bn;
+      const long long cost = (long long)tiles * bn * 16 + tiles;          // padded columns, then fewer tiles
+      if (best < 0 || cost < best) { best = cost; p.BN = bn; p.n_tiles = tiles; }
+    }
+    if (best < 0) return MSDA3D_EINVAL;
+  }
+  p.stage_bytes = p.dy_off + p.BN / 32 * convgen::kWDyChunkBytes;
+  const int smem = convgen::kWStages * p.stage_bytes + 1024 + 256;
   const long long kblocks = (long long)batch * p.td * p.th * p.tw;
-  const long long items = (long long)((p.nslabs + 3) / 4) * ((out_channels + bn - 1) / bn);
-  long long splits = (2LL * sm_count() + items - 1) / items;
-  const long long max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;
-  if (splits > max_splits) splits = max_splits;
+  const long long per_split = 3LL * p.chunks * p.n_tiles;
+  long long splits = (2LL * sm_count() + per_split - 1) / per_split;
+  if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = (kblocks + splits - 1) / splits;
   p.splits = (int)((kblocks + p.kb_per_split - 1) / p.kb_per_split);
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(convgen::conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (err != cudaSuccess) return (int)err;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)out_channels * 27 * in_channels * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  switch (bn) {
-    case 64: return launch_w<64>(st, p);
-    case 96: return launch_w<96>(st, p);
-    case 128: return launch_w<128>(st, p);
-    case 192: return launch_w<192>(st, p);
-    default: return launch_w<256>(st, p);
-  }
+  const long long work = per_split * p.splits;
+  const int grid = (int)(work < sm_count() ? work : sm_count());
+  convgen::conv_wgrad_kernel<<<grid, convgen::kThreadsW, smem, st>>>(p);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+// experiments only (tools/probe_kshift.py): see k_sw128_probe_kernel
+extern "C" int conv3d_gen_debug_k_probe(void *stream, const float *X, const float *Y, float *D, int row0, int group_stride_rows, int mode)
+{
+  if (!X || !Y || !D || row0 < 0 || group_stride_rows < 1 || row0 + 15 * group_stride_rows + 8 > convgen::kProbeRows) return MSDA3D_EINVAL;
+  convgen::k_sw128_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, Y, D, row0, group_stride_rows, mode);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
 }

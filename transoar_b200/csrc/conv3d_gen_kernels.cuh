@@ -228,58 +228,81 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// weight gradient
+// weight gradient: dW[co][tap][ci] = sum over output voxels v of dy[v][co] * x[stride * v + tap - 1][ci]
+//
+// The reduction index is the voxel, so both operands are MN-major (channels contiguous, 128-byte rows of 32 channels, 128-byte swizzle
+// with 32-byte atoms).  That operand form is address-based: an operand may start at ANY row of a tile in shared memory, and the "next 32
+// M-elements" may be reached with a leading-dimension offset of ONE ROW (tests/test_gpu_conv3d_tc.py::test_mn_major_overlapping_slab_probe).
+// So a K-block is a box of 8 x BH x BD output voxels (16 lines of 8 voxels along w) whose x HALO tile arrives by one TMA box per
+// parity class, and for every line ONE MMA (M = 128, N = BN, K = 8 voxels) multiplies
+//     A = the x rows of that line shifted by kh lines, its four M slabs = the SAME rows shifted by 0, 1, 2 (, 3) voxels = the kw taps
+//     B = the 8 dy rows of the line, N slabs = 32-channel chunks of dy (one TMA box each)
+// into the accumulator of (kh): the x tile is read from L2 once per (kd, ci chunk), not once per tap.  A work item is
+// (kd, ci chunk, co tile, voxel range); its accumulators (3 for stride 1, 6 for stride 2) stay in TMEM over the whole range and are then
+// added into the zero-initialised gradient with red.global.add.f32 (channels-last weight layout).
+// Stride 2: tap k reads parity class (k + 1) % 2 of x at output index o - (k == 0), so the taps {0, 2} of an axis are two shifts of the
+// ODD class and tap 1 is the EVEN class: four (h, w)-class boxes per stage, two MMAs per (kh, line) (odd-w class: kw 0 and 2 as
+// overlapping slabs; even-w class: kw 1), six accumulators.
 // ---------------------------------------------------------------------------------------------------------------
-struct WTap { signed char xmap, dw, dh, dd; };
+constexpr int kWMaxBoxes = 4, kWMaxGroups = 6, kWLines = 16;
 
-struct WProblem {
-  int batch, tw, th, td;          // grid of 32-voxel blocks over the OUTPUT volume (dy)
-  int bw, bh, bd;                 // block box, bw * bh * bd == 32
-  int CI, CO, chunks;             // chunks = ceil(CI / 32)
-  int nslabs;                     // 27 * chunks: M slab s = (tap s / chunks, ci chunk s % chunks)
-  int splits;
-  long long kb_per_split;         // voxel blocks per split
-  float *dw;                      // [CO][27][CI], zero-initialised
-  WTap taps[27];
-  CUtensorMap tmX[kMaxClasses];
-  CUtensorMap tmDy;
+struct WBox {
+  int cls_hw;        // tensor map = tmX[pd * 4 + cls_hw]
+  int ow, oh;        // box origin = (w0 + ow, h0 + oh)
+  int lw, lh;        // rows per line, lines per plane of the box
+  int off;           // byte offset in the stage
 };
-
-template <int BN> struct WCfg {
-  static constexpr int A_BYTES = 4 * kSlabBytes;                     // four x slabs: 32 voxels x 32 channels each
-  static constexpr int B_BYTES = (BN / 32) * kSlabBytes;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+struct WGroup {
+  int box, oh;       // A rows of output line (h, d): box row ((d * lh + h + oh) * lw)
+  int tap[4];        // M slab j (rows shifted by j voxels) -> kh * 3 + kw, or -1 (unused slab)
+};
+struct WProblem {
+  int batch, tw, th, td;          // grid of K-blocks over the OUTPUT volume (dy)
+  int BH, BD;                     // K-block = 8 x BH x BD voxels, BH * BD == 16
+  int CI, CO, chunks;             // chunks = ceil(CI / 32)
+  int BN, n_tiles;                // co tile (multiple of 32) and their number
+  int splits;
+  long long kb_per_split;
+  int nbox, ngroups;
+  int kd_cls[3], kd_off[3];       // tap kd reads d-class kd_cls at d0 + kd_off
+  int x_bytes, dy_off, stage_bytes;
+  float *dw;                      // [CO][27][CI], zero-initialised
+  WBox boxes[kWMaxBoxes];
+  WGroup groups[kWMaxGroups];
+  CUtensorMap tmX[kMaxClasses];   // per parity class (pd, ph, pw); stride 1: only [0]
+  CUtensorMap tmDy;               // box (32 co, 8, BH, BD, 1)
 };
 
 constexpr int kThreadsW = 192;    // warp 0 producer, warp 1 MMA, warps 2-5 epilogue (one per TMEM lane quarter = one M slab)
+constexpr int kWStages = 2;
+constexpr int kWDyChunkBytes = 128 * 128;
 
-template <int BN>
-__global__ void __launch_bounds__(kThreadsW, 1)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes)
+{
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+static __global__ void __launch_bounds__(kThreadsW, 1)
 conv_wgrad_kernel(const __grid_constant__ WProblem p)
 {
-  using C = WCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bars = base + kWStages * p.stage_bytes;
   auto full = [&](int s) { return bars + 8u * s; };
-  auto empty = [&](int s) { return bars + 8u * (C::STAGES + s); };
-  const uint32_t tfull = bars + 8u * (2 * C::STAGES), tempty = bars + 8u * (2 * C::STAGES + 1);
-  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 2);
+  auto empty = [&](int s) { return bars + 8u * (kWStages + s); };
+  const uint32_t tfull = bars + 8u * (2 * kWStages), tempty = bars + 8u * (2 * kWStages + 1);
+  const uint32_t tmem_slot = bars + 8u * (2 * kWStages + 2);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -288,90 +311,94 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int m_tiles = (p.nslabs + 3) / 4, n_tiles = (p.CO + BN - 1) / BN;
   const long long kblocks = (long long)p.batch * p.td * p.th * p.tw;
-  const long long work = (long long)m_tiles * n_tiles * p.splits;          // M tiles fastest: concurrent CTAs read the same voxel range
+  const int per_split = 3 * p.chunks * p.n_tiles;                       // (kd, chunk, co tile) fastest: concurrent CTAs read the same voxel range
+  const long long work = (long long)per_split * p.splits;
+  const int ndy = p.BN / 32;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long w = blockIdx.x; w < work; w += gridDim.x) {
-        const int mt = (int)(w % m_tiles), nt = (int)((w / m_tiles) % n_tiles), sp = (int)(w / ((long long)m_tiles * n_tiles));
-        const int nvalid = min(4, p.nslabs - 4 * mt);
+        const int r = (int)(w % per_split), sp = (int)(w / per_split);
+        const int kd = r % 3, ch = (r / 3) % p.chunks, nt = r / (3 * p.chunks);
         const long long kb0 = sp * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
         for (long long kb = kb0; kb < kb1; ++kb) {
           long long t = kb;
-          const int w0 = (int)(t % p.tw) * p.bw; t /= p.tw;
-          const int h0 = (int)(t % p.th) * p.bh; t /= p.th;
-          const int d0 = (int)(t % p.td) * p.bd; t /= p.td;
+          const int w0 = (int)(t % p.tw) * 8; t /= p.tw;
+          const int h0 = (int)(t % p.th) * p.BH; t /= p.th;
+          const int d0 = (int)(t % p.td) * p.BD; t /= p.td;
           const int n = (int)t;
           mbar_wait(empty(stage), phase ^ 1u);
-          mbar_expect_tx(full(stage), (uint32_t)(nvalid + BN / 32) * kSlabBytes);
-          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nvalid) {
-              const int s = 4 * mt + j, tap = s / p.chunks, ch = s % p.chunks;
-              const WTap tp = p.taps[tap];
-              tma_load_5d(sa + j * kSlabBytes, &p.tmX[tp.xmap], full(stage), ch * 32, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, n);
-            }
+          mbar_expect_tx(full(stage), (uint32_t)(p.x_bytes + ndy * kWDyChunkBytes));
+          const uint32_t sb = base + stage * p.stage_bytes;
+          for (int b = 0; b < p.nbox; ++b) {
+            const WBox &bx = p.boxes[b];
+            tma_load_5d(sb + bx.off, &p.tmX[p.kd_cls[kd] * 4 + bx.cls_hw], full(stage), ch * 32, w0 + bx.ow, h0 + bx.oh, d0 + p.kd_off[kd], n);
           }
-#pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_5d(sb + i * kSlabBytes, &p.tmDy, full(stage), nt * BN + 32 * i, w0, h0, d0, n);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          for (int i = 0; i < ndy; ++i) tma_load_5d(sb + p.dy_off + i * kWDyChunkBytes, &p.tmDy, full(stage), nt * p.BN + 32 * i, w0, h0, d0, n);
+          if (++stage == kWStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = instr_desc<BN, true, true, 1, float>();
+    // M = 128, N = BN, both operands MN-major (bits 15 / 16), TF32 in, fp32 out
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int stage = 0;
     uint32_t phase = 0, aphase = 0;
     for (long long w = blockIdx.x; w < work; w += gridDim.x) {
-      const int sp = (int)(w / ((long long)m_tiles * n_tiles));
+      const int sp = (int)(w / per_split);
       const long long kb0 = sp * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
       mbar_wait(tempty, aphase ^ 1u);
       tc_fence_after();
       for (long long kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full(stage), phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+        const uint32_t sb = base + stage * p.stage_bytes;
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = smem_desc<true>(sa + k * kstep_bytes<true>()), db = smem_desc<true>(sb + k * kstep_bytes<true>());
-            umma_tf32(tmem_u, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int g = 0; g < p.ngroups; ++g) {
+            const WGroup &gr = p.groups[g];
+            const WBox &bx = p.boxes[gr.box];
+            const uint32_t xa = sb + bx.off, acc = tmem_u + (uint32_t)(g * p.BN);
+            for (int line = 0; line < kWLines; ++line) {
+              const int h = line % p.BH, d = line / p.BH;
+              const uint64_t da = desc_mn(xa + (uint32_t)(((d * bx.lh + h + gr.oh) * bx.lw) * 128), 128);
+              const uint64_t db = desc_mn(sb + p.dy_off + (uint32_t)(line * 8 * 128), kWDyChunkBytes);
+              umma_tf32(acc, da, db, idesc, (kb > kb0 || line > 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty(stage));
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
       }
       if (elect_one()) umma_commit(tfull);
       __syncwarp();
       aphase ^= 1u;
     }
   } else {
-    const int q = warp & 3;                                        // TMEM lane quarter = M slab of the tile
+    const int q = warp & 3;                                        // TMEM lane quarter = M slab
     uint32_t aphase = 0;
     for (long long w = blockIdx.x; w < work; w += gridDim.x) {
-      const int mt = (int)(w % m_tiles), nt = (int)((w / m_tiles) % n_tiles);
+      const int r = (int)(w % per_split);
+      const int kd = r % 3, ch = (r / 3) % p.chunks, nt = r / (3 * p.chunks);
       mbar_wait(tfull, aphase);
       tc_fence_after();
-      const int s = 4 * mt + q;
-      const int tap = s / p.chunks, ci = (s % p.chunks) * 32 + lane;
-      const bool row_ok = s < p.nslabs && ci < p.CI;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t)c0 + ((uint32_t)(q * 32) << 16), v);
-        const int co0 = nt * BN + c0;
-        if (row_ok) {
+      const int ci = ch * 32 + lane;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int tl = p.groups[g].tap[q];
+        if (tl < 0) continue;                                      // warp-uniform: unused M slab
+        const int tap = kd * 9 + tl;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t)(g * p.BN + c0) + ((uint32_t)(q * 32) << 16), v);
+          const int co0 = nt * p.BN + c0;
           float *dst = p.dw + ((long long)co0 * 27 + tap) * p.CI + ci;           // lanes = consecutive ci: coalesced reductions
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (co0 + j < p.CO) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * 27 * p.CI), "f"(v[j]) : "memory");
+            if (co0 + j < p.CO && ci < p.CI) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * 27 * p.CI), "f"(v[j]) : "memory");
         }
       }
       tc_fence_before();
@@ -384,8 +411,57 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Probe (tests / experiments only): can a K-major, 128-byte-swizzled A operand start at a row that is NOT aligned to the 8-row
+// (1024-byte) swizzle atom, with 8-row groups that are NOT 1024 bytes apart?  That is what reading the kw / kh taps of a convolution
+// straight out of one halo tile in shared memory needs.  X [176 rows][32] is stored as TMA would store it (16-byte chunk c of the row at
+// byte address a lands at chunk c ^ ((a >> 7) & 7): the swizzle is a function of the ABSOLUTE shared-memory address), then ONE
+// 128 x 32 x 8 MMA reads rows row0 + (m / 8) * gs + m % 8.  mode bit 0: put (start >> 7) & 7 into the descriptor's base-offset field.
+//   D[m][n] = sum_{k < 8} X[row0 + (m / 8) * gs + m % 8][k] * Y[n][k]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kProbeRows = 176;
+static __global__ void __launch_bounds__(128) k_sw128_probe_kernel(const float *__restrict__ X, const float *__restrict__ Y, float *__restrict__ Dout,
+                                                                   int row0, int gs, int mode)
+{
+  __shared__ __align__(1024) uint8_t sX[kProbeRows * 128];
+  __shared__ __align__(1024) uint8_t sY[32 * 128];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  auto swz = [](uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); };
+  auto tf32 = [](float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); };
+  for (int i = t; i < kProbeRows * 32; i += 128) *reinterpret_cast<float *>(sX + swz((uint32_t)i * 4u)) = tf32(X[i]);
+  for (int i = t; i < 32 * 32; i += 128) *reinterpret_cast<float *>(sY + swz((uint32_t)i * 4u)) = tf32(Y[i]);
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (t == 0) {
+    constexpr uint32_t idesc = instr_desc<32, false, false, 1, float>();
+    const uint32_t a0 = smem_u32(sX) + (uint32_t)row0 * 128u;
+    uint64_t da = (uint64_t)((a0 & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((uint32_t)(gs * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    if (mode & 1) da |= (uint64_t)((a0 >> 7) & 7u) << 49;
+    umma_tf32(tm, da, smem_desc<false>(smem_u32(sY)), idesc, 0u);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16), v);
+  for (int n = 0; n < 32; ++n) Dout[(size_t)t * 32 + n] = v[n];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(32) : "memory");
 }
 
 }  // namespace convgen
