@@ -37,6 +37,11 @@ int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, int batch, i
 int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,
                      int out_channels, int stride, float *dw);
 
+/* Forward and input gradient have two kernels: "halo" (8 x 16 voxel tiles whose (kh, kw) taps are read out of one halo tile in shared memory;
+ * the fast one for volumes with >= ~16 rows) and "tap" (one TMA box per tap; any tile box, used for the small coarse levels).  0 = choose per
+ * problem (default), 1 = tap, 2 = halo wherever it fits.  Tests and timing experiments only. */
+void conv3d_gen_set_path(int path);
+
 /* Experiment hook (tools/probe_kshift.py): one 128 x 32 x 8 TF32 MMA whose K-major, 128-byte-swizzled A operand starts at row `row0` of a
  * [176][32] matrix held in shared memory with 8-row groups `group_stride_rows` rows apart; mode bit 0 sets the descriptor's base-offset field.
  * D[m][n] = sum_{k < 8} X[row0 + (m / 8) * group_stride_rows + m % 8][k] * Y[n][k], Y [32][32], D [128][32], device pointers. */

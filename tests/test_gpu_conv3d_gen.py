@@ -32,13 +32,22 @@ def _ints(g, lo, hi, shape):
 
 # (N, D, H, W), CI, CO: the model's channel pairs, ragged volumes, odd extents (stride 2 parity classes of unequal size),
 # one case with more tiles than SMs (persistent loop), one with several column tiles (CO = 384) and one with ragged channel chunks (40 / 72)
-CASES = [((1, 4, 8, 16), 24, 48), ((2, 5, 7, 9), 48, 48), ((1, 6, 10, 12), 48, 96), ((1, 3, 5, 8), 96, 384), ((1, 5, 5, 8), 384, 192),
+CASES = [((1, 4, 8, 16), 24, 48), ((1, 3, 37, 21), 24, 48), ((1, 2, 33, 10), 96, 40), ((2, 5, 7, 9), 48, 48), ((1, 6, 10, 12), 48, 96), ((1, 3, 5, 8), 96, 384), ((1, 5, 5, 8), 384, 192),
          ((1, 3, 6, 7), 40, 72), ((1, 20, 40, 64), 48, 48), ((2, 2, 3, 2), 768, 768)]
+
+
+@pytest.fixture(params=["auto", "tap", "halo"])
+def path(request):
+    """Both forward / input-gradient kernels on every case (include/conv3d_gen.h: conv3d_gen_set_path)."""
+    from transoar_b200 import _lib
+    _lib.lib().conv3d_gen_set_path({"auto": 0, "tap": 1, "halo": 2}[request.param])
+    yield request.param
+    _lib.lib().conv3d_gen_set_path(0)
 
 
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("shape,ci,co", CASES)
-def test_forward_exact_on_integers(shape, ci, co, stride):
+def test_forward_exact_on_integers(shape, ci, co, stride, path):
     from transoar_b200 import _lib
     N, D, H, W = shape
     g = torch.Generator().manual_seed(D * H + W + ci)
@@ -55,7 +64,7 @@ def test_forward_exact_on_integers(shape, ci, co, stride):
 
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("shape,ci,co", CASES)
-def test_input_gradient_exact_on_integers(shape, ci, co, stride):
+def test_input_gradient_exact_on_integers(shape, ci, co, stride, path):
     from transoar_b200 import _lib
     N, D, H, W = shape
     g = torch.Generator().manual_seed(D * H + W + co)

@@ -40,8 +40,11 @@ def timed(fn, reps=7):
 
 
 def main():
-    only = sys.argv[1:] or None
+    only = [a for a in sys.argv[1:] if not a.startswith("--")] or None
     lib = _lib.lib()
+    for a in sys.argv[1:]:
+        if a.startswith("--path="):
+            lib.conv3d_gen_set_path({"auto": 0, "tap": 1, "halo": 2}[a.split("=")[1]])
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     cl = lambda t: t.contiguous(memory_format=torch.channels_last_3d)

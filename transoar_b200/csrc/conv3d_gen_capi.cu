@@ -3,6 +3,7 @@
 #include "conv3d_gen_kernels.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/conv3d_gen.h"
@@ -141,6 +142,92 @@ template <bool B_MN> int dispatch_k(cudaStream_t st, int bn, const convgen::Prob
   }
 }
 
+template <int BN, bool B_MN> int launch_h(cudaStream_t st, const convgen::HProblem &p, const float *bias, int smem)
+{
+  auto kern = convgen::conv_halo_kernel<BN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (err != cudaSuccess) return (int)err;
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * ((p.N + BN - 1) / BN);
+  const int grid = (int)(work < sm_count() ? work : sm_count());
+  kern<<<grid, tcgemm::kThreads, smem, st>>>(p, bias);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+template <bool B_MN> int dispatch_h(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem)
+{
+  switch (bn) {
+    case 32: return launch_h<32, B_MN>(st, p, bias, smem);
+    case 64: return launch_h<64, B_MN>(st, p, bias, smem);
+    case 96: return launch_h<96, B_MN>(st, p, bias, smem);
+    case 128: return launch_h<128, B_MN>(st, p, bias, smem);
+    case 192: return launch_h<192, B_MN>(st, p, bias, smem);
+    default: return launch_h<256, B_MN>(st, p, bias, smem);
+  }
+}
+
+// 0 = choose per problem, 1 = always the per-tap kernel, 2 = the halo kernel wherever it fits (conv3d_gen_set_path; CONV3D_GEN_PATH=tap|halo)
+std::atomic<int> g_path{-1};
+int forced_path()
+{
+  int v = g_path.load();
+  if (v < 0) {
+    const char *e = getenv("CONV3D_GEN_PATH");
+    v = e == nullptr ? 0 : e[0] == 't' ? 1 : e[0] == 'h' ? 2 : 0;
+    g_path.store(v);
+  }
+  return v;
+}
+
+// the halo kernel pays for whole 8 x 16 tiles: use it where the tile rows are mostly real voxels
+bool halo_wanted(int rows_h, int rows_w)
+{
+  const int f = forced_path();
+  if (f == 1) return false;
+  if (f == 2) return true;
+  const int th = (rows_h + 15) / 16, tw = (rows_w + 7) / 8;
+  return (double)rows_h * rows_w >= 0.6 * (th * 16.0) * (tw * 8.0);
+}
+
+void h_add_box(convgen::HProblem &p, int b, int cls_hw, int ow, int oh, int lw, int lh)
+{
+  convgen::HBox &bx = p.boxes[b];
+  bx.cls_hw = cls_hw; bx.ow = ow; bx.oh = oh; bx.lw = lw; bx.bytes = lw * lh * 128;
+  bx.off = b == 0 ? 0 : (p.boxes[b - 1].off + p.boxes[b - 1].bytes + 1023) / 1024 * 1024;
+  p.a_bytes += bx.bytes;
+  p.a_stage_bytes = (bx.off + bx.bytes + 1023) / 1024 * 1024;
+  p.nbox = b + 1;
+}
+
+// ring depths that fit 227 KB next to the epilogue staging; returns the dynamic shared-memory size or 0 if the problem does not fit
+int h_plan_smem(convgen::HProblem &p, int bn)
+{
+  const int avail = 227 * 1024 - 1024 - 512 - convgen::kHEpiBytes;
+  for (int bs : {4, 3, 2}) {
+    int as = (avail - bs * bn * 128) / p.a_stage_bytes;
+    if (as > 4) as = 4;
+    if (as >= 2) {
+      p.a_stages = as; p.b_stages = bs;
+      return 1024 + as * p.a_stage_bytes + bs * bn * 128 + convgen::kHEpiBytes + 512;
+    }
+  }
+  return 0;
+}
+
+template <int BHL> int launch_w(cudaStream_t st, const convgen::WProblem &p, int grid, int smem)
+{
+  auto kern = convgen::conv_wgrad_kernel<BHL>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (err != cudaSuccess) return (int)err;
+  kern<<<grid, convgen::kThreadsW, smem, st>>>(p);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
 bool shape_ok(int batch, int D, int H, int W, int ci, int co, int stride)
 {
   if (batch <= 0 || D <= 0 || H <= 0 || W <= 0 || ci <= 0 || co <= 0 || ci % 4 || co % 4) return false;
@@ -155,6 +242,8 @@ inline int s2_off(int k) { return k == 0 ? -1 : 0; }
 
 }  // namespace
 
+extern "C" void conv3d_gen_set_path(int path) { g_path.store(path == 1 || path == 2 ? path : 0); }
+
 extern "C" int conv3d_gen_supported(int in_channels, int out_channels, int stride)
 {
   return in_channels > 0 && out_channels > 0 && in_channels % 4 == 0 && out_channels % 4 == 0 && (stride == 1 || stride == 2);
@@ -167,14 +256,55 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) return MSDA3D_EALIGN;
   ensure_context_on_this_thread();
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
+  const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
+  int rc;
+  if (halo_wanted(OH, OW)) {
+    convgen::HProblem h = {};
+    h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
+    h.N = out_channels; h.chunks = (in_channels + 31) / 32; h.nclass = 1;
+    convgen::HClass &hc = h.cls[0];
+    hc.nplanes = 3;
+    if (stride == 1) {
+      h_add_box(h, 0, 0, -1, -1, 10, 18);
+      if ((rc = make_vol_map(&h.tmA[0], x, vx, 1, 0, 0, 0, 10, 18, 1, false, true))) return rc;
+    } else {
+      h_add_box(h, 0, 3, -1, -1, 9, 17);             // odd h, odd w
+      h_add_box(h, 1, 2, 0, -1, 8, 17);              // odd h, even w
+      h_add_box(h, 2, 1, -1, 0, 9, 16);              // even h, odd w
+      h_add_box(h, 3, 0, 0, 0, 8, 16);               // even h, even w
+      for (int c = 0; c < 8; ++c)
+        if ((rc = make_vol_map(&h.tmA[c], x, vx, 2, c >> 2, (c >> 1) & 1, c & 1, 8 + (c & 1), 16 + ((c >> 1) & 1), 1, false, true))) return rc;
+    }
+    for (int kd = 0; kd < 3; ++kd) {
+      convgen::HPlane &hp = hc.planes[kd];
+      hp.cls_d = stride == 1 ? 0 : s2_par(kd);
+      hp.od = stride == 1 ? kd - 1 : s2_off(kd);
+      hp.ntaps = 9;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          convgen::HTap &t = hp.taps[kh * 3 + kw];
+          t.wtap = (kd * 3 + kh) * 3 + kw;
+          if (stride == 1) { t.box = 0; t.rowshift = (short)(kh * 10 + kw); }
+          else {
+            t.box = (short)((s2_par(kh) ? 0 : 2) + (s2_par(kw) ? 0 : 1));
+            t.rowshift = (short)((kh == 2 ? h.boxes[t.box].lw : 0) + (kw == 2 ? 1 : 0));
+          }
+        }
+    }
+    const int bn = choose_bn(out_channels);
+    const int smem = h_plan_smem(h, bn);
+    if (smem > 0) {
+      if ((rc = make_vol_map(&h.tmD[0], y, vy, 1, 0, 0, 0, 8, 4, 1, false, false))) return rc;
+      if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, bn, false))) return rc;
+      return dispatch_h<false>(reinterpret_cast<cudaStream_t>(stream), bn, h, bias, smem);
+    }
+  }
   convgen::Problem p = {};
   choose_box(128, OW, OH, OD, &p.BW, &p.BH, &p.BD);
   p.qh = p.BH < 32 / p.BW ? p.BH : 32 / p.BW;
   p.qd = 32 / (p.BW * p.qh);
   p.batch = batch; p.tw = (OW + p.BW - 1) / p.BW; p.th = (OH + p.BH - 1) / p.BH; p.td = (OD + p.BD - 1) / p.BD;
   p.N = out_channels; p.chunks = (in_channels + 31) / 32; p.nclass = 1; p.nsteps[0] = 27;
-  const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
-  int rc;
   if (stride == 1) {
     if ((rc = make_vol_map(&p.tmA[0], x, vx, 1, 0, 0, 0, p.BW, p.BH, p.BD, false, true))) return rc;
   } else {
@@ -202,6 +332,57 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(w)) & 15) return MSDA3D_EALIGN;
   ensure_context_on_this_thread();
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
+  const Vol vdy = {batch, OD, OH, OW, out_channels}, vdx = {batch, depth, height, width, in_channels};
+  int rc;
+  if (halo_wanted(OH, OW)) {
+    convgen::HProblem h = {};
+    h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
+    h.N = in_channels; h.chunks = (out_channels + 31) / 32;
+    if (stride == 1) {
+      h.nclass = 1;
+      h_add_box(h, 0, 0, -1, -1, 10, 18);
+      if ((rc = make_vol_map(&h.tmA[0], dy, vdy, 1, 0, 0, 0, 10, 18, 1, false, true))) return rc;
+      if ((rc = make_vol_map(&h.tmD[0], dx, vdx, 1, 0, 0, 0, 8, 4, 1, false, false))) return rc;
+      convgen::HClass &hc = h.cls[0];
+      hc.nplanes = 3;
+      for (int jd = 0; jd < 3; ++jd) {                     // box plane jd = dy plane i + jd - 1 = i + 1 - kd: kd = 2 - jd (same for h, w)
+        convgen::HPlane &hp = hc.planes[jd];
+        hp.cls_d = 0; hp.od = jd - 1; hp.ntaps = 9;
+        for (int jh = 0; jh < 3; ++jh)
+          for (int jw = 0; jw < 3; ++jw) {
+            convgen::HTap &t = hp.taps[jh * 3 + jw];
+            t.box = 0; t.rowshift = (short)(jh * 10 + jw); t.wtap = ((2 - jd) * 3 + (2 - jh)) * 3 + (2 - jw);
+          }
+      }
+    } else {
+      h.nclass = 8;
+      h_add_box(h, 0, 0, 0, 0, 9, 17);
+      if ((rc = make_vol_map(&h.tmA[0], dy, vdy, 1, 0, 0, 0, 9, 17, 1, false, true))) return rc;
+      for (int c = 0; c < 8; ++c) {
+        const int par[3] = {c >> 2, (c >> 1) & 1, c & 1};
+        if ((rc = make_vol_map(&h.tmD[c], dx, vdx, 2, par[0], par[1], par[2], 8, 4, 1, false, false))) return rc;
+        convgen::HClass &hc = h.cls[c];
+        hc.nplanes = 0;
+        for (int kd = 0; kd < 3; ++kd) {
+          if (par[0] == 0 ? kd != 1 : kd == 1) continue;
+          convgen::HPlane &hp = hc.planes[hc.nplanes++];
+          hp.cls_d = 0; hp.od = kd == 0 ? 1 : 0; hp.ntaps = 0;
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+              if ((par[1] == 0 ? kh != 1 : kh == 1) || (par[2] == 0 ? kw != 1 : kw == 1)) continue;
+              convgen::HTap &t = hp.taps[hp.ntaps++];
+              t.box = 0; t.rowshift = (short)((kh == 0 ? 9 : 0) + (kw == 0 ? 1 : 0)); t.wtap = (kd * 3 + kh) * 3 + kw;
+            }
+        }
+      }
+    }
+    const int bn = choose_bn(in_channels);
+    const int smem = h_plan_smem(h, bn);
+    if (smem > 0) {
+      if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, 32, true))) return rc;
+      return dispatch_h<true>(reinterpret_cast<cudaStream_t>(stream), bn, h, nullptr, smem);
+    }
+  }
   convgen::Problem p = {};
   // stride 1: tiles over dx; stride 2: every parity class of dx is tiled over the dy grid (its own extent is that or one less)
   choose_box(128, OW, OH, OD, &p.BW, &p.BH, &p.BD);
@@ -209,8 +390,6 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
   p.qd = 32 / (p.BW * p.qh);
   p.batch = batch; p.tw = (OW + p.BW - 1) / p.BW; p.th = (OH + p.BH - 1) / p.BH; p.td = (OD + p.BD - 1) / p.BD;
   p.N = in_channels; p.chunks = (out_channels + 31) / 32;
-  const Vol vdy = {batch, OD, OH, OW, out_channels}, vdx = {batch, depth, height, width, in_channels};
-  int rc;
   if ((rc = make_vol_map(&p.tmA[0], dy, vdy, 1, 0, 0, 0, p.BW, p.BH, p.BD, false, true))) return rc;
   if (stride == 1) {
     p.nclass = 1; p.nsteps[0] = 27;
@@ -325,18 +504,16 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
   if (splits < 1) splits = 1;
   p.kb_per_split = (kblocks + splits - 1) / splits;
   p.splits = (int)((kblocks + p.kb_per_split - 1) / p.kb_per_split);
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [&] { err = cudaFuncSetAttribute(convgen::conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  if (err != cudaSuccess) return (int)err;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)out_channels * 27 * in_channels * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   const long long work = per_split * p.splits;
   const int grid = (int)(work < sm_count() ? work : sm_count());
-  convgen::conv_wgrad_kernel<<<grid, convgen::kThreadsW, smem, st>>>(p);
-  ++g_msda3d_launches;
-  return (int)cudaGetLastError();
+  switch (p.BH) {
+    case 16: return launch_w<4>(st, p, grid, smem);
+    case 8: return launch_w<3>(st, p, grid, smem);
+    default: return launch_w<2>(st, p, grid, smem);
+  }
 }
 
 // experiments only (tools/probe_kshift.py): see k_sw128_probe_kernel

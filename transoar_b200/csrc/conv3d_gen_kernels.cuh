@@ -228,6 +228,226 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Forward / input gradient with the A operand read out of a HALO tile (conv_halo_kernel) -- the fast path for volumes with >= ~16 rows.
+//
+// conv_kmajor_kernel above fetches one 128 x 32 box per tap: every input voxel crosses L2 -> SM 27 times, and the L2 fabric (~45 B/clk per
+// SM measured here) is what bounds it.  A K-major, 128-byte-swizzled MMA operand may start at ANY row of a tile in shared memory and its
+// 8-row groups may be any number of rows apart (the swizzle is a function of the absolute shared-memory address, for the copy engine and
+// for the tensor core alike: tools/probe_kshift.py, profiles/r02_experiments.md).  So a tile is 8 (w) x 16 (h) x 1 (d) output voxels = 16
+// groups of 8 rows, ONE TMA box brings the (8 + 2) x (16 + 2) halo of one input plane (a "plane stage": 180 rows of 128 bytes), and the nine
+// (kh, kw) taps of that plane are nine descriptors into it: start row kh * 10 + kw, group stride 10 rows.  The input now crosses L2 -> SM
+// 4.2 times (three halo planes per output plane); the weights stream through their own ring, one BN x 32 block per (tap, chunk).
+// Stride 2 forward: a plane stage is the four (h, w) parity-class boxes of the plane's d class.  Stride 2 input gradient: per parity class
+// of dx a 9 x 17 box of dy, the taps of that class at row shifts {0, 1} x {0, 9}.  Everything is table-driven (HProblem).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHMaxBoxes = 4, kHMaxPlanes = 3, kHMaxTaps = 9;
+struct HBox {
+  int cls_hw;        // A tensor map = tmA[plane.cls_d * 4 + cls_hw]
+  int ow, oh;        // box origin = (w0 + ow, h0 + oh)
+  int lw;            // rows per line of the box = group stride of the operand
+  int off, bytes;    // byte offset in the A stage, box bytes
+};
+struct HTap { short box, rowshift; int wtap; };
+struct HPlane { int cls_d, od, ntaps; HTap taps[kHMaxTaps]; };
+struct HClass { int nplanes; HPlane planes[kHMaxPlanes]; };
+struct HProblem {
+  int batch, tw, th, td;          // tile grid: 8 x 16 x 1 voxels per tile
+  int N, chunks, nclass, nbox;
+  int a_bytes, a_stage_bytes, a_stages, b_stages;
+  HBox boxes[kHMaxBoxes];
+  HClass cls[kMaxClasses];
+  CUtensorMap tmA[kMaxClasses];
+  CUtensorMap tmD[kMaxClasses];   // box (32 channels, 8, 4, 1, 1): one TMEM lane quarter
+  CUtensorMap tmB;
+};
+constexpr int kHEpiBytes = kEpiWarps * 4096;
+constexpr int kHMaxStages = 8;
+
+__device__ __forceinline__ uint64_t desc_k_halo(uint32_t addr, uint32_t group_stride_bytes)
+{
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(group_stride_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ bias)
+{
+  constexpr int B_BYTES = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = base + p.a_stages * p.a_stage_bytes;
+  const uint32_t epi_base = b_base + p.b_stages * B_BYTES;
+  const uint32_t bars = epi_base + kHEpiBytes;
+  auto afull = [&](int s) { return bars + 8u * s; };
+  auto aempty = [&](int s) { return bars + 8u * (kHMaxStages + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * kHMaxStages + s); };
+  auto bempty = [&](int s) { return bars + 8u * (3 * kHMaxStages + s); };
+  auto tfull = [&](int a) { return bars + 8u * (4 * kHMaxStages + a); };
+  auto tempty = [&](int a) { return bars + 8u * (4 * kHMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (4 * kHMaxStages + 4);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = BN <= 16 ? 32 : BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kHMaxStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * n_tiles;
+  // work item -> (class, sample, plane, tile row, tile column, column tile); column tiles fastest (they share the A boxes in L2)
+  auto decode_item = [&](long long w, int &cls, int &n, int &d0, int &h0, int &w0, int &nt) {
+    nt = (int)(w % n_tiles); w /= n_tiles;
+    w0 = (int)(w % p.tw) * 8; w /= p.tw;
+    h0 = (int)(w % p.th) * 16; w /= p.th;
+    d0 = (int)(w % p.td); w /= p.td;
+    n = (int)(w % p.batch);
+    cls = (int)(w / p.batch);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+        int cls, n, d0, h0, w0, nt;
+        decode_item(w, cls, n, d0, h0, w0, nt);
+        const HClass &hc = p.cls[cls];
+        const int n0 = nt * BN;
+        for (int c = 0; c < p.chunks; ++c) {
+          for (int pl = 0; pl < hc.nplanes; ++pl) {
+            const HPlane &hp = hc.planes[pl];
+            mbar_wait(aempty(as), aph ^ 1u);
+            mbar_expect_tx(afull(as), (uint32_t)p.a_bytes);
+            const uint32_t sa = base + as * p.a_stage_bytes;
+            for (int b = 0; b < p.nbox; ++b) {
+              const HBox &bx = p.boxes[b];
+              tma_load_5d(sa + bx.off, &p.tmA[hp.cls_d * 4 + bx.cls_hw], afull(as), c * 32, w0 + bx.ow, h0 + bx.oh, d0 + hp.od, n);
+            }
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            for (int t = 0; t < hp.ntaps; ++t) {
+              mbar_wait(bempty(bs), bph ^ 1u);
+              mbar_expect_tx(bfull(bs), B_BYTES);
+              const uint32_t sb = b_base + bs * B_BYTES;
+              const int tap = hp.taps[t].wtap;
+              if (!B_MN) {
+                tma_load_3d(sb, &p.tmB, bfull(bs), c * 32, tap, n0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + i * kSlabBytes, &p.tmB, bfull(bs), n0 + 32 * i, tap, c * 32);
+              }
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc<BN, false, B_MN, 1, float>();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int as = 0, bs = 0, acs = 0;
+    uint32_t aph = 0, bph = 0, acph = 0;
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      int cls, n, d0, h0, w0, nt;
+      decode_item(w, cls, n, d0, h0, w0, nt);
+      const HClass &hc = p.cls[cls];
+      mbar_wait(tempty(acs), acph ^ 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_u + (uint32_t)(acs * BN);
+      uint32_t first = 0u;
+      for (int c = 0; c < p.chunks; ++c) {
+        for (int pl = 0; pl < hc.nplanes; ++pl) {
+          const HPlane &hp = hc.planes[pl];
+          mbar_wait(afull(as), aph);
+          tc_fence_after();
+          const uint32_t sa = base + as * p.a_stage_bytes;
+          for (int t = 0; t < hp.ntaps; ++t) {
+            mbar_wait(bfull(bs), bph);
+            tc_fence_after();
+            const uint32_t sb = b_base + bs * B_BYTES;
+            const HBox &bx = p.boxes[hp.taps[t].box];
+            const uint64_t da0 = desc_k_halo(sa + bx.off + (uint32_t)(hp.taps[t].rowshift * 128), (uint32_t)(bx.lw * 128));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                umma_tf32(acc, da0 + (uint64_t)(k * 2), smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>()), idesc, first | (uint32_t)(k > 0));
+              }
+              umma_commit(bempty(bs));
+            }
+            __syncwarp();
+            first = 1u;
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          }
+          if (elect_one()) umma_commit(aempty(as));
+          __syncwarp();
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+      if (elect_one()) umma_commit(tfull(acs));
+      __syncwarp();
+      if (++acs == 2) { acs = 0; acph ^= 1u; }
+    }
+  } else {
+    const int q = warp & 3;
+    int acs = 0;
+    uint32_t acph = 0;
+    const uint32_t buf = epi_base + (uint32_t)(warp - 2) * 4096u;
+    for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+      int cls, n, d0, h0, w0, nt;
+      decode_item(w, cls, n, d0, h0, w0, nt);
+      mbar_wait(tfull(acs), acph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t)(acs * BN + c0) + ((uint32_t)(q * 32) << 16), v);
+        const int n0 = nt * BN + c0;
+        if (n0 >= p.N) continue;                                  // warp-uniform
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)(lane * 128 + ((i ^ (lane & 7)) << 4))), "f"(v[4 * i]),
+                       "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"(&p.tmD[cls]), "r"(buf), "r"(n0), "r"(w0), "r"(h0 + 4 * q), "r"(d0), "r"(n) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(acs));
+      if (++acs == 2) { acs = 0; acph ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weight gradient: dW[co][tap][ci] = sum over output voxels v of dy[v][co] * x[stride * v + tap - 1][ci]
 //
 // The reduction index is the voxel, so both operands are MN-major (channels contiguous, 128-byte rows of 32 channels, 128-byte swizzle
@@ -282,7 +502,9 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes)
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
-static __global__ void __launch_bounds__(kThreadsW, 1)
+// BHL = log2(BH): the line -> (h, d) split is a compile-time shift, the 16 MMAs of a group are unrolled with constant multipliers
+template <int BHL>
+__global__ void __launch_bounds__(kThreadsW, 1)
 conv_wgrad_kernel(const __grid_constant__ WProblem p)
 {
   extern __shared__ uint8_t smem_raw[];
@@ -358,15 +580,18 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
         tc_fence_after();
         const uint32_t sb = base + stage * p.stage_bytes;
         if (elect_one()) {
+          const uint64_t db0 = desc_mn(sb + p.dy_off, kWDyChunkBytes);
           for (int g = 0; g < p.ngroups; ++g) {
             const WGroup &gr = p.groups[g];
             const WBox &bx = p.boxes[gr.box];
-            const uint32_t xa = sb + bx.off, acc = tmem_u + (uint32_t)(g * p.BN);
+            const uint32_t step_h = (uint32_t)(bx.lw * 128) >> 4, step_d = (uint32_t)(bx.lh * bx.lw * 128) >> 4;
+            const uint64_t da0 = desc_mn(sb + bx.off + (uint32_t)(gr.oh * bx.lw * 128), 128);
+            const uint32_t acc = tmem_u + (uint32_t)(g * p.BN);
+#pragma unroll
             for (int line = 0; line < kWLines; ++line) {
-              const int h = line % p.BH, d = line / p.BH;
-              const uint64_t da = desc_mn(xa + (uint32_t)(((d * bx.lh + h + gr.oh) * bx.lw) * 128), 128);
-              const uint64_t db = desc_mn(sb + p.dy_off + (uint32_t)(line * 8 * 128), kWDyChunkBytes);
-              umma_tf32(acc, da, db, idesc, (kb > kb0 || line > 0) ? 1u : 0u);
+              constexpr int BH = 1 << BHL;
+              const int h = line & (BH - 1), d = line >> BHL;
+              umma_tf32(acc, da0 + (uint64_t)(d * step_d + h * step_h), db0 + (uint64_t)(line * 8 * 128 >> 4), idesc, (kb > kb0 || line > 0) ? 1u : 0u);
             }
           }
           umma_commit(empty(stage));
