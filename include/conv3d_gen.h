@@ -9,8 +9,10 @@
  * kernel, include/conv3d_tc.h; the 1-channel stem its stencil, include/stem_conv.h.)
  *
  *   x    fp32 [N, D, H, W, CI]      channels-last (torch.channels_last_3d memory of an [N, CI, D, H, W] tensor), 16-byte aligned
- *   w    fp32 [CO, 27, CI]          the channels-last memory of torch's [CO, CI, 3, 3, 3] weight: w[co][(kd*3 + kh)*3 + kw][ci];
- *                                   read in place by forward AND input gradient (no transposed copy)
+ *   w    fp32 [27, CO, CI]          tap-major weights: w[(kd*3 + kh)*3 + kw][co][ci] = weight[co][ci][kd][kh][kw] -- one (tap, 32-channel)
+ *                                   block is then CO rows CI * 4 bytes apart, which the copy engine fetches as whole L2 lines; the SAME
+ *                                   tensor serves the forward (rows = co, K-major) and the input gradient (rows = the reduction index co,
+ *                                   MN-major 32 x 32 slabs), so no transposed copy exists
  *   y    fp32 [N, OD, OH, OW, CO]   OD = ceil(D / stride) etc. (= floor((D + 2 - 3) / stride) + 1)
  *   bias fp32 [CO] or NULL
  * Cross-correlation, as torch.  depth / height / width are always the INPUT volume's.  Device pointers, work enqueued on `stream`, no
@@ -46,6 +48,10 @@ void conv3d_gen_set_path(int path);
  * [176][32] matrix held in shared memory with 8-row groups `group_stride_rows` rows apart; mode bit 0 sets the descriptor's base-offset field.
  * D[m][n] = sum_{k < 8} X[row0 + (m / 8) * group_stride_rows + m % 8][k] * Y[n][k], Y [32][32], D [128][32], device pointers. */
 int conv3d_gen_debug_k_probe(void *stream, const float *X, const float *Y, float *D, int row0, int group_stride_rows, int mode);
+
+/* Experiment hook (tools/probe_mma_rate.py): clocks for `iters` back-to-back 128 x n x 8 TF32 MMAs with zero operands in shared-memory layout
+ * 0 (K-major, 128-byte swizzle), 1 (K-major, 32-byte swizzle) or 2 (MN-major, 32-byte atoms); out_clocks: one int64 on the device. */
+int conv3d_gen_debug_mma_rate(void *stream, int layout, int n, int iters, long long *out_clocks);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,11 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _taps(w):
+    """[CO, CI, 3, 3, 3] -> the tap-major [27, CO, CI] tensor the C ABI takes (include/conv3d_gen.h)."""
+    return w.permute(2, 3, 4, 0, 1).reshape(27, w.shape[0], w.shape[1]).contiguous()
+
+
 def _ints(g, lo, hi, shape):
     return torch.randint(lo, hi + 1, shape, generator=g).float().to(DEV)
 
@@ -56,7 +61,7 @@ def test_forward_exact_on_integers(shape, ci, co, stride, path):
     b = _ints(g, -5, 5, (co,))
     od, oh, ow = ((v + stride - 1) // stride for v in (D, H, W))
     y = _cl(torch.full((N, co, od, oh, ow), float("nan"), device=DEV))
-    rc = _lib.lib().conv3d_gen_forward(_stream(), _p(x), _p(w), _p(b), N, D, H, W, ci, co, stride, _p(y))
+    rc = _lib.lib().conv3d_gen_forward(_stream(), _p(x), _p(_taps(w)), _p(b), N, D, H, W, ci, co, stride, _p(y))
     assert rc == 0
     ref = F.conv3d(x.double(), w.double(), b.double(), stride, 1).round()
     assert y.shape == ref.shape and torch.equal(y.double(), ref)
@@ -72,7 +77,7 @@ def test_input_gradient_exact_on_integers(shape, ci, co, stride, path):
     dy = _cl(_ints(g, -3, 3, (N, co, od, oh, ow)))
     w = _cl(_ints(g, -2, 2, (co, ci, 3, 3, 3)))
     dx = _cl(torch.full((N, ci, D, H, W), float("nan"), device=DEV))
-    rc = _lib.lib().conv3d_gen_dgrad(_stream(), _p(dy), _p(w), N, D, H, W, ci, co, stride, _p(dx))
+    rc = _lib.lib().conv3d_gen_dgrad(_stream(), _p(dy), _p(_taps(w)), N, D, H, W, ci, co, stride, _p(dx))
     assert rc == 0
     ref = torch.nn.grad.conv3d_input((N, ci, D, H, W), w.double(), dy.double(), stride=stride, padding=1).round()
     assert torch.equal(dx.double(), ref)

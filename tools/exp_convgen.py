@@ -44,7 +44,7 @@ def main():
     lib = _lib.lib()
     for a in sys.argv[1:]:
         if a.startswith("--path="):
-            lib.conv3d_gen_set_path({"auto": 0, "tap": 1, "halo": 2}[a.split("=")[1]])
+            lib.conv3d_gen_set_path({"auto": 0, "tap": 1, "halo": 2, "halo1": 6}[a.split("=")[1]])
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     cl = lambda t: t.contiguous(memory_format=torch.channels_last_3d)
@@ -55,13 +55,14 @@ def main():
         N = 2
         x = cl(torch.randn(N, ci, D, H, W, device=DEV))
         w = cl(torch.randn(co, ci, 3, 3, 3, device=DEV) / (27 * ci) ** 0.5)
+        wt = w.permute(2, 3, 4, 0, 1).reshape(27, co, ci).contiguous()
         b = torch.randn(co, device=DEV) if bias else None
         od, oh, ow = ((v + s - 1) // s for v in (D, H, W))
         y = cl(torch.empty(N, co, od, oh, ow, device=DEV))
         dy = cl(torch.randn(N, co, od, oh, ow, device=DEV))
         dx, dw = torch.empty_like(x), torch.empty_like(w)
-        ours = {"fwd": lambda: lib.conv3d_gen_forward(st(), p(x), p(w), p(b), N, D, H, W, ci, co, s, p(y)),
-                "dgrad": lambda: lib.conv3d_gen_dgrad(st(), p(dy), p(w), N, D, H, W, ci, co, s, p(dx)),
+        ours = {"fwd": lambda: lib.conv3d_gen_forward(st(), p(x), p(wt), p(b), N, D, H, W, ci, co, s, p(y)),
+                "dgrad": lambda: lib.conv3d_gen_dgrad(st(), p(dy), p(wt), N, D, H, W, ci, co, s, p(dx)),
                 "wgrad": lambda: lib.conv3d_gen_wgrad(st(), p(x), p(dy), N, D, H, W, ci, co, s, p(dw))}
         cb = lambda mask: torch.ops.aten.convolution_backward(dy, x, w, None, [s] * 3, [1] * 3, [1] * 3, False, [0] * 3, 1, mask)
         theirs = {"fwd": lambda: F.conv3d(x, w, b, s, 1), "dgrad": lambda: cb([True, False, False]), "wgrad": lambda: cb([False, True, False])}

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "conv3d_gen_dgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
     "conv3d_gen_wgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
     "conv3d_gen_set_path": (None, [_ci]),
+    "conv3d_gen_debug_mma_rate": (_ci, [_vp, _ci, _ci, _ci, _vp]),
     "conv3d_gen_debug_k_probe": (_ci, [_vp] * 4 + [_ci] * 3),
     # include/fused_ln.h
     "fused_ln_workspace_floats": (ctypes.c_longlong, [_ci]),

@@ -65,9 +65,10 @@ class Conv3dGenFunction(Function):
     def forward(ctx, x, weight, bias, stride):
         if not x.is_cuda:
             raise RuntimeError("conv3d_k3_gen: Not implemented on the CPU")
-        x, w = _cl(x), _cl(weight)                                       # w memory: [CO][27][CI]
+        x = _cl(x)
         N, ci, D, H, W = x.shape
-        co = w.shape[0]
+        co = weight.shape[0]
+        w = weight.permute(2, 3, 4, 0, 1).reshape(27, co, ci).contiguous()          # tap-major [27][CO][CI], shared by forward and input gradient
         od, oh, ow = ((v + stride - 1) // stride for v in (D, H, W))
         y = _empty_cl((N, co, od, oh, ow), x.device)
         with torch.cuda.device(x.device):
@@ -75,6 +76,7 @@ class Conv3dGenFunction(Function):
         _lib.check(rc, "conv3d_gen_forward")
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.has_bias = stride, bias is not None
+        ctx.w_cl = weight.is_contiguous(memory_format=torch.channels_last_3d) and not weight.is_contiguous()
         return y
 
     @staticmethod
@@ -82,7 +84,7 @@ class Conv3dGenFunction(Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         N, ci, D, H, W = x.shape
-        co = w.shape[0]
+        co = w.shape[1]
         dy = _cl(dy)
         dx = dw = db = None
         lib = _lib.lib()
@@ -91,8 +93,10 @@ class Conv3dGenFunction(Function):
                 dx = _empty_cl(x.shape, x.device)
                 _lib.check(lib.conv3d_gen_dgrad(_stream(), _p(dy), _p(w), N, D, H, W, ci, co, ctx.stride, _p(dx)), "conv3d_gen_dgrad")
             if ctx.needs_input_grad[1]:
-                dw = _empty_cl(w.shape, x.device)
+                dw = _empty_cl((co, ci, 3, 3, 3), x.device)                      # the kernel writes channels-last weight memory [CO][27][CI]
                 _lib.check(lib.conv3d_gen_wgrad(_stream(), _p(x), _p(dy), N, D, H, W, ci, co, ctx.stride, _p(dw)), "conv3d_gen_wgrad")
+                if not ctx.w_cl:
+                    dw = dw.contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy.permute(0, 2, 3, 4, 1).reshape(-1, co))
         return dx, dw, db, None

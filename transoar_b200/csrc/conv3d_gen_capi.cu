@@ -74,14 +74,15 @@ int make_vol_map(CUtensorMap *map, const float *ptr, const Vol &v, int step, int
   return r == CUDA_SUCCESS ? 0 : MSDA3D_EINVAL;
 }
 
-// weights in channels-last memory [CO][27][CI] as the 3-D tensor (ci, tap, co); box = 32 ci x 1 tap x rows co
-int make_weight_map(CUtensorMap *map, const float *w, int CI, int CO, int rows, bool mn_major)
+// tap-major weights [27][CO][CI] as the 3-D tensor (ci, co, tap); box = 32 ci x rows co x 1 tap: the rows of one (tap, chunk) block are
+// CI * 4 bytes apart (with the channels-last layout [CO][27][CI] they are 27 * CI * 4 bytes apart and every 128-byte row is its own L2 request)
+int make_weight_map(CUtensorMap *map, const float *w, int CI, int CO, int rows, bool mn_major, int taps = 1)
 {
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) return MSDA3D_ENODEV;
-  const cuuint64_t gdim[3] = {(cuuint64_t)CI, 27, (cuuint64_t)CO};
-  const cuuint64_t gstride[2] = {(cuuint64_t)CI * 4, (cuuint64_t)CI * 27 * 4};
-  const cuuint32_t box[3] = {32, 1, (cuuint32_t)rows};
+  const cuuint64_t gdim[3] = {(cuuint64_t)CI, (cuuint64_t)CO, 27};
+  const cuuint64_t gstride[2] = {(cuuint64_t)CI * 4, (cuuint64_t)CI * CO * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)rows, (cuuint32_t)taps};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float *>(w), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -123,7 +124,7 @@ template <int BN, bool B_MN> int launch_k(cudaStream_t st, const convgen::Proble
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); });
   if (err != cudaSuccess) return (int)err;
-  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * ((p.N + BN - 1) / BN);
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * ((p.N + BN - 1) / BN) * p.ksplit;
   const int grid = (int)(work < sm_count() ? work : sm_count());
   kern<<<grid, tcgemm::kThreads, C::SMEM_BYTES, st>>>(p, bias);
   ++g_msda3d_launches;
@@ -142,9 +143,9 @@ template <bool B_MN> int dispatch_k(cudaStream_t st, int bn, const convgen::Prob
   }
 }
 
-template <int BN, bool B_MN> int launch_h(cudaStream_t st, const convgen::HProblem &p, const float *bias, int smem)
+template <int BN, bool B_MN, int CH, int REG> int launch_h(cudaStream_t st, const convgen::HProblem &p, const float *bias, int smem)
 {
-  auto kern = convgen::conv_halo_kernel<BN, B_MN>;
+  auto kern = convgen::conv_halo_kernel<BN, B_MN, CH, REG>;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -156,16 +157,25 @@ template <int BN, bool B_MN> int launch_h(cudaStream_t st, const convgen::HProbl
   return (int)cudaGetLastError();
 }
 
-template <bool B_MN> int dispatch_h(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem)
+std::atomic<int> g_hdbg{0};
+std::atomic<int> g_chains{0};      // 0 = default (two accumulation chains where TMEM allows), 1 = one chain (conv3d_gen_set_path bit 2: experiments)
+
+// reg: 0 = table-driven taps (stride 2), 1 = stride-1 forward, 2 = stride-1 input gradient (unrolled constant taps)
+template <bool B_MN, int REG> int dispatch_h2(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem)
 {
   switch (bn) {
-    case 32: return launch_h<32, B_MN>(st, p, bias, smem);
-    case 64: return launch_h<64, B_MN>(st, p, bias, smem);
-    case 96: return launch_h<96, B_MN>(st, p, bias, smem);
-    case 128: return launch_h<128, B_MN>(st, p, bias, smem);
-    case 192: return launch_h<192, B_MN>(st, p, bias, smem);
-    default: return launch_h<256, B_MN>(st, p, bias, smem);
+    case 32: return launch_h<32, B_MN, 2, REG>(st, p, bias, smem);
+    case 64: return launch_h<64, B_MN, 2, REG>(st, p, bias, smem);
+    case 96: return launch_h<96, B_MN, 2, REG>(st, p, bias, smem);
+    case 128: return launch_h<128, B_MN, 2, REG>(st, p, bias, smem);
+    case 192: return launch_h<192, B_MN, 1, REG>(st, p, bias, smem);
+    default: return launch_h<256, B_MN, 1, REG>(st, p, bias, smem);
   }
+}
+template <bool B_MN> int dispatch_h(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem, int reg)
+{
+  if (reg == 0 || g_chains.load() == 1) return dispatch_h2<B_MN, 0>(st, bn, p, bias, smem);     // (set_path bit 2: force the table-driven loop, experiments)
+  return B_MN ? dispatch_h2<B_MN, 2>(st, bn, p, bias, smem) : dispatch_h2<B_MN, 1>(st, bn, p, bias, smem);
 }
 
 // 0 = choose per problem, 1 = always the per-tap kernel, 2 = the halo kernel wherever it fits (conv3d_gen_set_path; CONV3D_GEN_PATH=tap|halo)
@@ -182,13 +192,24 @@ int forced_path()
 }
 
 // the halo kernel pays for whole 8 x 16 tiles: use it where the tile rows are mostly real voxels
-bool halo_wanted(int rows_h, int rows_w)
+bool halo_wanted(int rows_h, int rows_w, long long planes)
 {
   const int f = forced_path();
   if (f == 1) return false;
   if (f == 2) return true;
   const int th = (rows_h + 15) / 16, tw = (rows_w + 7) / 8;
+  if (planes * th * tw < sm_count() / 2) return false;             // few tiles: the per-tap kernel splits the K loop over the idle SMs
   return (double)rows_h * rows_w >= 0.6 * (th * 16.0) * (tw * 8.0);
+}
+
+// few-tile layers (the coarse pyramid levels): split the (tap, chunk) loop so that every SM has a work item
+int choose_ksplit(long long items, int ksteps)
+{
+  if (items >= sm_count()) return 1;
+  long long ks = sm_count() / items;
+  const int cap = ksteps / 8 > 0 ? ksteps / 8 : 1;
+  if (ks > cap) ks = cap;
+  return ks < 1 ? 1 : (int)ks;
 }
 
 void h_add_box(convgen::HProblem &p, int b, int cls_hw, int ow, int oh, int lw, int lh)
@@ -201,16 +222,36 @@ void h_add_box(convgen::HProblem &p, int b, int cls_hw, int ow, int oh, int lw, 
   p.nbox = b + 1;
 }
 
-// ring depths that fit 227 KB next to the epilogue staging; returns the dynamic shared-memory size or 0 if the problem does not fit
-int h_plan_smem(convgen::HProblem &p, int bn)
+// ring depths that fit 227 KB next to the epilogue staging: three plane stages (each feeds up to nine taps), the rest goes to the ring
+// of weight blocks -- those are small (BN x 128 bytes) and the ring must hold a load latency's worth of them.  Returns the dynamic
+// shared-memory size, or 0 if the problem does not fit.
+int h_plan_smem(convgen::HProblem &p, int bn, bool taps_consecutive_by_9)
 {
+  // taps per weight box: every stage costs a barrier round trip in the single producer / issuer threads (~500 clocks measured), which
+  // four MMAs of a narrow tile (N <= 128) do not cover
+  p.tps = bn <= 32 ? 9 : bn <= 128 ? 3 : 1;
+  p.dbg = g_hdbg.load();
+  (void)taps_consecutive_by_9;
   const int avail = 227 * 1024 - 1024 - 512 - convgen::kHEpiBytes;
-  for (int bs : {4, 3, 2}) {
-    int as = (avail - bs * bn * 128) / p.a_stage_bytes;
-    if (as > 4) as = 4;
-    if (as >= 2) {
+  const int b_bytes = p.tps * bn * 128;
+  for (int as : {3, 2}) {
+    int bs = (avail - as * p.a_stage_bytes) / b_bytes;
+    if (bs > convgen::kHMaxBStages) bs = convgen::kHMaxBStages;
+    if (bs >= 3 || (as == 2 && bs >= 2)) {
       p.a_stages = as; p.b_stages = bs;
-      return 1024 + as * p.a_stage_bytes + bs * bn * 128 + convgen::kHEpiBytes + 512;
+      // weight-box bookkeeping of every tap: box start (a multiple of tps: the tap index is kd * 9 + kh * 3 + kw), slot, first-of-box flag
+      for (int c = 0; c < p.nclass; ++c)
+        for (int pl = 0; pl < p.cls[c].nplanes; ++pl) {
+          convgen::HPlane &hp = p.cls[c].planes[pl];
+          for (int t = 0; t < hp.ntaps; ++t) {
+            convgen::HTap &tp = hp.taps[t];
+            const int wtap = tp.wtap0;                               // the builders leave the tap index here
+            tp.slot = wtap % p.tps;
+            tp.wtap0 = wtap - tp.slot;
+          }
+          for (int t = 0; t < hp.ntaps; ++t) hp.taps[t].newgrp = (t == 0 || hp.taps[t].wtap0 != hp.taps[t - 1].wtap0) ? 1 : 0;
+        }
+      return 1024 + as * p.a_stage_bytes + bs * b_bytes + convgen::kHEpiBytes + 512;
     }
   }
   return 0;
@@ -242,7 +283,12 @@ inline int s2_off(int k) { return k == 0 ? -1 : 0; }
 
 }  // namespace
 
-extern "C" void conv3d_gen_set_path(int path) { g_path.store(path == 1 || path == 2 ? path : 0); }
+extern "C" void conv3d_gen_set_path(int path)
+{
+  g_path.store((path & 3) == 1 || (path & 3) == 2 ? (path & 3) : 0);
+  g_chains.store((path & 4) ? 1 : 0);
+  g_hdbg.store((path >> 3) & 15);
+}
 
 extern "C" int conv3d_gen_supported(int in_channels, int out_channels, int stride)
 {
@@ -258,7 +304,7 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
   int rc;
-  if (halo_wanted(OH, OW)) {
+  if (halo_wanted(OH, OW, (long long)batch * OD)) {
     convgen::HProblem h = {};
     h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
     h.N = out_channels; h.chunks = (in_channels + 31) / 32; h.nclass = 1;
@@ -283,20 +329,20 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) {
           convgen::HTap &t = hp.taps[kh * 3 + kw];
-          t.wtap = (kd * 3 + kh) * 3 + kw;
-          if (stride == 1) { t.box = 0; t.rowshift = (short)(kh * 10 + kw); }
+          t.wtap0 = (kd * 3 + kh) * 3 + kw;
+          if (stride == 1) { t.a_off = (kh * 10 + kw) * 128; t.sbo = 10 * 128; }
           else {
-            t.box = (short)((s2_par(kh) ? 0 : 2) + (s2_par(kw) ? 0 : 1));
-            t.rowshift = (short)((kh == 2 ? h.boxes[t.box].lw : 0) + (kw == 2 ? 1 : 0));
+            const convgen::HBox &bx = h.boxes[(s2_par(kh) ? 0 : 2) + (s2_par(kw) ? 0 : 1)];
+            t.a_off = bx.off + ((kh == 2 ? bx.lw : 0) + (kw == 2 ? 1 : 0)) * 128; t.sbo = bx.lw * 128;
           }
         }
     }
     const int bn = choose_bn(out_channels);
-    const int smem = h_plan_smem(h, bn);
+    const int smem = h_plan_smem(h, bn, true);
     if (smem > 0) {
       if ((rc = make_vol_map(&h.tmD[0], y, vy, 1, 0, 0, 0, 8, 4, 1, false, false))) return rc;
-      if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, bn, false))) return rc;
-      return dispatch_h<false>(reinterpret_cast<cudaStream_t>(stream), bn, h, bias, smem);
+      if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, bn, false, h.tps))) return rc;
+      return dispatch_h<false>(reinterpret_cast<cudaStream_t>(stream), bn, h, bias, smem, stride == 1 ? 1 : 0);
     }
   }
   convgen::Problem p = {};
@@ -322,6 +368,11 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
   if ((rc = make_vol_map(&p.tmD[0], y, vy, 1, 0, 0, 0, p.BW, p.qh, p.qd, false, false))) return rc;
   const int bn = choose_bn(out_channels);
   if ((rc = make_weight_map(&p.tmB, w, in_channels, out_channels, bn, false))) return rc;
+  p.ksplit = choose_ksplit((long long)batch * p.td * p.th * p.tw * ((out_channels + bn - 1) / bn), 27 * p.chunks);
+  if (p.ksplit > 1) {
+    const cudaError_t e = cudaMemsetAsync(y, 0, (size_t)batch * OD * OH * OW * out_channels * sizeof(float), reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return (int)e;
+  }
   return dispatch_k<false>(reinterpret_cast<cudaStream_t>(stream), bn, p, bias);
 }
 
@@ -334,7 +385,7 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   const Vol vdy = {batch, OD, OH, OW, out_channels}, vdx = {batch, depth, height, width, in_channels};
   int rc;
-  if (halo_wanted(OH, OW)) {
+  if (halo_wanted(OH, OW, (long long)batch * OD * (stride == 1 ? 1 : 8))) {
     convgen::HProblem h = {};
     h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
     h.N = in_channels; h.chunks = (out_channels + 31) / 32;
@@ -351,7 +402,7 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
         for (int jh = 0; jh < 3; ++jh)
           for (int jw = 0; jw < 3; ++jw) {
             convgen::HTap &t = hp.taps[jh * 3 + jw];
-            t.box = 0; t.rowshift = (short)(jh * 10 + jw); t.wtap = ((2 - jd) * 3 + (2 - jh)) * 3 + (2 - jw);
+            t.a_off = (jh * 10 + jw) * 128; t.sbo = 10 * 128; t.wtap0 = ((2 - jd) * 3 + (2 - jh)) * 3 + (2 - jw);
           }
       }
     } else {
@@ -371,16 +422,16 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
             for (int kw = 0; kw < 3; ++kw) {
               if ((par[1] == 0 ? kh != 1 : kh == 1) || (par[2] == 0 ? kw != 1 : kw == 1)) continue;
               convgen::HTap &t = hp.taps[hp.ntaps++];
-              t.box = 0; t.rowshift = (short)((kh == 0 ? 9 : 0) + (kw == 0 ? 1 : 0)); t.wtap = (kd * 3 + kh) * 3 + kw;
+              t.a_off = ((kh == 0 ? 9 : 0) + (kw == 0 ? 1 : 0)) * 128; t.sbo = 9 * 128; t.wtap0 = (kd * 3 + kh) * 3 + kw;
             }
         }
       }
     }
     const int bn = choose_bn(in_channels);
-    const int smem = h_plan_smem(h, bn);
+    const int smem = h_plan_smem(h, bn, true);
     if (smem > 0) {
       if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, 32, true))) return rc;
-      return dispatch_h<true>(reinterpret_cast<cudaStream_t>(stream), bn, h, nullptr, smem);
+      return dispatch_h<true>(reinterpret_cast<cudaStream_t>(stream), bn, h, nullptr, smem, stride == 1 ? 2 : 0);
     }
   }
   convgen::Problem p = {};
@@ -423,6 +474,11 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
   }
   const int bn = choose_bn(in_channels);
   if ((rc = make_weight_map(&p.tmB, w, in_channels, out_channels, 32, true))) return rc;
+  p.ksplit = choose_ksplit((long long)p.nclass * batch * p.td * p.th * p.tw * ((in_channels + bn - 1) / bn), (stride == 1 ? 27 : 8) * p.chunks);
+  if (p.ksplit > 1) {
+    const cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)batch * depth * height * width * in_channels * sizeof(float), reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return (int)e;
+  }
   return dispatch_k<true>(reinterpret_cast<cudaStream_t>(stream), bn, p, nullptr);
 }
 
@@ -521,6 +577,19 @@ extern "C" int conv3d_gen_debug_k_probe(void *stream, const float *X, const floa
 {
   if (!X || !Y || !D || row0 < 0 || group_stride_rows < 1 || row0 + 15 * group_stride_rows + 8 > convgen::kProbeRows) return MSDA3D_EINVAL;
   convgen::k_sw128_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, Y, D, row0, group_stride_rows, mode);
+  ++g_msda3d_launches;
+  return (int)cudaGetLastError();
+}
+
+// experiments only (tools/probe_mma_rate.py): see mma_rate_probe_kernel
+extern "C" int conv3d_gen_debug_mma_rate(void *stream, int layout, int n, int iters, long long *out_clocks)
+{
+  if (!out_clocks || layout < 0 || layout > 2 || n < 16 || n > 256 || n % 16 || iters < 1) return MSDA3D_EINVAL;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(convgen::mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024); });
+  if (err != cudaSuccess) return (int)err;
+  convgen::mma_rate_probe_kernel<<<1, 128, 66 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(layout, n, iters, out_clocks);
   ++g_msda3d_launches;
   return (int)cudaGetLastError();
 }

@@ -13,7 +13,7 @@
 //     ONE 5-D TMA box (32 channels, BW, BH, BD, 1) at the tile origin shifted by the tap brings the 128 x 32 A operand (rows of 128 bytes,
 //     128-byte swizzle: exactly the K-major operand form of tc_gemm_kernels.cuh); voxels outside the volume and channels past the tensor's
 //     count are zero-filled by the copy engine -- that is the convolution's zero padding and the channel padding.  The B operand comes
-//     straight from the channels-last weight tensor [CO][27][CI] through a 3-D tensor map: K-major rows for the forward (reduction = ci),
+//     from the tap-major weight tensor [27][CO][CI] through a 3-D tensor map: K-major rows for the forward (reduction = ci),
 //     MN-major 32 x 32 slabs for the input gradient (reduction = co, n = ci), so no transposed / re-laid-out weight copy exists.
 //     Stride 2 without element strides: the eight parity classes of a volume (even / odd index per axis) are eight plain 5-D tensors with
 //     doubled strides.  Forward: tap k reads class (k + 1) % 2 at index o + (k == 0 ? -1 : 0) per axis.  Input gradient: the inputs of
@@ -52,6 +52,7 @@ struct Problem {
   int N;                          // columns of D (output channels of this launch)
   int chunks;                     // ceil(reduction channels / 32)
   int nclass;
+  int ksplit;                     // > 1: the (tap, chunk) K-steps of a tile are split over ksplit work items that ADD into a zero-filled D (few-tile layers)
   int nsteps[kMaxClasses];
   Step steps[kMaxClasses][kMaxSteps];
   CUtensorMap tmA[kMaxClasses];
@@ -71,10 +72,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 }
 
 // work item w -> (class, sample, tile origin, column tile); column tiles fastest so that neighbouring CTAs share the A boxes in L2
-struct Item { int cls, n, w0, h0, d0, nt; };
+struct Item { int cls, n, w0, h0, d0, nt, ks; };
 __device__ __forceinline__ Item decode(const Problem &p, long long w, int n_tiles)
 {
   Item it;
+  it.ks = (int)(w % p.ksplit); w /= p.ksplit;
   it.nt = (int)(w % n_tiles); w /= n_tiles;
   it.w0 = (int)(w % p.tw) * p.BW; w /= p.tw;
   it.h0 = (int)(w % p.th) * p.BH; w /= p.th;
@@ -118,7 +120,12 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int n_tiles = (p.N + BN - 1) / BN;
-  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * n_tiles;
+  const long long work = (long long)p.nclass * p.batch * p.td * p.th * p.tw * n_tiles * p.ksplit;
+  // K-steps kb = s * chunks + c of a tile; split ks takes [ks * per, (ks + 1) * per)
+  auto k_range = [&](const Item &it, int &kb0, int &kb1) {
+    const int total = p.nsteps[it.cls] * p.chunks, per = (total + p.ksplit - 1) / p.ksplit;
+    kb0 = it.ks * per; kb1 = min(total, kb0 + per);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -126,21 +133,25 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
       uint32_t phase = 0;
       for (long long w = blockIdx.x; w < work; w += gridDim.x) {
         const Item it = decode(p, w, n_tiles);
-        const int n0 = it.nt * BN, ns = p.nsteps[it.cls];
-        for (int s = 0; s < ns; ++s) {
-          const Step st = p.steps[it.cls][s];
-          for (int c = 0; c < p.chunks; ++c) {
+        const int n0 = it.nt * BN;
+        int kb0, kb1;
+        k_range(it, kb0, kb1);
+        {
+          int sidx = kb0 / p.chunks, c = kb0 % p.chunks;            // one division per work item, not per K-step: this thread's loop sets the pace
+          Step st = p.steps[it.cls][sidx];
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty(stage), phase ^ 1u);
             mbar_expect_tx(full(stage), C::STAGE_BYTES);
             const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
             tma_load_5d(sa, &p.tmA[st.amap], full(stage), c * 32, it.w0 + st.dw, it.h0 + st.dh, it.d0 + st.dd, it.n);
             if (!B_MN) {
-              tma_load_3d(sb, &p.tmB, full(stage), c * 32, st.tap, n0);                           // BN rows (n) x 32 reduction channels
+              tma_load_3d(sb, &p.tmB, full(stage), c * 32, n0, st.tap);                           // BN rows (n) x 32 reduction channels
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + i * kSlabBytes, &p.tmB, full(stage), n0 + 32 * i, st.tap, c * 32);   // 32 reduction rows x 32 n
+              for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + i * kSlabBytes, &p.tmB, full(stage), n0 + 32 * i, c * 32, st.tap);   // 32 reduction rows x 32 n
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            if (++c == p.chunks) { c = 0; ++sidx; if (kb + 1 < kb1) st = p.steps[it.cls][sidx]; }
           }
         }
       }
@@ -152,11 +163,12 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
     uint32_t phase = 0, aphase = 0;
     for (long long w = blockIdx.x; w < work; w += gridDim.x) {
       const Item it = decode(p, w, n_tiles);
-      const int ksteps = p.nsteps[it.cls] * p.chunks;
+      int kb0, kb1;
+      k_range(it, kb0, kb1);
       mbar_wait(tempty(as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t acc = tmem_u + (uint32_t)(as * BN);
-      for (int kb = 0; kb < ksteps; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
@@ -164,7 +176,7 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = smem_desc<false>(sa + k * kstep_bytes<false>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
-            umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty(stage));
         }
@@ -184,6 +196,8 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
     const int qh0 = (r0 / p.BW) % p.BH, qd0 = r0 / (p.BW * p.BH);
     for (long long w = blockIdx.x; w < work; w += gridDim.x) {
       const Item it = decode(p, w, n_tiles);
+      int kb0, kb1;
+      k_range(it, kb0, kb1);
       mbar_wait(tfull(as), aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -191,8 +205,8 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
         float v[32];
         tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(q * 32) << 16), v);
         const int n0 = it.nt * BN + c0;
-        if (n0 >= p.N) continue;                                  // warp-uniform
-        if (bias != nullptr) {
+        if (n0 >= p.N || kb0 >= kb1) continue;                    // warp-uniform; an empty K split (a class with fewer taps than splits) adds nothing
+        if (bias != nullptr && it.ks == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
         }
@@ -206,8 +220,12 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                       ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
+          if (p.ksplit > 1)                                        // partial sums of the K splits are combined by the copy engine (fp32 add in L2)
+            asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                         ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                         ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         tma_buf ^= 1;
@@ -247,13 +265,19 @@ struct HBox {
   int lw;            // rows per line of the box = group stride of the operand
   int off, bytes;    // byte offset in the A stage, box bytes
 };
-struct HTap { short box, rowshift; int wtap; };
+struct HTap {
+  int a_off, sbo;    // A operand: byte offset in the A stage (box + row shift), group stride in bytes
+  int wtap0, slot;   // the weight block: taps [wtap0, wtap0 + tps) arrive as ONE box, this tap is slot `slot` of it
+  int newgrp;        // 1: this tap starts a new weight box
+};
 struct HPlane { int cls_d, od, ntaps; HTap taps[kHMaxTaps]; };
 struct HClass { int nplanes; HPlane planes[kHMaxPlanes]; };
 struct HProblem {
   int batch, tw, th, td;          // tile grid: 8 x 16 x 1 voxels per tile
   int N, chunks, nclass, nbox;
   int a_bytes, a_stage_bytes, a_stages, b_stages;
+  int dbg;                        // timing experiments (conv3d_gen_set_path bits 3-5): 1 = no MMAs, 2 = no A loads, 4 = no B loads, 8 = no stores
+  int tps;                        // taps per weight box (9, 3 or 1): amortises the barrier round trip of a stage over 4 * tps MMAs
   HBox boxes[kHMaxBoxes];
   HClass cls[kMaxClasses];
   CUtensorMap tmA[kMaxClasses];
@@ -261,35 +285,46 @@ struct HProblem {
   CUtensorMap tmB;
 };
 constexpr int kHEpiBytes = kEpiWarps * 4096;
-constexpr int kHMaxStages = 8;
+constexpr int kHMaxAStages = 4, kHMaxBStages = 16;   // the weight blocks are small (BN x 128 bytes): a deep ring keeps enough bytes in flight
 
 __device__ __forceinline__ uint64_t desc_k_halo(uint32_t addr, uint32_t group_stride_bytes)
 {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(group_stride_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN, bool B_MN>
+// CH = independent accumulation chains: consecutive taps go to CH different accumulators (summed by the epilogue), so that consecutive
+// small-N MMAs do not wait for each other's accumulator
+// REG: 0 = table-driven taps (stride 2); 1 = stride-1 forward, 2 = stride-1 input gradient: the nine taps of a plane are compile-time
+// constants and their 36 MMAs are issued from one unrolled block with constant descriptor increments -- the issuing warp executes a
+// dependent instruction chain at ~5 clocks per instruction, and a table-driven tap costs it ~350 clocks (profiles/r02_experiments.md)
+template <int BN> __host__ __device__ constexpr int halo_tps() { return BN <= 32 ? 9 : BN <= 128 ? 3 : 1; }
+
+template <int BN, bool B_MN, int CH, int REG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ bias)
 {
-  constexpr int B_BYTES = BN * 128;
+  constexpr int B_TAP_BYTES = BN * 128;
+  const int B_BYTES = p.tps * B_TAP_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = base + p.a_stages * p.a_stage_bytes;
   const uint32_t epi_base = b_base + p.b_stages * B_BYTES;
   const uint32_t bars = epi_base + kHEpiBytes;
   auto afull = [&](int s) { return bars + 8u * s; };
-  auto aempty = [&](int s) { return bars + 8u * (kHMaxStages + s); };
-  auto bfull = [&](int s) { return bars + 8u * (2 * kHMaxStages + s); };
-  auto bempty = [&](int s) { return bars + 8u * (3 * kHMaxStages + s); };
-  auto tfull = [&](int a) { return bars + 8u * (4 * kHMaxStages + a); };
-  auto tempty = [&](int a) { return bars + 8u * (4 * kHMaxStages + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (4 * kHMaxStages + 4);
+  auto aempty = [&](int s) { return bars + 8u * (kHMaxAStages + s); };
+  auto bfull = [&](int s) { return bars + 8u * (2 * kHMaxAStages + s); };
+  auto bempty = [&](int s) { return bars + 8u * (2 * kHMaxAStages + kHMaxBStages + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * kHMaxAStages + 2 * kHMaxBStages + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * kHMaxAStages + 2 * kHMaxBStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kHMaxAStages + 2 * kHMaxBStages + 4);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  constexpr int TMEM_COLS = BN <= 16 ? 32 : BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;
+  constexpr int ACC_COLS = CH * BN;                                   // one accumulator set: CH chains of BN columns
+  static_assert(2 * ACC_COLS <= 512, "TMEM columns");
+  constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kHMaxStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int s = 0; s < kHMaxAStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < kHMaxBStages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -329,23 +364,52 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
           for (int pl = 0; pl < hc.nplanes; ++pl) {
             const HPlane &hp = hc.planes[pl];
             mbar_wait(aempty(as), aph ^ 1u);
-            mbar_expect_tx(afull(as), (uint32_t)p.a_bytes);
             const uint32_t sa = base + as * p.a_stage_bytes;
-            for (int b = 0; b < p.nbox; ++b) {
-              const HBox &bx = p.boxes[b];
-              tma_load_5d(sa + bx.off, &p.tmA[hp.cls_d * 4 + bx.cls_hw], afull(as), c * 32, w0 + bx.ow, h0 + bx.oh, d0 + hp.od, n);
+            if (p.dbg & 2) {
+              mbar_arrive(afull(as));
+            } else {
+              mbar_expect_tx(afull(as), (uint32_t)p.a_bytes);
+              for (int b = 0; b < p.nbox; ++b) {
+                const HBox &bx = p.boxes[b];
+                tma_load_5d(sa + bx.off, &p.tmA[hp.cls_d * 4 + bx.cls_hw], afull(as), c * 32, w0 + bx.ow, h0 + bx.oh, d0 + hp.od, n);
+              }
             }
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
-            for (int t = 0; t < hp.ntaps; ++t) {
-              mbar_wait(bempty(bs), bph ^ 1u);
-              mbar_expect_tx(bfull(bs), B_BYTES);
-              const uint32_t sb = b_base + bs * B_BYTES;
-              const int tap = hp.taps[t].wtap;
-              if (!B_MN) {
-                tma_load_3d(sb, &p.tmB, bfull(bs), c * 32, tap, n0);
-              } else {
+            if (REG != 0) {
+              constexpr int TPS = halo_tps<BN>();
 #pragma unroll
-                for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + i * kSlabBytes, &p.tmB, bfull(bs), n0 + 32 * i, tap, c * 32);
+              for (int g = 0; g < 9 / TPS; ++g) {
+                // forward: taps pl * 9 + g * TPS ...; input gradient: plane pl holds kd = 2 - pl and its box rows run against the tap order
+                const int tap = REG == 1 ? pl * 9 + g * TPS : (TPS == 9 ? (2 - pl) * 9 : TPS == 3 ? (2 - pl) * 9 + (2 - g) * 3 : 26 - (pl * 9 + g));
+                mbar_wait(bempty(bs), bph ^ 1u);
+                if (p.dbg & 4) { mbar_arrive(bfull(bs)); if (++bs == p.b_stages) { bs = 0; bph ^= 1u; } continue; }
+                mbar_expect_tx(bfull(bs), (uint32_t)B_BYTES);
+                const uint32_t sb = b_base + bs * B_BYTES;
+                if (!B_MN) {
+                  tma_load_3d(sb, &p.tmB, bfull(bs), c * 32, n0, tap);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < TPS; ++j)
+#pragma unroll
+                    for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + j * B_TAP_BYTES + i * kSlabBytes, &p.tmB, bfull(bs), n0 + 32 * i, c * 32, tap + j);
+                }
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+              }
+              continue;
+            }
+            for (int t = 0; t < hp.ntaps; ++t) {
+              if (!hp.taps[t].newgrp) continue;
+              mbar_wait(bempty(bs), bph ^ 1u);
+              if (p.dbg & 4) { mbar_arrive(bfull(bs)); if (++bs == p.b_stages) { bs = 0; bph ^= 1u; } continue; }
+              mbar_expect_tx(bfull(bs), (uint32_t)B_BYTES);
+              const uint32_t sb = b_base + bs * B_BYTES;
+              const int tap = hp.taps[t].wtap0;
+              if (!B_MN) {
+                tma_load_3d(sb, &p.tmB, bfull(bs), c * 32, n0, tap);                     // box (32 ci, BN co, tps taps)
+              } else {
+                for (int j = 0; j < p.tps; ++j)
+#pragma unroll
+                  for (int i = 0; i < BN / 32; ++i) tma_load_3d(sb + j * B_TAP_BYTES + i * kSlabBytes, &p.tmB, bfull(bs), n0 + 32 * i, c * 32, tap + j);
               }
               if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
             }
@@ -364,30 +428,69 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
       const HClass &hc = p.cls[cls];
       mbar_wait(tempty(acs), acph ^ 1u);
       tc_fence_after();
-      const uint32_t acc = tmem_u + (uint32_t)(acs * BN);
-      uint32_t first = 0u;
+      const uint32_t acc0 = tmem_u + (uint32_t)(acs * ACC_COLS);
+      int tapno = 0;
       for (int c = 0; c < p.chunks; ++c) {
         for (int pl = 0; pl < hc.nplanes; ++pl) {
           const HPlane &hp = hc.planes[pl];
           mbar_wait(afull(as), aph);
           tc_fence_after();
           const uint32_t sa = base + as * p.a_stage_bytes;
-          for (int t = 0; t < hp.ntaps; ++t) {
-            mbar_wait(bfull(bs), bph);
-            tc_fence_after();
-            const uint32_t sb = b_base + bs * B_BYTES;
-            const HBox &bx = p.boxes[hp.taps[t].box];
-            const uint64_t da0 = desc_k_halo(sa + bx.off + (uint32_t)(hp.taps[t].rowshift * 128), (uint32_t)(bx.lw * 128));
-            if (elect_one()) {
+          if (REG != 0) {
+            constexpr int TPS = halo_tps<BN>();
+            const uint64_t da_plane = desc_k_halo(sa, 10 * 128);
+            const uint32_t first_plane = (c == 0 && pl == 0) ? 1u : 0u;
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                umma_tf32(acc, da0 + (uint64_t)(k * 2), smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>()), idesc, first | (uint32_t)(k > 0));
+            for (int g = 0; g < 9 / TPS; ++g) {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+              const uint64_t db_stage = smem_desc<B_MN>(b_base + bs * B_BYTES);
+              if (elect_one()) {
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                  for (int j = 0; j < TPS; ++j) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int t = g * TPS + j;                                 // box rows (jh, jw) = (t / 3, t % 3): compile-time after unrolling
+                    const uint32_t a_off = (uint32_t)(((t / 3) * 10 + (t % 3)) * 128);
+                    const int slot = REG == 1 ? j : TPS - 1 - j;
+                    const uint32_t acc = acc0 + (uint32_t)((t % CH) * BN);
+                    const uint32_t later = (t >= CH) ? 1u : (first_plane ^ 1u);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                      umma_tf32(acc, da_plane + (uint64_t)((a_off + k * 32) >> 4), db_stage + (uint64_t)((slot * B_TAP_BYTES + k * (int)kstep_bytes<B_MN>()) >> 4),
+                                idesc, later | (uint32_t)(k > 0));
+                  }
+                }
+                umma_commit(bempty(bs));
               }
-              umma_commit(bempty(bs));
+              __syncwarp();
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            }
+            tapno += 9;
+          } else
+          for (int t = 0; t < hp.ntaps; ++t) {
+            const HTap &tp = hp.taps[t];
+            if (tp.newgrp) {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+            }
+            const uint32_t sb = b_base + bs * B_BYTES + (uint32_t)(tp.slot * B_TAP_BYTES);
+            const uint64_t da0 = desc_k_halo(sa + (uint32_t)tp.a_off, (uint32_t)tp.sbo);
+            const uint32_t acc = acc0 + (uint32_t)((tapno % CH) * BN);
+            const uint32_t later = tapno >= CH ? 1u : 0u;                 // the first tap of each chain overwrites
+            const bool last_of_group = t + 1 == hp.ntaps || hp.taps[t + 1].newgrp != 0;
+            if (elect_one()) {
+              if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  umma_tf32(acc, da0 + (uint64_t)(k * 2), smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>()), idesc, later | (uint32_t)(k > 0));
+                }
+              }
+              if (last_of_group) umma_commit(bempty(bs));
             }
             __syncwarp();
-            first = 1u;
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            ++tapno;
+            if (last_of_group) { if (++bs == p.b_stages) { bs = 0; bph ^= 1u; } }
           }
           if (elect_one()) umma_commit(aempty(as));
           __syncwarp();
@@ -406,14 +509,28 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
     for (long long w = blockIdx.x; w < work; w += gridDim.x) {
       int cls, n, d0, h0, w0, nt;
       decode_item(w, cls, n, d0, h0, w0, nt);
+      int ntaps_total = 0;
+      for (int pl = 0; pl < p.cls[cls].nplanes; ++pl) ntaps_total += p.cls[cls].planes[pl].ntaps;
+      ntaps_total *= p.chunks;
       mbar_wait(tfull(acs), acph);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
         float v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t)(acs * BN + c0) + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + c0) + ((uint32_t)(q * 32) << 16), v);
         const int n0 = nt * BN + c0;
         if (n0 >= p.N) continue;                                  // warp-uniform
+        if (CH > 1 && ntaps_total > 1) {                          // (a class with a single tap never touched the second chain)
+#pragma unroll
+          for (int ch = 1; ch < CH; ++ch) {
+            if (ch < ntaps_total) {
+              float u[32];
+              tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + ch * BN + c0) + ((uint32_t)(q * 32) << 16), u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
+          }
+        }
         if (bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
@@ -426,7 +543,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
                        "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 8)) {
           asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                        ::"l"(&p.tmD[cls]), "r"(buf), "r"(n0), "r"(w0), "r"(h0 + 4 * q), "r"(d0), "r"(n) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -687,6 +804,60 @@ static __global__ void __launch_bounds__(128) k_sw128_probe_kernel(const float *
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(32) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Probe (experiments only, tools/probe_mma_rate.py): how many clocks does ONE tcgen05.mma.kind::tf32 of shape 128 x N x 8 take when issued
+// back to back, as a function of the shared-memory operand layout?  layout 0 = K-major 128-byte swizzle (rows of 128 bytes, the MMA reads 32
+// bytes of each), 1 = K-major 32-byte swizzle (rows of 32 bytes: a 128 x 8 operand is 4 KB contiguous), 2 = MN-major (128-byte swizzle, 32-byte
+// atoms).  The operands are zeros; `iters` MMAs accumulate into one TMEM tile; out[0] = clocks from the first issue to the commit's arrival.
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) mma_rate_probe_kernel(int layout, int N, int iters, long long *out)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < (64 * 1024) / 4; i += 128) reinterpret_cast<float *>(smem_raw)[i] = 0.f;
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0) {
+    const uint32_t a_addr = base, b_addr = base + 32 * 1024;
+    uint64_t da, db;
+    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (layout == 0) {            // K-major SW128: SBO 1024
+      da = (uint64_t)((a_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      db = (uint64_t)((b_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    } else if (layout == 1) {     // K-major SW32: rows of 32 bytes, 8-row groups 256 bytes apart
+      da = (uint64_t)((a_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+      db = (uint64_t)((b_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+    } else {                      // MN-major, 32-byte atoms: slabs of 32 mn-elements, LBO = slab (32 rows x 128 B), SBO 512
+      idesc |= (1u << 15) | (1u << 16);
+      da = desc_mn(a_addr, 4096);
+      db = desc_mn(b_addr, 4096);
+    }
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) umma_tf32(tm, da, db, idesc, i > 0 ? 1u : 0u);
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (t == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256) : "memory");
 }
 
 }  // namespace convgen
