@@ -3,13 +3,17 @@
 
 Module / parameter names equal the reference's (``_encoder._stages.<i>._block.<k>``, ``_decoder._lateral/_up/_out/_refine``)
 so reference checkpoints load.  The encoder's first convolution (1 input channel) is a direct sm_100a stencil (include/stem_conv.h) when the model is
-channels-last; the other 3D convolutions and transposed convolutions stay library calls (cuDNN tensor-core kernels); every
+channels-last; every other 3x3x3 convolution (stride 1 / 2, with / without bias) runs on the general tcgen05 implicit-GEMM kernels
+(include/conv3d_gen.h), the 1x1 lateral and the kernel-2 / stride-2 transposed convolutions as GEMMs over the NDHWC rows (transoar_b200/conv3d_gen.py) --
+cuDNN is only the route of NCDHW / autocast / strict-fp32 models; every
 InstanceNorm3d -> ReLU pair runs as a fused sm_100a kernel (include/instnorm.h); the deformable refinement (`use_decoder_attn`) runs on the sm_100a kernels through
 ``transoar_b200.refine.DecoderDefAttnBlock``; the Swin encoder variant (``use_encoder_attn``, encoder_blocks.py:56-334) through
 ``transoar_b200.swin``."""
 import torch
 from torch import nn
 
+from .conv3d_gen import (conv3d_1x1, conv3d_k3_gen, conv_1x1_eligible, conv_gen_eligible, conv_transpose3d_k2s2,
+                         conv_transpose_eligible)
 from .conv3d_tc import conv3d_k3, conv_tc_eligible
 from .instnorm import instance_norm_relu
 from .position_encoding import PositionEmbeddingSine3D
@@ -36,6 +40,8 @@ class EncoderCnnBlock(nn.Module):
         cl_model = conv2.weight.is_contiguous(memory_format=torch.channels_last_3d) and not conv2.weight.is_contiguous()
         if cl_model and stem_eligible(conv1, x):
             x = stem_conv3d(x, conv1.weight)                    # 1 -> C direct stencil, writes NDHWC (include/stem_conv.h)
+        elif cl_model and conv_gen_eligible(conv1, x):
+            x = conv3d_k3_gen(x, conv1.weight, conv1.bias, conv1.stride[0])      # stride-2 stage entry on the general tcgen05 kernel (include/conv3d_gen.h)
         else:
             x = conv1(x)
             if cl_model and conv1.in_channels == 1 and not x.is_contiguous(memory_format=torch.channels_last_3d):
@@ -43,7 +49,12 @@ class EncoderCnnBlock(nn.Module):
                 x = x.contiguous(memory_format=torch.channels_last_3d)
         x = instance_norm_relu(x, norm1.weight, norm1.bias, norm1.eps)
         # narrow full-resolution stage (24 -> 24): tcgen05 implicit-GEMM convolution, forward and input gradient (include/conv3d_tc.h)
-        x = conv3d_k3(x, conv2.weight) if conv_tc_eligible(conv2, x) else conv2(x)
+        if conv_tc_eligible(conv2, x):
+            x = conv3d_k3(x, conv2.weight)
+        elif cl_model and conv_gen_eligible(conv2, x):
+            x = conv3d_k3_gen(x, conv2.weight, conv2.bias, 1)                    # every wider stage: the general tcgen05 kernel
+        else:
+            x = conv2(x)
         return instance_norm_relu(x, norm2.weight, norm2.bias, norm2.eps)
 
 
@@ -119,20 +130,28 @@ class Decoder(nn.Module):
 
     def forward(self, x):
         feats = list(x.values())[-self._lateral_levels:]
-        lateral = [conv(f) for conv, f in zip(self._lateral, feats)]
-        top_down, up = [], None
-        for idx, cur in enumerate(reversed(lateral)):                                     # coarsest first (:110-118)
+        # channels-last model: lateral 1x1 convolutions and the k = s = 2 transposed convolutions are GEMMs over the NDHWC rows (include/tc_gemm.h),
+        # the 3x3x3 output convolutions run on the general tcgen05 kernel (include/conv3d_gen.h); otherwise the library modules
+        own = self._out[0].weight.is_contiguous(memory_format=torch.channels_last_3d) and not self._out[0].weight.is_contiguous()
+        lateral = [conv3d_1x1(f, conv.weight, conv.bias) if own and conv_1x1_eligible(conv, f) else conv(f) for conv, f in zip(self._lateral, feats)]
+        top_down, cur = [], None
+        for idx, lat in enumerate(reversed(lateral)):                                     # coarsest first (:110-118)
             if idx != 0:
-                cur = cur + up
-            if idx < self._lateral_levels - 1:
-                up = self._up[idx](cur)
+                up = self._up[idx - 1]
+                if own and conv_transpose_eligible(up, cur) and lat.is_contiguous(memory_format=torch.channels_last_3d):
+                    cur = conv_transpose3d_k2s2(cur, up.weight, up.bias, lat)             # up(cur) + lat: the pixel shuffle rides in the addition
+                else:
+                    cur = lat + up(cur)
+            else:
+                cur = lat
             top_down.append(cur)
         fine_first = top_down[::-1]
         if self._seg_proxy:
             pairs = [(fine_first[stage], stage) for stage in self._required_stages]
         else:
             pairs = zip(fine_first, self._required_stages)                                # :124 (positional pairing, as the reference)
-        outputs = {"P" + str(stage): self._out[i](f) for i, (f, stage) in enumerate(pairs)}
+        outputs = {"P" + str(stage): conv3d_k3_gen(f, self._out[i].weight, self._out[i].bias, 1) if own and conv_gen_eligible(self._out[i], f)
+                   else self._out[i](f) for i, (f, stage) in enumerate(pairs)}
         if self._refine_fmaps:
             fmaps = [outputs[name] for name in self._refine_feature_levels]
             refined = self._refine(fmaps, [self._pos_enc(f) for f in fmaps])

@@ -143,9 +143,9 @@ template <bool B_MN> int dispatch_k(cudaStream_t st, int bn, const convgen::Prob
   }
 }
 
-template <int BN, bool B_MN, int CH, int REG> int launch_h(cudaStream_t st, const convgen::HProblem &p, const float *bias, int smem)
+template <int BN, bool B_MN, int CH, int REG, int T = 1> int launch_h(cudaStream_t st, const convgen::HProblem &p, const float *bias, int smem)
 {
-  auto kern = convgen::conv_halo_kernel<BN, B_MN, CH, REG>;
+  auto kern = convgen::conv_halo_kernel<BN, B_MN, CH, REG, T>;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -172,8 +172,18 @@ template <bool B_MN, int REG> int dispatch_h2(cudaStream_t st, int bn, const con
     default: return launch_h<256, B_MN, 1, REG>(st, p, bias, smem);
   }
 }
+template <bool B_MN, int REG> int dispatch_pair(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem)
+{
+  switch (bn) {
+    case 32: return launch_h<32, B_MN, 1, REG, 2>(st, p, bias, smem);
+    case 64: return launch_h<64, B_MN, 1, REG, 2>(st, p, bias, smem);
+    case 96: return launch_h<96, B_MN, 1, REG, 2>(st, p, bias, smem);
+    default: return launch_h<128, B_MN, 1, REG, 2>(st, p, bias, smem);
+  }
+}
 template <bool B_MN> int dispatch_h(cudaStream_t st, int bn, const convgen::HProblem &p, const float *bias, int smem, int reg)
 {
+  if (p.pair) return B_MN ? dispatch_pair<B_MN, 2>(st, bn, p, bias, smem) : dispatch_pair<B_MN, 1>(st, bn, p, bias, smem);
   if (reg == 0 || g_chains.load() == 1) return dispatch_h2<B_MN, 0>(st, bn, p, bias, smem);     // (set_path bit 2: force the table-driven loop, experiments)
   return B_MN ? dispatch_h2<B_MN, 2>(st, bn, p, bias, smem) : dispatch_h2<B_MN, 1>(st, bn, p, bias, smem);
 }
@@ -192,14 +202,17 @@ int forced_path()
 }
 
 // the halo kernel pays for whole 8 x 16 tiles: use it where the tile rows are mostly real voxels
-bool halo_wanted(int rows_h, int rows_w, long long planes)
+bool halo_wanted(int stride, int rows_h, int rows_w, long long planes)
 {
   const int f = forced_path();
   if (f == 1) return false;
   if (f == 2) return true;
+  // measured per layer (profiles/r02_experiments.md): the halo kernel wins where its unrolled constant-tap loop applies (stride 1) and
+  // the 16-row tiles are mostly real voxels; stride 2 runs its table-driven loop, which the per-tap kernel matches or beats
+  if (stride != 1) return false;
   const int th = (rows_h + 15) / 16, tw = (rows_w + 7) / 8;
   if (planes * th * tw < sm_count() / 2) return false;             // few tiles: the per-tap kernel splits the K loop over the idle SMs
-  return (double)rows_h * rows_w >= 0.6 * (th * 16.0) * (tw * 8.0);
+  return (double)rows_h * rows_w >= 0.8 * (th * 16.0) * (tw * 8.0);
 }
 
 // few-tile layers (the coarse pyramid levels): split the (tap, chunk) loop so that every SM has a work item
@@ -210,6 +223,12 @@ int choose_ksplit(long long items, int ksteps)
   const int cap = ksteps / 8 > 0 ? ksteps / 8 : 1;
   if (ks > cap) ks = cap;
   return ks < 1 ? 1 : (int)ks;
+}
+
+// tile pairs (two 8 x 16 tiles side by side in w sharing the weight blocks): stride 1, narrow column tiles, W a multiple of 16
+bool pair_wanted(int stride, int bn, int rows_w)
+{
+  return stride == 1 && bn <= 128 && rows_w % 16 == 0 && g_chains.load() != 1;
 }
 
 void h_add_box(convgen::HProblem &p, int b, int cls_hw, int ow, int oh, int lw, int lh)
@@ -237,7 +256,7 @@ int h_plan_smem(convgen::HProblem &p, int bn, bool taps_consecutive_by_9)
   for (int as : {3, 2}) {
     int bs = (avail - as * p.a_stage_bytes) / b_bytes;
     if (bs > convgen::kHMaxBStages) bs = convgen::kHMaxBStages;
-    if (bs >= 3 || (as == 2 && bs >= 2)) {
+    if (bs >= 3 || (bs >= 2 && (as == 2 || p.pair))) {
       p.a_stages = as; p.b_stages = bs;
       // weight-box bookkeeping of every tap: box start (a multiple of tps: the tap index is kd * 9 + kh * 3 + kw), slot, first-of-box flag
       for (int c = 0; c < p.nclass; ++c)
@@ -304,15 +323,17 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
   int rc;
-  if (halo_wanted(OH, OW, (long long)batch * OD)) {
+  if (halo_wanted(stride, OH, OW, (long long)batch * OD)) {
     convgen::HProblem h = {};
     h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
     h.N = out_channels; h.chunks = (in_channels + 31) / 32; h.nclass = 1;
     convgen::HClass &hc = h.cls[0];
     hc.nplanes = 3;
+    h.pair = pair_wanted(stride, choose_bn(out_channels), OW) ? 1 : 0;
+    if (h.pair) h.tw = (OW + 15) / 16;
     if (stride == 1) {
-      h_add_box(h, 0, 0, -1, -1, 10, 18);
-      if ((rc = make_vol_map(&h.tmA[0], x, vx, 1, 0, 0, 0, 10, 18, 1, false, true))) return rc;
+      h_add_box(h, 0, 0, -1, -1, h.pair ? 18 : 10, 18);
+      if ((rc = make_vol_map(&h.tmA[0], x, vx, 1, 0, 0, 0, h.pair ? 18 : 10, 18, 1, false, true))) return rc;
     } else {
       h_add_box(h, 0, 3, -1, -1, 9, 17);             // odd h, odd w
       h_add_box(h, 1, 2, 0, -1, 8, 17);              // odd h, even w
@@ -385,14 +406,16 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   const Vol vdy = {batch, OD, OH, OW, out_channels}, vdx = {batch, depth, height, width, in_channels};
   int rc;
-  if (halo_wanted(OH, OW, (long long)batch * OD * (stride == 1 ? 1 : 8))) {
+  if (halo_wanted(stride, OH, OW, (long long)batch * OD * (stride == 1 ? 1 : 8))) {
     convgen::HProblem h = {};
     h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
     h.N = in_channels; h.chunks = (out_channels + 31) / 32;
+    h.pair = pair_wanted(stride, choose_bn(in_channels), OW) ? 1 : 0;
+    if (h.pair) h.tw = (OW + 15) / 16;
     if (stride == 1) {
       h.nclass = 1;
-      h_add_box(h, 0, 0, -1, -1, 10, 18);
-      if ((rc = make_vol_map(&h.tmA[0], dy, vdy, 1, 0, 0, 0, 10, 18, 1, false, true))) return rc;
+      h_add_box(h, 0, 0, -1, -1, h.pair ? 18 : 10, 18);
+      if ((rc = make_vol_map(&h.tmA[0], dy, vdy, 1, 0, 0, 0, h.pair ? 18 : 10, 18, 1, false, true))) return rc;
       if ((rc = make_vol_map(&h.tmD[0], dx, vdx, 1, 0, 0, 0, 8, 4, 1, false, false))) return rc;
       convgen::HClass &hc = h.cls[0];
       hc.nplanes = 3;

@@ -276,6 +276,7 @@ struct HProblem {
   int batch, tw, th, td;          // tile grid: 8 x 16 x 1 voxels per tile
   int N, chunks, nclass, nbox;
   int a_bytes, a_stage_bytes, a_stages, b_stages;
+  int pair;                       // 1: tile pairs (T = 2 instantiation): 16 x 16 voxel work items, halo box 18 x 18
   int dbg;                        // timing experiments (conv3d_gen_set_path bits 3-5): 1 = no MMAs, 2 = no A loads, 4 = no B loads, 8 = no stores
   int tps;                        // taps per weight box (9, 3 or 1): amortises the barrier round trip of a stage over 4 * tps MMAs
   HBox boxes[kHMaxBoxes];
@@ -299,7 +300,9 @@ __device__ __forceinline__ uint64_t desc_k_halo(uint32_t addr, uint32_t group_st
 // dependent instruction chain at ~5 clocks per instruction, and a table-driven tap costs it ~350 clocks (profiles/r02_experiments.md)
 template <int BN> __host__ __device__ constexpr int halo_tps() { return BN <= 32 ? 9 : BN <= 128 ? 3 : 1; }
 
-template <int BN, bool B_MN, int CH, int REG>
+// T = 2 (stride 1 only): a work item is TWO tiles side by side in w (16 x 16 voxels, halo box 18 x 18) that share every weight block --
+// the weights are what a narrow layer pulls most of from L2 (27 x BN x 128 bytes per 128 voxels and chunk against 23 KB of halo per plane)
+template <int BN, bool B_MN, int CH, int REG, int T = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ bias)
 {
@@ -318,7 +321,9 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
   auto tempty = [&](int a) { return bars + 8u * (2 * kHMaxAStages + 2 * kHMaxBStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kHMaxAStages + 2 * kHMaxBStages + 4);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  constexpr int ACC_COLS = CH * BN;                                   // one accumulator set: CH chains of BN columns
+  static_assert(T == 1 || (REG != 0 && CH == 1), "tile pairs: regular taps, one chain");
+  constexpr int ACC_COLS = T * CH * BN;                               // one accumulator set: T tiles x CH chains of BN columns
+  constexpr int LW = 8 * T + 2;                                       // rows per line of the stride-1 halo box
   static_assert(2 * ACC_COLS <= 512, "TMEM columns");
   constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
 
@@ -344,7 +349,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
   // work item -> (class, sample, plane, tile row, tile column, column tile); column tiles fastest (they share the A boxes in L2)
   auto decode_item = [&](long long w, int &cls, int &n, int &d0, int &h0, int &w0, int &nt) {
     nt = (int)(w % n_tiles); w /= n_tiles;
-    w0 = (int)(w % p.tw) * 8; w /= p.tw;
+    w0 = (int)(w % p.tw) * (8 * T); w /= p.tw;
     h0 = (int)(w % p.th) * 16; w /= p.th;
     d0 = (int)(w % p.td); w /= p.td;
     n = (int)(w % p.batch);
@@ -438,7 +443,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
           const uint32_t sa = base + as * p.a_stage_bytes;
           if (REG != 0) {
             constexpr int TPS = halo_tps<BN>();
-            const uint64_t da_plane = desc_k_halo(sa, 10 * 128);
+            const uint64_t da_plane = desc_k_halo(sa, LW * 128);
             const uint32_t first_plane = (c == 0 && pl == 0) ? 1u : 0u;
 #pragma unroll
             for (int g = 0; g < 9 / TPS; ++g) {
@@ -451,14 +456,17 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
                   for (int j = 0; j < TPS; ++j) {
                     constexpr int dummy = 0; (void)dummy;
                     const int t = g * TPS + j;                                 // box rows (jh, jw) = (t / 3, t % 3): compile-time after unrolling
-                    const uint32_t a_off = (uint32_t)(((t / 3) * 10 + (t % 3)) * 128);
                     const int slot = REG == 1 ? j : TPS - 1 - j;
-                    const uint32_t acc = acc0 + (uint32_t)((t % CH) * BN);
                     const uint32_t later = (t >= CH) ? 1u : (first_plane ^ 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                      umma_tf32(acc, da_plane + (uint64_t)((a_off + k * 32) >> 4), db_stage + (uint64_t)((slot * B_TAP_BYTES + k * (int)kstep_bytes<B_MN>()) >> 4),
-                                idesc, later | (uint32_t)(k > 0));
+                    for (int hf = 0; hf < T; ++hf) {                           // the tile pair: same weights, A rows 8 voxels further
+                      const uint32_t a_off = (uint32_t)(((t / 3) * LW + (t % 3) + 8 * hf) * 128);
+                      const uint32_t acc = acc0 + (uint32_t)((hf * CH + t % CH) * BN);
+#pragma unroll
+                      for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_tf32(acc, da_plane + (uint64_t)((a_off + k * 32) >> 4), db_stage + (uint64_t)((slot * B_TAP_BYTES + k * (int)kstep_bytes<B_MN>()) >> 4),
+                                  idesc, later | (uint32_t)(k > 0));
+                    }
                   }
                 }
                 umma_commit(bempty(bs));
@@ -515,9 +523,11 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
       mbar_wait(tfull(acs), acph);
       tc_fence_after();
 #pragma unroll 1
+      for (int hf = 0; hf < T; ++hf)
+#pragma unroll 1
       for (int c0 = 32 * ((warp - 2) >> 2); c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
         float v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + c0) + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + hf * CH * BN + c0) + ((uint32_t)(q * 32) << 16), v);
         const int n0 = nt * BN + c0;
         if (n0 >= p.N) continue;                                  // warp-uniform
         if (CH > 1 && ntaps_total > 1) {                          // (a class with a single tap never touched the second chain)
@@ -525,7 +535,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
           for (int ch = 1; ch < CH; ++ch) {
             if (ch < ntaps_total) {
               float u[32];
-              tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + ch * BN + c0) + ((uint32_t)(q * 32) << 16), u);
+              tmem_ld_32x32(tmem_base + (uint32_t)(acs * ACC_COLS + (hf * CH + ch) * BN + c0) + ((uint32_t)(q * 32) << 16), u);
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += u[j];
             }
@@ -545,7 +555,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
         __syncwarp();
         if (lane == 0 && !(p.dbg & 8)) {
           asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                       ::"l"(&p.tmD[cls]), "r"(buf), "r"(n0), "r"(w0), "r"(h0 + 4 * q), "r"(d0), "r"(n) : "memory");
+                       ::"l"(&p.tmD[cls]), "r"(buf), "r"(n0), "r"(w0 + 8 * hf), "r"(h0 + 4 * q), "r"(d0), "r"(n) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
