@@ -34,6 +34,13 @@ int conv3d_gen_forward(void *stream, const float *x, const float *w, const float
 int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, int batch, int depth, int height, int width, int in_channels,
                      int out_channels, int stride, float *dx);
 
+/* The same stride-2 input gradient for narrow layers (CI <= 64) with the eight parity classes of dx folded into the column extent of one
+ * implicit GEMM.  w_fold fp32 [8, 8 * CIP, CO], CIP = CI rounded up to 32: w_fold[(dd*2 + dh)*2 + dw][cls * CIP + ci][co] = weight[co][ci][kd][kh][kw]
+ * with, per axis, k = 1 for (class bit 0, delta 0), k = 2 for (1, 0), k = 0 for (1, 1), and zeros for (0, 1) and for ci >= CI
+ * (transoar_b200/conv3d_gen.py::fold_stride2_weights builds it).  Every element of dx is written. */
+int conv3d_gen_dgrad_s2_folded(void *stream, const float *dy, const float *w_fold, int batch, int depth, int height, int width, int in_channels,
+                               int out_channels, float *dx);
+
 /* dw [CO, 27, CI] (channels-last weight memory) = sum over output voxels of dy[v][co] * x[stride * v + tap - 1][ci].  dw is zero-filled by the
  * call, then accumulated with fp32 reductions (split over voxel ranges: the summation order is not deterministic). */
 int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, int batch, int depth, int height, int width, int in_channels,

@@ -83,6 +83,23 @@ def test_input_gradient_exact_on_integers(shape, ci, co, stride, path):
     assert torch.equal(dx.double(), ref)
 
 
+@pytest.mark.parametrize("shape,ci,co", [c for c in CASES if c[1] <= 64])
+def test_folded_stride2_input_gradient_exact_on_integers(shape, ci, co):
+    """The class-folded stride-2 input gradient (narrow layers) through its own entry point and the python weight folding."""
+    from transoar_b200 import _lib
+    from transoar_b200.conv3d_gen import fold_stride2_weights
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(D * H + W + co + 1)
+    od, oh, ow = ((v + 1) // 2 for v in (D, H, W))
+    dy = _cl(_ints(g, -3, 3, (N, co, od, oh, ow)))
+    w = _cl(_ints(g, -2, 2, (co, ci, 3, 3, 3)))
+    dx = _cl(torch.full((N, ci, D, H, W), float("nan"), device=DEV))
+    rc = _lib.lib().conv3d_gen_dgrad_s2_folded(_stream(), _p(dy), _p(fold_stride2_weights(_taps(w))), N, D, H, W, ci, co, _p(dx))
+    assert rc == 0
+    ref = torch.nn.grad.conv3d_input((N, ci, D, H, W), w.double(), dy.double(), stride=2, padding=1).round()
+    assert torch.equal(dx.double(), ref)
+
+
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("shape,ci,co", CASES)
 def test_weight_gradient_exact_on_integers(shape, ci, co, stride):

@@ -64,6 +64,10 @@ def main():
         ours = {"fwd": lambda: lib.conv3d_gen_forward(st(), p(x), p(wt), p(b), N, D, H, W, ci, co, s, p(y)),
                 "dgrad": lambda: lib.conv3d_gen_dgrad(st(), p(dy), p(wt), N, D, H, W, ci, co, s, p(dx)),
                 "wgrad": lambda: lib.conv3d_gen_wgrad(st(), p(x), p(dy), N, D, H, W, ci, co, s, p(dw))}
+        if s == 2 and ci <= 64:
+            from transoar_b200.conv3d_gen import fold_stride2_weights
+            wf = fold_stride2_weights(wt)
+            ours["dgrad"] = lambda: lib.conv3d_gen_dgrad_s2_folded(st(), p(dy), p(wf), N, D, H, W, ci, co, p(dx))
         cb = lambda mask: torch.ops.aten.convolution_backward(dy, x, w, None, [s] * 3, [1] * 3, [1] * 3, False, [0] * 3, 1, mask)
         theirs = {"fwd": lambda: F.conv3d(x, w, b, s, 1), "dgrad": lambda: cb([True, False, False]), "wgrad": lambda: cb([False, True, False])}
         gf = 2.0 * N * od * oh * ow * 27 * ci * co / 1e9

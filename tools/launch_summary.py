@@ -5,7 +5,7 @@ import csv
 import re
 import sys
 
-OURS = ("msda3d::", "convtc::", "roiattn::", "winattn::", "instnorm::", "tcgemm::", "stemconv::", "fusedln::")
+OURS = ("msda3d::", "convtc::", "convgen::", "roiattn::", "winattn::", "instnorm::", "tcgemm::", "stemconv::", "fusedln::")
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
 hdr, data = rows[0], rows[1:]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "conv3d_gen_supported": (_ci, [_ci, _ci, _ci]),
     "conv3d_gen_forward": (_ci, [_vp] * 4 + [_ci] * 7 + [_vp]),
     "conv3d_gen_dgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
+    "conv3d_gen_dgrad_s2_folded": (_ci, [_vp] * 3 + [_ci] * 6 + [_vp]),
     "conv3d_gen_wgrad": (_ci, [_vp] * 3 + [_ci] * 7 + [_vp]),
     "conv3d_gen_set_path": (None, [_ci]),
     "conv3d_gen_debug_mma_rate": (_ci, [_vp, _ci, _ci, _ci, _vp]),

@@ -60,6 +60,31 @@ def conv_transpose_eligible(conv, x):
             and tuple(conv.output_padding) == (0, 0, 0))
 
 
+_FOLD_IDX = {}
+
+
+def fold_stride2_weights(w_taps):
+    """[27, CO, CI] tap-major weights -> w_fold [8, 8 * CIP, CO] of include/conv3d_gen.h::conv3d_gen_dgrad_s2_folded: block (delta, class) holds
+    the transposed weights of the tap that connects dy[j + delta] with the class's dx[2 j + p] (per axis k = 1 / 2 / 0 for (p, delta) =
+    (0, 0) / (1, 0) / (1, 1)), zeros where there is none."""
+    _, co, ci = w_taps.shape
+    cip = (ci + 31) // 32 * 32
+    key = w_taps.device
+    if key not in _FOLD_IDX:
+        k_of = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
+        idx = []
+        for delta in range(8):
+            for cls in range(8):
+                ks = [k_of.get(((cls >> s) & 1, (delta >> s) & 1)) for s in (2, 1, 0)]        # (d, h, w)
+                idx.append(27 if None in ks else (ks[0] * 3 + ks[1]) * 3 + ks[2])
+        _FOLD_IDX[key] = torch.tensor(idx, dtype=torch.long, device=w_taps.device)
+    ext = torch.cat((w_taps, w_taps.new_zeros(1, co, ci)))
+    sel = ext.index_select(0, _FOLD_IDX[key]).view(8, 8, co, ci).transpose(2, 3)                # [delta, class, ci, co]
+    out = w_taps.new_zeros(8, 8, cip, co)
+    out[:, :, :ci] = sel
+    return out.view(8, 8 * cip, co)
+
+
 class Conv3dGenFunction(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride):
@@ -91,7 +116,11 @@ class Conv3dGenFunction(Function):
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
                 dx = _empty_cl(x.shape, x.device)
-                _lib.check(lib.conv3d_gen_dgrad(_stream(), _p(dy), _p(w), N, D, H, W, ci, co, ctx.stride, _p(dx)), "conv3d_gen_dgrad")
+                if ctx.stride == 2 and ci <= 64:                                # narrow stage entries: parity classes folded into N
+                    _lib.check(lib.conv3d_gen_dgrad_s2_folded(_stream(), _p(dy), _p(fold_stride2_weights(w)), N, D, H, W, ci, co, _p(dx)),
+                               "conv3d_gen_dgrad_s2_folded")
+                else:
+                    _lib.check(lib.conv3d_gen_dgrad(_stream(), _p(dy), _p(w), N, D, H, W, ci, co, ctx.stride, _p(dx)), "conv3d_gen_dgrad")
             if ctx.needs_input_grad[1]:
                 dw = _empty_cl((co, ci, 3, 3, 3), x.device)                      # the kernel writes channels-last weight memory [CO][27][CI]
                 _lib.check(lib.conv3d_gen_wgrad(_stream(), _p(x), _p(dy), N, D, H, W, ci, co, ctx.stride, _p(dw)), "conv3d_gen_wgrad")

@@ -52,6 +52,7 @@ struct Problem {
   int N;                          // columns of D (output channels of this launch)
   int chunks;                     // ceil(reduction channels / 32)
   int nclass;
+  int fold_cip;                   // > 0: class-folded stride-2 input gradient: column block c * fold_cip .. belongs to parity class c of dx (see conv3d_gen_dgrad_s2_folded)
   int ksplit;                     // > 1: the (tap, chunk) K-steps of a tile are split over ksplit work items that ADD into a zero-filled D (few-tile layers)
   int nsteps[kMaxClasses];
   Step steps[kMaxClasses][kMaxSteps];
@@ -220,12 +221,13 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
+          const int dcls = p.fold_cip > 0 ? n0 / p.fold_cip : it.cls, dch = p.fold_cip > 0 ? n0 % p.fold_cip : n0;
           if (p.ksplit > 1)                                        // partial sums of the K splits are combined by the copy engine (fp32 add in L2)
             asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                         ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
+                         ::"l"(&p.tmD[dcls]), "r"(buf), "r"(dch), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
           else
             asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                         ::"l"(&p.tmD[it.cls]), "r"(buf), "r"(n0), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
+                         ::"l"(&p.tmD[dcls]), "r"(buf), "r"(dch), "r"(it.w0), "r"(it.h0 + qh0), "r"(it.d0 + qd0), "r"(it.n) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         tma_buf ^= 1;
