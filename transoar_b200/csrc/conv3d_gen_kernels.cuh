@@ -173,12 +173,11 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
         mbar_wait(full(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+        const uint64_t da0 = smem_desc<false>(sa), db0 = smem_desc<B_MN>(sb);        // built once per stage; the k-steps are constant increments
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = smem_desc<false>(sa + k * kstep_bytes<false>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
-            umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(acc, da0 + (uint64_t)(k * kstep_bytes<false>() >> 4), db0 + (uint64_t)(k * kstep_bytes<B_MN>() >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty(stage));
         }
         __syncwarp();
