@@ -63,14 +63,25 @@ class Matcher(nn.Module):
 
     @torch.no_grad()
     def forward(self, outputs, tgt_boxes, tgt_valid, anchors):
-        logits = outputs["pred_logits"]
-        B, Nq, _ = logits.shape
+        best, soft = self.match_layers([outputs], tgt_boxes, tgt_valid, anchors)
+        return best[0], soft[0]
+
+    @torch.no_grad()
+    def match_layers(self, layers, tgt_boxes, tgt_valid, anchors):
+        """The matcher for several decoder layers at once (the final layer + the auxiliary ones, criterion.py:113-120): everything carries
+        a leading layer axis, so the ~40 tiny kernels of one match are launched once, not once per layer.  Returns best [L, B, organs],
+        soft_labels [L, B, organs, Q]."""
+        logits = torch.stack([o["pred_logits"] for o in layers])                            # [L, B, Nq, 1]
+        L, B, Nq, _ = logits.shape
         O = self.num_organs
         Q = Nq // O
-        boxes = anchors[None].expand(B, -1, -1) if self.anchor_matching else outputs["pred_boxes"]
-        boxes = boxes.reshape(B, O, Q, -1).float()
-        logits = logits.reshape(B, O, Q).float()
-        tgt = tgt_boxes[:, :, None, :]                                                       # [B, O, 1, 6]
+        if self.anchor_matching:
+            boxes = anchors[None, None].expand(1, B, -1, -1)                                 # the same for every layer: computed once
+        else:
+            boxes = torch.stack([o["pred_boxes"] for o in layers])
+        boxes = boxes.reshape(boxes.shape[0], B, O, Q, -1).float()
+        logits = logits.reshape(L, B, O, Q).float()
+        tgt = tgt_boxes[None, :, :, None, :]                                                 # [1, B, O, 1, 6]
         cost_class = -logits.sigmoid()
         cost_bbox = (boxes - tgt).abs().sum(-1)                                              # cdist(p=1), matcher.py:50
         cost_giou = -paired_giou_3d(box_cxcyczwhd_to_xyzxyz(boxes.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(tgt))
@@ -81,8 +92,8 @@ class Matcher(nn.Module):
         else:
             hi, lo = cost_giou.amax(-1, keepdim=True), cost_giou.amin(-1, keepdim=True)
             soft = ((cost_giou - hi) / (lo - hi)).clamp(min=0)                               # matcher.py:59
-        soft = torch.where(tgt_valid[:, :, None], soft, torch.full_like(soft, -1.0))         # matcher.py:44-45
-        return best, soft
+        soft = torch.where(tgt_valid[None, :, :, None], soft, torch.full_like(soft, -1.0))   # matcher.py:44-45
+        return best, soft.expand(L, -1, -1, -1)
 
     @staticmethod
     def dense_matches(best, tgt_valid, Q):
@@ -119,24 +130,28 @@ class TransoarCriterion(nn.Module):
             self._dice_loss = SoftDiceLoss()
 
     def loss_class(self, outputs, soft_labels):
-        """BCE-with-logits over the queries of the classes present in the sample (criterion.py:40-49)."""
+        """BCE-with-logits over the queries of the classes present in the sample (criterion.py:40-49).  ``soft_labels`` may carry a leading
+        layer axis ([L, B, organs, Q]): one loss per layer, all evaluated on these logits."""
+        lead = soft_labels.shape[:-3]
         logits = outputs["pred_logits"].flatten().float()
-        labels = soft_labels.flatten()
+        labels = soft_labels.reshape(*lead, -1)
         keep = (labels != -1).float()
-        per = F.binary_cross_entropy_with_logits(logits, labels.clamp(min=0), reduction="none")
-        return (per * keep).sum() / keep.sum()
+        per = F.binary_cross_entropy_with_logits(logits.expand_as(labels), labels.clamp(min=0), reduction="none")
+        return (per * keep).sum(-1) / keep.sum(-1)
 
     def loss_bboxes(self, outputs, tgt_boxes, tgt_valid, best, num_boxes):
-        """L1 + GIoU of the matched query of every present class against its target (criterion.py:52-77)."""
+        """L1 + GIoU of the matched query of every present class against its target (criterion.py:52-77).  ``best`` may carry a leading
+        layer axis ([L, B, organs]): one pair of losses per layer."""
         B, Nq, _ = outputs["pred_boxes"].shape
         O = self.num_classes
-        preds = outputs["pred_boxes"].reshape(B, O, Nq // O, -1).float()
-        matched = torch.gather(preds, 2, best[:, :, None, None].expand(-1, -1, 1, preds.shape[-1])).squeeze(2)     # [B, O, 6]
+        lead = best.shape[:-2]
+        preds = outputs["pred_boxes"].reshape(B, O, Nq // O, -1).float().expand(*lead, -1, -1, -1, -1)
+        matched = torch.gather(preds, -2, best[..., None, None].expand(*best.shape, 1, preds.shape[-1])).squeeze(-2)   # [(L,) B, O, 6]
         w = tgt_valid.float()
-        loss_bbox = ((matched - tgt_boxes).abs().sum(-1) * w).sum() / num_boxes
+        loss_bbox = ((matched - tgt_boxes).abs().sum(-1) * w).sum((-2, -1)) / num_boxes
         giou = paired_giou_3d(box_cxcyczwhd_to_xyzxyz(matched.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(tgt_boxes))
         # classes absent from a sample have a zero target box (0/0 GIoU): mask them out before they can poison the sum
-        loss_giou = (torch.where(tgt_valid, 1 - giou, torch.zeros_like(giou))).sum() / num_boxes
+        loss_giou = (torch.where(tgt_valid, 1 - giou, torch.zeros_like(giou))).sum((-2, -1)) / num_boxes
         return loss_bbox, loss_giou
 
     def loss_segmentation(self, outputs, targets):
@@ -149,17 +164,18 @@ class TransoarCriterion(nn.Module):
         dev = outputs["pred_logits"].device
         tgt_boxes, tgt_valid = targets if isinstance(targets, tuple) else dense_targets(targets, self.num_classes, dev)
         num_boxes = tgt_valid.sum().clamp(min=1).float()
-        best, soft = self.matcher(outputs, tgt_boxes, tgt_valid, anchors)
+        # the final layer and the auxiliary layers in ONE pass (leading layer axis): the reference re-runs the matcher on every auxiliary
+        # layer's logits but evaluates all losses on the FINAL layer's predictions (criterion.py:118-119 pass `outputs`, not `aux_outputs`)
+        layers = [outputs] + list(outputs.get("aux_outputs", []))
+        best, soft = self.matcher.match_layers(layers, tgt_boxes, tgt_valid, anchors)
         loss_bbox, loss_giou = self.loss_bboxes(outputs, tgt_boxes, tgt_valid, best, num_boxes)
+        loss_cls = self.loss_class(outputs, soft)
         zero = torch.zeros((), device=dev)
-        losses = {"bbox": loss_bbox, "giou": loss_giou, "cls": self.loss_class(outputs, soft), "segce": zero, "segdice": zero}
+        losses = {"bbox": loss_bbox[0], "giou": loss_giou[0], "cls": loss_cls[0], "segce": zero, "segdice": zero}
         if self._seg_proxy:
             losses["segce"], losses["segdice"] = self.loss_segmentation(outputs, seg_targets)
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            best, soft = self.matcher(aux, tgt_boxes, tgt_valid, anchors)
-            # the reference evaluates these on `outputs`, not on `aux` (criterion.py:118-119); kept for loss parity
-            losses[f"bbox_{i}"], losses[f"giou_{i}"] = self.loss_bboxes(outputs, tgt_boxes, tgt_valid, best, num_boxes)
-            losses[f"cls_{i}"] = self.loss_class(outputs, soft)
+        for i in range(len(layers) - 1):
+            losses[f"bbox_{i}"], losses[f"giou_{i}"], losses[f"cls_{i}"] = loss_bbox[i + 1], loss_giou[i + 1], loss_cls[i + 1]
         return losses
 
 
