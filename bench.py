@@ -15,7 +15,8 @@ Multi-GPU   : one process per GPU, volumes sharded by rank (weak scaling); the o
 `roofline`  : the dominant kernel of the step (msda3d backward) -- algorithmic bytes / CUDA-event time of its launches inside
               the timed region, against the measured HBM peak.
 `msda3d_op` : the operator alone (forward + gradient of both refinement layers) incl. the reference's own CUDA op on the same
-              inputs; `tc_gemm`, `roi_attention`, `instnorm_relu`: the other hand-written kernels of the path.
+              inputs; `tc_gemm`, `roi_attention`, `instnorm_relu`, `conv3d` (every AttnFPN 3x3x3 layer against cuDNN): the other
+              hand-written kernels of the path.
 `ref_gpu_model`: the UNMODIFIED reference model (baseline/_ref) with its OWN compiled CUDA op (oracle/_ref) running the same
               training step on the same GPU in the same run -- the comparator BASELINE.json's north_star names.
 `cpu_baseline` / `--impl reference`: the unmodified reference's use_cuda=False route of the same training step on the host
@@ -421,8 +422,74 @@ def measure_kernels(dev, rank):
                             "fwd_bwd_gbs": 8 * nbytes / in_fbm / 1e6, "fwd_bwd_frac_of_hbm_peak": 8 * nbytes / in_fbm / 1e6 / peaks["hbm_gbs"],
                             "bytes_model": "fwd: 2 reads + 1 write of the activation; bwd: 4 reads + 1 write"}
     del x, dy
+
+    # the AttnFPN 3x3x3 convolutions of the step (batch 2 x 160x160x256) on the general tcgen05 kernels (include/conv3d_gen.h) against cuDNN
+    # (autotuned, TF32) on the same tensors: forward, input gradient, weight gradient
+    try:
+        out["conv3d"] = measure_conv_layers(dev, tf32_peak)
+    except Exception as exc:                                                                # keep the headline if an extra fails
+        out["conv3d"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     torch.cuda.empty_cache()
     return out
+
+
+CONV_LAYERS = [("enc1.conv1", 24, 48, 2, (160, 160, 256), False), ("enc1.conv2", 48, 48, 1, (80, 80, 128), False),
+               ("enc2.conv1", 48, 96, 2, (80, 80, 128), False), ("enc2.conv2", 96, 96, 1, (40, 40, 64), False),
+               ("enc3.conv1", 96, 192, 2, (40, 40, 64), False), ("enc3.conv2", 192, 192, 1, (20, 20, 32), False),
+               ("enc4.conv1", 192, 384, 2, (20, 20, 32), False), ("enc4.conv2", 384, 384, 1, (10, 10, 16), False),
+               ("enc5.conv1", 384, 768, 2, (10, 10, 16), False), ("enc5.conv2", 768, 768, 1, (5, 5, 8), False),
+               ("out.P2", 96, 384, 1, (40, 40, 64), True), ("out.P3", 192, 384, 1, (20, 20, 32), True),
+               ("out.P4", 384, 384, 1, (10, 10, 16), True), ("out.P5", 384, 384, 1, (5, 5, 8), True)]
+
+
+def measure_conv_layers(dev, tf32_peak):
+    """name, CI, CO, stride, input volume, bias of every 3x3x3 convolution of the VISCERAL AttnFPN besides the 1-channel stem and the 24 -> 24
+    layer (their own kernels): encoder_blocks.py:28-46 stages 1-5, attn_fpn.py:65-74 output convolutions."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from transoar_b200 import _lib
+    from transoar_b200.conv3d_gen import fold_stride2_weights
+    lib = _lib.lib()
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last_3d)
+    was = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    rows, tot = [], {k: [0.0, 0.0] for k in ("fwd", "dgrad", "wgrad")}
+    try:
+        for name, ci, co, s, (D, H, W), bias in CONV_LAYERS:
+            N = BATCH
+            x = cl(torch.randn(N, ci, D, H, W, device=dev))
+            w = cl(torch.randn(co, ci, 3, 3, 3, device=dev) / (27 * ci) ** 0.5)
+            wt = w.permute(2, 3, 4, 0, 1).reshape(27, co, ci).contiguous()
+            b = torch.randn(co, device=dev) if bias else None
+            od, oh, ow = ((v + s - 1) // s for v in (D, H, W))
+            y, dy = cl(torch.empty(N, co, od, oh, ow, device=dev)), cl(torch.randn(N, co, od, oh, ow, device=dev))
+            dx, dw = torch.empty_like(x), torch.empty_like(w)
+            ours = {"fwd": lambda: lib.conv3d_gen_forward(st(), p(x), p(wt), p(b), N, D, H, W, ci, co, s, p(y)),
+                    "dgrad": lambda: lib.conv3d_gen_dgrad(st(), p(dy), p(wt), N, D, H, W, ci, co, s, p(dx)),
+                    "wgrad": lambda: lib.conv3d_gen_wgrad(st(), p(x), p(dy), N, D, H, W, ci, co, s, p(dw))}
+            if s == 2 and ci <= 64:
+                wf = fold_stride2_weights(wt)
+                ours["dgrad"] = lambda: lib.conv3d_gen_dgrad_s2_folded(st(), p(dy), p(wf), N, D, H, W, ci, co, p(dx))
+            cb = lambda mask: torch.ops.aten.convolution_backward(dy, x, w, None, [s] * 3, [1] * 3, [1] * 3, False, [0] * 3, 1, mask)
+            lib_ = {"fwd": lambda: F.conv3d(x, w, b, s, 1), "dgrad": lambda: cb([True, False, False]), "wgrad": lambda: cb([False, True, False])}
+            gf = 2.0 * N * od * oh * ow * 27 * ci * co / 1e9
+            row = {"layer": name, "ci": ci, "co": co, "stride": s, "gflop": round(gf, 1)}
+            for k in ("fwd", "dgrad", "wgrad"):
+                if ours[k]() != 0:
+                    raise RuntimeError(f"conv3d_gen {k} failed on {name}")
+                a, c = _event_ms(ours[k], 2, 5), _event_ms(lib_[k], 2, 5)
+                tot[k][0] += a
+                tot[k][1] += c
+                row[k] = {"ms": round(a, 4), "cudnn_ms": round(c, 4), "frac_of_tf32_peak": round(gf / a / tf32_peak, 3)}
+            rows.append(row)
+            del x, w, wt, y, dy, dx, dw
+    finally:
+        torch.backends.cudnn.benchmark = was
+    return {"bound": "tensor", "peak_tflops": tf32_peak, "layers": rows,
+            "total_ms": {k: {"ours": round(v[0], 3), "cudnn": round(v[1], 3)} for k, v in tot.items()}}
 
 
 def measure_reference_gpu_model(dev, rank, steps=6, warm=3):

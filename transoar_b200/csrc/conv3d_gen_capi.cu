@@ -276,9 +276,9 @@ int h_plan_smem(convgen::HProblem &p, int bn, bool taps_consecutive_by_9)
   return 0;
 }
 
-template <int BHL> int launch_w(cudaStream_t st, const convgen::WProblem &p, int grid, int smem)
+template <int BHL, int GEO> int launch_w(cudaStream_t st, const convgen::WProblem &p, int grid, int smem)
 {
-  auto kern = convgen::conv_wgrad_kernel<BHL>;
+  auto kern = convgen::conv_wgrad_kernel<BHL, GEO>;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -575,7 +575,9 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
     if (best < 0) return MSDA3D_EINVAL;
   }
   p.stage_bytes = p.dy_off + p.BN / 32 * convgen::kWDyChunkBytes;
-  const int smem = convgen::kWStages * p.stage_bytes + 1024 + 256;
+  p.stages = (227 * 1024 - 1024 - 256) / p.stage_bytes;
+  if (p.stages > convgen::kWMaxStages) p.stages = convgen::kWMaxStages;
+  const int smem = p.stages * p.stage_bytes + 1024 + 256;
   const long long kblocks = (long long)batch * p.td * p.th * p.tw;
   const long long per_split = 3LL * p.chunks * p.n_tiles;
   long long splits = (2LL * sm_count() + per_split - 1) / per_split;
@@ -588,10 +590,18 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
   if (e != cudaSuccess) return (int)e;
   const long long work = per_split * p.splits;
   const int grid = (int)(work < sm_count() ? work : sm_count());
-  switch (p.BH) {
-    case 16: return launch_w<4>(st, p, grid, smem);
-    case 8: return launch_w<3>(st, p, grid, smem);
-    default: return launch_w<2>(st, p, grid, smem);
+  // GEO 1 / 2: the stage geometry as compile-time constants (same numbers as the tables above; WGeo in the kernel header)
+  if (stride == 1) {
+    switch (p.BH) {
+      case 16: return launch_w<4, 1>(st, p, grid, smem);
+      case 8: return launch_w<3, 1>(st, p, grid, smem);
+      default: return launch_w<2, 1>(st, p, grid, smem);
+    }
+  }
+  switch (p.BH) {                       // stride 2: the table-driven loop (the 96-MMA constant-geometry unroll measured 30 % slower: 180 registers)
+    case 16: return launch_w<4, 0>(st, p, grid, smem);
+    case 8: return launch_w<3, 0>(st, p, grid, smem);
+    default: return launch_w<2, 0>(st, p, grid, smem);
   }
 }
 

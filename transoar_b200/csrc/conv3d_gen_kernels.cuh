@@ -613,7 +613,7 @@ struct WProblem {
   long long kb_per_split;
   int nbox, ngroups;
   int kd_cls[3], kd_off[3];       // tap kd reads d-class kd_cls at d0 + kd_off
-  int x_bytes, dy_off, stage_bytes;
+  int x_bytes, dy_off, stage_bytes, stages;
   float *dw;                      // [CO][27][CI], zero-initialised
   WBox boxes[kWMaxBoxes];
   WGroup groups[kWMaxGroups];
@@ -622,7 +622,7 @@ struct WProblem {
 };
 
 constexpr int kThreadsW = 192;    // warp 0 producer, warp 1 MMA, warps 2-5 epilogue (one per TMEM lane quarter = one M slab)
-constexpr int kWStages = 2;
+constexpr int kWMaxStages = 4;   // ring depth is WProblem.stages: as many stages as fit (a stage is 57 - 110 KB; with two, every load latency is exposed)
 constexpr int kWDyChunkBytes = 128 * 128;
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes)
@@ -630,22 +630,38 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes)
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
-// BHL = log2(BH): the line -> (h, d) split is a compile-time shift, the 16 MMAs of a group are unrolled with constant multipliers
-template <int BHL>
+// Box geometry of a stage as compile-time constants (the host builds WProblem.boxes / groups from the same numbers): with GEO != 0 every
+// descriptor of the 48 / 96 MMAs of a stage is the stage's base descriptor plus a constant, so the issuing thread spends ~4 instructions per
+// MMA instead of ~10 (it runs a dependent chain at ~5 clocks per instruction; a 128 x 64 x 8 MMA takes 48 clocks).
+template <int BH> struct WGeo {
+  static constexpr int BD = 16 / BH;
+  __host__ __device__ static constexpr int align1k(int b) { return (b + 1023) / 1024 * 1024; }
+  // stride 2: boxes (odd h, odd w), (odd h, even w), (even h, odd w), (even h, even w)
+  __host__ __device__ static constexpr int lw(int b) { return (b & 1) ? 8 : 9; }
+  __host__ __device__ static constexpr int lh(int b) { return b < 2 ? BH + 1 : BH; }
+  __host__ __device__ static constexpr int bytes(int b) { return lw(b) * lh(b) * BD * 128; }
+  __host__ __device__ static constexpr int off(int b) { return b == 0 ? 0 : align1k(off(b - 1) + bytes(b - 1)); }
+  __host__ __device__ static constexpr int gbox(int g) { return g < 4 ? (g & 1) : 2 + (g & 1); }     // groups: (kh 0: box 0, 1), (kh 2: box 0, 1), (kh 1: box 2, 3)
+  __host__ __device__ static constexpr int goh(int g) { return (g == 2 || g == 3) ? 1 : 0; }
+};
+
+// BHL = log2(BH): the line -> (h, d) split is a compile-time shift, the 16 MMAs of a group are unrolled with constant multipliers.
+// GEO: 0 = geometry from the tables, 1 = stride 1 (one 10 x (BH + 2) x BD box, groups = kh), 2 = stride 2 (WGeo).
+template <int BHL, int GEO = 0>
 __global__ void __launch_bounds__(kThreadsW, 1)
 conv_wgrad_kernel(const __grid_constant__ WProblem p)
 {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + kWStages * p.stage_bytes;
+  const uint32_t bars = base + p.stages * p.stage_bytes;
   auto full = [&](int s) { return bars + 8u * s; };
-  auto empty = [&](int s) { return bars + 8u * (kWStages + s); };
-  const uint32_t tfull = bars + 8u * (2 * kWStages), tempty = bars + 8u * (2 * kWStages + 1);
-  const uint32_t tmem_slot = bars + 8u * (2 * kWStages + 2);
+  auto empty = [&](int s) { return bars + 8u * (kWMaxStages + s); };
+  const uint32_t tfull = bars + 8u * (2 * kWMaxStages), tempty = bars + 8u * (2 * kWMaxStages + 1);
+  const uint32_t tmem_slot = bars + 8u * (2 * kWMaxStages + 2);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kWMaxStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -688,7 +704,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
             tma_load_5d(sb + bx.off, &p.tmX[p.kd_cls[kd] * 4 + bx.cls_hw], full(stage), ch * 32, w0 + bx.ow, h0 + bx.oh, d0 + p.kd_off[kd], n);
           }
           for (int i = 0; i < ndy; ++i) tma_load_5d(sb + p.dy_off + i * kWDyChunkBytes, &p.tmDy, full(stage), nt * p.BN + 32 * i, w0, h0, d0, n);
-          if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -709,6 +725,34 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
         const uint32_t sb = base + stage * p.stage_bytes;
         if (elect_one()) {
           const uint64_t db0 = desc_mn(sb + p.dy_off, kWDyChunkBytes);
+          constexpr int BH = 1 << BHL;
+          if (GEO == 1) {
+            const uint64_t da_stage = desc_mn(sb, 128);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              const uint32_t acc = tmem_u + (uint32_t)(g * p.BN);
+#pragma unroll
+              for (int line = 0; line < kWLines; ++line) {
+                const int h = line & (BH - 1), d = line >> BHL;
+                umma_tf32(acc, da_stage + (uint64_t)(((d * (BH + 2) + h + g) * 10 * 128) >> 4), db0 + (uint64_t)(line * 8 * 128 >> 4), idesc,
+                          (kb > kb0 || line > 0) ? 1u : 0u);
+              }
+            }
+          } else if (GEO == 2) {
+            using G = WGeo<BH>;
+            const uint64_t da_stage = desc_mn(sb, 128);
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {
+              const uint32_t acc = tmem_u + (uint32_t)(g * p.BN);
+#pragma unroll
+              for (int line = 0; line < kWLines; ++line) {
+                const int h = line & (BH - 1), d = line >> BHL;
+                constexpr int dummy = 0; (void)dummy;
+                umma_tf32(acc, da_stage + (uint64_t)((G::off(G::gbox(g)) + (d * G::lh(G::gbox(g)) + h + G::goh(g)) * G::lw(G::gbox(g)) * 128) >> 4),
+                          db0 + (uint64_t)(line * 8 * 128 >> 4), idesc, (kb > kb0 || line > 0) ? 1u : 0u);
+              }
+            }
+          } else
           for (int g = 0; g < p.ngroups; ++g) {
             const WGroup &gr = p.groups[g];
             const WBox &bx = p.boxes[gr.box];
@@ -717,7 +761,6 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
             const uint32_t acc = tmem_u + (uint32_t)(g * p.BN);
 #pragma unroll
             for (int line = 0; line < kWLines; ++line) {
-              constexpr int BH = 1 << BHL;
               const int h = line & (BH - 1), d = line >> BHL;
               umma_tf32(acc, da0 + (uint64_t)(d * step_d + h * step_h), db0 + (uint64_t)(line * 8 * 128 >> 4), idesc, (kb > kb0 || line > 0) ? 1u : 0u);
             }
@@ -725,7 +768,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
           umma_commit(empty(stage));
         }
         __syncwarp();
-        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       if (elect_one()) umma_commit(tfull);
       __syncwarp();
