@@ -185,6 +185,7 @@ template <bool B_MN> int dispatch_h(cudaStream_t st, int bn, const convgen::HPro
 {
   if (p.pair) return B_MN ? dispatch_pair<B_MN, 2>(st, bn, p, bias, smem) : dispatch_pair<B_MN, 1>(st, bn, p, bias, smem);
   if (reg == 0 || g_chains.load() == 1) return dispatch_h2<B_MN, 0>(st, bn, p, bias, smem);     // (set_path bit 2: force the table-driven loop, experiments)
+  if (reg == 3) return dispatch_h2<false, 3>(st, bn, p, bias, smem);
   return B_MN ? dispatch_h2<B_MN, 2>(st, bn, p, bias, smem) : dispatch_h2<B_MN, 1>(st, bn, p, bias, smem);
 }
 
@@ -202,14 +203,14 @@ int forced_path()
 }
 
 // the halo kernel pays for whole 8 x 16 tiles: use it where the tile rows are mostly real voxels
-bool halo_wanted(int stride, int rows_h, int rows_w, long long planes)
+bool halo_wanted(int stride, int rows_h, int rows_w, long long planes, bool forward = false)
 {
   const int f = forced_path();
   if (f == 1) return false;
   if (f == 2) return true;
   // measured per layer (profiles/r02_experiments.md): the halo kernel wins where its unrolled constant-tap loop applies (stride 1) and
   // the 16-row tiles are mostly real voxels; stride 2 runs its table-driven loop, which the per-tap kernel matches or beats
-  if (stride != 1) return false;
+  if (stride != 1 && !forward) return false;
   const int th = (rows_h + 15) / 16, tw = (rows_w + 7) / 8;
   if (planes * th * tw < sm_count() / 2) return false;             // few tiles: the per-tap kernel splits the K loop over the idle SMs
   return (double)rows_h * rows_w >= 0.8 * (th * 16.0) * (tw * 8.0);
@@ -244,13 +245,12 @@ void h_add_box(convgen::HProblem &p, int b, int cls_hw, int ow, int oh, int lw, 
 // ring depths that fit 227 KB next to the epilogue staging: three plane stages (each feeds up to nine taps), the rest goes to the ring
 // of weight blocks -- those are small (BN x 128 bytes) and the ring must hold a load latency's worth of them.  Returns the dynamic
 // shared-memory size, or 0 if the problem does not fit.
-int h_plan_smem(convgen::HProblem &p, int bn, bool taps_consecutive_by_9)
+int h_plan_smem(convgen::HProblem &p, int bn)
 {
   // taps per weight box: every stage costs a barrier round trip in the single producer / issuer threads (~500 clocks measured), which
   // four MMAs of a narrow tile (N <= 128) do not cover
   p.tps = bn <= 32 ? 9 : bn <= 128 ? 3 : 1;
   p.dbg = g_hdbg.load();
-  (void)taps_consecutive_by_9;
   const int avail = 227 * 1024 - 1024 - 512 - convgen::kHEpiBytes;
   const int b_bytes = p.tps * bn * 128;
   for (int as : {3, 2}) {
@@ -323,7 +323,7 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
   const int OD = (depth + stride - 1) / stride, OH = (height + stride - 1) / stride, OW = (width + stride - 1) / stride;
   const Vol vx = {batch, depth, height, width, in_channels}, vy = {batch, OD, OH, OW, out_channels};
   int rc;
-  if (halo_wanted(stride, OH, OW, (long long)batch * OD)) {
+  if (halo_wanted(stride, OH, OW, (long long)batch * OD, true)) {
     convgen::HProblem h = {};
     h.batch = batch; h.tw = (OW + 7) / 8; h.th = (OH + 15) / 16; h.td = OD;
     h.N = out_channels; h.chunks = (in_channels + 31) / 32; h.nclass = 1;
@@ -359,11 +359,11 @@ extern "C" int conv3d_gen_forward(void *stream, const float *x, const float *w, 
         }
     }
     const int bn = choose_bn(out_channels);
-    const int smem = h_plan_smem(h, bn, true);
+    const int smem = h_plan_smem(h, bn);
     if (smem > 0) {
       if ((rc = make_vol_map(&h.tmD[0], y, vy, 1, 0, 0, 0, 8, 4, 1, false, false))) return rc;
       if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, bn, false, h.tps))) return rc;
-      return dispatch_h<false>(reinterpret_cast<cudaStream_t>(stream), bn, h, bias, smem, stride == 1 ? 1 : 0);
+      return dispatch_h<false>(reinterpret_cast<cudaStream_t>(stream), bn, h, bias, smem, stride == 1 ? 1 : 3);
     }
   }
   convgen::Problem p = {};
@@ -451,7 +451,7 @@ extern "C" int conv3d_gen_dgrad(void *stream, const float *dy, const float *w, i
       }
     }
     const int bn = choose_bn(in_channels);
-    const int smem = h_plan_smem(h, bn, true);
+    const int smem = h_plan_smem(h, bn);
     if (smem > 0) {
       if ((rc = make_weight_map(&h.tmB, w, in_channels, out_channels, 32, true))) return rc;
       return dispatch_h<true>(reinterpret_cast<cudaStream_t>(stream), bn, h, nullptr, smem, stride == 1 ? 2 : 0);

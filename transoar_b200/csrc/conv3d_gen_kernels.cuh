@@ -7,7 +7,7 @@
 //
 // Implicit GEMM, no im2col copy anywhere:
 //
-//   forward / input gradient ("K-major" kernel, conv_kmajor_kernel)
+//   forward / input gradient, per-tap kernel (conv_kmajor_kernel) -- the coarse pyramid levels and stride 2
 //     D[v, n] = sum over steps s, reduction channels r of  A_s[v + delta_s, r] * B[tap_s][n][r]      (+ bias[n])
 //     A tile of 128 output voxels is a BW x BH x BD box of the volume.  One K-step = one tap and one chunk of 32 reduction channels:
 //     ONE 5-D TMA box (32 channels, BW, BH, BD, 1) at the tile origin shifted by the tap brings the 128 x 32 A operand (rows of 128 bytes,
@@ -18,18 +18,17 @@
 //     Stride 2 without element strides: the eight parity classes of a volume (even / odd index per axis) are eight plain 5-D tensors with
 //     doubled strides.  Forward: tap k reads class (k + 1) % 2 at index o + (k == 0 ? -1 : 0) per axis.  Input gradient: the inputs of
 //     parity class p receive dx[2 j + p] = sum over the taps with k = 1 (p = 0) or k in {0, 2} (p = 1) per axis of dy[j + (k == 0)] W[k]:
-//     eight stride-1 problems on the dy grid with 1 / 2 / 4 / 8 taps, each stored through the tensor map of ITS class of dx.
+//     eight stride-1 problems on the dy grid with 1 / 2 / 4 / 8 taps, each stored through the tensor map of ITS class of dx -- or, for narrow
+//     layers, ONE problem whose N extent is the eight classes side by side (fold_cip: 8 wide K-steps instead of 27 narrow ones).
+//     Few-tile layers split the (tap, chunk) loop over the idle SMs; the copy engine adds the partial tiles (cp.reduce.async.bulk.tensor).
 //     The epilogue writes with 5-D bulk tensor stores (one per 32-voxel x 32-channel chunk), which also clip ragged volumes / channels.
 //
-//   weight gradient (conv_wgrad_kernel)
-//     dW[co][tap][ci] = sum over output voxels v of dy[v][co] * x[stride * v + tap - 1][ci]
-//     The reduction index is the voxel, so both operands are MN-major (channels contiguous): 32-voxel x 32-channel slabs in the 128-byte
-//     swizzle / 32-byte atom form, each ONE 5-D TMA box.  The M extent of a tile is four x slabs = four (tap, ci-chunk) pairs -- so narrow
-//     layers (24 / 48 channels) still fill the 128 rows of the MMA with different taps --, the N extent is BN output channels of dy.
-//     Split over voxel ranges; partial tiles are added into the zero-initialised gradient with red.global.add.f32, already in the
-//     channels-last weight layout [CO][27][CI].
+//   forward / input gradient, halo kernel (conv_halo_kernel) -- stride 1 on volumes with >= 16 rows: see the comment at the kernel
+//   weight gradient (conv_wgrad_kernel): halo tiles, kw taps as overlapping MN-major slabs: see the comment at the kernel
 //
-// Roles, barriers, ring and TMEM double buffering are those of tc_gemm_kernels.cuh.
+// Roles, barriers, rings and TMEM double buffering are those of tc_gemm_kernels.cuh.  What bounds a NARROW implicit GEMM (N <= 128) is the
+// single issuing thread (a dependent instruction chain, ~5 clocks per instruction), not the tensor pipe (128 x N x 8 takes max(32 + N/4, N/2)
+// clocks in every operand layout) and not L2: profiles/r02_experiments.md section 8a.  Hence unrolled constant taps, tile pairs, class folding.
 #pragma once
 
 #include "tc_gemm_kernels.cuh"
@@ -173,11 +172,12 @@ conv_kmajor_kernel(const __grid_constant__ Problem p, const float *__restrict__ 
         mbar_wait(full(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-        const uint64_t da0 = smem_desc<false>(sa), db0 = smem_desc<B_MN>(sb);        // built once per stage; the k-steps are constant increments
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(acc, da0 + (uint64_t)(k * kstep_bytes<false>() >> 4), db0 + (uint64_t)(k * kstep_bytes<B_MN>() >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = smem_desc<false>(sa + k * kstep_bytes<false>()), db = smem_desc<B_MN>(sb + k * kstep_bytes<B_MN>());
+            umma_tf32(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(empty(stage));
         }
         __syncwarp();
@@ -296,7 +296,7 @@ __device__ __forceinline__ uint64_t desc_k_halo(uint32_t addr, uint32_t group_st
 
 // CH = independent accumulation chains: consecutive taps go to CH different accumulators (summed by the epilogue), so that consecutive
 // small-N MMAs do not wait for each other's accumulator
-// REG: 0 = table-driven taps (stride 2); 1 = stride-1 forward, 2 = stride-1 input gradient: the nine taps of a plane are compile-time
+// REG: 0 = table-driven taps; 1 = stride-1 forward, 2 = stride-1 input gradient, 3 = stride-2 forward: the nine taps of a plane are compile-time
 // constants and their 36 MMAs are issued from one unrolled block with constant descriptor increments -- the issuing warp executes a
 // dependent instruction chain at ~5 clocks per instruction, and a table-driven tap costs it ~350 clocks (profiles/r02_experiments.md)
 template <int BN> __host__ __device__ constexpr int halo_tps() { return BN <= 32 ? 9 : BN <= 128 ? 3 : 1; }
@@ -386,7 +386,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
 #pragma unroll
               for (int g = 0; g < 9 / TPS; ++g) {
                 // forward: taps pl * 9 + g * TPS ...; input gradient: plane pl holds kd = 2 - pl and its box rows run against the tap order
-                const int tap = REG == 1 ? pl * 9 + g * TPS : (TPS == 9 ? (2 - pl) * 9 : TPS == 3 ? (2 - pl) * 9 + (2 - g) * 3 : 26 - (pl * 9 + g));
+                const int tap = (REG == 1 || REG == 3) ? pl * 9 + g * TPS : (TPS == 9 ? (2 - pl) * 9 : TPS == 3 ? (2 - pl) * 9 + (2 - g) * 3 : 26 - (pl * 9 + g));
                 mbar_wait(bempty(bs), bph ^ 1u);
                 if (p.dbg & 4) { mbar_arrive(bfull(bs)); if (++bs == p.b_stages) { bs = 0; bph ^= 1u; } continue; }
                 mbar_expect_tx(bfull(bs), (uint32_t)B_BYTES);
@@ -445,6 +445,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
           if (REG != 0) {
             constexpr int TPS = halo_tps<BN>();
             const uint64_t da_plane = desc_k_halo(sa, LW * 128);
+            const uint64_t da_s2_9 = desc_k_halo(sa, 9 * 128), da_s2_8 = desc_k_halo(sa, 8 * 128);      // REG 3: odd-w / even-w class boxes
             const uint32_t first_plane = (c == 0 && pl == 0) ? 1u : 0u;
 #pragma unroll
             for (int g = 0; g < 9 / TPS; ++g) {
@@ -455,10 +456,23 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
                 if (!(p.dbg & 1)) {
 #pragma unroll
                   for (int j = 0; j < TPS; ++j) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int t = g * TPS + j;                                 // box rows (jh, jw) = (t / 3, t % 3): compile-time after unrolling
-                    const int slot = REG == 1 ? j : TPS - 1 - j;
+                    const int slot = (REG == 1 || REG == 3) ? j : TPS - 1 - j;
                     const uint32_t later = (t >= CH) ? 1u : (first_plane ^ 1u);
+                    if (REG == 3) {
+                      // stride-2 forward: tap (kh, kw) = (t / 3, t % 3) reads the (h, w) parity-class box (kh != 1, kw != 1) of the plane stage --
+                      // boxes (odd, odd) 9 x 17 rows, (odd, even) 8 x 17, (even, odd) 9 x 16, (even, even) 8 x 16 at 1 KB-aligned offsets --
+                      // one line further for kh = 2, one row further for kw = 2
+                      constexpr int kOff[4] = {0, 20480, 37888, 56320};
+                      const int kh = t / 3, kw = t % 3;
+                      const int box = (kh != 1 ? 0 : 2) + (kw != 1 ? 0 : 1), lw = kw != 1 ? 9 : 8;
+                      const uint32_t a_off = (uint32_t)(kOff[box] + ((kh == 2 ? lw : 0) + (kw == 2 ? 1 : 0)) * 128);
+                      const uint32_t acc = acc0 + (uint32_t)((t % CH) * BN);
+#pragma unroll
+                      for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_tf32(acc, (kw != 1 ? da_s2_9 : da_s2_8) + (uint64_t)((a_off + k * 32) >> 4),
+                                  db_stage + (uint64_t)((slot * B_TAP_BYTES + k * (int)kstep_bytes<B_MN>()) >> 4), idesc, later | (uint32_t)(k > 0));
+                    } else {
 #pragma unroll
                     for (int hf = 0; hf < T; ++hf) {                           // the tile pair: same weights, A rows 8 voxels further
                       const uint32_t a_off = (uint32_t)(((t / 3) * LW + (t % 3) + 8 * hf) * 128);
@@ -467,6 +481,7 @@ conv_halo_kernel(const __grid_constant__ HProblem p, const float *__restrict__ b
                       for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_tf32(acc, da_plane + (uint64_t)((a_off + k * 32) >> 4), db_stage + (uint64_t)((slot * B_TAP_BYTES + k * (int)kstep_bytes<B_MN>()) >> 4),
                                   idesc, later | (uint32_t)(k > 0));
+                    }
                     }
                   }
                 }
@@ -747,7 +762,6 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
 #pragma unroll
               for (int line = 0; line < kWLines; ++line) {
                 const int h = line & (BH - 1), d = line >> BHL;
-                constexpr int dummy = 0; (void)dummy;
                 umma_tf32(acc, da_stage + (uint64_t)((G::off(G::gbox(g)) + (d * G::lh(G::gbox(g)) + h + G::goh(g)) * G::lw(G::gbox(g)) * 128) >> 4),
                           db0 + (uint64_t)(line * 8 * 128 >> 4), idesc, (kb > kb0 || line > 0) ? 1u : 0u);
               }
