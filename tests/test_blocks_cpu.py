@@ -37,3 +37,30 @@ def test_refine_block_state_dict_is_checkpoint_compatible():
     assert float(attn.sampling_offsets.weight.detach().abs().max()) == 0.0
     assert float(attn.attention_weights.weight.detach().abs().max()) == 0.0
     assert float(attn.value_proj.bias.detach().abs().max()) == 0.0
+
+
+def test_folded_stride2_weights_reproduce_the_input_gradient():
+    """transoar_b200.conv3d_gen.fold_stride2_weights (the weight layout of include/conv3d_gen.h::conv3d_gen_dgrad_s2_folded): summing, for every
+    parity class of dx, the eight 2x2x2 neighbours of dy against the folded blocks must equal torch's conv3d_input for stride 2."""
+    import torch
+    from transoar_b200.conv3d_gen import fold_stride2_weights
+    co, ci, (N, D, H, W) = 5, 3, (1, 5, 4, 7)
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(co, ci, 3, 3, 3, generator=g, dtype=torch.float64)
+    od, oh, ow = (D + 1) // 2, (H + 1) // 2, (W + 1) // 2
+    dy = torch.randn(N, co, od, oh, ow, generator=g, dtype=torch.float64)
+    wf = fold_stride2_weights(w.permute(2, 3, 4, 0, 1).reshape(27, co, ci).contiguous())          # [8, 8 * 32, co]
+    assert wf.shape == (8, 8 * 32, co)
+    dyp = torch.nn.functional.pad(dy, (0, 1, 0, 1, 0, 1))
+    dx = torch.zeros(N, ci, D, H, W, dtype=torch.float64)
+    for cls in range(8):
+        pd, ph, pw = (cls >> 2) & 1, (cls >> 1) & 1, cls & 1
+        blocks = wf[:, cls * 32:cls * 32 + ci]                                                  # [8 deltas, ci, co]
+        for delta in range(8):
+            dd, dh, dw = (delta >> 2) & 1, (delta >> 1) & 1, delta & 1
+            contrib = torch.einsum("ic,ncdhw->nidhw", blocks[delta], dyp[:, :, dd:dd + od, dh:dh + oh, dw:dw + ow])
+            tgt = dx[:, :, pd::2, ph::2, pw::2]
+            tgt += contrib[:, :, :tgt.shape[2], :tgt.shape[3], :tgt.shape[4]]
+        assert float(wf[:, cls * 32 + ci:(cls + 1) * 32].abs().max()) == 0.0                       # channel padding is zero
+    ref = torch.nn.grad.conv3d_input((N, ci, D, H, W), w, dy, stride=2, padding=1)
+    assert float((dx - ref).abs().max()) < 1e-12
