@@ -660,7 +660,8 @@ def run_other_workload(args):
               "config": {"workload": args.workload, "volume": "x".join(map(str, wl["volume"])), "batch_per_gpu": BATCH, "what": wl["what"],
                          "step": "forward + matcher + losses + backward + AdamW; nothing skipped",
                          "precision": "torch.autocast(bfloat16): bf16 tcgen05 GEMMs (kind::f16) for every Linear, bf16 `value` into the msda3d kernels with fp32 "
-                                      "locations / weights, bf16 NDHWC InstanceNorm kernels, cuDNN bf16 convolutions; fp32 master weights and optimiser",
+                                      "locations / weights; the convolutional backbone stays on this library's fp32-storage / TF32-multiply tcgen05 convolutions and fp32 "
+                                      "InstanceNorm kernels (higher precision than bf16; no cuDNN launch); fp32 master weights and optimiser",
                          "l2": "activations of hundreds of MB per tensor: far larger than the 126 MB L2; no explicit flush",
                          "execution": "CUDA graph replay" if use_graph else "eager launches",
                          "parallelism": "volumes sharded over ranks; one NCCL gradient all-reduce per step"},

@@ -22,6 +22,15 @@ from .stem_conv import stem_conv3d, stem_eligible
 from .swin import ConvPatchMerging, EncoderSwinBlock, PatchMerging
 
 
+def _tf32_backbone_under_autocast(conv, x):
+    """Inside a bf16 autocast region (the reference's trainer runs the model under autocast, trainer.py:67-69) a channels-last CUDA model keeps
+    its convolutional backbone on this library's fp32-storage / TF32-multiply kernels: autocast would hand the convolutions to cuDNN in bf16,
+    which this library has no kernels for -- TF32 is the HIGHER precision (10 mantissa bits against 7), so the 1e-2 bf16 parity bound holds a
+    fortiori.  The transformer parts (every Linear, the op, the attention kernels) stay on their bf16 routes."""
+    return (torch.is_autocast_enabled() and x.is_cuda and torch.backends.cudnn.allow_tf32 and conv.weight.dtype == torch.float32
+            and conv.weight.is_contiguous(memory_format=torch.channels_last_3d) and not conv.weight.is_contiguous())
+
+
 class EncoderCnnBlock(nn.Module):
     """(Conv3d no-bias -> InstanceNorm3d(affine) -> ReLU) x 2; the first conv carries the stride (encoder_blocks.py:14-54)."""
 
@@ -34,6 +43,12 @@ class EncoderCnnBlock(nn.Module):
         self._block = nn.Sequential(*layers)
 
     def forward(self, x):
+        if _tf32_backbone_under_autocast(self._block[3], x):
+            with torch.autocast(device_type="cuda", enabled=False):
+                return self._forward(x.float())
+        return self._forward(x)
+
+    def _forward(self, x):
         # same Sequential (so the reference's parameter names are kept), but each InstanceNorm3d -> ReLU pair runs as one
         # fused sm_100a kernel (transoar_b200/instnorm.py) instead of cuDNN batch-norm + an elementwise ReLU
         conv1, norm1, _, conv2, norm2, _ = self._block
@@ -130,6 +145,18 @@ class Decoder(nn.Module):
 
     def forward(self, x):
         feats = list(x.values())[-self._lateral_levels:]
+        if _tf32_backbone_under_autocast(self._out[0], feats[0]):
+            with torch.autocast(device_type="cuda", enabled=False):
+                outputs = self._fpn([f.float() for f in feats])
+        else:
+            outputs = self._fpn(feats)
+        if self._refine_fmaps:
+            fmaps = [outputs[name] for name in self._refine_feature_levels]
+            refined = self._refine(fmaps, [self._pos_enc(f) for f in fmaps])
+            outputs.update(zip(self._refine_feature_levels, refined))
+        return outputs
+
+    def _fpn(self, feats):
         # channels-last model: lateral 1x1 convolutions and the k = s = 2 transposed convolutions are GEMMs over the NDHWC rows (include/tc_gemm.h),
         # the 3x3x3 output convolutions run on the general tcgen05 kernel (include/conv3d_gen.h); otherwise the library modules
         own = self._out[0].weight.is_contiguous(memory_format=torch.channels_last_3d) and not self._out[0].weight.is_contiguous()
@@ -152,10 +179,6 @@ class Decoder(nn.Module):
             pairs = zip(fine_first, self._required_stages)                                # :124 (positional pairing, as the reference)
         outputs = {"P" + str(stage): conv3d_k3_gen(f, self._out[i].weight, self._out[i].bias, 1) if own and conv_gen_eligible(self._out[i], f)
                    else self._out[i](f) for i, (f, stage) in enumerate(pairs)}
-        if self._refine_fmaps:
-            fmaps = [outputs[name] for name in self._refine_feature_levels]
-            refined = self._refine(fmaps, [self._pos_enc(f) for f in fmaps])
-            outputs.update(zip(self._refine_feature_levels, refined))
         return outputs
 
 
