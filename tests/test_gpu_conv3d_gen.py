@@ -38,7 +38,9 @@ def _ints(g, lo, hi, shape):
 # (N, D, H, W), CI, CO: the model's channel pairs, ragged volumes, odd extents (stride 2 parity classes of unequal size),
 # one case with more tiles than SMs (persistent loop), one with several column tiles (CO = 384) and one with ragged channel chunks (40 / 72)
 CASES = [((1, 4, 8, 16), 24, 48), ((1, 3, 37, 21), 24, 48), ((1, 2, 33, 10), 96, 40), ((2, 5, 7, 9), 48, 48), ((1, 6, 10, 12), 48, 96), ((1, 3, 5, 8), 96, 384), ((1, 5, 5, 8), 384, 192),
-         ((1, 3, 6, 7), 40, 72), ((1, 20, 40, 64), 48, 48), ((2, 2, 3, 2), 768, 768)]
+         ((1, 3, 6, 7), 40, 72), ((1, 20, 40, 64), 48, 48), ((2, 2, 3, 2), 768, 768),
+         # edges: the smallest channel counts, a single voxel row / column, more samples than the model uses, a volume of one 16 x 16 tile pair
+         ((3, 2, 2, 2), 4, 4), ((1, 2, 2, 17), 8, 12), ((4, 3, 16, 16), 24, 24), ((1, 2, 40, 8), 100, 36)]
 
 
 @pytest.fixture(params=["auto", "tap", "halo"])
