@@ -575,6 +575,7 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
     if (best < 0) return MSDA3D_EINVAL;
   }
   p.stage_bytes = p.dy_off + p.BN / 32 * convgen::kWDyChunkBytes;
+  p.dbg = g_hdbg.load();
   p.stages = (227 * 1024 - 1024 - 256) / p.stage_bytes;
   if (p.stages > convgen::kWMaxStages) p.stages = convgen::kWMaxStages;
   const int smem = p.stages * p.stage_bytes + 1024 + 256;
@@ -661,12 +662,15 @@ extern "C" int conv3d_gen_debug_k_probe(void *stream, const float *X, const floa
 // experiments only (tools/probe_mma_rate.py): see mma_rate_probe_kernel
 extern "C" int conv3d_gen_debug_mma_rate(void *stream, int layout, int n, int iters, long long *out_clocks)
 {
+  // layout bits 0-1: operand layout; bits 4-7: rotate over this many different operand tiles (0 = always the same tile)
+  const int rotate = ((layout >> 4) & 15) >= 2 ? 4 : 1;
+  layout &= 15;
   if (!out_clocks || layout < 0 || layout > 2 || n < 16 || n > 256 || n % 16 || iters < 1) return MSDA3D_EINVAL;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] { err = cudaFuncSetAttribute(convgen::mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024); });
   if (err != cudaSuccess) return (int)err;
-  convgen::mma_rate_probe_kernel<<<1, 128, 66 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(layout, n, iters, out_clocks);
+  convgen::mma_rate_probe_kernel<<<1, 128, 66 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(layout, n, iters, out_clocks, rotate);
   ++g_msda3d_launches;
   return (int)cudaGetLastError();
 }

@@ -629,6 +629,7 @@ struct WProblem {
   int nbox, ngroups;
   int kd_cls[3], kd_off[3];       // tap kd reads d-class kd_cls at d0 + kd_off
   int x_bytes, dy_off, stage_bytes, stages;
+  int dbg;                        // timing experiments (conv3d_gen_set_path bits 3-5): 1 = no MMAs, 2 = no loads, 4 = no reductions
   float *dw;                      // [CO][27][CI], zero-initialised
   WBox boxes[kWMaxBoxes];
   WGroup groups[kWMaxGroups];
@@ -712,6 +713,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
           const int d0 = (int)(t % p.td) * p.BD; t /= p.td;
           const int n = (int)t;
           mbar_wait(empty(stage), phase ^ 1u);
+          if (p.dbg & 2) { mbar_arrive(full(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(full(stage), (uint32_t)(p.x_bytes + ndy * kWDyChunkBytes));
           const uint32_t sb = base + stage * p.stage_bytes;
           for (int b = 0; b < p.nbox; ++b) {
@@ -739,6 +741,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
         tc_fence_after();
         const uint32_t sb = base + stage * p.stage_bytes;
         if (elect_one()) {
+          if (!(p.dbg & 1)) {
           const uint64_t db0 = desc_mn(sb + p.dy_off, kWDyChunkBytes);
           constexpr int BH = 1 << BHL;
           if (GEO == 1) {
@@ -779,6 +782,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
               umma_tf32(acc, da0 + (uint64_t)(d * step_d + h * step_h), db0 + (uint64_t)(line * 8 * 128 >> 4), idesc, (kb > kb0 || line > 0) ? 1u : 0u);
             }
           }
+          }
           umma_commit(empty(stage));
         }
         __syncwarp();
@@ -808,7 +812,7 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
           float *dst = p.dw + ((long long)co0 * 27 + tap) * p.CI + ci;           // lanes = consecutive ci: coalesced reductions
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (co0 + j < p.CO && ci < p.CI) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * 27 * p.CI), "f"(v[j]) : "memory");
+            if (co0 + j < p.CO && ci < p.CI && !(p.dbg & 4)) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * 27 * p.CI), "f"(v[j]) : "memory");
         }
       }
       tc_fence_before();
@@ -880,7 +884,7 @@ static __global__ void __launch_bounds__(128) k_sw128_probe_kernel(const float *
 // bytes of each), 1 = K-major 32-byte swizzle (rows of 32 bytes: a 128 x 8 operand is 4 KB contiguous), 2 = MN-major (128-byte swizzle, 32-byte
 // atoms).  The operands are zeros; `iters` MMAs accumulate into one TMEM tile; out[0] = clocks from the first issue to the commit's arrival.
 // ---------------------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(128) mma_rate_probe_kernel(int layout, int N, int iters, long long *out)
+static __global__ void __launch_bounds__(128) mma_rate_probe_kernel(int layout, int N, int iters, long long *out, int rotate)
 {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -915,7 +919,11 @@ static __global__ void __launch_bounds__(128) mma_rate_probe_kernel(int layout, 
     }
     const long long t0 = clock64();
     if (elect_one()) {
-      for (int i = 0; i < iters; ++i) umma_tf32(tm, da, db, idesc, i > 0 ? 1u : 0u);
+      // rotate > 1: consecutive MMAs read `rotate` different operand tiles (4 KB apart) instead of the same one
+      for (int i = 0; i < iters; ++i) {
+        const uint64_t sh = (uint64_t)((i & (rotate - 1)) * (4096 >> 4));       // rotate is a power of two (1 = always the same tile)
+        umma_tf32(tm, da + sh, db + sh, idesc, i > 0 ? 1u : 0u);
+      }
       umma_commit(smem_u32(&bar));
     }
     __syncwarp();
