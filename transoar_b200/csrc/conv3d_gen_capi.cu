@@ -220,10 +220,17 @@ bool halo_wanted(int stride, int rows_h, int rows_w, long long planes, bool forw
 int choose_ksplit(long long items, int ksteps)
 {
   if (items >= sm_count()) return 1;
-  long long ks = sm_count() / items;
+  // the split with the shortest makespan: rounds of work items on the persistent CTAs x (K-steps per item + its fixed cost, ~6 K-steps
+  // for the accumulator hand-over and the stores)
+  const long long sms = sm_count();
   const int cap = ksteps / 8 > 0 ? ksteps / 8 : 1;
-  if (ks > cap) ks = cap;
-  return ks < 1 ? 1 : (int)ks;
+  long long best = -1;
+  int best_ks = 1;
+  for (int ks = 1; ks <= cap; ++ks) {
+    const long long per = (ksteps + ks - 1) / ks, rounds = (items * ks + sms - 1) / sms, span = rounds * (per + 6);
+    if (best < 0 || span < best) { best = span; best_ks = ks; }
+  }
+  return best_ks;
 }
 
 // tile pairs (two 8 x 16 tiles side by side in w sharing the weight blocks): stride 1, narrow column tiles, W a multiple of 16
@@ -581,11 +588,21 @@ extern "C" int conv3d_gen_wgrad(void *stream, const float *x, const float *dy, i
   const int smem = p.stages * p.stage_bytes + 1024 + 256;
   const long long kblocks = (long long)batch * p.td * p.th * p.tw;
   const long long per_split = 3LL * p.chunks * p.n_tiles;
-  long long splits = (2LL * sm_count() + per_split - 1) / per_split;
-  if (splits > kblocks) splits = kblocks;
-  if (splits < 1) splits = 1;
-  p.kb_per_split = (kblocks + splits - 1) / splits;
-  p.splits = (int)((kblocks + p.kb_per_split - 1) / p.kb_per_split);
+  // voxel-range splits: the persistent CTAs take work items round robin, so the kernel lasts ceil(items / SMs) rounds of kb_per_split
+  // K-blocks -- pick the split count with the shortest makespan (300 items on 148 SMs is three rounds for four CTAs: 33 % tail)
+  {
+    const long long sms = sm_count();
+    long long best_span = -1, best_s = 1;
+    const long long s_max = kblocks < (8 * sms) / per_split + 1 ? kblocks : (8 * sms) / per_split + 1;
+    for (long long s = 1; s <= s_max; ++s) {
+      const long long kbps = (kblocks + s - 1) / s, actual = (kblocks + kbps - 1) / kbps;
+      const long long rounds = (per_split * actual + sms - 1) / sms;
+      const long long span = rounds * (kbps + 2);                          // + the epilogue of a work item, in K-block units
+      if (best_span < 0 || span < best_span) { best_span = span; best_s = s; }
+    }
+    p.kb_per_split = (kblocks + best_s - 1) / best_s;
+    p.splits = (int)((kblocks + p.kb_per_split - 1) / p.kb_per_split);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)out_channels * 27 * in_channels * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;

@@ -706,12 +706,16 @@ conv_wgrad_kernel(const __grid_constant__ WProblem p)
         const int r = (int)(w % per_split), sp = (int)(w / per_split);
         const int kd = r % 3, ch = (r / 3) % p.chunks, nt = r / (3 * p.chunks);
         const long long kb0 = sp * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+        // block coordinates: divided out once per work item, then counted up (this thread's loop is on the critical path and a 64-bit
+        // division costs it ~500 clocks)
+        long long t0 = kb0;
+        int iw = (int)(t0 % p.tw); t0 /= p.tw;
+        int ih = (int)(t0 % p.th); t0 /= p.th;
+        int id = (int)(t0 % p.td);
+        int in = (int)(t0 / p.td);
         for (long long kb = kb0; kb < kb1; ++kb) {
-          long long t = kb;
-          const int w0 = (int)(t % p.tw) * 8; t /= p.tw;
-          const int h0 = (int)(t % p.th) * p.BH; t /= p.th;
-          const int d0 = (int)(t % p.td) * p.BD; t /= p.td;
-          const int n = (int)t;
+          const int w0 = iw * 8, h0 = ih * p.BH, d0 = id * p.BD, n = in;
+          if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
           mbar_wait(empty(stage), phase ^ 1u);
           if (p.dbg & 2) { mbar_arrive(full(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(full(stage), (uint32_t)(p.x_bytes + ndy * kWDyChunkBytes));
