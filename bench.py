@@ -823,17 +823,25 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 10))
+        def e2e_step(i):
+            # what a training loop with a data loader does: launch the step, start the NEXT batch's host -> device copy (it runs under
+            # this step's kernels), then block on this step's loss.  Every step copies its 52 MB from pinned host memory and reads its loss.
+            loss = ts.step(vols_host[i % n_sets], targets[i % n_sets])
+            ts.prefetch(vols_host[(i + 1) % n_sets])
+            return float(loss.item())
         for i in range(2):
-            float(ts.step(vols_host[i % n_sets], targets[i % n_sets]).item())
+            e2e_step(i)
         fence()
         t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            float(ts.step(vols_host[i % n_sets], targets[i % n_sets]).item())
+        for i in range(2, 2 + e2e_steps):
+            e2e_step(i)
         fence()
         dt = reduce_max(time.perf_counter() - t0)
         e2e = {"value": world * BATCH * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": vols_host[0].numel() * 4, "d2h_bytes_per_step": 4,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-               "api": "transoar_b200.engine.TrainStep.step(volumes_in_pinned_host_memory, targets) -> loss; float(loss) on the host every step"}
+               "api": "loss = TrainStep.step(volumes_in_pinned_host_memory, targets); TrainStep.prefetch(next_volumes_in_pinned_host_memory); "
+                      "float(loss) on the host every step -- every step's volumes cross PCIe inside the timed region, the copy of step i + 1 "
+                      "overlapping the kernels of step i"}
     params = sum(p.numel() for p in ts.net.parameters())
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     del ts, vols_dev, vols_host

@@ -107,3 +107,32 @@ def test_graph_step_follows_the_eager_step():
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
         torch.cuda.empty_cache()
+
+
+def test_prefetched_volumes_reach_the_step_unchanged():
+    """engine.TrainStep.prefetch: the next step's host -> device copy on a copy stream.  The step that follows must see exactly the
+    prefetched host tensor (and an un-prefetched tensor must still be copied in line), in graph mode where the captured graph reads one
+    fixed device buffer."""
+    from transoar_b200.engine import TrainStep, synthetic_targets, visceral_train_config
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        shape = (64, 64, 128)
+        cfg = visceral_train_config()
+        cfg["neck_input_shape"] = tuple(s // 4 for s in shape)
+        torch.manual_seed(0)
+        ts = TrainStep(cfg, DEV, cudnn_autotune=False, graph=True, graph_warmup=1)
+        gen = torch.Generator().manual_seed(5)
+        xs = [torch.rand(1, 1, *shape, generator=gen).pin_memory() for _ in range(3)]
+        tg = synthetic_targets(cfg, 1, 0, DEV)
+        for i in range(5):
+            loss = ts.step(xs[i % 3], tg)
+            torch.cuda.synchronize()
+            assert torch.equal(ts._staging.cpu(), xs[i % 3]), f"step {i} ran on other volumes"
+            if i != 2:                                   # step 3 arrives without a prefetch: copied in line
+                ts.prefetch(xs[(i + 1) % 3])
+            assert float(loss) == float(loss) and float(loss) > 0
+        assert ts._cuda_graph is not None
+        ts.close()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
+        torch.cuda.empty_cache()

@@ -255,18 +255,46 @@ class TrainStep:
         self.optim = torch.optim.AdamW(groups, lr=float(config["lr_backbone"]), weight_decay=float(config["weight_decay"]),
                                        capturable=self.graph, fused=True)
         self._staging = None
+        self._copy_stream = self._prefetch_buf = self._prefetch_done = self._prefetch_read = self._prefetch_src = None
         self._cuda_graph, self._seen, self._static = None, 0, None
         self._stream = torch.cuda.Stream(self.device) if self.graph else None
 
+    def prefetch(self, volumes):
+        """Start the host -> device copy of the NEXT step's volumes (pinned host memory) on a copy stream, so that it runs under the
+        current step's kernels instead of in front of the next step.  Call it after ``step`` and before reading the loss; the next
+        ``step`` must be given the same host tensor.  Optional: a ``step`` without a matching prefetch copies in line as before."""
+        if volumes.is_cuda:
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        if self._prefetch_buf is None or self._prefetch_buf.shape != volumes.shape:
+            self._prefetch_buf = torch.empty(volumes.shape, dtype=torch.float32, device=self.device)
+        if self._prefetch_read is not None:
+            self._copy_stream.wait_event(self._prefetch_read)         # the previous step's device-side copy has read the buffer
+        with torch.cuda.stream(self._copy_stream):
+            self._prefetch_buf.copy_(volumes, non_blocking=True)
+            self._prefetch_done = torch.cuda.Event()
+            self._prefetch_done.record(self._copy_stream)
+        self._prefetch_src = (volumes.data_ptr(), tuple(volumes.shape))
+
     def to_device(self, volumes):
-        """Host volumes (ideally pinned) -> a reused device buffer, asynchronously on the current stream."""
+        """Host volumes (ideally pinned) -> a reused device buffer, asynchronously on the current stream (or, if ``prefetch`` was called
+        for this host tensor, a device-to-device copy of the already transferred volumes)."""
         if volumes.is_cuda and not self.graph:
             return volumes
         if self._staging is None or self._staging.shape != volumes.shape:
             self._staging = torch.empty(volumes.shape, dtype=torch.float32, device=self.device)
             self._cuda_graph = None                                   # a graph captured for another shape is void
         if volumes.data_ptr() != self._staging.data_ptr():
-            self._staging.copy_(volumes, non_blocking=True)
+            if self._prefetch_src == (volumes.data_ptr(), tuple(volumes.shape)):
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(self._prefetch_done)
+                self._staging.copy_(self._prefetch_buf, non_blocking=True)
+                self._prefetch_read = torch.cuda.Event()
+                self._prefetch_read.record(cur)
+                self._prefetch_src = None
+            else:
+                self._staging.copy_(volumes, non_blocking=True)
         return self._staging
 
     def invalidate_graph(self):
