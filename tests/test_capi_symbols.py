@@ -16,7 +16,7 @@ def _declared():
     for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names |= set(re.findall(r"\b((?:msda3d|roi_attn|win_attn|instnorm|tc_gemm|tc_colsum|stem_conv3d|conv3d_tc|conv3d_gen|fused_ln|hash_rng)(?:_[a-z0-9_]+)?)\s*\(", text))
+        names |= set(re.findall(r"\b((?:msda3d|roi_attn|win_attn|instnorm|tc_gemm|tc_colsum|stem_conv3d|conv3d_tc|conv3d_gen|criterion|fused_ln|hash_rng)(?:_[a-z0-9_]+)?)\s*\(", text))
     return sorted(names)
 
 

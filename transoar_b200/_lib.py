@@ -68,6 +68,9 @@ _SIGNATURES = {
     "conv3d_gen_set_path": (None, [_ci]),
     "conv3d_gen_debug_mma_rate": (_ci, [_vp, _ci, _ci, _ci, _vp]),
     "conv3d_gen_debug_k_probe": (_ci, [_vp] * 4 + [_ci] * 3),
+    # include/criterion.h
+    "criterion_fused_supported": (_ci, [_ci, _ci]),
+    "criterion_fused": (_ci, [_vp] * 7 + [_ci] * 4 + [ctypes.c_float] * 3 + [_vp] * 4),
     # include/fused_ln.h
     "fused_ln_workspace_floats": (ctypes.c_longlong, [_ci]),
     "fused_ln_forward": (_ci, [_vp] * 5 + [ctypes.c_longlong, _ci, ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong] + [_vp] * 4),

@@ -17,6 +17,8 @@ Behaviour kept from the reference on purpose:
 Differences: ``num_top_queries`` is fixed at 1 (the only value the reference's criterion ever passes); on exact cost ties the
 first query wins (the reference inherits whatever CPU ``topk`` returns); targets whose labels repeat inside a sample keep the
 last box (the reference keeps the last one in its dict too, matcher.py:34)."""
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -119,6 +121,43 @@ class SoftDiceLoss(nn.Module):
         return 1 - dc[1:].mean()
 
 
+class FusedCriterionFunction(torch.autograd.Function):
+    """Matcher + the three losses of every decoder layer + their gradients in ONE kernel launch (include/criterion.h).  Returns ``losses``
+    [3, L] (rows cls / bbox / giou; column 0 = final layer); gradients flow to the final layer's logits and boxes only -- the auxiliary
+    layers' logits feed the (non-differentiable) matcher alone, as in the reference (criterion.py:113-120)."""
+
+    @staticmethod
+    def forward(ctx, logits_layers, final_logits, final_boxes, anchors, tgt_boxes, tgt_valid, num_organs, cost_class, cost_bbox, cost_giou):
+        import ctypes
+        from . import _lib
+        L, B, Nq = logits_layers.shape
+        Q = Nq // num_organs
+        f32 = lambda t: t.detach().float().contiguous()
+        ll, fl, fb, an, tb = f32(logits_layers), f32(final_logits).reshape(B, Nq), f32(final_boxes), f32(anchors), f32(tgt_boxes)
+        tv = tgt_valid.to(torch.uint8).contiguous()
+        dev = fl.device
+        losses = torch.empty(3, L, dtype=torch.float32, device=dev)
+        g_logits = torch.empty(B, Nq, dtype=torch.float32, device=dev)
+        g_boxes = torch.empty(2, L, B, Nq, 6, dtype=torch.float32, device=dev)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            rc = _lib.lib().criterion_fused(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(ll), p(fl), p(fb), p(an), p(tb), p(tv), L, B,
+                                            num_organs, Q, float(cost_class), float(cost_bbox), float(cost_giou), p(losses), p(g_logits), p(g_boxes), None)
+        _lib.check(rc, "criterion_fused")
+        ctx.save_for_backward(g_logits, g_boxes)
+        ctx.shapes = (final_logits.shape, final_logits.dtype, final_boxes.dtype)
+        return losses
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g_logits, g_boxes = ctx.saved_tensors
+        shape, ldt, bdt = ctx.shapes
+        d_logits = (g_logits * g[0].sum()).reshape(shape).to(ldt) if ctx.needs_input_grad[1] else None
+        d_boxes = torch.einsum("kl,klbnd->bnd", g[1:], g_boxes).to(bdt) if ctx.needs_input_grad[2] else None
+        return None, d_logits, d_boxes, None, None, None, None, None, None, None
+
+
 class TransoarCriterion(nn.Module):
     """criterion.py:9-125.  ``forward(outputs, targets, seg_targets, anchors)`` -> the reference's loss dict."""
 
@@ -128,6 +167,17 @@ class TransoarCriterion(nn.Module):
         self._seg_proxy, self._seg_fg_bg = seg_proxy, seg_fg_bg
         if seg_proxy:
             self._dice_loss = SoftDiceLoss()
+
+    # the single-kernel route (include/criterion.h) on CUDA; False = the batched torch route (tests compare the two; TRANSOAR_B200_CRITERION=torch
+    # selects it for A/B timing)
+    fused = os.environ.get("TRANSOAR_B200_CRITERION", "fused") != "torch"
+
+    def _fused_ok(self, outputs, layers):
+        lg = outputs["pred_logits"]
+        if not (self.fused and lg.is_cuda and self.matcher.anchor_matching and not self._seg_proxy and self.matcher.num_organs == self.num_classes):
+            return False
+        from . import _lib
+        return lg.shape[1] % self.num_classes == 0 and bool(_lib.lib().criterion_fused_supported(lg.shape[1] // self.num_classes, len(layers)))
 
     def loss_class(self, outputs, soft_labels):
         """BCE-with-logits over the queries of the classes present in the sample (criterion.py:40-49).  ``soft_labels`` may carry a leading
@@ -149,8 +199,10 @@ class TransoarCriterion(nn.Module):
         matched = torch.gather(preds, -2, best[..., None, None].expand(*best.shape, 1, preds.shape[-1])).squeeze(-2)   # [(L,) B, O, 6]
         w = tgt_valid.float()
         loss_bbox = ((matched - tgt_boxes).abs().sum(-1) * w).sum((-2, -1)) / num_boxes
-        giou = paired_giou_3d(box_cxcyczwhd_to_xyzxyz(matched.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(tgt_boxes))
-        # classes absent from a sample have a zero target box (0/0 GIoU): mask them out before they can poison the sum
+        # classes absent from a sample have a zero target box (0/0 GIoU): give them a harmless stand-in box, so that neither the value nor --
+        # through `where`'s zero gradient times an infinite derivative -- the gradient can turn into NaN, then mask them out of the sum
+        safe_tgt = torch.where(tgt_valid[..., None], tgt_boxes, torch.full_like(tgt_boxes, 0.5))
+        giou = paired_giou_3d(box_cxcyczwhd_to_xyzxyz(matched.clamp(min=0)), box_cxcyczwhd_to_xyzxyz(safe_tgt))
         loss_giou = (torch.where(tgt_valid, 1 - giou, torch.zeros_like(giou))).sum((-2, -1)) / num_boxes
         return loss_bbox, loss_giou
 
@@ -167,6 +219,16 @@ class TransoarCriterion(nn.Module):
         # the final layer and the auxiliary layers in ONE pass (leading layer axis): the reference re-runs the matcher on every auxiliary
         # layer's logits but evaluates all losses on the FINAL layer's predictions (criterion.py:118-119 pass `outputs`, not `aux_outputs`)
         layers = [outputs] + list(outputs.get("aux_outputs", []))
+        if self._fused_ok(outputs, layers):
+            logits_layers = torch.stack([o["pred_logits"].detach() for o in layers]).squeeze(-1)
+            m = self.matcher
+            loss = FusedCriterionFunction.apply(logits_layers, outputs["pred_logits"], outputs["pred_boxes"], anchors, tgt_boxes, tgt_valid,
+                                                self.num_classes, m.cost_class, m.cost_bbox, m.cost_giou)
+            zero = torch.zeros((), device=dev)
+            losses = {"bbox": loss[1, 0], "giou": loss[2, 0], "cls": loss[0, 0], "segce": zero, "segdice": zero}
+            for i in range(len(layers) - 1):
+                losses[f"bbox_{i}"], losses[f"giou_{i}"], losses[f"cls_{i}"] = loss[1, i + 1], loss[2, i + 1], loss[0, i + 1]
+            return losses
         best, soft = self.matcher.match_layers(layers, tgt_boxes, tgt_valid, anchors)
         loss_bbox, loss_giou = self.loss_bboxes(outputs, tgt_boxes, tgt_valid, best, num_boxes)
         loss_cls = self.loss_class(outputs, soft)
