@@ -264,7 +264,7 @@ class FocusedDecoder(nn.Module):
     def forward(self, src, query_embed, pos):
         assert query_embed is not None
         src = src.flatten(2).transpose(1, 2).contiguous()          # a view + one plain copy when the backbone is channels-last
-        pos = pos.flatten(2).transpose(1, 2)
+        pos = pos[:1].flatten(2).transpose(1, 2)                    # the sine encoding is batch-independent: one copy, broadcast in src + pos
         bs, _, c = src.shape
         query_pos, tgt = torch.split(query_embed, c, dim=1)
         return self.decoder(tgt.unsqueeze(0).expand(bs, -1, -1), src, pos, query_pos.unsqueeze(0).expand(bs, -1, -1))

@@ -117,7 +117,9 @@ class DecoderDefAttnBlock(nn.Module):
             cached = self._level_cache[(shapes_py, dev)] = (ss, starts)
         spatial_shapes, level_start_index = cached
         src = torch.cat([f.flatten(2).transpose(1, 2) for f in fmaps], 1)                                  # [N, S, C]
-        pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[l].view(1, 1, -1)
+        # the sine encodings are the same for every sample of the batch: one copy [1, S, C], broadcast in `src + pos` (the reference carries
+        # N identical copies through the level-embedding addition and the concatenation, decoder_blocks.py:69-95)
+        pos = torch.cat([p[:1].flatten(2).transpose(1, 2) + self.level_embed[l].view(1, 1, -1)
                          for l, p in enumerate(pos_embeds)], 1)
         memory = self.refine_def_attn(src, spatial_shapes, level_start_index, pos, shapes_key=shapes_py)
         bs, c = fmaps[0].shape[:2]
