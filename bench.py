@@ -804,7 +804,7 @@ def main():
     peaks = load_peaks()
     peak = peaks["hbm_gbs"]
     fwd_avg, bwd_avg = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
-    roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_vec_kernel<float,16,1,3> + the cudaMemsetAsync zero-fill of grad_value "
+    roofline = {"bound": "hbm", "kernel": "msda3d backward: bwd_duo_kernel<FUSED=1> (two w-neighbouring queries per lane group) + the cudaMemsetAsync zero-fill of grad_value "
                                           f"({LAYERS} launches per step, the largest single kernel of the step)",
                 "achieved": bb / bwd_avg / 1e6, "peak": peak, "unit": "GB/s", "frac": bb / bwd_avg / 1e6 / peak,
                 "traffic": load_ncu_traffic("backward"), "peak_source": peaks["source"], "algorithmic_bytes": bb,

@@ -138,7 +138,12 @@ int msda3d_debug_indices(void *stream, int dtype, const int64_t *spatial_shapes,
  * MSDA3D_EINVAL.  "nv" = 0|1|2: 16-byte vectors per lane in the vector kernels (0 = automatic);  "grid_mult" = CTAs
  * per SM cap of the launch (0 = automatic);  "order" = 0 automatic | 1 linear | 2 brick unit order (brick needs
  * num_query == spatial_size);  "diag_bwd_skip_red" = 1 drops the grad_value reductions
- * (WRONG results; isolates their cost). */
+ * (WRONG results; isolates their cost);  "duo" = 1 (default) | 0: backward of fp32 / 64-channel / brick-order problems with two
+ * w-neighbouring queries per lane group sharing corner rows and reductions (bwd_duo_kernel) or the one-unit kernel;
+ * "rot" = 0 | 1 | 2 | 4 | 5 | 6: sample-order rotation per warp / per unit (+4: consecutive CTAs on different (batch, head)
+ * slabs) in the one-unit backward;  "duo_cfg" = 0 | 1 | 2: CTA shape of bwd_duo_kernel (256 x 2, 128 x 5, 128 x 6 per SM);
+ * "pair", "stage": earlier experiments.  The environment variable TRANSOAR_B200_TUNING="key=value,..."
+ * applies them when the python package loads the library. */
 int msda3d_set_tuning(const char *key, int value);
 
 /* Number of kernel launches this library has issued in the calling process (bench.py's gpu_launches). */

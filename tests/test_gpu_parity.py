@@ -500,3 +500,34 @@ def test_tma_staged_forward_experiment_is_bit_identical(ctas, widen):
     finally:
         lib.msda3d_set_tuning(b"stage", 0)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dist,jitter", [("B0", 0.0), ("B0", 0.05), ("B", 0.0), ("A", 0.0)])
+@pytest.mark.parametrize("widen", [False, True])
+def test_backward_pair_kernel_joint_and_single_paths(dist, jitter, widen):
+    """bwd_duo_kernel (two w-neighbouring queries per lane group; the default for fp32 / 64 channels / brick order): on the model's
+    sampling pattern (dist B0 = the untrained module's offsets, optionally with a small jitter) nearly every pair takes the joint
+    same-cell / adjacent-cell path, with dist A (uniform locations) nearly every pair takes the one-unit path.  All of them must match
+    the oracle to 1e-4, and grad_loc / grad_attn_weight must be BIT-identical to the one-unit kernel (msda3d_set_tuning("duo", 0)):
+    the pair kernel shares gathers and reductions, not arithmetic."""
+    g = synth.Geometry("duo", ((8, 8, 16), (4, 4, 8), (2, 2, 4), (1, 1, 2)), 6, 64, 4)       # brick order (queries = voxels), C = 64
+    x = synth.make_inputs(g, 2, dist, seed=23, device=DEV)
+    if jitter:
+        gen = torch.Generator().manual_seed(5)
+        norm = torch.tensor([[w, h, d] for d, h, w in g.shapes], dtype=torch.float32)
+        x["loc"] = (x["loc"].cpu() + jitter * torch.randn(x["loc"].shape, generator=gen) / norm[None, None, None, :, None, :]).to(DEV).contiguous()
+    if widen:
+        x["loc"] = (x["loc"] * 1.5 - 0.25).contiguous()
+    lib = _lib.lib()
+    n0 = lib.msda3d_launch_count()
+    gv, gl, ga = _run_bwd(x)
+    assert lib.msda3d_launch_count() == n0 + 1
+    _, wv, wl, wa = _oracle(x)
+    assert _relerr(_np(gv), wv) < 1e-4 and _relerr(_np(gl), wl) < 1e-4 and _relerr(_np(ga), wa) < 1e-4
+    assert lib.msda3d_set_tuning(b"duo", 0) == 0
+    try:
+        gv1, gl1, ga1 = _run_bwd(x)
+    finally:
+        lib.msda3d_set_tuning(b"duo", 1)
+    assert torch.equal(gl, gl1) and torch.equal(ga, ga1)
+    assert _relerr(_np(gv), _np(gv1)) < 2e-5

@@ -116,6 +116,11 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         if handle.msda3d_abi_version() != 1:
             raise RuntimeError("libmsda3d.so ABI version mismatch; rebuild it")
+        # experiment switches of include/msda3d.h (msda3d_set_tuning) from the environment, e.g. TRANSOAR_B200_TUNING="duo=0,rot=0"
+        for item in filter(None, os.environ.get("TRANSOAR_B200_TUNING", "").split(",")):
+            key, _, val = item.partition("=")
+            if handle.msda3d_set_tuning(key.strip().encode(), int(val)) != 0:
+                raise RuntimeError(f"TRANSOAR_B200_TUNING: unknown switch or value {item!r}")
         _lib = handle
     return _lib
 

@@ -58,6 +58,9 @@ std::atomic<int> g_tune_nv{0};          // 0 = automatic, 1 / 2 = forced (msda3d
 std::atomic<int> g_tune_grid_mult{0};   // 0 = automatic: CTAs per SM for the persistent grid
 std::atomic<int> g_tune_order{0};       // 0 = automatic (brick order when Lq == S), 1 = linear, 2 = brick
 std::atomic<int> g_tune_stage{0};       // experiment: forward with the coarsest level staged in shared memory by TMA bulk copies (2 / 3 / 4 = CTAs per SM)
+std::atomic<int> g_tune_rot{0};         // backward: sample-order rotation 1 = per warp, 2 = per unit; + 4 = consecutive CTAs on different (batch, head) slabs (kernels.cuh, ROT)
+std::atomic<int> g_tune_duo{1};         // backward with two w-neighbouring queries per lane group (kernels.cuh, bwd_duo_kernel): 1 = on (default), 0 = bwd_vec_kernel
+std::atomic<int> g_tune_duo_cfg{0};     // experiment: CTA shape of bwd_duo_kernel: 0 = 256 threads x 2 per SM, 1 = 128 x 5 (96 registers), 2 = 128 x 6 (80)
 std::atomic<int> g_tune_pair{0};        // 1 = pair-combining backward (kernels.cuh, PAIR) in brick order for 16-lane fp32 units; measured slower, off by default
 
 template <typename VT> bool vec_shape(int C, int &G, int &NV)
@@ -192,15 +195,33 @@ int backward_half_or_float(cudaStream_t st, const Dims &d, const void *gout, con
                                                                  d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d))
       if (skip == 2) MSDA3D_DIAG(2); else if (skip == 3) MSDA3D_DIAG(3); else MSDA3D_DIAG(4);
 #undef MSDA3D_DIAG
-    } else if (g_diag_skip_red.load()) {
+    } else if (g_diag_skip_red.load() && !(std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_duo.load() == 1)) {
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd, 1><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
                                 d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl, (float *)ga, use_brick(d)));
+    } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_duo.load() == 1 && skip <= 1) {
+      // two w-neighbouring queries per lane group share corner rows and reductions (kernels.cuh, bwd_duo_kernel)
+#define MSDA3D_DUO(R, SK)                                                                                                              \
+  bwd_duo_kernel<0, R, SK><<<grid, kThreads, 0, st>>>((const float *)gout, (const float *)value, shapes, starts, (const float *)loc,   \
+                                                      (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P, (float *)gv, (float *)gl,      \
+                                                      (float *)ga, nullptr, 0, 0, 0)
+      const int r = g_tune_rot.load();
+      if (skip == 1) MSDA3D_DUO(6, 1);
+      else if (r >= 5) MSDA3D_DUO(6, 0); else if (r == 4) MSDA3D_DUO(4, 0); else if (r >= 1) MSDA3D_DUO(2, 0); else MSDA3D_DUO(0, 0);
+#undef MSDA3D_DUO
     } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 1) {
       // w-neighbouring units of a warp combine their grad_value contributions before the reductions (kernels.cuh, PAIR)
       bwd_vec_kernel<float, 16, 1, 2, 0, 0, 1><<<grid, kThreads, 0, st>>>(
           (const float *)gout, (const float *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, d.P,
           (float *)gv, (float *)gl, (float *)ga, 1);
+    } else if (std::is_same<VT, float>::value && g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_rot.load() != 0) {
+      // the units of a CTA walk their samples in rotated order (kernels.cuh, ROT)
+#define MSDA3D_ROT(R)                                                                                                                     \
+  bwd_vec_kernel<float, 16, 1, 3, 0, 0, 0, R><<<grid, kThreads, 0, st>>>((const float *)gout, (const float *)value, shapes, starts,      \
+                                                                         (const float *)loc, (const float *)aw, d.N, d.S, d.M, d.L, d.Lq, \
+                                                                         d.P, (float *)gv, (float *)gl, (float *)ga, 1)
+      switch (g_tune_rot.load()) { case 1: MSDA3D_ROT(1); break; case 2: MSDA3D_ROT(2); break; case 4: MSDA3D_ROT(4); break; case 5: MSDA3D_ROT(5); break; default: MSDA3D_ROT(6); break; }
+#undef MSDA3D_ROT
     } else {
       VEC_DISPATCH(g_, nv_, bwd_vec_kernel<VT, G, NV, MinBlocks<VT, NV>::bwd><<<grid, kThreads, 0, st>>>(
                                 (const VT *)gout, (const VT *)value, shapes, starts, (const float *)loc, (const float *)aw, d.N,
@@ -233,6 +254,9 @@ int msda3d_set_tuning(const char *key, int value)
   if (k == "stage" && value >= 0 && value <= 4) { g_tune_stage = value; return MSDA3D_OK; }
   if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
   if (k == "pair" && value >= 0 && value <= 1) { g_tune_pair = value; return MSDA3D_OK; }
+  if (k == "duo" && value >= 0 && value <= 1) { g_tune_duo = value; return MSDA3D_OK; }
+  if (k == "duo_cfg" && value >= 0 && value <= 2) { g_tune_duo_cfg = value; return MSDA3D_OK; }
+  if (k == "rot" && value >= 0 && value <= 6 && value != 3) { g_tune_rot = value; return MSDA3D_OK; }
   return MSDA3D_EINVAL;
 }
 
@@ -403,11 +427,43 @@ int msda3d_backward_fused_ld(void *stream, const float *grad_output, const float
   if (e != cudaSuccess) return (int)e;
   const long long units = (long long)d.N * d.Lq * d.M, rb = ref_batch == 1 ? 0 : (long long)d.Lq * d.L * 3;
   const int grid = vec_grid(units, g_);
+  if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_duo.load() == 1) {
+#define MSDA3D_DUO(R, SK)                                                                                                                    \
+  bwd_duo_kernel<1, R, SK><<<grid, kThreads, 0, st>>>(grad_output, value, spatial_shapes, level_start_index, sampling_offsets,               \
+                                                      merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M, d.L, d.Lq, d.P, grad_value, \
+                                                      grad_sampling_offsets, merged_ld ? grad_sampling_offsets : grad_attn_logits,           \
+                                                      reference_points, rb, merged_ld, 3 * d.M * d.L * d.P)
+    const int r = g_tune_rot.load();
+    if (g_tune_duo_cfg.load() != 0) {                              // experiment: smaller CTAs, more resident warps
+      const int grid2 = vec_grid(units, 32);
+      auto kern = g_tune_duo_cfg.load() == 1 ? bwd_duo_kernel<1, 0, 0, 128, 5> : bwd_duo_kernel<1, 0, 0, 128, 6>;
+      if (g_diag_skip_red.load() == 1) kern = g_tune_duo_cfg.load() == 1 ? bwd_duo_kernel<1, 0, 1, 128, 5> : bwd_duo_kernel<1, 0, 1, 128, 6>;
+      kern<<<grid2, 128, 0, st>>>(grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits,
+                                  d.N, d.S, d.M, d.L, d.Lq, d.P, grad_value, grad_sampling_offsets,
+                                  merged_ld ? grad_sampling_offsets : grad_attn_logits, reference_points, rb, merged_ld, 3 * d.M * d.L * d.P);
+    } else
+    if (g_diag_skip_red.load() == 1) MSDA3D_DUO(6, 1);
+    else if (r >= 5) MSDA3D_DUO(6, 0); else if (r == 4) MSDA3D_DUO(4, 0); else if (r >= 1) MSDA3D_DUO(2, 0); else MSDA3D_DUO(0, 0);
+#undef MSDA3D_DUO
+    ++g_launches;
+    return (int)cudaGetLastError();
+  }
   if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_pair.load() == 1) {
     bwd_vec_kernel<float, 16, 1, 2, 0, 1, 1><<<grid, kThreads, 0, st>>>(
         grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M, d.L,
         d.Lq, d.P, grad_value, grad_sampling_offsets, merged_ld ? grad_sampling_offsets : grad_attn_logits, 1, reference_points, rb, merged_ld,
         3 * d.M * d.L * d.P);
+    ++g_launches;
+    return (int)cudaGetLastError();
+  }
+  if (g_ == 16 && nv_ == 1 && use_brick(d) && g_tune_rot.load() != 0) {
+#define MSDA3D_ROT(R)                                                                                                                         \
+  bwd_vec_kernel<float, 16, 1, 3, 0, 1, 0, R><<<grid, kThreads, 0, st>>>(                                                                    \
+      grad_output, value, spatial_shapes, level_start_index, sampling_offsets, merged_ld ? sampling_offsets : attn_logits, d.N, d.S, d.M, d.L, \
+      d.Lq, d.P, grad_value, grad_sampling_offsets, merged_ld ? grad_sampling_offsets : grad_attn_logits, 1, reference_points, rb, merged_ld,  \
+      3 * d.M * d.L * d.P)
+    switch (g_tune_rot.load()) { case 1: MSDA3D_ROT(1); break; case 2: MSDA3D_ROT(2); break; case 4: MSDA3D_ROT(4); break; case 5: MSDA3D_ROT(5); break; default: MSDA3D_ROT(6); break; }
+#undef MSDA3D_ROT
     ++g_launches;
     return (int)cudaGetLastError();
   }

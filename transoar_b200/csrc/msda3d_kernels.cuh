@@ -609,6 +609,34 @@ template <int G> __device__ __forceinline__ float group_sum(float v)
 // sample, evaluated separably (along w, then h, then d).  The reference spends 24 FMAs per channel on the same sums.
 struct SampleGrads { float a, w, h, d; };    // per-lane partial sums over this lane's channels (unscaled)
 
+// The four trilinear forms of a sample from its eight dots, evaluated separably (along w, then h, then d).
+__device__ __forceinline__ SampleGrads grads_from_dots(const float (&dot)[8], const float4 pa, const float4 pb, const int flags)
+{
+  // separable evaluation of the four trilinear forms; s?l / s?h = -1 / +1 where that side is inside, else 0
+  const float sdl = (flags & 2) ? -1.f : 0.f, sdh = (flags & 4) ? 1.f : 0.f;
+  const float shl = (flags & 8) ? -1.f : 0.f, shh = (flags & 16) ? 1.f : 0.f;
+  const float swl = (flags & 32) ? -1.f : 0.f, swh = (flags & 64) ? 1.f : 0.f;
+  float A[4], Bw[4];                                       // index = 2*kd + kh
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    A[i] = pb.z * dot[2 * i] + pb.w * dot[2 * i + 1];
+    Bw[i] = swl * dot[2 * i] + swh * dot[2 * i + 1];
+  }
+  float A2[2], Bh[2], Bw2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    A2[i] = pb.x * A[2 * i] + pb.y * A[2 * i + 1];
+    Bh[i] = shl * A[2 * i] + shh * A[2 * i + 1];
+    Bw2[i] = pb.x * Bw[2 * i] + pb.y * Bw[2 * i + 1];
+  }
+  SampleGrads g;
+  g.a = pa.z * A2[0] + pa.w * A2[1];
+  g.d = sdl * A2[0] + sdh * A2[1];
+  g.h = pa.z * Bh[0] + pa.w * Bh[1];
+  g.w = pa.z * Bw2[0] + pa.w * Bw2[1];
+  return g;
+}
+
 template <typename VT, int G, int NV>
 __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ value, const float (&top)[Vec16<VT>::N * NV],
                                                        const float4 pa, const float4 pb, const int4 pc, unsigned lane_off,
@@ -633,29 +661,7 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
       for (int c = 0; c < VEC; ++c) dot[k] = fmaf(top[nv * VEC + c], v[k][c], dot[k]);
     }
   }
-  // separable evaluation of the four trilinear forms; s?l / s?h = -1 / +1 where that side is inside, else 0
-  const float sdl = (pc.w & 2) ? -1.f : 0.f, sdh = (pc.w & 4) ? 1.f : 0.f;
-  const float shl = (pc.w & 8) ? -1.f : 0.f, shh = (pc.w & 16) ? 1.f : 0.f;
-  const float swl = (pc.w & 32) ? -1.f : 0.f, swh = (pc.w & 64) ? 1.f : 0.f;
-  float A[4], Bw[4];                                       // index = 2*kd + kh
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    A[i] = pb.z * dot[2 * i] + pb.w * dot[2 * i + 1];
-    Bw[i] = swl * dot[2 * i] + swh * dot[2 * i + 1];
-  }
-  float A2[2], Bh[2], Bw2[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    A2[i] = pb.x * A[2 * i] + pb.y * A[2 * i + 1];
-    Bh[i] = shl * A[2 * i] + shh * A[2 * i + 1];
-    Bw2[i] = pb.x * Bw[2 * i] + pb.y * Bw[2 * i + 1];
-  }
-  SampleGrads g;
-  g.a = pa.z * A2[0] + pa.w * A2[1];
-  g.d = sdl * A2[0] + sdh * A2[1];
-  g.h = pa.z * Bh[0] + pa.w * Bh[1];
-  g.w = pa.z * Bw2[0] + pa.w * Bw2[1];
-  return g;
+  return grads_from_dots(dot, pa, pb, pc.w);
 }
 
 // grad_value gets w_k * (t_c * attn) per corner as 128-bit reductions (skipped where the corner weight is zero).  On
@@ -672,7 +678,7 @@ __device__ __forceinline__ SampleGrads sample_backward(const VT *__restrict__ va
 // price of ~35 shuffles per sample and 122 registers (2 CTAs per SM).  Only the order of the fp32 sums changes.  MEASURED SLOWER on
 // B200 (5.16 -> 5.98 ms without jitter, 5.69 -> 6.96 ms with; profiles/r01_experiments.md section 8), so it is off unless
 // msda3d_set_tuning("pair", 1) asks for it.
-template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0, int PAIR = 0>
+template <typename VT, int G, int NV, int MINB, int SKIP_RED = 0, int FUSED = 0, int PAIR = 0, int ROT = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
@@ -695,13 +701,28 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, g0 = lane - gl;
   const int MC = M * C, LP = L * P;
   const long long total = (long long)N * Lq * M;
+  // Sample-order rotation (ROT: 1 = per warp, 2 = per unit).  In brick order the units of a CTA are neighbouring query voxels of one
+  // head; walking their samples in the same order makes all of them reduce into the same few coarse-level voxels at the same moment
+  // (same-address reductions serialise in one L2 slice).  Starting unit i at sample i spreads the CTA over the (level, point) slots.
+  // ROT & 4: consecutive CTAs (the ones resident together) take their runs of slots from DIFFERENT (batch, head) slabs instead of from
+  // neighbouring bricks of one slab, so concurrently running CTAs do not meet in the same coarse-level voxels either.
+  const int rot0 = (ROT & 3) == 0 ? 0 : ((ROT & 3) == 1 ? warp * UPW : warp * UPW + lane / G);
+  static_assert(ROT == 0 || PAIR == 0, "rotation and pair combining exclude each other");
   if (brick && threadIdx.x == 0) make_brick_plan<UPB>(bp, lv, L);
   __syncthreads();
   const long long slots = brick ? (long long)N * M * bp.nb : (total + UPB - 1) / UPB;
   const long long per = (slots + gridDim.x - 1) / gridDim.x;
-  const long long t_end = min(slots, (blockIdx.x + 1) * per);
+  long long t_end = min(slots, (blockIdx.x + 1) * per);
   const unsigned lane_off = gl * VEC;                               // vector nv of this lane starts at nv*G*VEC + gl*VEC
-  for (long long t = blockIdx.x * per; t < t_end; ++t) {
+  long long t_begin = blockIdx.x * per;
+  if ((ROT & 4) != 0) {
+    const int K = N * M, Rk = (int)gridDim.x / K;
+    long long run = blockIdx.x;
+    if (run < (long long)Rk * K) run = (run % K) * Rk + run / K;
+    t_begin = run * per;
+    t_end = min(slots, (run + 1) * per);
+  }
+  for (long long t = t_begin; t < t_end; ++t) {
     const UnitCoords uc = slot_unit<UPB>(brick != 0, t, warp * UPW + lane / G, total, bp, lv, L, M, Lq);
     float top[CPL];
 #pragma unroll
@@ -722,7 +743,10 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
       __syncwarp();
       float r_a = 0.f, r_w = 0.f, r_h = 0.f, r_d = 0.f;            // lane j keeps the sums of sample s0 + j
       const int cnt = min(G, LP - s0);
-      for (int j = 0; j < cnt; ++j) {
+      const int jr = (ROT & 3) == 0 ? 0 : rot0 % cnt;
+      for (int jj = 0; jj < cnt; ++jj) {
+        int j = jj;
+        if ((ROT & 3) != 0) { j += jr; if (j >= cnt) j -= cnt; }
         const int4 pc = sC[warp][g0 + j];
         SampleGrads q = {0.f, 0.f, 0.f, 0.f};
         if constexpr (PAIR != 0) {
@@ -824,6 +848,230 @@ bwd_vec_kernel(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
         gl_[1] = __int2float_rn(li.y) * (r_h * mine.a.y);
         gl_[2] = __int2float_rn(li.x) * (r_d * mine.a.y);
         grad_aw[uc.u * LP + s] = r_a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bwd_duo_kernel: the backward with TWO w-neighbouring query voxels per 16-lane group (fp32, C = 64, brick order).
+//
+// The refinement's queries are the voxels of the pyramid and their offsets come from one Linear layer, so two w-neighbouring queries
+// of one head sample, level by level, the SAME cell (coarser levels: the pair is 1/2 ... 1/8 voxel apart) or w-ADJACENT cells (the
+// pair's own level) unless their offsets differ by a large part of a voxel.  A group that owns both queries then needs 8 (same cell)
+// or 12 (adjacent cells) corner rows instead of 16: that many gathers (the rows feed both units' dots) and that many grad_value
+// reductions (one per row, carrying both units' contributions).  The L2 atomic units and the L1 data pipe -- the two resources that
+// bound bwd_vec_kernel -- see up to half of the traffic.  Detection is exact (corner offsets and clamped strides of the two prepared
+// samples are compared), everything else -- pairs at volume borders, offsets that disagree -- takes the one-unit path of
+// bwd_vec_kernel, unit by unit.  No shuffles and no shared-memory accumulation are involved (the pair lives in ONE lane's registers),
+// which is what made the earlier combining experiments slower (PAIR above; profiles/r01_experiments.md sections 4 and 8).
+// Rows i = 2 * kd + kh; columns c = position along w: A's low / high corners are columns 0 / 1, B's are delta / delta + 1.
+// ---------------------------------------------------------------------------------------------------------------
+// Sum eight per-lane values over the 16 lanes of a group with 8 shuffles instead of 32: every butterfly step halves the number of
+// values a lane carries (it keeps one half of them and hands the other half to its partner).  Returns, in lane gl, the group's
+// total of x[gl >> 1].
+__device__ __forceinline__ float group_sum8_packed(const float (&x)[8], int gl)
+{
+  const bool h1 = (gl & 8) != 0, h2 = (gl & 4) != 0, h3 = (gl & 2) != 0;
+  float y[4], z[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = (h1 ? x[4 + i] : x[i]) + __shfl_xor_sync(0xffffffffu, h1 ? x[i] : x[4 + i], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) z[i] = (h2 ? y[2 + i] : y[i]) + __shfl_xor_sync(0xffffffffu, h2 ? y[i] : y[2 + i], 4);
+  float t = (h3 ? z[1] : z[0]) + __shfl_xor_sync(0xffffffffu, h3 ? z[0] : z[1], 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
+}
+
+template <int SKIP_RED>
+__device__ __forceinline__ SampleGrads duo_single(const float *__restrict__ value, const float (&top)[4], const float4 pa, const float4 pb,
+                                                  const int4 pc, unsigned lane_off, float *__restrict__ grad_value)
+{
+  float w[8];
+  unsigned o[8];
+  const SampleGrads q = sample_backward<float, 16, 1>(value, top, pa, pb, pc, lane_off, w, o);
+  if (SKIP_RED == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (w[k] != 0.f) {
+        const float wk = w[k] * pa.y;
+        red_add_v4(grad_value + o[k], wk * top[0], wk * top[1], wk * top[2], wk * top[3]);
+      }
+    }
+  }
+  return q;
+}
+
+template <int FUSED, int ROT, int SKIP_RED = 0, int THREADS = kThreads, int MINB = 2>
+__global__ void __launch_bounds__(THREADS, MINB)
+bwd_duo_kernel(const float *__restrict__ grad_out, const float *__restrict__ value, const int64_t *__restrict__ shapes,
+               const int64_t *__restrict__ starts, const float *__restrict__ loc, const float *__restrict__ aw, int N, int S,
+               int M, int L, int Lq, int P, float *__restrict__ grad_value, float *__restrict__ grad_loc,
+               float *__restrict__ grad_aw, const float *__restrict__ ref, long long ref_bstride, long long fused_ld, int logit_col)
+{
+  using V = Vec16<float>;
+  constexpr int G = 16, VEC = 4, C = 64, WARPS = THREADS / 32, UPB = WARPS * 4;      // a slot = one head x one 2x4x4 brick = 32 units (256 threads)
+  __shared__ int4 lv[kMaxLevels];
+  __shared__ BrickPlan bp;
+  __shared__ float4 sA[2][WARPS][32];
+  __shared__ float4 sB[2][WARPS][32];
+  __shared__ int4 sC[2][WARPS][32];
+  __shared__ float4 sR[WARPS * 2][G][2];                          // per group and sample: the eight sums {A: a, w, h, d; B: a, w, h, d}
+  if (threadIdx.x < L)
+    lv[threadIdx.x] = make_int4((int)shapes[3 * threadIdx.x], (int)shapes[3 * threadIdx.x + 1],
+                                (int)shapes[3 * threadIdx.x + 2], (int)starts[threadIdx.x]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, g0 = lane - gl, grp = warp * 2 + lane / G;
+  const int MC = M * C, LP = L * P;
+  const long long total = (long long)N * Lq * M;
+  if (threadIdx.x == 0) make_brick_plan<UPB>(bp, lv, L);
+  __syncthreads();
+  const long long slots = (long long)N * M * bp.nb;
+  const long long per = (slots + gridDim.x - 1) / gridDim.x;
+  long long run = blockIdx.x;
+  if ((ROT & 4) != 0) {                                           // consecutive CTAs on different (batch, head) slabs (bwd_vec_kernel, ROT)
+    const int K = N * M, Rk = (int)gridDim.x / K;
+    if (run < (long long)Rk * K) run = (run % K) * Rk + run / K;
+  }
+  const long long t_begin = run * per, t_end = min(slots, (run + 1) * per);
+  const unsigned lane_off = gl * VEC;
+  const int rot0 = (ROT & 3) == 0 ? 0 : ((ROT & 3) == 1 ? warp * 2 : grp);
+  for (long long t = t_begin; t < t_end; ++t) {
+    const UnitCoords ucA = slot_unit<UPB>(true, t, 2 * grp, total, bp, lv, L, M, Lq);
+    const UnitCoords ucB = slot_unit<UPB>(true, t, 2 * grp + 1, total, bp, lv, L, M, Lq);
+    float topA[VEC], topB[VEC];
+    V::load_stream(grad_out + ucA.u * C + lane_off, topA);
+    V::load_stream(grad_out + ucB.u * C + lane_off, topB);
+
+    for (int s0 = 0; s0 < LP; s0 += G) {
+      float wmA = 0.f, wmB = 0.f;
+      const PreparedSample mA = FUSED ? prepare_sample_fused<G>(lv, loc + fused_off_base(ucA, LP, M, fused_ld), aw + fused_logit_base(ucA, LP, M, fused_ld, logit_col),
+                                                                ref, ref_bstride, ucA, s0 + gl, LP, P, L, M, Lq, S, MC, C, wmA)
+                                      : prepare_sample(lv, loc, aw, ucA, s0 + gl, LP, P, S, MC, C);
+      const PreparedSample mB = FUSED ? prepare_sample_fused<G>(lv, loc + fused_off_base(ucB, LP, M, fused_ld), aw + fused_logit_base(ucB, LP, M, fused_ld, logit_col),
+                                                                ref, ref_bstride, ucB, s0 + gl, LP, P, L, M, Lq, S, MC, C, wmB)
+                                      : prepare_sample(lv, loc, aw, ucB, s0 + gl, LP, P, S, MC, C);
+      const float attA = mA.a.y, attB = mB.a.y;
+      __syncwarp();
+      sA[0][warp][lane] = mA.a; sB[0][warp][lane] = mA.b; sC[0][warp][lane] = mA.c;
+      sA[1][warp][lane] = mB.a; sB[1][warp][lane] = mB.b; sC[1][warp][lane] = mB.c;
+      __syncwarp();
+      float rA_a = 0.f, rA_w = 0.f, rA_h = 0.f, rA_d = 0.f, rB_a = 0.f, rB_w = 0.f, rB_h = 0.f, rB_d = 0.f;   // lane j keeps the sums of sample s0 + j
+      const int cnt = min(G, LP - s0);
+      const int jr = (ROT & 3) == 0 ? 0 : rot0 % cnt;
+      for (int jj = 0; jj < cnt; ++jj) {
+        int j = jj;
+        if ((ROT & 3) != 0) { j += jr; if (j >= cnt) j -= cnt; }
+        const int4 pcA = sC[0][warp][g0 + j], pcB = sC[1][warp][g0 + j];
+        SampleGrads qA = {0.f, 0.f, 0.f, 0.f}, qB = {0.f, 0.f, 0.f, 0.f};
+        const bool actA = pcA.w != 0, actB = pcB.w != 0;
+        if (actA || actB) {
+          const float4 paA = sA[0][warp][g0 + j], pbA = sB[0][warp][g0 + j], paB = sA[1][warp][g0 + j], pbB = sB[1][warp][g0 + j];
+          const unsigned offA = __float_as_uint(paA.x), offB = __float_as_uint(paB.x);
+          const bool geom = actA && actB && pcA.x == pcB.x && pcA.y == pcB.y && pcA.z == pcB.z;
+          const bool same = geom && offA == offB;
+          const bool shift = geom && pcA.z != 0 && offB == offA + (unsigned)pcA.z;
+          if (same || shift) {
+            unsigned orow[4];
+            orow[0] = offA + lane_off; orow[1] = orow[0] + pcA.y; orow[2] = orow[0] + pcA.x; orow[3] = orow[2] + pcA.y;
+            const unsigned sw = (unsigned)pcA.z;
+            float v[4][3][VEC];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              V::load(value + orow[i], v[i][0]);
+              V::load(value + (orow[i] + sw), v[i][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (shift) {
+                V::load(value + (orow[i] + 2u * sw), v[i][2]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) v[i][2][c] = 0.f;
+              }
+            }
+            float dotA[8], dotB[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float dA0 = 0.f, dA1 = 0.f, dB0 = 0.f, dB1 = 0.f, dB2 = 0.f;
+#pragma unroll
+              for (int c = 0; c < VEC; ++c) {
+                dA0 = fmaf(topA[c], v[i][0][c], dA0); dA1 = fmaf(topA[c], v[i][1][c], dA1);
+                dB0 = fmaf(topB[c], v[i][0][c], dB0); dB1 = fmaf(topB[c], v[i][1][c], dB1); dB2 = fmaf(topB[c], v[i][2][c], dB2);
+              }
+              dotA[2 * i] = dA0; dotA[2 * i + 1] = dA1;
+              dotB[2 * i] = shift ? dB1 : dB0; dotB[2 * i + 1] = shift ? dB2 : dB1;
+            }
+            qA = grads_from_dots(dotA, paA, pbA, pcA.w);
+            qB = grads_from_dots(dotB, paB, pbB, pcB.w);
+            if (SKIP_RED == 0) {
+              // row weights (d x h) in the product order of corner_weights_axes, times the unit's attention weight (cuh:151,166)
+              const float rwA[4] = {__fmul_rn(paA.z, pbA.x), __fmul_rn(paA.z, pbA.y), __fmul_rn(paA.w, pbA.x), __fmul_rn(paA.w, pbA.y)};
+              const float rwB[4] = {__fmul_rn(paB.z, pbB.x), __fmul_rn(paB.z, pbB.y), __fmul_rn(paB.w, pbB.x), __fmul_rn(paB.w, pbB.y)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float wAl = __fmul_rn(rwA[i], pbA.z), wAh = __fmul_rn(rwA[i], pbA.w);
+                const float wBl = __fmul_rn(rwB[i], pbB.z), wBh = __fmul_rn(rwB[i], pbB.w);
+                const float a0 = wAl * paA.y, a1 = wAh * paA.y;
+                const float b0 = (shift ? 0.f : wBl) * paB.y, b1 = (shift ? wBl : wBh) * paB.y, b2 = wBh * paB.y;
+                if (wAl != 0.f || (!shift && wBl != 0.f))
+                  red_add_v4(grad_value + orow[i], fmaf(b0, topB[0], a0 * topA[0]), fmaf(b0, topB[1], a0 * topA[1]),
+                             fmaf(b0, topB[2], a0 * topA[2]), fmaf(b0, topB[3], a0 * topA[3]));
+                if (wAh != 0.f || (shift ? wBl != 0.f : wBh != 0.f))
+                  red_add_v4(grad_value + (orow[i] + sw), fmaf(b1, topB[0], a1 * topA[0]), fmaf(b1, topB[1], a1 * topA[1]),
+                             fmaf(b1, topB[2], a1 * topA[2]), fmaf(b1, topB[3], a1 * topA[3]));
+                if (shift && wBh != 0.f)
+                  red_add_v4(grad_value + (orow[i] + 2u * sw), b2 * topB[0], b2 * topB[1], b2 * topB[2], b2 * topB[3]);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int u = 0; u < 2; ++u) {                           // one code copy for both units (instruction-cache footprint)
+              const float4 pa = u ? paB : paA, pb = u ? pbB : pbA;
+              const int4 pc = u ? pcB : pcA;
+              if (pc.w == 0) continue;
+              const float top[VEC] = {u ? topB[0] : topA[0], u ? topB[1] : topA[1], u ? topB[2] : topA[2], u ? topB[3] : topA[3]};
+              const SampleGrads q = duo_single<SKIP_RED>(value, top, pa, pb, pc, lane_off, grad_value);
+              if (u) qB = q; else qA = q;
+            }
+          }
+        }
+        const float x[8] = {qA.a, qA.w, qA.h, qA.d, qB.a, qB.w, qB.h, qB.d};
+        const float tot = group_sum8_packed(x, gl);                // lane gl: total of x[gl >> 1]
+        if ((gl & 1) == 0) reinterpret_cast<float *>(&sR[grp][j][0])[gl >> 1] = tot;
+      }
+      __syncwarp();
+      {
+        if (gl < cnt) {                                            // lane j takes the sums of sample s0 + j
+          const float4 ra = sR[grp][gl][0], rb = sR[grp][gl][1];
+          rA_a = ra.x; rA_w = ra.y; rA_h = ra.z; rA_d = ra.w; rB_a = rb.x; rB_w = rb.y; rB_h = rb.z; rB_d = rb.w;
+        }
+      }
+      const int s = s0 + gl;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const UnitCoords &uc = u ? ucB : ucA;
+        const float r_a = u ? rB_a : rA_a, r_w = u ? rB_w : rA_w, r_h = u ? rB_h : rA_h, r_d = u ? rB_d : rA_d;
+        const float att = u ? attB : attA, w_mine = u ? wmB : wmA;
+        if (FUSED) {
+          const float dot = group_sum_f<G>(w_mine * r_a);          // softmax backward needs the whole unit: every lane takes part
+          if (uc.active && s < LP) {
+            const int4 li = lv[s / P];
+            const float fw = __int2float_rn(li.z), fh = __int2float_rn(li.y), fd = __int2float_rn(li.x);
+            float *gl_ = grad_loc + fused_off_base(uc, LP, M, fused_ld) + 3 * s;
+            gl_[0] = __fdiv_rn(fw * (r_w * att), fw);
+            gl_[1] = __fdiv_rn(fh * (r_h * att), fh);
+            gl_[2] = __fdiv_rn(fd * (r_d * att), fd);
+            grad_aw[fused_logit_base(uc, LP, M, fused_ld, logit_col) + s] = w_mine * (r_a - dot);
+          }
+        } else if (uc.active && s < LP) {
+          const int4 li = lv[s / P];
+          float *gl_ = grad_loc + (uc.u * LP + s) * 3;
+          gl_[0] = __int2float_rn(li.z) * (r_w * att);
+          gl_[1] = __int2float_rn(li.y) * (r_h * att);
+          gl_[2] = __int2float_rn(li.x) * (r_d * att);
+          grad_aw[uc.u * LP + s] = r_a;
+        }
       }
     }
   }
