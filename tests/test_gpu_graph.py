@@ -82,7 +82,7 @@ def test_replayed_graph_draws_new_dropout_masks():
 
 def test_graph_step_follows_the_eager_step():
     """Same weights, same inputs, dropout off (eval-mode modules but gradients and AdamW on): the replayed graph must reproduce the
-    eager losses step for step -- the fp32 atomics of the msda3d backward are the only source of differences."""
+    eager losses step for step -- the fp32 atomics of the msda3d backward are the only source of differences (see the tolerance note)."""
     from transoar_b200.engine import TrainStep, synthetic_targets, visceral_train_config
     prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
     try:
@@ -100,9 +100,13 @@ def test_graph_step_follows_the_eager_step():
         le = [float(eager.step(xs[i % 3], tgs[i % 3])) for i in range(6)]
         lg = [float(graph.step(xs[i % 3], tgs[i % 3])) for i in range(6)]
         assert graph._cuda_graph is not None
-        for a, b in zip(le, lg):
-            assert abs(a - b) < 1e-2 * abs(a), (le, lg)
-        assert le[-1] < le[0]
+        # Steps 0 and 1 (the loss after one replayed optimizer update) must agree to fp32 noise.  From step 2 on the trajectory is
+        # chaotic in BOTH modes: the order of the msda3d backward's fp32 reductions differs run to run by ~1e-6, AdamW turns that
+        # into +-lr on near-zero gradients and the Hungarian matching flips an assignment -- eight eager-vs-graph runs on one box
+        # took two or three distinct branches per step (step 2: 10.5835 / 10.5485, step 5: 10.52 ... 10.69), eager and graph alike.
+        for i, (a, b) in enumerate(zip(le, lg)):
+            assert abs(a - b) < (1e-5 if i < 2 else 5e-2) * abs(a), (le, lg)
+        assert le[-1] < le[0] and lg[-1] < lg[0]
         graph.close()
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
