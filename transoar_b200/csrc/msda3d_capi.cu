@@ -17,6 +17,7 @@
 using namespace msda3d;
 
 std::atomic<unsigned long long> g_msda3d_launches{0};   // shared with roi_attn_capi.cu
+extern std::atomic<int> g_roi_splits;                    // roi_attn_capi.cu: token splits per box (msda3d_set_tuning "roi_splits")
 
 namespace {
 
@@ -255,6 +256,7 @@ int msda3d_set_tuning(const char *key, int value)
   if (k == "order" && value >= 0 && value <= 2) { g_tune_order = value; return MSDA3D_OK; }
   if (k == "pair" && value >= 0 && value <= 1) { g_tune_pair = value; return MSDA3D_OK; }
   if (k == "duo" && value >= 0 && value <= 1) { g_tune_duo = value; return MSDA3D_OK; }
+  if (k == "roi_splits" && value >= 0 && value <= 16) { g_roi_splits = value; return MSDA3D_OK; }
   if (k == "duo_cfg" && value >= 0 && value <= 2) { g_tune_duo_cfg = value; return MSDA3D_OK; }
   if (k == "rot" && value >= 0 && value <= 6 && value != 3) { g_tune_rot = value; return MSDA3D_OK; }
   return MSDA3D_EINVAL;

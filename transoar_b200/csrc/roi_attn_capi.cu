@@ -7,6 +7,7 @@
 #include "../../include/roi_attn.h"
 
 extern std::atomic<unsigned long long> g_msda3d_launches;
+std::atomic<int> g_roi_splits{0};        // token splits per box forced by msda3d_set_tuning("roi_splits", n); 0 = pick_splits' own choice
 
 namespace {
 
@@ -38,11 +39,16 @@ int launch_bwd(cudaStream_t st, int G, int B, const float *q, const float *k, co
   return (int)cudaGetLastError();
 }
 
-// Token splits per box: enough CTAs for ~4 per SM, at most 16 (each split re-reads Q and adds a partial state).
+// Token splits per box: enough CTAs for ~20 per SM, at most 16 (each split re-reads Q and adds a partial state).  The boxes of an atlas
+// differ 2.7x in size (3024 ... 8265 tokens in the VISCERAL config) and a CTA walks its share serially, so with one wave of CTAs
+// (the earlier "~4 per SM": 2 splits) the largest box set the time; several small waves balance themselves.  Sweep on B200
+// (tools/exp_roi_splits.py, profiles/r04i_roi_splits.txt): 2 splits 0.416 / 1.225 ms (forward / backward), 10 splits 0.286 / 0.978 ms.
 int pick_splits(int G, int H, int B)
 {
+  const int forced = g_roi_splits.load();                         // msda3d_set_tuning("roi_splits", n): experiment switch, 0 = automatic
+  if (forced > 0) return forced > 16 ? 16 : forced;
   const long long ctas = (long long)G * H * B;
-  long long s = (148LL * 4 + ctas - 1) / ctas;
+  long long s = (148LL * 20 + ctas - 1) / ctas;
   return (int)(s < 1 ? 1 : s > 16 ? 16 : s);
 }
 
