@@ -101,3 +101,25 @@ def test_install_into_reference_requires_the_reference_package():
     else:  # pragma: no cover - only when the reference happens to be importable
         mod = transoar_b200.install_into_reference()
         assert mod.MSDA is MSDA
+
+
+def test_tuning_switches_and_their_environment_hook(monkeypatch):
+    """include/msda3d.h msda3d_set_tuning: known keys / ranges are accepted, anything else is MSDA3D_EINVAL; TRANSOAR_B200_TUNING applies
+    the switches when the package loads the library and rejects a typo loudly (no GPU needed: the switches are host state)."""
+    from transoar_b200 import _lib
+    lib = _lib.lib()
+    for key, good, bad in ((b"duo", 0, 2), (b"rot", 6, 3), (b"duo_cfg", 2, 3), (b"roi_splits", 16, 17), (b"pair", 1, 2), (b"order", 2, 3)):
+        assert lib.msda3d_set_tuning(key, good) == 0
+        assert lib.msda3d_set_tuning(key, bad) != 0
+        assert lib.msda3d_set_tuning(key, 1 if key == b"duo" else 0) == 0                  # back to the defaults
+    assert lib.msda3d_set_tuning(b"no_such_switch", 1) != 0
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("TRANSOAR_B200_TUNING", "duo=0, rot=4")
+    assert _lib.lib().msda3d_set_tuning(b"duo", 1) == 0 and _lib.lib().msda3d_set_tuning(b"rot", 0) == 0
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("TRANSOAR_B200_TUNING", "duoo=1")
+    with pytest.raises(RuntimeError, match="TRANSOAR_B200_TUNING"):
+        _lib.lib()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.delenv("TRANSOAR_B200_TUNING")
+    _lib.lib()
