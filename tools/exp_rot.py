@@ -36,6 +36,7 @@ for sigma in [float(v) for v in os.environ.get('SIGMAS', '0.03,1.0').split(',')]
         _lib.lib().msda3d_set_tuning(b"diag_bwd_skip_red", 1 if rot % 10000 >= 2000 else 0)
         _lib.lib().msda3d_set_tuning(b"duo_cfg", rot // 10000)
         _lib.lib().msda3d_set_tuning(b"rot", rot % 100)
+        _lib.lib().msda3d_set_tuning(b"grid_mult", int(os.environ.get("GRID_MULT", "0")))
         f = lambda: MSDA.ms_deform_attn_backward_merged(value, shapes, starts, ref, merged, gout, L, P)
         gv, gm = f()
         t = timeit(f)
