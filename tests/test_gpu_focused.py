@@ -165,10 +165,34 @@ def test_transoarnet_against_reference_fixture():
         if "pg." + k in z.files and float(np.abs(z["pg." + k]).max()) > 1e-6:
             # encoder parameter gradients are fp32 sums over up to 8.4 M voxels behind six InstanceNorm stages, driven by a
             # loss that only sees 14 queries: heavy cancellation, the CPU fixture and the GPU differ by up to ~7 % of the
-            # tensor's max there (measured) purely from accumulation order; everything outside the encoder is tight
+            # tensor's max there (measured) purely from accumulation order; everything outside the encoder is tight.
+            # Yardstick (tests/golden/transoarnet_fp64.npz, tests/test_model_yardstick_cpu.py): the REFERENCE's own fp32 CPU
+            # run is up to 2.7 % of the tensor's max away from its float64 run in exactly these tensors, < 4e-5 in all others
             errs["grad " + k] = (_rel(p.grad, t("pg." + k)), 1e-1 if k.startswith("_backbone._encoder") else 5e-3)
+    _report_against_fp64(out, net)
     bad = {k: v for k, v in errs.items() if not v[0] < v[1]}
     assert not bad, f"{len(bad)} of {len(errs)} quantities off: {bad}"
+
+
+def _report_against_fp64(out, net):
+    """Not an assertion: per tensor, this run's distance to the reference's float64 run next to the reference's own fp32 CPU distance
+    (``e32.*``), written to gpurun_out/ when that directory exists so the ratio can be read after a GPU run."""
+    try:
+        import json
+        z64 = np.load(os.path.join(GOLDEN, "transoarnet_fp64.npz"))
+        got = {"pred_logits": out["pred_logits"], "pred_boxes": out["pred_boxes"], "aux0_boxes": out["aux_outputs"][0]["pred_boxes"]}
+        got.update({"pg." + k: p.grad for k, p in net.named_parameters() if p.grad is not None and "pg." + k in z64.files})
+        rows = {}
+        for k, v in got.items():
+            ref = z64[k]
+            err = float(np.abs(v.detach().double().cpu().numpy() - ref).max() / max(float(np.abs(ref).max()), 1e-30))
+            rows[k] = {"gpu_vs_fp64": err, "reference_cpu_fp32_vs_fp64": float(z64["e32." + k])}
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "model_parity_vs_fp64.json"), "w") as f:
+                json.dump(rows, f, indent=1)
+    except Exception as exc:                                   # a report must never fail the parity test
+        print("fp64 report skipped:", exc)
 
 
 @pytest.mark.parametrize("hd,H,per,grid", [(48, 8, 27, (6, 7, 9)), (16, 2, 1, (3, 3, 3)), (32, 3, 7, (5, 4, 8)), (64, 2, 54, (4, 6, 5)),
