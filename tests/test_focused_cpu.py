@@ -74,3 +74,17 @@ def test_mirrors_are_checkpoint_compatible_and_keep_the_dead_q_proj():
     assert len(dec.decoder.layers) == 3 and dec.decoder.return_intermediate
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         layer(torch.zeros(1, 14, 96), None, None, torch.zeros(1, 256, 96))
+
+
+def test_key_value_tokens_must_match_the_grid_the_boxes_were_built_for():
+    """a feature map other than the one the RoI boxes were built for would index past the key / value tokens.  The reference
+    fails at ``attn += mask`` (focused_decoder.py:243-245: [Nq, X*Y*Z] does not broadcast against [B, H, Nq, Nkv]); the mirror raises before
+    any device work."""
+    boxes = torch.tensor([[0, 0, 0, 2, 2, 2], [1, 1, 1, 3, 3, 3]], dtype=torch.int32)
+    attn = focused.FocusedAttn(32, 2, boxes, grid_shape=(3, 3, 3))
+    q = torch.zeros(1, 2, 32)
+    for nkv in (26, 28, 54):
+        with pytest.raises(RuntimeError, match=r"RoI boxes were built for a \(3, 3, 3\) feature map"):
+            attn(q, torch.zeros(1, nkv, 32), torch.zeros(1, nkv, 32))
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):         # the right token count reaches the native op
+        attn(q, torch.zeros(1, 27, 32), torch.zeros(1, 27, 32))
