@@ -156,6 +156,8 @@ def train(config, args):
             print(json.dumps(record), flush=True)
             if not config["debug_mode"]:
                 save_checkpoint(path_to_run / "model_last.pt", epoch, metric_max_val, ts.net, ts.optim, scheduler)
+    if log is not None:
+        log.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
