@@ -101,3 +101,23 @@ def test_op_backward_uses_vector_reductions_and_the_staged_forward_uses_bulk_cop
     # the op's kernels run on CUDA cores: no tensor-core / tensor-map instruction, and no packed fp32 arithmetic yet
     assert _total(sass["msda3d"], "UTC") == 0 and _total(sass["msda3d"], "UTMALDG") == 0
     assert _total(sass["msda3d"], "FFMA2") == 0 and _total(sass["msda3d"], "FMUL2") == 0
+
+
+def test_register_and_stack_budgets_of_the_shipped_kernels():
+    """`cuobjdump -res-usage`: the tcgen05 kernels keep everything in registers (no stack frame = no spills), and the op's default
+    kernels fit the occupancy DESIGN.md quotes: forward <= 64 registers (4 CTAs of 256 threads per SM), one-unit backward <= 80 (3 CTAs),
+    pair kernel <= 128 (2 CTAs)."""
+    try:
+        out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True, timeout=600).stdout
+    except (subprocess.SubprocessError, OSError) as exc:
+        pytest.skip(f"cuobjdump -res-usage failed: {exc}")
+    rows = {n: (int(reg), int(stack)) for n, reg, stack in re.findall(r"Function (\S+):\n\s+REG:(\d+) STACK:(\d+)", out)}
+    assert len(rows) >= 400
+    for prefix in ("_ZN6tcgemm", "_ZN6convtc", "_ZN7convgen", "_ZN7winattn", "_ZN7fusedln", "_ZN4crit"):
+        fam = {n: v for n, v in rows.items() if n.startswith(prefix)}
+        assert fam and all(stack == 0 for _, stack in fam.values()), prefix
+    reg = lambda frag: [v[0] for n, v in rows.items() if frag in n]
+    assert reg("fwd_vec_kernelIfLi16ELi1ELi4E") and max(reg("fwd_vec_kernelIfLi16ELi1ELi4E")) <= 64
+    assert reg("bwd_vec_kernelIfLi16ELi1ELi3E") and max(reg("bwd_vec_kernelIfLi16ELi1ELi3E")) <= 80
+    shipped_duo = [v for n, v in rows.items() if "bwd_duo_kernel" in n and "Li256ELi2E" in n]
+    assert shipped_duo and max(r for r, _ in shipped_duo) <= 128 and max(s for _, s in shipped_duo) <= 16
