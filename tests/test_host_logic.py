@@ -1,5 +1,6 @@
 """Host-side mirror of the reference interface: error behaviour, module surface, synthetic input generators."""
 import math
+import os
 
 import pytest
 import torch
@@ -123,3 +124,32 @@ def test_tuning_switches_and_their_environment_hook(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.delenv("TRANSOAR_B200_TUNING")
     _lib.lib()
+
+
+def test_only_the_checkers_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under transoar_b200/ (the product) or tools/install_reference.py may import it; the only
+    importers are tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference / ref_* legs) and measurement tools."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def imports_oracle(path):
+        with open(path) as f:
+            tree = ast.parse(f.read(), path)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                return True
+            if isinstance(node, ast.ImportFrom) and node.level == 0 and (node.module or "").split(".")[0] == "oracle":
+                return True
+        return False
+
+    product = []
+    for d, _, files in os.walk(os.path.join(root, "transoar_b200")):
+        product += [os.path.join(d, f) for f in files if f.endswith(".py")]
+    assert len(product) >= 25
+    offenders = [os.path.relpath(p, root) for p in product if imports_oracle(p)]
+    assert not offenders, offenders
+    # ... and the library itself links nothing from oracle/
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", os.path.join(root, "transoar_b200", "libmsda3d.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "torch" not in needed and "libcudart" not in needed          # static CUDA runtime, no torch types
+    assert imports_oracle(os.path.join(root, "bench.py")) and imports_oracle(os.path.join(root, "__graft_entry__.py"))
