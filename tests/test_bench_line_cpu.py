@@ -55,3 +55,27 @@ def test_roofline_is_algorithmic_bytes_over_measured_time_over_measured_peak(lin
     assert r["traffic"] is None or r["traffic"] >= 0.9 * bwd_bytes                  # measured DRAM bytes cannot be far below compulsory
     # the dominant kernel's two launches per step cannot exceed the step
     assert 2 * line["kernels"]["msda3d_bwd_ms"] < line["ms_per_step"]
+
+
+def test_dominant_kernels_share_agrees_between_events_and_the_ncu_launch_list(line):
+    """The contract's cross-check: ncu's per-launch times are cold-cache and serialised, so the roofline kernel's SHARE of the step -- not
+    its absolute time -- must agree between the CUDA-event timing of the bench line and the launch list of the same code."""
+    import csv
+    rows = []
+    with open(os.path.join(ROOT, "profiles", "r04j_launches.csv")) as f:
+        for r in csv.reader(l for l in f if l.startswith('"')):
+            rows.append(r)
+    head, rows = rows[0], rows[1:]
+    name, unit, val = head.index("Kernel Name"), head.index("Metric Unit"), head.index("Metric Value")
+    scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}
+    ms = [(r[name], float(r[val].replace(",", "")) * scale[r[unit]]) for r in rows]
+    total = sum(t for _, t in ms)
+    duo = [t for n, t in ms if "bwd_duo_kernel" in n]
+    assert len(ms) >= 700 and len(duo) == 2                               # one eager step: two refinement layers
+    share_ncu = sum(duo) / total
+    share_events = 2 * line["kernels"]["msda3d_bwd_ms"] / line["ms_per_step"]
+    assert abs(share_ncu - share_events) < 0.02, (share_ncu, share_events)
+    ours = sum(t for n, t in ms if any(ns in n for ns in ("msda3d::", "tcgemm::", "convgen::", "convtc::", "roiattn::", "instnorm::", "fusedln::",
+                                                          "stemconv::", "crit::", "winattn::")))
+    assert ours / total > 0.85                                            # the step is this library's kernels
+    assert not any("cudnn" in n.lower() or "implicit_gemm" in n or "implicit_convolve" in n for n, _ in ms)      # no cuDNN convolution left in the step
