@@ -84,3 +84,59 @@ def test_cpu_reference_route_of_the_train_step_runs_and_learns():
     tg = synthetic_targets(cfg, 1, 0, "cpu")
     losses = [ts.step(x, tg)[1] for _ in range(2)]
     assert all(l == l and l < 1e3 for l in losses) and losses[1] < losses[0]
+
+
+def test_reference_arm_runs_on_rank_zero_only(monkeypatch, capfd):
+    """`--impl reference` under torchrun (N > 1): rank 0 alone times the host arm and prints the line; every other rank exits 0 without
+    work and without output."""
+    import argparse
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(bench, "CpuArm", lambda *a, **k: (_ for _ in ()).throw(AssertionError("rank 1 must not build the CPU arm")))
+    assert bench.run_reference_arm(argparse.Namespace(gpus=2, steps=3, warmup=1)) == 0
+    assert capfd.readouterr().out == ""
+
+
+def test_reference_arm_line_and_wall_budget(monkeypatch):
+    """The host arm's JSON line (contract keys of `--impl reference`) and its wall budget: with steps that would overrun the budget the
+    warm-up is cut to the one step already done and the timed steps stop early, and `steps` / `warmup` say what was actually run."""
+    import argparse
+
+    class FakeArm:
+        threads, kind = 16, "reference"
+
+        def __init__(self, threads):
+            self.calls = 0
+
+        def step(self):
+            self.calls += 1
+            clock.now += self.sec                           # the arm's wall budget is read from the clock, not from the returned times
+            return self.sec
+
+        def sample_text(self, times, warm):
+            return f"{len(times)} timed / {warm} warm"
+
+    class clock:
+        now = 0.0
+        perf_counter = staticmethod(lambda: clock.now)
+
+    lines = []
+    monkeypatch.setattr(bench, "time", clock)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setattr(bench, "CpuArm", FakeArm)
+    monkeypatch.setattr(bench, "emit", lines.append)
+    # cheap steps: everything requested is run
+    FakeArm.sec = 0.001
+    assert bench.run_reference_arm(argparse.Namespace(gpus=1, steps=4, warmup=2)) == 0
+    line = lines.pop()
+    assert line["impl"] == "reference" and line["steps"] == 4 and line["warmup"] == 2 and line["gpu_launches"] == 0
+    assert line["metric"] == bench.METRIC and line["unit"] == bench.UNIT and line["config"] == bench.workload_config()
+    assert line["value"] == pytest.approx(bench.CPU_STEP_VOLUMES / 0.001) and line["ms_per_step"] == pytest.approx(1.0)
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 16 and line["cpu_baseline"]["value"] == line["value"]
+    # steps that claim 400 s each against a 780 s budget: one warm-up, then no more than the two timed steps the mean needs
+    monkeypatch.setenv("TRANSOAR_REF_BUDGET_S", "780")
+    FakeArm.sec = 400.0
+    assert bench.run_reference_arm(argparse.Namespace(gpus=1, steps=20, warmup=5)) == 0
+    line = lines.pop()
+    assert line["warmup"] == 1 and line["steps"] == 2 and line["steps_requested"] == 20 and line["warmup_requested"] == 5
