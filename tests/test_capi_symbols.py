@@ -66,3 +66,31 @@ def test_header_cites_the_reference_interfaces_it_replaces():
     text = open(os.path.join(ROOT, "include", "msda3d.h")).read()
     for needle in ("ms_deform_im2col_cuda.cuh:1094-1125", "cuh:1127-1507", "ms_deform_attn_cuda.cu", "vision.cpp:13-16"):
         assert needle in text
+
+
+def test_missing_library_fails_loudly_and_nothing_falls_back():
+    """The product path must fail when the CUDA extension is missing: a fresh interpreter whose MSDA3D_LIB points at a file that does not
+    exist raises from the first native call -- the loader names the build command and there is no CPU / PyTorch route to fall into."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from transoar_b200 import _lib\n"
+        "from transoar_b200.ops.functions import MSDeformAttnFunction\n"
+        "try:\n"
+        "    _lib.lib()\n"
+        "except RuntimeError as e:\n"
+        "    assert 'is missing' in str(e) and 'no CPU or PyTorch fallback' in str(e), e\n"
+        "else:\n"
+        "    raise SystemExit('loader returned a library that does not exist')\n"
+        "import transoar_b200.instnorm as I\n"
+        "try:\n"
+        "    I.instance_norm_relu(torch.zeros(1, 2, 2, 2, 2), torch.ones(2), torch.zeros(2))\n"
+        "except RuntimeError as e:\n"
+        "    print('LOUD', type(e).__name__)\n"
+        "else:\n"
+        "    raise SystemExit('instance_norm_relu computed something without the library')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MSDA3D_LIB="/nonexistent/libmsda3d.so", PYTHONPATH=root)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert res.returncode == 0 and "LOUD" in res.stdout, res.stdout + res.stderr
