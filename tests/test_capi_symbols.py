@@ -94,3 +94,18 @@ def test_missing_library_fails_loudly_and_nothing_falls_back():
     env = dict(os.environ, MSDA3D_LIB="/nonexistent/libmsda3d.so", PYTHONPATH=root)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
     assert res.returncode == 0 and "LOUD" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("zero", range(7))
+def test_empty_problems_are_rejected_not_launched(zero):
+    """any of N, S, M, C, L, Lq, P equal to 0 is MSDA3D_EINVAL for forward and backward (the reference launches
+    zero blocks and prints the launch error, cuh:1119-1123)."""
+    lib = _lib.lib()
+    buf = (ctypes.c_double * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    dims = [1, 8, 1, 4, 1, 1, 1]
+    dims[zero] = 0
+    before = lib.msda3d_launch_count()
+    assert lib.msda3d_forward(None, 0, p, p, p, p, p, *dims, p) == -1
+    assert lib.msda3d_backward(None, 0, p, p, p, p, p, p, *dims, p, p, p) == -1
+    assert lib.msda3d_launch_count() == before
